@@ -1,0 +1,129 @@
+/* TEST INFRASTRUCTURE ONLY -- the CPU oracle.  Nothing in the product path
+ * (bbcat-dsp_b200/, include/) may include, link or call anything declared here;
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs do.
+ *
+ * Plain-C restatement of the bbcat-dsp partitioned-convolution path:
+ *   - the in-tree pieces (formats / mixing / interpolator / fractional sample /
+ *     delay ring) follow /root/reference/src line by line and are PINNED against
+ *     the reference's own code compiled into oracle/_ref/libbbcref.so and against
+ *     tests/golden/ *.npz generated from it (tools/gen_golden.py);
+ *   - BlockConvolver / Convolver / FFT are ABSENT from the mounted reference
+ *     (README:38-51 vs src/CMakeLists.txt:2-25) and FFTW (debian/control:5) is not
+ *     installed, so upols.c / convolver.c implement SURVEY.md 8.A (normative) with an
+ *     own FFT, and are pinned against a float64 direct convolution (direct.c) and
+ *     numpy/scipy float64.  PARITY UNPINNED against any BBC convolver output: none
+ *     exists in the tree (no tests, no golden vectors).
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* SampleFormat_t numeric values, SoundFormatConversions.h:20-37 */
+enum {
+  ORC_FMT_UNKNOWN = 0,
+  ORC_FMT_16BIT = 1,
+  ORC_FMT_24BIT = 2,
+  ORC_FMT_32BIT = 3,
+  ORC_FMT_FLOAT = 4,
+  ORC_FMT_DOUBLE = 5,
+  ORC_FMT_COUNT = 6
+};
+
+/* ---- formats.c : SoundFormatConversions.cpp / SoundFormatRawConversions.cpp ---- */
+unsigned orc_get_bits_per_sample(int fmt);
+unsigned orc_get_bytes_per_sample(int fmt);
+int orc_block_transfer_sanity_checks(unsigned* src_channel, unsigned* src_channels, unsigned* dst_channel,
+                                     unsigned* dst_channels, unsigned* nchannels, unsigned* nframes,
+                                     int allowsinglechannel);
+void orc_transfer_samples(const void* src, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                          void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                          unsigned nchannels, unsigned nframes);
+void orc_transfer_samples_linear(const void* src, int srctype, void* dst, int dsttype, unsigned nsamples);
+
+/* ---- mixing.c : SoundMixing.h/.cpp, Interpolator.h ---- */
+void orc_mix_samples_f32(const float* src, unsigned src_channel, unsigned src_channels, float* dst,
+                         unsigned dst_channel, unsigned dst_channels, unsigned nchannels, unsigned nframes, float mul);
+void orc_mix_samples_f64(const double* src, unsigned src_channel, unsigned src_channels, double* dst,
+                         unsigned dst_channel, unsigned dst_channels, unsigned nchannels, unsigned nframes, double mul);
+/* interp_state = {target, current}, advanced in place */
+void orc_mix_samples_interp(const float* src, unsigned src_channel, unsigned src_channels, float* dst,
+                            unsigned dst_channel, unsigned dst_channels, unsigned nchannels, unsigned nframes,
+                            float* interp_state, float inc);
+void orc_interpolator_step(float* interp_state, float inc, unsigned nsteps);
+
+/* ---- fracsample.c : FractionalSample.cpp ---- */
+unsigned orc_fractional_sample_additional_delay_required(void);
+double orc_fractional_sample_f32(const float* buffer, unsigned channel, unsigned channels, unsigned length, double pos);
+double orc_fractional_sample_f64(const double* buffer, unsigned channel, unsigned channels, unsigned length, double pos);
+void orc_fractional_samples_f32(const float* buffer, unsigned channel, unsigned channels, unsigned length,
+                                const double* pos, unsigned n, double* out);
+void orc_fractional_samples_f64(const double* buffer, unsigned channel, unsigned channels, unsigned length,
+                                const double* pos, unsigned n, double* out);
+
+/* ---- delaybuf.c : SoundDelayBuffer.cpp:26-191 ---- */
+typedef struct orc_delay orc_delay;
+orc_delay* orc_delay_create(void);
+void orc_delay_destroy(orc_delay* d);
+void orc_delay_set_size(orc_delay* d, unsigned chans, unsigned length, int fmt);
+unsigned orc_delay_get_channels(const orc_delay* d);
+unsigned orc_delay_get_length(const orc_delay* d);
+unsigned orc_delay_get_write_position(const orc_delay* d);
+int orc_delay_get_format(const orc_delay* d);
+unsigned orc_delay_write_samples(orc_delay* d, const void* src, int srcformat, unsigned channel, unsigned nchannels,
+                                 unsigned nframes);
+void orc_delay_increment_write_position(orc_delay* d, unsigned nframes);
+unsigned orc_delay_read_samples(orc_delay* d, void* dst, int dstformat, unsigned delay, unsigned channel,
+                                unsigned nchannels, unsigned nframes);
+unsigned orc_delay_copy_buffer(const orc_delay* d, void* dst, unsigned maxbytes);
+
+/* ---- fft.c : own FFT (FFTW stand-in, unnormalised both directions) ---- */
+/* complex in-place FFT of n (power of two) interleaved float pairs; inverse != 0 conjugates the kernel */
+void orc_cfft(float* data, unsigned n, int inverse);
+/* real -> half-complex: in[n] real, out[n/2+1] interleaved complex */
+void orc_rfft(const float* in, float* out, unsigned n);
+/* half-complex -> real, unnormalised (caller scales by 1/n) */
+void orc_irfft(const float* in, float* out, unsigned n);
+
+/* ---- upols.c : SURVEY.md 8.A BlockConvolver ---- */
+typedef struct orc_filter orc_filter;
+orc_filter* orc_filter_create(const float* ir, unsigned length, unsigned block);
+void orc_filter_destroy(orc_filter* f);
+unsigned orc_filter_partitions(const orc_filter* f);
+unsigned orc_filter_block(const orc_filter* f);
+const float* orc_filter_spectra(const orc_filter* f); /* [P][B+1] interleaved complex */
+
+typedef struct orc_blockconv orc_blockconv;
+orc_blockconv* orc_blockconv_create(unsigned block, unsigned max_partitions);
+void orc_blockconv_destroy(orc_blockconv* bc);
+void orc_blockconv_set_filter(orc_blockconv* bc, const orc_filter* f, int crossfade);
+void orc_blockconv_convolve(orc_blockconv* bc, const float* in, float* out);
+
+/* ---- convolver.c : SURVEY.md 8.A multichannel Convolver ---- */
+enum { ORC_MODE_PER_CHANNEL = 0, ORC_MODE_ROUTED = 1, ORC_MODE_MIMO = 2 };
+typedef struct orc_convolver orc_convolver;
+orc_convolver* orc_convolver_create(unsigned block, unsigned max_partitions, unsigned n_inputs, unsigned n_outputs,
+                                    unsigned n_paths, int mode, unsigned ring_len, int fractional_delay,
+                                    int nthreads);
+void orc_convolver_destroy(orc_convolver* c);
+void orc_convolver_set_route(orc_convolver* c, unsigned path, unsigned input, unsigned output, float gain);
+void orc_convolver_set_filter(orc_convolver* c, unsigned path, const orc_filter* f, int crossfade, double delay);
+/* nframes must be a multiple of block */
+int orc_convolver_process(orc_convolver* c, const void* in, int infmt, int in_be, unsigned in_channels, void* out,
+                          int outfmt, int out_be, unsigned out_channels, unsigned nframes);
+
+/* ---- direct.c : float64 truth ---- */
+/* y[n] = sum_j h[j] x[n-j] for n in [n0, n0+count), zero history before x[0] */
+void orc_direct_convolve(const double* x, unsigned nx, const double* h, unsigned nh, unsigned n0, unsigned count,
+                         double* y, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

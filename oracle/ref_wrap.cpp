@@ -1,0 +1,138 @@
+/* TEST INFRASTRUCTURE ONLY -- not part of the product.
+ *
+ * extern "C" handles over the reference's own in-tree code so that tests (via
+ * ctypes) can run the real bbcat-dsp functions.  This file contains no
+ * reference code: it only #includes the headers where they lie under
+ * /root/reference/src and forwards calls.  Built by oracle/Makefile into
+ * oracle/_ref/libbbcref.so together with the unmodified reference sources
+ *   SoundFormatConversions.cpp, SoundFormatRawConversions.cpp, SoundMixing.cpp,
+ *   FractionalSample.cpp, SoundDelayBuffer.cpp
+ */
+#include "SoundFormatConversions.h"
+#include "SoundMixing.h"
+#include "Interpolator.h"
+#include "FractionalSample.h"
+#include "SoundDelayBuffer.h"
+#include "MultilayerBuffer.h"
+
+using namespace bbcat;
+
+extern "C" {
+
+unsigned ref_get_bits_per_sample(int fmt) { return GetBitsPerSample((SampleFormat_t)fmt); }
+unsigned ref_get_bytes_per_sample(int fmt) { return GetBytesPerSample((SampleFormat_t)fmt); }
+
+int ref_block_transfer_sanity_checks(unsigned* src_channel, unsigned* src_channels, unsigned* dst_channel,
+                                     unsigned* dst_channels, unsigned* nchannels, unsigned* nframes,
+                                     int allowsinglechannel) {
+  return BlockTransferSanityChecks(*src_channel, *src_channels, *dst_channel, *dst_channels, *nchannels, *nframes,
+                                   allowsinglechannel != 0)
+             ? 1
+             : 0;
+}
+
+void ref_transfer_samples(const void* src, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                          void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                          unsigned nchannels, unsigned nframes) {
+  TransferSamples(src, (SampleFormat_t)srctype, src_be != 0, src_channel, src_channels, dst, (SampleFormat_t)dsttype,
+                  dst_be != 0, dst_channel, dst_channels, nchannels, nframes, NULL);
+}
+
+void ref_transfer_samples_linear(const void* src, int srctype, void* dst, int dsttype, unsigned nsamples) {
+  TransferSamplesLinear(src, (SampleFormat_t)srctype, dst, (SampleFormat_t)dsttype, nsamples, NULL);
+}
+
+void ref_mix_samples_f32(const float* src, unsigned src_channel, unsigned src_channels, float* dst,
+                         unsigned dst_channel, unsigned dst_channels, unsigned nchannels, unsigned nframes, float mul) {
+  MixSamples<float>(src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul);
+}
+
+void ref_mix_samples_f64(const double* src, unsigned src_channel, unsigned src_channels, double* dst,
+                         unsigned dst_channel, unsigned dst_channels, unsigned nchannels, unsigned nframes,
+                         double mul) {
+  MixSamples<double>(src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul);
+}
+
+/* interp_state = {target, current}; updated in place like the caller's Interpolator object */
+void ref_mix_samples_interp(const float* src, unsigned src_channel, unsigned src_channels, float* dst,
+                            unsigned dst_channel, unsigned dst_channels, unsigned nchannels, unsigned nframes,
+                            float* interp_state, float inc) {
+  Interpolator interp(interp_state[0], interp_state[1]);
+  MixSamples(src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, interp, inc);
+  interp_state[0] = interp.GetTarget();
+  interp_state[1] = (float)interp;
+}
+
+void ref_interpolator_step(float* interp_state, float inc, unsigned nsteps) {
+  Interpolator interp(interp_state[0], interp_state[1]);
+  for (unsigned i = 0; i < nsteps; i++) interp += inc;
+  interp_state[0] = interp.GetTarget();
+  interp_state[1] = (float)interp;
+}
+
+unsigned ref_fractional_sample_additional_delay_required(void) { return FractionalSampleAdditionalDelayRequired(); }
+
+void ref_fractional_samples_f32(const float* buffer, unsigned channel, unsigned channels, unsigned length,
+                                const double* pos, unsigned n, double* out) {
+  for (unsigned i = 0; i < n; i++) out[i] = FractionalSample(buffer, channel, channels, length, pos[i]);
+}
+
+void ref_fractional_samples_f64(const double* buffer, unsigned channel, unsigned channels, unsigned length,
+                                const double* pos, unsigned n, double* out) {
+  for (unsigned i = 0; i < n; i++) out[i] = FractionalSample(buffer, channel, channels, length, pos[i]);
+}
+
+/* ---- SoundDelayBuffer ---- */
+void* ref_delay_create(void) { return new SoundDelayBuffer(); }
+void ref_delay_destroy(void* h) { delete (SoundDelayBuffer*)h; }
+void ref_delay_set_size(void* h, unsigned chans, unsigned length, int fmt) {
+  ((SoundDelayBuffer*)h)->SetSize(chans, length, (SampleFormat_t)fmt);
+}
+unsigned ref_delay_get_channels(void* h) { return ((SoundDelayBuffer*)h)->GetChannels(); }
+unsigned ref_delay_get_length(void* h) { return ((SoundDelayBuffer*)h)->GetLength(); }
+unsigned ref_delay_get_write_position(void* h) { return ((SoundDelayBuffer*)h)->GetWritePosition(); }
+int ref_delay_get_format(void* h) { return (int)((SoundDelayBuffer*)h)->GetFormat(); }
+unsigned ref_delay_write_samples(void* h, const void* src, int srcformat, unsigned channel, unsigned nchannels,
+                                 unsigned nframes) {
+  return ((SoundDelayBuffer*)h)->WriteSamples((const uint8_t*)src, (SampleFormat_t)srcformat, channel, nchannels, nframes);
+}
+void ref_delay_increment_write_position(void* h, unsigned nframes) {
+  ((SoundDelayBuffer*)h)->IncrementWritePosition(nframes);
+}
+unsigned ref_delay_read_samples(void* h, void* dst, int dstformat, unsigned delay, unsigned channel,
+                                unsigned nchannels, unsigned nframes) {
+  return ((SoundDelayBuffer*)h)->ReadSamples((uint8_t*)dst, (SampleFormat_t)dstformat, delay, channel, nchannels, nframes);
+}
+/* raw copy of the ring contents (format-native bytes); returns bytes copied */
+unsigned ref_delay_copy_buffer(void* h, void* dst, unsigned maxbytes) {
+  SoundDelayBuffer* d = (SoundDelayBuffer*)h;
+  unsigned bytes = d->GetChannels() * d->GetLength() * GetBytesPerSample(d->GetFormat());
+  const uint8_t* p = NULL;
+  const float* pf;
+  const double* pd;
+  const sint32_t* p32;
+  const sint16_t* p16;
+  if (d->GetBuffer(&pf)) p = (const uint8_t*)pf;
+  else if (d->GetBuffer(&pd)) p = (const uint8_t*)pd;
+  else if (d->GetBuffer(&p32)) p = (const uint8_t*)p32;
+  else if (d->GetBuffer(&p16)) p = (const uint8_t*)p16;
+  if (!p || bytes > maxbytes) return 0;
+  memcpy(dst, p, bytes);
+  return bytes;
+}
+
+/* ---- MultilayerBuffer<float> ("next" row) ---- */
+void* ref_mlb_create(unsigned channels, unsigned layers) { return new MultilayerBuffer<float>(channels, layers); }
+void ref_mlb_destroy(void* h) { delete (MultilayerBuffer<float>*)h; }
+void ref_mlb_write_layer(void* h, unsigned layer, const float* src, unsigned srcchannel, unsigned nsrcchannels,
+                         unsigned dstchannel, unsigned nchannels, unsigned nframes) {
+  ((MultilayerBuffer<float>*)h)->WriteLayer(layer, src, srcchannel, nsrcchannels, dstchannel, nchannels, nframes, true);
+}
+unsigned ref_mlb_available_frames(void* h) { return ((MultilayerBuffer<float>*)h)->GetAvailableFrames(); }
+unsigned ref_mlb_read_buffer(void* h, unsigned srcchannel, float* dst, unsigned dstchannel, unsigned ndstchannels,
+                             unsigned nchannels, unsigned nframes, int overwrite) {
+  return ((MultilayerBuffer<float>*)h)->ReadBuffer(srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, true,
+                                                   overwrite != 0);
+}
+
+}  // extern "C"

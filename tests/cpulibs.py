@@ -1,0 +1,361 @@
+"""ctypes bindings for the CPU checkers (TEST INFRASTRUCTURE).
+
+  oracle/liboracle.so        plain-C restatement (prefix ``orc_``), always available
+  oracle/_ref/libbbcref.so   the reference's own in-tree code (prefix ``ref_``); prebuilt in the
+                             dev container, travels to the GPU box as a built file
+
+Both expose the same signatures for the pieces that exist in the reference tree, so a
+``CpuLib`` wraps either.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+FMT_16, FMT_24, FMT_32, FMT_FLOAT, FMT_DOUBLE = 1, 2, 3, 4, 5
+FMT_BYTES = {1: 2, 2: 3, 3: 4, 4: 4, 5: 8}
+FMT_NAMES = {1: "s16", 2: "s24", 3: "s32", 4: "f32", 5: "f64"}
+
+u32 = C.c_uint
+vp = C.c_void_p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(vp)
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "all"])
+
+
+class CpuLib:
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        L = self.lib
+        p = prefix
+
+        def fn(name, res, args):
+            f = getattr(L, p + name)
+            f.restype = res
+            f.argtypes = args
+            return f
+
+        self._bits = fn("get_bits_per_sample", u32, [C.c_int])
+        self._bytes = fn("get_bytes_per_sample", u32, [C.c_int])
+        self._sanity = fn("block_transfer_sanity_checks", C.c_int, [C.POINTER(u32)] * 6 + [C.c_int])
+        self._transfer = fn("transfer_samples", None,
+                            [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32])
+        self._linear = fn("transfer_samples_linear", None, [vp, C.c_int, vp, C.c_int, u32])
+        self._mix32 = fn("mix_samples_f32", None, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_float])
+        self._mix64 = fn("mix_samples_f64", None, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_double])
+        self._mixi = fn("mix_samples_interp", None, [vp, u32, u32, vp, u32, u32, u32, u32, vp, C.c_float])
+        self._istep = fn("interpolator_step", None, [vp, C.c_float, u32])
+        self._fadd = fn("fractional_sample_additional_delay_required", u32, [])
+        self._frac32 = fn("fractional_samples_f32", None, [vp, u32, u32, u32, vp, u32, vp])
+        self._frac64 = fn("fractional_samples_f64", None, [vp, u32, u32, u32, vp, u32, vp])
+        self._dl_create = fn("delay_create", vp, [])
+        self._dl_destroy = fn("delay_destroy", None, [vp])
+        self._dl_set_size = fn("delay_set_size", None, [vp, u32, u32, C.c_int])
+        self._dl_channels = fn("delay_get_channels", u32, [vp])
+        self._dl_length = fn("delay_get_length", u32, [vp])
+        self._dl_wpos = fn("delay_get_write_position", u32, [vp])
+        self._dl_format = fn("delay_get_format", C.c_int, [vp])
+        self._dl_write = fn("delay_write_samples", u32, [vp, vp, C.c_int, u32, u32, u32])
+        self._dl_inc = fn("delay_increment_write_position", None, [vp, u32])
+        self._dl_read = fn("delay_read_samples", u32, [vp, vp, C.c_int, u32, u32, u32, u32])
+        self._dl_copy = fn("delay_copy_buffer", u32, [vp, vp, u32])
+
+    # ---- formats ----
+    def bits_per_sample(self, fmt):
+        return self._bits(fmt)
+
+    def bytes_per_sample(self, fmt):
+        return self._bytes(fmt)
+
+    def sanity(self, src_channel, src_channels, dst_channel, dst_channels, nchannels, nframes, allow=True):
+        v = [u32(x & 0xFFFFFFFF) for x in (src_channel, src_channels, dst_channel, dst_channels, nchannels, nframes)]
+        ok = self._sanity(*[C.byref(x) for x in v], int(allow))
+        return bool(ok), tuple(x.value for x in v)
+
+    def transfer(self, src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                 dst_channels, nchannels, nframes):
+        """src/dst: uint8 numpy byte buffers (dst modified in place)."""
+        self._transfer(_ptr(src), srctype, int(src_be), src_channel, src_channels, _ptr(dst), dsttype, int(dst_be),
+                       dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes)
+
+    def transfer_linear(self, src, srctype, dst, dsttype, nsamples):
+        self._linear(_ptr(src), srctype, _ptr(dst), dsttype, nsamples)
+
+    # ---- mixing ----
+    def mix(self, src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul=1.0):
+        if src.dtype == np.float32:
+            self._mix32(_ptr(src), src_channel, src_channels, _ptr(dst), dst_channel, dst_channels,
+                        nchannels & 0xFFFFFFFF, nframes, mul)
+        else:
+            self._mix64(_ptr(src), src_channel, src_channels, _ptr(dst), dst_channel, dst_channels,
+                        nchannels & 0xFFFFFFFF, nframes, mul)
+
+    def mix_interp(self, src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, state,
+                   inc):
+        """state: float32[2] = (target, current), advanced in place."""
+        self._mixi(_ptr(src), src_channel, src_channels, _ptr(dst), dst_channel, dst_channels,
+                   nchannels & 0xFFFFFFFF, nframes, _ptr(state), inc)
+
+    def interp_step(self, state, inc, nsteps):
+        self._istep(_ptr(state), inc, nsteps)
+
+    # ---- fractional sample ----
+    def frac_additional(self):
+        return self._fadd()
+
+    def frac(self, buffer, channel, channels, length, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        out = np.empty(pos.shape, dtype=np.float64)
+        f = self._frac32 if buffer.dtype == np.float32 else self._frac64
+        f(_ptr(buffer), channel, channels, length, _ptr(pos), pos.size, _ptr(out))
+        return out
+
+    # ---- delay buffer ----
+    def delay(self):
+        return CpuDelay(self)
+
+
+class CpuDelay:
+    def __init__(self, lib):
+        self.l = lib
+        self.h = lib._dl_create()
+
+    def close(self):
+        if self.h:
+            self.l._dl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_size(self, chans, length, fmt=FMT_FLOAT):
+        self.l._dl_set_size(self.h, chans, length, fmt)
+
+    channels = property(lambda s: s.l._dl_channels(s.h))
+    length = property(lambda s: s.l._dl_length(s.h))
+    write_position = property(lambda s: s.l._dl_wpos(s.h))
+    format = property(lambda s: s.l._dl_format(s.h))
+
+    def write(self, src, srcformat, channel, nchannels, nframes):
+        return self.l._dl_write(self.h, _ptr(src), srcformat, channel, nchannels & 0xFFFFFFFF, nframes)
+
+    def increment(self, nframes):
+        self.l._dl_inc(self.h, nframes)
+
+    def read(self, dst, dstformat, delay, channel, nchannels, nframes):
+        return self.l._dl_read(self.h, _ptr(dst), dstformat, delay, channel, nchannels & 0xFFFFFFFF, nframes)
+
+    def raw(self):
+        n = self.channels * self.length * FMT_BYTES[self.format]
+        out = np.zeros(n, dtype=np.uint8)
+        got = self.l._dl_copy(self.h, _ptr(out), n)
+        assert got == n
+        return out
+
+
+class Oracle(CpuLib):
+    """liboracle.so: adds FFT / UPOLS / Convolver / direct convolution."""
+
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        super().__init__(path, "orc_")
+        L = self.lib
+        L.orc_cfft.argtypes = [vp, u32, C.c_int]
+        L.orc_rfft.argtypes = [vp, vp, u32]
+        L.orc_irfft.argtypes = [vp, vp, u32]
+        L.orc_filter_create.restype = vp
+        L.orc_filter_create.argtypes = [vp, u32, u32]
+        L.orc_filter_destroy.argtypes = [vp]
+        L.orc_filter_partitions.restype = u32
+        L.orc_filter_partitions.argtypes = [vp]
+        L.orc_filter_spectra.restype = C.POINTER(C.c_float)
+        L.orc_filter_spectra.argtypes = [vp]
+        L.orc_blockconv_create.restype = vp
+        L.orc_blockconv_create.argtypes = [u32, u32]
+        L.orc_blockconv_destroy.argtypes = [vp]
+        L.orc_blockconv_set_filter.argtypes = [vp, vp, C.c_int]
+        L.orc_blockconv_convolve.argtypes = [vp, vp, vp]
+        L.orc_convolver_create.restype = vp
+        L.orc_convolver_create.argtypes = [u32, u32, u32, u32, u32, C.c_int, u32, C.c_int, C.c_int]
+        L.orc_convolver_destroy.argtypes = [vp]
+        L.orc_convolver_set_route.argtypes = [vp, u32, u32, u32, C.c_float]
+        L.orc_convolver_set_filter.argtypes = [vp, u32, vp, C.c_int, C.c_double]
+        L.orc_convolver_process.restype = C.c_int
+        L.orc_convolver_process.argtypes = [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]
+        L.orc_direct_convolve.argtypes = [vp, u32, vp, u32, u32, u32, vp, C.c_int]
+
+    def rfft(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros(x.size + 2, dtype=np.float32)
+        self.lib.orc_rfft(_ptr(x), _ptr(out), x.size)
+        return out.view(np.complex64)
+
+    def irfft(self, X, n):
+        X = np.ascontiguousarray(X, dtype=np.complex64)
+        out = np.zeros(n, dtype=np.float32)
+        self.lib.orc_irfft(_ptr(X.view(np.float32)), _ptr(out), n)
+        return out
+
+    def cfft(self, z, inverse=False):
+        z = np.array(z, dtype=np.complex64)
+        self.lib.orc_cfft(_ptr(z.view(np.float32)), z.size, int(inverse))
+        return z
+
+    def filter(self, ir, block):
+        return OracleFilter(self, ir, block)
+
+    def blockconv(self, block, max_partitions):
+        return OracleBlockConv(self, block, max_partitions)
+
+    def convolver(self, **kw):
+        return OracleConvolver(self, **kw)
+
+    def direct(self, x, h, n0=0, count=None, nthreads=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        if count is None:
+            count = x.size - n0
+        y = np.zeros(count, dtype=np.float64)
+        self.lib.orc_direct_convolve(_ptr(x), x.size, _ptr(h), h.size, n0, count, _ptr(y),
+                                     nthreads or (os.cpu_count() or 1))
+        return y
+
+
+class OracleFilter:
+    def __init__(self, orc, ir, block):
+        self.orc = orc
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        self.h = orc.lib.orc_filter_create(_ptr(ir), ir.size, block)
+        self.block = block
+        self.partitions = orc.lib.orc_filter_partitions(self.h)
+
+    def spectra(self):
+        K = self.block + 1
+        p = self.orc.lib.orc_filter_spectra(self.h)
+        a = np.ctypeslib.as_array(p, shape=(self.partitions * K * 2,)).copy()
+        return a.view(np.complex64).reshape(self.partitions, K)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.orc.lib.orc_filter_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class OracleBlockConv:
+    def __init__(self, orc, block, max_partitions):
+        self.orc = orc
+        self.block = block
+        self.h = orc.lib.orc_blockconv_create(block, max_partitions)
+        self._keep = []
+
+    def set_filter(self, f, crossfade=False):
+        self._keep.append(f)
+        self.orc.lib.orc_blockconv_set_filter(self.h, f.h if f is not None else None, int(crossfade))
+
+    def convolve(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.size == self.block
+        y = np.zeros(self.block, dtype=np.float32)
+        self.orc.lib.orc_blockconv_convolve(self.h, _ptr(x), _ptr(y))
+        return y
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.orc.lib.orc_blockconv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+MODE_PER_CHANNEL, MODE_ROUTED, MODE_MIMO = 0, 1, 2
+
+
+class OracleConvolver:
+    def __init__(self, orc, block, max_partitions, n_inputs, n_outputs=None, n_paths=None, mode=MODE_PER_CHANNEL,
+                 ring_len=0, fractional_delay=False, nthreads=None):
+        self.orc = orc
+        self.block = block
+        n_outputs = n_inputs if n_outputs is None else n_outputs
+        if mode == MODE_PER_CHANNEL:
+            n_paths = n_inputs
+        elif mode == MODE_MIMO:
+            n_paths = n_inputs * n_outputs
+        self.n_inputs, self.n_outputs, self.n_paths = n_inputs, n_outputs, n_paths
+        self.h = orc.lib.orc_convolver_create(block, max_partitions, n_inputs, n_outputs, n_paths, mode, ring_len,
+                                              int(fractional_delay), nthreads or (os.cpu_count() or 1))
+        self._keep = []
+
+    def set_route(self, path, inp, out, gain=1.0):
+        self.orc.lib.orc_convolver_set_route(self.h, path, inp, out, gain)
+
+    def set_filter(self, path, f, crossfade=False, delay=0.0):
+        self._keep.append(f)
+        self.orc.lib.orc_convolver_set_filter(self.h, path, f.h if f is not None else None, int(crossfade), delay)
+
+    def process(self, inp, infmt, in_channels, outfmt, out_channels, nframes, in_be=False, out_be=False, out=None):
+        """inp: uint8 byte buffer (or typed array) of interleaved PCM; returns uint8 byte buffer."""
+        inp = np.ascontiguousarray(inp).view(np.uint8).reshape(-1)
+        assert inp.size == nframes * in_channels * FMT_BYTES[infmt]
+        if out is None:
+            out = np.zeros(nframes * out_channels * FMT_BYTES[outfmt], dtype=np.uint8)
+        rc = self.orc.lib.orc_convolver_process(self.h, _ptr(inp), infmt, int(in_be), in_channels, _ptr(out), outfmt,
+                                                int(out_be), out_channels, nframes)
+        assert rc == 0, rc
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.orc.lib.orc_convolver_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+_ORACLE = None
+_REF = None
+
+
+def oracle():
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE
+
+
+def ref_path():
+    return os.path.join(ORACLE_DIR, "_ref", "libbbcref.so")
+
+
+def have_ref():
+    return os.path.exists(ref_path())
+
+
+def reference():
+    """The reference's own code (oracle/_ref); None when it was never built."""
+    global _REF
+    if _REF is None and have_ref():
+        _REF = CpuLib(ref_path(), "ref_")
+    return _REF
