@@ -1,0 +1,419 @@
+"""bbcat-dsp_b200 -- Python host binding of libbbx.so (the B200 partitioned-convolution engine).
+
+Thin ctypes layer over the C ABI in include/bbx.h; names follow the bbcat-dsp interfaces the ABI
+replaces (TransferSamples, MixSamples, FractionalSample, SoundDelayBuffer, BlockConvolver, Convolver).
+There is no CPU path here: importing works without a GPU (so the symbol table can be checked), but
+every compute call raises BbxError when the CUDA library or device is missing.
+
+The directory name carries a hyphen; import it as ``bbcat_dsp_b200`` (see bbcat_dsp_b200.py at the
+repo root).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbbx.so")
+
+FMT_UNKNOWN, FMT_16BIT, FMT_24BIT, FMT_32BIT, FMT_FLOAT, FMT_DOUBLE = 0, 1, 2, 3, 4, 5
+FMT_BYTES = {1: 2, 2: 3, 3: 4, 4: 4, 5: 8}
+MODE_PER_CHANNEL, MODE_ROUTED, MODE_MIMO = 0, 1, 2
+
+u8, u32, u64, vp = C.c_uint8, C.c_uint32, C.c_uint64, C.c_void_p
+
+
+class BbxError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("block_size", u32), ("max_partitions", u32), ("n_inputs", u32),
+                ("n_outputs", u32), ("n_paths", u32), ("mode", C.c_int), ("max_blocks", u32), ("max_delay", u32),
+                ("fractional_delay", C.c_int), ("ring_length", u32), ("mac_ctas_per_sm", u32), ("reserved", u32 * 7)]
+
+
+# every symbol include/bbx.h declares: name -> (restype, argtypes)
+_RECT = [u32, u32]
+SYMBOLS = {
+    "bbx_version": (C.c_int, []),
+    "bbx_last_error": (C.c_char_p, []),
+    "bbx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "bbx_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+    "bbx_host_free": (C.c_int, [vp]),
+    "bbx_shard_range": (C.c_int, [u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]),
+    "bbx_get_bits_per_sample": (u8, [C.c_int]),
+    "bbx_get_bytes_per_sample": (u8, [C.c_int]),
+    "bbx_block_transfer_sanity_checks": (C.c_int, [C.POINTER(u32)] * 6 + [C.c_int]),
+    "bbx_transfer_samples": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32]),
+    "bbx_transfer_samples_dev": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, vp]),
+    "bbx_transfer_samples_linear": (C.c_int, [vp, C.c_int, vp, C.c_int, u32]),
+    "bbx_mix_samples_f32": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_float]),
+    "bbx_mix_samples_f64": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_double]),
+    "bbx_mix_samples_interp": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, vp, C.c_float]),
+    "bbx_mix_samples_f32_dev": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_float, vp]),
+    "bbx_mix_samples_interp_dev": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, vp, C.c_float, vp]),
+    "bbx_interpolator_step": (C.c_int, [vp, C.c_float, u32]),
+    "bbx_fractional_sample_additional_delay_required": (u32, []),
+    "bbx_fractional_samples_f32": (C.c_int, [vp, u32, u32, u32, vp, u32, vp]),
+    "bbx_fractional_samples_f64": (C.c_int, [vp, u32, u32, u32, vp, u32, vp]),
+    "bbx_fractional_samples_f32_dev": (C.c_int, [vp, u32, u32, u32, vp, u32, vp, vp]),
+    "bbx_delay_create": (C.c_int, [C.POINTER(vp)]),
+    "bbx_delay_destroy": (C.c_int, [vp]),
+    "bbx_delay_set_size": (C.c_int, [vp, u32, u32, C.c_int]),
+    "bbx_delay_get_channels": (u32, [vp]),
+    "bbx_delay_get_length": (u32, [vp]),
+    "bbx_delay_get_write_position": (u32, [vp]),
+    "bbx_delay_get_format": (C.c_int, [vp]),
+    "bbx_delay_write_samples": (u32, [vp, vp, C.c_int, u32, u32, u32]),
+    "bbx_delay_increment_write_position": (C.c_int, [vp, u32]),
+    "bbx_delay_read_samples": (u32, [vp, vp, C.c_int, u32, u32, u32, u32]),
+    "bbx_delay_read_sample": (C.c_float, [vp, u32, u32]),
+    "bbx_delay_get_buffer_dev": (vp, [vp]),
+    "bbx_delay_copy_buffer": (u32, [vp, vp, u32]),
+    "bbx_engine_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
+    "bbx_engine_destroy": (C.c_int, [vp]),
+    "bbx_engine_get_ring_length": (u32, [vp]),
+    "bbx_engine_get_stream": (vp, [vp]),
+    "bbx_filter_create": (C.c_int, [vp, vp, u32, C.POINTER(vp)]),
+    "bbx_filter_destroy": (C.c_int, [vp]),
+    "bbx_filter_partitions": (u32, [vp]),
+    "bbx_set_route": (C.c_int, [vp, u32, u32, u32, C.c_float]),
+    "bbx_set_filter": (C.c_int, [vp, u32, vp, C.c_int, C.c_double]),
+    "bbx_process": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
+    "bbx_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
+    "bbx_engine_sync": (C.c_int, [vp]),
+    "bbx_blockconvolver_convolve": (C.c_int, [vp, vp, vp]),
+    "bbx_engine_timer_start": (C.c_int, [vp]),
+    "bbx_engine_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "bbx_engine_launch_count": (u64, [vp]),
+    "bbx_engine_profile_mac": (C.c_int, [vp, C.c_int]),
+    "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+    "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libbbx.so (once).  Fails loudly: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BbxError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C bbcat-dsp_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BbxError("libbbx error %d: %s" % (rc, lib().bbx_last_error().decode("utf-8", "replace")))
+
+
+def _p(a):
+    """void* of a numpy array / integer device pointer / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return vp(a)
+    assert a.flags["C_CONTIGUOUS"], "buffer must be C-contiguous"
+    return a.ctypes.data_as(vp)
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().bbx_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def shard_range(nchannels, rank, world):
+    first, count = u32(0), u32(0)
+    _check(lib().bbx_shard_range(nchannels, rank, world, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+# ---- a1/a2 --------------------------------------------------------------------------------
+def GetBitsPerSample(fmt):
+    return lib().bbx_get_bits_per_sample(fmt)
+
+
+def GetBytesPerSample(fmt):
+    return lib().bbx_get_bytes_per_sample(fmt)
+
+
+def BlockTransferSanityChecks(src_channel, src_channels, dst_channel, dst_channels, nchannels, nframes,
+                              allowsinglechannel=True):
+    v = [u32(x & 0xFFFFFFFF) for x in (src_channel, src_channels, dst_channel, dst_channels, nchannels, nframes)]
+    ok = lib().bbx_block_transfer_sanity_checks(*[C.byref(x) for x in v], int(allowsinglechannel))
+    return bool(ok), tuple(x.value for x in v)
+
+
+# ---- a3-a7 --------------------------------------------------------------------------------
+def TransferSamples(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel, dst_channels,
+                    nchannels=0xFFFFFFFF, nframes=1):
+    """Host byte buffers (numpy uint8 or typed arrays); dst is modified in place."""
+    _check(lib().bbx_transfer_samples(_p(src), srctype, int(src_be), src_channel, src_channels, _p(dst), dsttype,
+                                      int(dst_be), dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes))
+
+
+def TransferSamplesDev(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                       dst_channels, nchannels, nframes, stream=None):
+    """Device pointers (ints, e.g. torch.Tensor.data_ptr())."""
+    _check(lib().bbx_transfer_samples_dev(_p(src), srctype, int(src_be), src_channel, src_channels, _p(dst), dsttype,
+                                          int(dst_be), dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes,
+                                          _p(stream)))
+
+
+def TransferSamplesLinear(src, srctype, dst, dsttype, nsamples=1):
+    _check(lib().bbx_transfer_samples_linear(_p(src), srctype, _p(dst), dsttype, nsamples))
+
+
+# ---- a8/a9 --------------------------------------------------------------------------------
+def MixSamples(src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul=1.0,
+               interp=None, inc=0.0):
+    """MixSamples<T> (float32/float64 arrays) or, with interp=float32[2] (target, current), the
+    interpolated form; interp is advanced in place."""
+    if interp is not None:
+        _check(lib().bbx_mix_samples_interp(_p(src), src_channel, src_channels, _p(dst), dst_channel, dst_channels,
+                                            nchannels & 0xFFFFFFFF, nframes, _p(interp), inc))
+    elif src.dtype == np.float32:
+        _check(lib().bbx_mix_samples_f32(_p(src), src_channel, src_channels, _p(dst), dst_channel, dst_channels,
+                                         nchannels & 0xFFFFFFFF, nframes, mul))
+    else:
+        _check(lib().bbx_mix_samples_f64(_p(src), src_channel, src_channels, _p(dst), dst_channel, dst_channels,
+                                         nchannels & 0xFFFFFFFF, nframes, mul))
+
+
+def InterpolatorStep(state, inc, nsteps=1):
+    _check(lib().bbx_interpolator_step(_p(state), inc, nsteps))
+
+
+# ---- a10 ----------------------------------------------------------------------------------
+def FractionalSampleAdditionalDelayRequired():
+    return lib().bbx_fractional_sample_additional_delay_required()
+
+
+def FractionalSample(buffer, channel, channels, length, pos):
+    """Batched FractionalSample: pos may be a scalar or an array of positions."""
+    scalar = np.isscalar(pos)
+    pos = np.ascontiguousarray(np.atleast_1d(pos), dtype=np.float64)
+    out = np.empty(pos.shape, dtype=np.float64)
+    f = lib().bbx_fractional_samples_f32 if buffer.dtype == np.float32 else lib().bbx_fractional_samples_f64
+    _check(f(_p(buffer), channel, channels, length, _p(pos), pos.size, _p(out)))
+    return float(out[0]) if scalar else out
+
+
+# ---- a11 ----------------------------------------------------------------------------------
+class SoundDelayBuffer:
+    def __init__(self):
+        h = vp()
+        _check(lib().bbx_delay_create(C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_delay_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def SetSize(self, chans, length, fmt=FMT_FLOAT):
+        _check(lib().bbx_delay_set_size(self.h, chans, length, fmt))
+
+    def GetChannels(self):
+        return lib().bbx_delay_get_channels(self.h)
+
+    def GetLength(self):
+        return lib().bbx_delay_get_length(self.h)
+
+    def GetWritePosition(self):
+        return lib().bbx_delay_get_write_position(self.h)
+
+    def GetFormat(self):
+        return lib().bbx_delay_get_format(self.h)
+
+    def WriteSamples(self, src, srcformat, channel=0, nchannels=0xFFFFFFFF, nframes=1):
+        return lib().bbx_delay_write_samples(self.h, _p(src), srcformat, channel, nchannels & 0xFFFFFFFF, nframes)
+
+    def IncrementWritePosition(self, nframes=1):
+        _check(lib().bbx_delay_increment_write_position(self.h, nframes))
+
+    def ReadSamples(self, dst, dstformat, delay, channel=0, nchannels=0xFFFFFFFF, nframes=1):
+        return lib().bbx_delay_read_samples(self.h, _p(dst), dstformat, delay, channel, nchannels & 0xFFFFFFFF, nframes)
+
+    def ReadSample(self, channel, delay):
+        return lib().bbx_delay_read_sample(self.h, channel, delay)
+
+    def raw(self):
+        n = self.GetChannels() * self.GetLength() * FMT_BYTES[self.GetFormat()]
+        out = np.zeros(n, dtype=np.uint8)
+        got = lib().bbx_delay_copy_buffer(self.h, _p(out), n)
+        if got != n:
+            raise BbxError("bbx_delay_copy_buffer returned %d of %d bytes" % (got, n))
+        return out
+
+
+# ---- a12-a14 ------------------------------------------------------------------------------
+class Filter:
+    """Immutable filter object: an impulse response partitioned at the engine's block size."""
+
+    def __init__(self, engine, ir):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        h = vp()
+        _check(lib().bbx_filter_create(engine.h, _p(ir), ir.size, C.byref(h)))
+        self.h = h
+        self.engine = engine
+        self.partitions = lib().bbx_filter_partitions(h)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.engine, "h", None):
+            lib().bbx_filter_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+
+class Convolver:
+    """Multichannel partitioned convolver on one GPU (Convolver, README:43-44)."""
+
+    def __init__(self, block_size, max_partitions, n_inputs, n_outputs=0, n_paths=0, mode=MODE_PER_CHANNEL,
+                 max_blocks=1, max_delay=0, fractional_delay=False, ring_length=0, device=0, mac_ctas_per_sm=0):
+        cfg = Config()
+        cfg.device = device
+        cfg.block_size = block_size
+        cfg.max_partitions = max_partitions
+        cfg.n_inputs = n_inputs
+        cfg.n_outputs = n_outputs
+        cfg.n_paths = n_paths
+        cfg.mode = mode
+        cfg.max_blocks = max_blocks
+        cfg.max_delay = max_delay
+        cfg.fractional_delay = int(fractional_delay)
+        cfg.ring_length = ring_length
+        cfg.mac_ctas_per_sm = mac_ctas_per_sm
+        h = vp()
+        _check(lib().bbx_engine_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.block_size = block_size
+        self.mode = mode
+        self.n_inputs = n_inputs
+        self.n_outputs = n_inputs if mode == MODE_PER_CHANNEL else n_outputs
+        self.n_paths = n_inputs if mode == MODE_PER_CHANNEL else (n_inputs * n_outputs if mode == MODE_MIMO else n_paths)
+        self.max_blocks = max(1, max_blocks)
+        self.ring_length = lib().bbx_engine_get_ring_length(h)
+        self._filters = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            for f in self._filters:
+                f.close()
+            self._filters = []
+            lib().bbx_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def CreateFilter(self, ir):
+        f = Filter(self, ir)
+        self._filters.append(f)
+        return f
+
+    def SetRoute(self, path, inp, out, gain=1.0):
+        _check(lib().bbx_set_route(self.h, path, inp, out, gain))
+
+    def SelectFilter(self, path, flt, delay=0.0, crossfade=False):
+        _check(lib().bbx_set_filter(self.h, path, flt.h if flt is not None else None, int(crossfade), delay))
+
+    def Convolve(self, inp, infmt, in_channels, outfmt, out_channels, nframes, in_be=False, out_be=False, out=None):
+        """Host buffers.  inp: interleaved PCM bytes/typed array; returns the output byte buffer."""
+        inp = np.ascontiguousarray(inp).view(np.uint8).reshape(-1)
+        assert inp.size == nframes * in_channels * FMT_BYTES[infmt], "input size does not match the geometry"
+        if out is None:
+            out = np.zeros(nframes * out_channels * FMT_BYTES[outfmt], dtype=np.uint8)
+        _check(lib().bbx_process(self.h, _p(inp), infmt, int(in_be), in_channels, _p(out), outfmt, int(out_be),
+                                 out_channels, nframes))
+        return out
+
+    def ConvolveHostPtr(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes):
+        """Raw host pointers (e.g. pinned buffers); synchronous, copies included."""
+        _check(lib().bbx_process(self.h, vp(in_ptr), infmt, 0, in_channels, vp(out_ptr), outfmt, 0, out_channels, nframes))
+
+    def ConvolveDev(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes, in_be=False, out_be=False):
+        """Device pointers (ints); asynchronous on the engine stream."""
+        _check(lib().bbx_process_dev(self.h, vp(in_ptr), infmt, int(in_be), in_channels, vp(out_ptr), outfmt, int(out_be),
+                                     out_channels, nframes))
+
+    def Sync(self):
+        _check(lib().bbx_engine_sync(self.h))
+
+    # measurement hooks
+    def timer_start(self):
+        _check(lib().bbx_engine_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().bbx_engine_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return lib().bbx_engine_launch_count(self.h)
+
+    def profile_mac(self, enable=True):
+        _check(lib().bbx_engine_profile_mac(self.h, int(enable)))
+
+    def mac_time(self):
+        ms, n, units, nbytes = C.c_float(0), u64(0), u64(0), u64(0)
+        _check(lib().bbx_engine_mac_time(self.h, C.byref(ms), C.byref(n), C.byref(units), C.byref(nbytes)))
+        return {"ms": ms.value, "launches": n.value, "channel_blocks": units.value, "algorithmic_bytes": nbytes.value}
+
+    def flush_l2(self, nbytes=256 << 20):
+        _check(lib().bbx_engine_flush_l2(self.h, nbytes))
+
+
+class BlockConvolver:
+    """Single-channel partitioned convolution (BlockConvolver, README:38-39): Convolve() one block."""
+
+    def __init__(self, block_size, max_partitions, device=0):
+        self.engine = Convolver(block_size, max_partitions, 1, device=device)
+        self.block_size = block_size
+
+    def CreateFilter(self, ir):
+        return self.engine.CreateFilter(ir)
+
+    def SetFilter(self, flt, crossfade=False):
+        self.engine.SelectFilter(0, flt, 0.0, crossfade)
+
+    def Convolve(self, block):
+        block = np.ascontiguousarray(block, dtype=np.float32)
+        assert block.size == self.block_size
+        out = np.zeros(self.block_size, dtype=np.float32)
+        _check(lib().bbx_blockconvolver_convolve(self.engine.h, _p(block), _p(out)))
+        return out
+
+    def close(self):
+        self.engine.close()
+
+
+class PinnedBuffer:
+    """Pinned host memory from bbx_host_alloc, viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        p = vp()
+        _check(lib().bbx_host_alloc(C.byref(p), nbytes))
+        self.ptr = p.value
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().bbx_host_free(vp(self.ptr))
+            self.ptr = None
+
+    __del__ = close

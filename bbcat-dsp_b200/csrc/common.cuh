@@ -1,0 +1,51 @@
+// common.cuh -- error plumbing and small helpers shared by the libbbx translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/bbx.h"
+
+namespace bbx {
+
+// last error message of the calling thread (bbx_last_error)
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define BBX_CUDA_TRY(expr)                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      bbx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return BBX_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define BBX_REQUIRE(cond, ...)     \
+  do {                             \
+    if (!(cond)) {                 \
+      bbx::set_error(__VA_ARGS__); \
+      return BBX_ERR_INVALID;      \
+    }                              \
+  } while (0)
+
+inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// growable device scratch used by the host-pointer entry points (one per thread)
+struct DeviceScratch {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int device = -1;
+  int ensure(size_t bytes);
+  ~DeviceScratch();
+};
+DeviceScratch& scratch(int which);  // which = 0..3, thread-local
+
+// make sure a CUDA device is usable; sets the error and returns BBX_ERR_CUDA otherwise
+int require_device();
+
+}  // namespace bbx

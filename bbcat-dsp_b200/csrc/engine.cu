@@ -1,0 +1,1209 @@
+// engine.cu -- the partitioned-convolution engine of libbbx (BlockConvolver / Convolver path).
+//
+// The reference's BlockConvolver.{h,cpp}, Convolver.{h,cpp}, FFT*.cpp and simd_utils (README:38-51,
+// 68-69) are absent from the mounted tree; behaviour follows SURVEY.md 8.A.  Data flow of one
+// bbx_process call over T blocks of B frames (all kernels on the engine stream):
+//
+//   k_pcm_in   interleaved PCM (any SampleFormat_t, LE/BE) -> planar fp32 xin[input][(T+1)B]
+//              (block 0 of the row is the previous call's last block = the overlap-save history)
+//   k_rfft     window [prev | cur] (2B floats, contiguous in xin) -> packed spectrum -> FDL ring slot
+//              FDL[input][(head+t) mod R][B] complex, R >= Pmax + Tmax - 1
+//   k_fdl_mac  Y[job] = sum over (term, p) H[term][p] * FDL[input(term)][(head+t-p) mod R]
+//              the hot kernel: streams H and FDL rows (8B bytes each, 4 KB at B=512) with 128-bit
+//              loads, flattened (job, term, p) row space split evenly over a grid sized to the
+//              SM count, per-CTA partial sums written to Ypart (deterministic, no atomics)
+//   k_irfft    sum the partials in fixed order -> C2R -> keep samples B..2B-1 -> filter crossfade
+//              -> per-stream delay ring ybuf[stream][Rd]
+//   k_pcm_out  delayed ring reads (integer or 14-tap fractional, delay crossfade) -> MixSamples-order
+//              mixdown -> float -> output SampleFormat_t, interleaved
+//
+// HBM layout: H per filter [P][B] float2 (1/N folded in), FDL [n_in][R][B] float2, both rows
+// 16-byte aligned so one thread owns one float4 column (2 bins) across all partitions.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "fft.cuh"
+#include "formats.cuh"
+#include "fracsample.cuh"
+
+namespace bbx {
+
+static constexpr uint32_t kNoJob = 0xFFFFFFFFu;
+static constexpr uint32_t kSameJob = 0xFFFFFFFEu;  // crossfade a stream with itself (delay-only switch)
+static constexpr int kNumSMs = 148;
+
+// ------------------------------------------------------------------------------------------
+// k_pcm_in
+// ------------------------------------------------------------------------------------------
+struct PcmInArgs {
+  const uint8_t* pcm;
+  int fmt;
+  int be;
+  uint32_t in_channels, n_inputs;
+  uint32_t B, T;
+  float* xin_cur;         // [n_inputs][xstride]
+  const float* xin_prev;  // previous call's buffer
+  uint32_t xstride;
+  uint32_t prev_off;      // offset of the previous call's last block inside xin_prev rows
+};
+
+__global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
+  __shared__ float tile[32][33];
+  const uint32_t f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool is_prev = f0 < a.B;  // B is a multiple of 32: a tile never straddles the boundary
+  const uint32_t bps = fmt_bytes(a.fmt);
+  if (!is_prev) {
+    // phase 1: lanes over channels (contiguous bytes within a frame)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t fl = warp + 8 * i, c = c0 + lane;
+      uint32_t frame = f0 + fl - a.B;
+      float v = 0.f;
+      if (c < a.n_inputs) v = load_as_f32(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps, a.fmt, a.be != 0);
+      tile[fl][lane] = v;
+    }
+    __syncthreads();
+  }
+  // phase 2: lanes over frames (contiguous floats of one planar row)
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t cl = warp + 8 * i, c = c0 + cl;
+    if (c >= a.n_inputs) continue;
+    uint32_t f = f0 + lane;
+    float v = is_prev ? a.xin_prev[(uint64_t)c * a.xstride + a.prev_off + f] : tile[lane][cl];
+    a.xin_cur[(uint64_t)c * a.xstride + f] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_rfft : windows of 2B floats -> packed spectra
+// ------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(M / 4) k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride,
+                                                float2* __restrict__ dst, uint64_t dst_ch_stride, uint32_t R,
+                                                uint32_t slot0, const float2* __restrict__ tw, float scale) {
+  __shared__ float2 s[M];
+  const uint32_t ch = blockIdx.x, t = blockIdx.y;
+  const float2* win = reinterpret_cast<const float2*>(src + ch * ch_stride + (uint64_t)t * win_stride);
+  constexpr int Q = M / 4;
+#pragma unroll
+  for (int h = 0; h < 4; h++) s[threadIdx.x + h * Q] = win[threadIdx.x + h * Q];
+  __syncthreads();
+  cfft_smem<M, false>(s, tw);
+  const uint32_t slot = (slot0 + t) % R;
+  rfft_split_store<M>(s, tw, dst + ch * dst_ch_stride + (uint64_t)slot * M, scale);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_fdl_mac : the hot kernel
+// ------------------------------------------------------------------------------------------
+struct MacSeg {
+  const float4* H;    // filter spectra, row 0 (row stride = B/2 float4)
+  uint32_t fdl_ch;    // input channel whose FDL this term reads
+  uint32_t p0, np;    // partition range of this segment
+  uint32_t slot;      // partial-sum slot the run is written to
+  uint32_t flags;     // bit0: reset accumulator before, bit1: write accumulator after
+  uint32_t pad;
+};
+static_assert(sizeof(MacSeg) == 32, "MacSeg layout");
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  // read-once data: bypass L1 allocation
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// acc += h * x for two packed complex bins; bin 0 of a row is (DC, Nyquist): two real products
+__device__ __forceinline__ void cmac2(float4& acc, const float4& h, const float4& x, bool bin0) {
+  const float u = bin0 ? x.y : x.x;  // operand of h.y in the "imaginary" lane
+  const float v = bin0 ? 0.f : x.y;  // cross terms vanish for the packed bin
+  acc.x = fmaf(h.x, x.x, acc.x);
+  acc.x = fmaf(-h.y, v, acc.x);
+  acc.y = fmaf(h.y, u, acc.y);
+  acc.y = fmaf(h.x, v, acc.y);
+  acc.z = fmaf(h.z, x.z, acc.z);
+  acc.z = fmaf(-h.w, x.w, acc.z);
+  acc.w = fmaf(h.z, x.w, acc.w);
+  acc.w = fmaf(h.w, x.z, acc.w);
+}
+
+template <int U, int THREADS, int OCC>
+__global__ void __launch_bounds__(THREADS, OCC)
+k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float4* __restrict__ fdl,
+          float4* __restrict__ ypart, uint32_t halfB, uint32_t R, uint32_t head0, uint32_t t0, uint32_t slot_stride) {
+  const uint32_t t = t0 + blockIdx.z;
+  const uint32_t head = (head0 + t) % R;
+  const uint32_t col = blockIdx.y * THREADS + threadIdx.x;
+  const bool bin0 = (col == 0);
+  const uint32_t sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t si = sb; si < se; si++) {
+    const MacSeg sg = segs[si];
+    if (sg.flags & 1u) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* hp = sg.H + (uint64_t)sg.p0 * halfB + col;
+    const float4* xbase = fdl + (uint64_t)sg.fdl_ch * R * halfB + col;
+    int slot = (int)head - (int)sg.p0;  // p0 < R
+    if (slot < 0) slot += (int)R;
+    uint32_t p = 0;
+    for (; p + U <= sg.np; p += U) {
+      float4 h[U], x[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        int s = slot - u;
+        s += (s >> 31) & (int)R;  // ring wrap, once per row
+        h[u] = ld_stream(hp + (uint64_t)u * halfB);
+        x[u] = __ldg(xbase + (uint64_t)s * halfB);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) cmac2(acc, h[u], x[u], bin0);
+      hp += (uint64_t)U * halfB;
+      slot -= U;
+      if (slot < 0) slot += (int)R;
+    }
+    for (; p < sg.np; p++) {
+      float4 h = ld_stream(hp);
+      float4 x = __ldg(xbase + (uint64_t)slot * halfB);
+      cmac2(acc, h, x, bin0);
+      hp += halfB;
+      slot -= 1;
+      if (slot < 0) slot += (int)R;
+    }
+    if (sg.flags & 2u) ypart[((uint64_t)blockIdx.z * slot_stride + sg.slot) * halfB + col] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_irfft : partial sums -> time domain -> crossfade -> delay ring
+// ------------------------------------------------------------------------------------------
+struct PlanView {
+  const uint32_t* job_slot_first;
+  const uint32_t* job_slot_count;
+  const uint32_t* xjob;  // per stream: extra job to crossfade into, kNoJob, or kSameJob
+};
+
+template <int M>
+__device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, uint32_t first, uint32_t count,
+                                             float2* __restrict__ x, float2* __restrict__ s,
+                                             const float2* __restrict__ tw, float (&o)[4]) {
+  constexpr int Q = M / 4;
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    const int k = threadIdx.x + h * Q;
+    float2 a = make_float2(0.f, 0.f);
+    for (uint32_t sl = 0; sl < count; sl++) {  // fixed order: deterministic sums
+      float2 v = ypart_t[(uint64_t)(first + sl) * M + k];
+      a.x += v.x;
+      a.y += v.y;
+    }
+    x[k] = a;
+  }
+  __syncthreads();
+  irfft_unsplit<M>(x, tw, s);
+  __syncthreads();
+  cfft_smem<M, true>(s, tw);
+  // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(j + hQ) + {0,1}, h < 2
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    float2 z = s[M / 2 + threadIdx.x + h * Q];
+    o[2 * h] = z.x;
+    o[2 * h + 1] = z.y;
+  }
+  __syncthreads();
+}
+
+template <int M>
+__global__ void __launch_bounds__(M / 4) k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk,
+                                                 PlanView steady, uint32_t n_first, const float2* __restrict__ tw,
+                                                 float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0) {
+  extern __shared__ float2 k_irfft_smem[];  // 2M float2: summed spectrum + FFT workspace (64 KB at M = 4096)
+  float2* x = k_irfft_smem;
+  float2* s = k_irfft_smem + M;
+  constexpr int Q = M / 4;
+  const uint32_t stream = blockIdx.x, t = blockIdx.y;
+  const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
+  const PlanView pv = first ? first_blk : steady;
+  const float2* ypart_t = ypart + (uint64_t)t * slot_stride * M;
+  float o[4];
+  job_to_block<M>(ypart_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, o);
+  const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
+  if (xj != kNoJob) {
+    float o2[4];
+    if (xj == kSameJob) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) o2[i] = o[i];
+    } else {
+      job_to_block<M>(ypart_t, pv.job_slot_first[xj], pv.job_slot_count[xj], x, s, tw, o2);
+    }
+    // out = (1-g) o_f + g o_f', g_n = n/B  (MixSamples + Interpolator ramp, sampled before the step)
+    const float inc = 1.0f / (float)M;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const uint32_t n = 2 * (threadIdx.x + h * Q) + c;
+        const float g = __fmul_rn((float)n, inc);
+        const float a = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
+        const float b = __fmul_rn(g, o2[2 * h + c]);
+        o[2 * h + c] = __fadd_rn(a, b);
+      }
+  }
+  float* ring = ybuf + (uint64_t)stream * Rd;
+  const uint32_t w = (wpos0 + t * (uint32_t)M) % Rd;
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const uint32_t n = 2 * (threadIdx.x + h * Q) + c;
+      uint32_t idx = w + n;
+      if (idx >= Rd) idx -= Rd;
+      ring[idx] = o[2 * h + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pcm_out : delay read + mixdown + format conversion
+// ------------------------------------------------------------------------------------------
+struct RouteView {
+  const uint32_t* out_first;   // [n_outputs+1] CSR over outputs
+  const uint32_t* route_stream;  // ascending stream index per output
+  const float* gain;           // per stream
+  const double* delay_cur;     // per stream, delay in force after this call's first block boundary
+  const double* delay_old;     // per stream, delay before it
+  const uint32_t* dflags;      // per stream, bit0: crossfade old->cur over the first block
+};
+
+struct PcmOutArgs {
+  uint8_t* pcm;
+  int fmt;
+  int be;
+  uint32_t out_channels, n_outputs;
+  uint32_t B, T;
+  const float* ybuf;
+  uint32_t Rd, wpos0;
+  int fractional;
+  RouteView rv;
+};
+
+__device__ __forceinline__ float delayed_read(const float* __restrict__ ring, uint32_t Rd, uint32_t w, uint32_t n, double d,
+                                              int fractional) {
+  if (fractional) {
+    // FractionalSample(ring, 0, 1, Rd, fmod((w + n + Rd) - d, Rd))   (src/FractionalSample.cpp:312-341)
+    const double pos = fmod((double)(w + n + Rd) - d, (double)Rd);
+    return __double2float_rn(fractional_sample_dev<float>(ring, 0, 1, Rd, pos));
+  }
+  const uint32_t di = (uint32_t)d % Rd;  // ring[(w + n - d) mod R]   (src/SoundDelayBuffer.cpp:141)
+  return ring[(w + n + Rd - di) % Rd];
+}
+
+__global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
+  __shared__ float tile[32][33];
+  const uint32_t f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t t = f0 / a.B;               // a tile lies inside one block (B % 32 == 0)
+  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
+  const float inc = 1.0f / (float)a.B;
+  // phase 1: lanes over frames (ring reads are contiguous), one output channel per warp pass
+#pragma unroll 1
+  for (int i = 0; i < 4; i++) {
+    const uint32_t cl = warp + 8 * i, o = c0 + cl;
+    float bus = 0.f;
+    if (o < a.n_outputs) {
+      const uint32_t n = f0 + lane - t * a.B;  // frame inside the block
+      const uint32_t rb = a.rv.out_first[o], re = a.rv.out_first[o + 1];
+      for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
+        const uint32_t st = a.rv.route_stream[r];
+        const float gain = a.rv.gain[st];
+        if (!(gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
+        const float* ring = a.ybuf + (uint64_t)st * a.Rd;
+        float v = delayed_read(ring, a.Rd, w, n, a.rv.delay_cur[st], a.fractional);
+        if (t == 0 && (a.rv.dflags[st] & 1u)) {
+          const float vo = delayed_read(ring, a.Rd, w, n, a.rv.delay_old[st], a.fractional);
+          const float g = __fmul_rn((float)n, inc);
+          v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
+        }
+        bus = __fadd_rn(bus, __fmul_rn(gain, v));  // dst += mul * src, rounded separately
+      }
+    }
+    tile[lane][cl] = bus;
+  }
+  __syncthreads();
+  // phase 2: lanes over channels (contiguous bytes of one interleaved frame)
+  const uint32_t bps = fmt_bytes(a.fmt);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t fl = warp + 8 * i, o = c0 + lane;
+    if (o >= a.n_outputs) continue;
+    const uint32_t frame = f0 + fl;
+    store_from_f32(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0);
+  }
+}
+
+__global__ void k_flush(float4* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+}
+
+}  // namespace bbx
+
+using namespace bbx;
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+struct bbx_filter {
+  bbx_engine* engine;
+  float2* H;  // device [P][B]
+  uint32_t P;
+};
+
+struct PathState {
+  uint32_t input = 0, output = 0;
+  float gain = 1.0f;
+  const bbx_filter* cur = nullptr;
+  const bbx_filter* pend = nullptr;
+  bool has_pending = false, xfade = false;
+  double delay = 0.0, pend_delay = 0.0;
+};
+
+// one job = one accumulated output spectrum: a list of (filter, input) terms
+struct JobTerm {
+  const bbx_filter* f;
+  uint32_t input;
+};
+
+// device-resident MAC plan + host mirror
+struct MacPlan {
+  // host staging (pinned) and device blob, same layout
+  uint8_t* h_blob = nullptr;
+  uint8_t* d_blob = nullptr;
+  size_t blob_bytes = 0;
+  // offsets inside the blob
+  size_t off_segs = 0, off_cta = 0, off_first = 0, off_count = 0, off_xjob = 0;
+  uint32_t n_ctas = 0, n_slots = 0, n_jobs = 0, total_rows = 0;
+  bool valid = false;
+  const MacSeg* segs() const { return (const MacSeg*)(d_blob + off_segs); }
+  const uint32_t* cta_seg_begin() const { return (const uint32_t*)(d_blob + off_cta); }
+  PlanView view() const {
+    PlanView v;
+    v.job_slot_first = (const uint32_t*)(d_blob + off_first);
+    v.job_slot_count = (const uint32_t*)(d_blob + off_count);
+    v.xjob = (const uint32_t*)(d_blob + off_xjob);
+    return v;
+  }
+};
+
+struct bbx_engine {
+  bbx_config cfg;
+  int device = 0;
+  uint32_t B = 0, Pmax = 0, n_in = 0, n_out = 0, n_paths = 0, n_streams = 0, Tmax = 1;
+  uint32_t R = 0;   // FDL ring slots
+  uint32_t Rd = 0;  // delay ring frames
+  uint32_t xstride = 0;
+  int mode = 0;
+  cudaStream_t stream = nullptr;
+  // device buffers
+  float2* tw = nullptr;
+  float* xin[2] = {nullptr, nullptr};
+  float2* fdl = nullptr;
+  float2* ypart = nullptr;
+  float* ybuf = nullptr;
+  uint8_t* d_in = nullptr;
+  uint8_t* d_out = nullptr;
+  size_t d_io_bytes = 0;
+  float4* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // route tables (device blob + pinned staging)
+  uint8_t* h_route = nullptr;
+  uint8_t* d_route = nullptr;
+  size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0;
+  bool route_dirty = true;
+  // plans
+  MacPlan plan_first, plan_steady;
+  uint32_t max_segs = 0, max_slots = 0, max_ctas = 0, max_jobs = 0;
+  bool steady_dirty = true;
+  // state
+  std::vector<PathState> paths;
+  uint32_t head = 0, wpos = 0, parity = 0, tprev = 1;
+  // measurement
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  cudaEvent_t ev_upload = nullptr;  // last H2D copy out of the pinned plan/route staging
+  bool upload_pending = false;
+  uint32_t mac_occ = 2;
+  uint64_t launches = 0;
+  bool profile_mac = false;
+  std::vector<cudaEvent_t> mac_events;  // pairs
+  size_t mac_events_used = 0;
+  double mac_ms_total = 0.0;
+  uint64_t mac_launches = 0, mac_units = 0, mac_bytes = 0;
+  int last_infmt = FMT_F32, last_outfmt = FMT_F32;
+};
+
+namespace {
+
+template <int M>
+void launch_rfft_t(const float* src, uint64_t ch_stride, uint32_t win_stride, float2* dst, uint64_t dst_ch_stride, uint32_t R,
+                   uint32_t slot0, const float2* tw, float scale, uint32_t nch, uint32_t T, cudaStream_t st) {
+  k_rfft<M><<<dim3(nch, T), M / 4, 0, st>>>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale);
+}
+
+int launch_rfft(uint32_t B, const float* src, uint64_t ch_stride, uint32_t win_stride, float2* dst, uint64_t dst_ch_stride,
+                uint32_t R, uint32_t slot0, const float2* tw, float scale, uint32_t nch, uint32_t T, cudaStream_t st) {
+  switch (B) {
+    case 64: launch_rfft_t<64>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    case 128: launch_rfft_t<128>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    case 256: launch_rfft_t<256>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    case 512: launch_rfft_t<512>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    case 1024: launch_rfft_t<1024>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    case 2048: launch_rfft_t<2048>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    case 4096: launch_rfft_t<4096>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale, nch, T, st); break;
+    default: set_error("unsupported block size %u", B); return BBX_ERR_UNSUPPORTED;
+  }
+  BBX_CUDA_TRY(cudaGetLastError());
+  return BBX_OK;
+}
+
+template <int M>
+void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, cudaStream_t st) {
+  constexpr size_t smem = 2 * sizeof(float2) * M;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_irfft<M><<<dim3(e->n_streams, T), M / 4, smem, st>>>(e->ypart, e->max_slots, e->plan_first.view(), e->plan_steady.view(),
+                                                      n_first, e->tw, e->ybuf, e->Rd, e->wpos);
+}
+
+int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first) {
+  cudaStream_t st = e->stream;
+  switch (e->B) {
+    case 64: launch_irfft_t<64>(e, T, n_first, st); break;
+    case 128: launch_irfft_t<128>(e, T, n_first, st); break;
+    case 256: launch_irfft_t<256>(e, T, n_first, st); break;
+    case 512: launch_irfft_t<512>(e, T, n_first, st); break;
+    case 1024: launch_irfft_t<1024>(e, T, n_first, st); break;
+    case 2048: launch_irfft_t<2048>(e, T, n_first, st); break;
+    case 4096: launch_irfft_t<4096>(e, T, n_first, st); break;
+    default: set_error("unsupported block size %u", e->B); return BBX_ERR_UNSUPPORTED;
+  }
+  BBX_CUDA_TRY(cudaGetLastError());
+  return BBX_OK;
+}
+
+template <int THREADS>
+void launch_mac_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cudaStream_t st) {
+  const uint32_t halfB = e->B / 2;
+  dim3 grid(pl.n_ctas, halfB / THREADS, nt);
+  float4* yp = (float4*)e->ypart + (uint64_t)t0 * e->max_slots * halfB;
+  const MacSeg* segs = pl.segs();
+  const uint32_t* cta = pl.cta_seg_begin();
+  const float4* fdl = (const float4*)e->fdl;
+  // resident CTAs per SM <-> loads in flight per thread: fewer, fatter CTAs unroll deeper
+  switch (e->mac_occ) {
+    case 1: k_fdl_mac<16, THREADS, 1><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
+    case 2: k_fdl_mac<8, THREADS, 2><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
+    case 3: k_fdl_mac<6, THREADS, 3><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
+    default: k_fdl_mac<4, THREADS, 4><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
+  }
+}
+
+int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
+  if (pl.n_ctas == 0 || nt == 0) return BBX_OK;
+  cudaStream_t st = e->stream;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e->profile_mac) {
+    if (e->mac_events_used + 2 > e->mac_events.size()) {
+      size_t old = e->mac_events.size();
+      e->mac_events.resize(old + 64);
+      for (size_t i = old; i < e->mac_events.size(); i++) BBX_CUDA_TRY(cudaEventCreate(&e->mac_events[i]));
+    }
+    ev0 = e->mac_events[e->mac_events_used++];
+    ev1 = e->mac_events[e->mac_events_used++];
+    BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+  }
+  const uint32_t halfB = e->B / 2;
+  if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
+  else if (halfB == 128) launch_mac_t<128>(e, pl, t0, nt, st);
+  else if (halfB == 64) launch_mac_t<64>(e, pl, t0, nt, st);
+  else launch_mac_t<32>(e, pl, t0, nt, st);
+  BBX_CUDA_TRY(cudaGetLastError());
+  if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
+  e->launches++;
+  e->mac_launches++;
+  e->mac_units += (uint64_t)e->n_streams * nt;
+  // 16 P K + 16 K + (bytes_in + bytes_out) B per channel-block, K = B + 1
+  const uint64_t K = e->B + 1;
+  e->mac_bytes += (uint64_t)nt * (16ull * pl.total_rows * K + 16ull * K * e->n_streams +
+                                  (uint64_t)e->B * (fmt_bytes(e->last_infmt) * e->n_in + fmt_bytes(e->last_outfmt) * e->n_out));
+  return BBX_OK;
+}
+
+// The pinned plan/route staging is rewritten by the host; wait until the previous upload has read it.
+int wait_uploads(bbx_engine* e) {
+  if (e->upload_pending) {
+    BBX_CUDA_TRY(cudaEventSynchronize(e->ev_upload));
+    e->upload_pending = false;
+  }
+  return BBX_OK;
+}
+int mark_upload(bbx_engine* e) {
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_upload, e->stream));
+  e->upload_pending = true;
+  return BBX_OK;
+}
+
+// Build a MAC plan from a job list into plan.h_blob (pinned) and enqueue its upload.
+int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm>>& jobs, const std::vector<uint32_t>& xjob) {
+  uint32_t total = 0;
+  for (auto& j : jobs)
+    for (auto& tm : j) total += tm.f ? tm.f->P : 0;
+  {
+    int wrc = wait_uploads(e);
+    if (wrc) return wrc;
+  }
+  MacSeg* segs = (MacSeg*)(pl.h_blob + pl.off_segs);
+  uint32_t* cta = (uint32_t*)(pl.h_blob + pl.off_cta);
+  uint32_t* jfirst = (uint32_t*)(pl.h_blob + pl.off_first);
+  uint32_t* jcount = (uint32_t*)(pl.h_blob + pl.off_count);
+  uint32_t* xj = (uint32_t*)(pl.h_blob + pl.off_xjob);
+  BBX_REQUIRE(jobs.size() <= e->max_jobs, "internal: too many jobs");
+  pl.n_jobs = (uint32_t)jobs.size();
+  pl.total_rows = total;
+  for (uint32_t s = 0; s < e->n_streams; s++) xj[s] = s < xjob.size() ? xjob[s] : kNoJob;
+  if (total == 0) {
+    for (uint32_t j = 0; j < jobs.size(); j++) jfirst[j] = jcount[j] = 0;
+    pl.n_ctas = 0;
+    pl.n_slots = 0;
+  } else {
+    // even split of the flattened row space; small problems get fewer, fatter CTAs
+    const uint32_t min_rows = 4;
+    uint32_t G = std::min(e->max_ctas, std::max(1u, total / min_rows));
+    uint32_t rpc = ceil_div(total, G);
+    G = ceil_div(total, rpc);
+    uint32_t nseg = 0, nslot = 0, row = 0, cur_cta = 0;
+    cta[0] = 0;
+    int run_job = -1;  // job of the open run inside the current CTA
+    for (uint32_t j = 0; j < jobs.size(); j++) {
+      jfirst[j] = nslot;
+      uint32_t before = nslot;
+      bool job_has_run = false;
+      for (auto& tm : jobs[j]) {
+        if (!tm.f) continue;
+        uint32_t p = 0;
+        while (p < tm.f->P) {
+          uint32_t cta_end = (cur_cta + 1) * rpc;
+          if (row == cta_end) {  // move to the next CTA
+            cur_cta++;
+            cta[cur_cta] = nseg;
+            run_job = -1;
+            continue;
+          }
+          uint32_t np = std::min(tm.f->P - p, cta_end - row);
+          BBX_REQUIRE(nseg < e->max_segs, "internal: MAC plan overflow (segments)");
+          MacSeg& sg = segs[nseg];
+          sg.H = (const float4*)tm.f->H;
+          sg.fdl_ch = tm.input;
+          sg.p0 = p;
+          sg.np = np;
+          sg.pad = 0;
+          if (run_job == (int)j) {
+            // continue the open run: the previous segment no longer writes
+            segs[nseg - 1].flags &= ~2u;
+            sg.flags = 2u;
+            sg.slot = segs[nseg - 1].slot;
+          } else {
+            BBX_REQUIRE(nslot < e->max_slots, "internal: MAC plan overflow (slots)");
+            sg.flags = 1u | 2u;
+            sg.slot = nslot++;
+            run_job = (int)j;
+            job_has_run = true;
+          }
+          nseg++;
+          p += np;
+          row += np;
+        }
+      }
+      (void)job_has_run;
+      jcount[j] = nslot - before;
+    }
+    for (uint32_t c = cur_cta + 1; c <= G; c++) cta[c] = nseg;
+    pl.n_ctas = G;
+    pl.n_slots = nslot;
+  }
+  pl.valid = true;
+  BBX_CUDA_TRY(cudaMemcpyAsync(pl.d_blob, pl.h_blob, pl.blob_bytes, cudaMemcpyHostToDevice, e->stream));
+  return mark_upload(e);
+}
+
+int alloc_plan(bbx_engine* e, MacPlan& pl) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  pl.off_segs = take(sizeof(MacSeg) * e->max_segs);
+  pl.off_cta = take(sizeof(uint32_t) * (e->max_ctas + 2));
+  pl.off_first = take(sizeof(uint32_t) * e->max_jobs);
+  pl.off_count = take(sizeof(uint32_t) * e->max_jobs);
+  pl.off_xjob = take(sizeof(uint32_t) * std::max(1u, e->n_streams));
+  pl.blob_bytes = off;
+  BBX_CUDA_TRY(cudaHostAlloc((void**)&pl.h_blob, off, cudaHostAllocDefault));
+  memset(pl.h_blob, 0, off);
+  BBX_CUDA_TRY(cudaMalloc((void**)&pl.d_blob, off));
+  BBX_CUDA_TRY(cudaMemset(pl.d_blob, 0, off));
+  return BBX_OK;
+}
+
+// jobs for the given choice of filter per path; MIMO groups the paths of one output into one job
+void make_jobs(const bbx_engine* e, bool use_pending, std::vector<std::vector<JobTerm>>& jobs) {
+  jobs.clear();
+  auto pick = [&](const PathState& p) { return (use_pending && p.has_pending) ? p.pend : p.cur; };
+  if (e->mode == BBX_MODE_MIMO) {
+    jobs.resize(e->n_out);
+    for (uint32_t o = 0; o < e->n_out; o++)
+      for (uint32_t i = 0; i < e->n_in; i++) {
+        const PathState& p = e->paths[(size_t)o * e->n_in + i];
+        const bbx_filter* f = pick(p);
+        if (f) jobs[o].push_back({f, i});
+      }
+  } else {
+    jobs.resize(e->n_paths);
+    for (uint32_t k = 0; k < e->n_paths; k++) {
+      const PathState& p = e->paths[k];
+      const bbx_filter* f = pick(p);
+      if (f) jobs[k].push_back({f, p.input});
+    }
+  }
+}
+
+int upload_routes(bbx_engine* e, bool first_block_transition) {
+  {
+    int wrc = wait_uploads(e);
+    if (wrc) return wrc;
+  }
+  uint32_t* ofirst = (uint32_t*)(e->h_route + e->roff_first);
+  uint32_t* rstream = (uint32_t*)(e->h_route + e->roff_stream);
+  float* gain = (float*)(e->h_route + e->roff_gain);
+  double* dcur = (double*)(e->h_route + e->roff_dcur);
+  double* dold = (double*)(e->h_route + e->roff_dold);
+  uint32_t* flags = (uint32_t*)(e->h_route + e->roff_flags);
+  if (e->mode == BBX_MODE_MIMO) {
+    for (uint32_t o = 0; o < e->n_out; o++) {
+      ofirst[o] = o;
+      rstream[o] = o;
+      gain[o] = 1.0f;
+      dcur[o] = dold[o] = 0.0;
+      flags[o] = 0;
+    }
+    ofirst[e->n_out] = e->n_out;
+  } else {
+    uint32_t n = 0;
+    for (uint32_t o = 0; o < e->n_out; o++) {
+      ofirst[o] = n;
+      for (uint32_t k = 0; k < e->n_paths; k++)
+        if (e->paths[k].output == o) rstream[n++] = k;
+    }
+    ofirst[e->n_out] = n;
+    for (uint32_t k = 0; k < e->n_paths; k++) {
+      const PathState& p = e->paths[k];
+      gain[k] = p.gain;
+      bool sw = first_block_transition && p.has_pending;
+      dcur[k] = sw ? p.pend_delay : p.delay;
+      dold[k] = p.delay;
+      flags[k] = (sw && p.xfade && p.pend_delay != p.delay) ? 1u : 0u;
+    }
+  }
+  BBX_CUDA_TRY(cudaMemcpyAsync(e->d_route, e->h_route, e->route_bytes, cudaMemcpyHostToDevice, e->stream));
+  return mark_upload(e);
+}
+
+RouteView route_view(const bbx_engine* e) {
+  RouteView v;
+  v.out_first = (const uint32_t*)(e->d_route + e->roff_first);
+  v.route_stream = (const uint32_t*)(e->d_route + e->roff_stream);
+  v.gain = (const float*)(e->d_route + e->roff_gain);
+  v.delay_cur = (const double*)(e->d_route + e->roff_dcur);
+  v.delay_old = (const double*)(e->d_route + e->roff_dold);
+  v.dflags = (const uint32_t*)(e->d_route + e->roff_flags);
+  return v;
+}
+
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+}  // namespace
+
+extern "C" {
+
+int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
+  BBX_REQUIRE(cfg && out, "bbx_engine_create: null argument");
+  int rc = require_device();
+  if (rc) return rc;
+  BBX_REQUIRE(is_pow2(cfg->block_size) && cfg->block_size >= 64 && cfg->block_size <= 4096,
+              "block_size %u must be a power of two in [64, 4096]", cfg->block_size);
+  BBX_REQUIRE(cfg->n_inputs > 0, "n_inputs must be > 0");
+  BBX_REQUIRE(cfg->mode >= BBX_MODE_PER_CHANNEL && cfg->mode <= BBX_MODE_MIMO, "bad mode %d", cfg->mode);
+  bbx_engine* e = new bbx_engine();
+  e->cfg = *cfg;
+  e->device = cfg->device;
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  e->B = cfg->block_size;
+  e->Pmax = std::max(1u, cfg->max_partitions);
+  e->n_in = cfg->n_inputs;
+  e->mode = cfg->mode;
+  if (e->mode == BBX_MODE_PER_CHANNEL) {
+    e->n_out = e->n_in;
+    e->n_paths = e->n_in;
+    e->n_streams = e->n_in;
+  } else if (e->mode == BBX_MODE_ROUTED) {
+    BBX_REQUIRE(cfg->n_outputs > 0 && cfg->n_paths > 0, "ROUTED mode needs n_outputs and n_paths");
+    e->n_out = cfg->n_outputs;
+    e->n_paths = cfg->n_paths;
+    e->n_streams = cfg->n_paths;
+  } else {
+    BBX_REQUIRE(cfg->n_outputs > 0, "MIMO mode needs n_outputs");
+    BBX_REQUIRE(cfg->max_delay == 0, "MIMO mode has no per-path delay (frequency-domain mixdown)");
+    e->n_out = cfg->n_outputs;
+    e->n_paths = e->n_in * e->n_out;
+    e->n_streams = e->n_out;
+  }
+  e->Tmax = std::max(1u, cfg->max_blocks);
+  e->R = e->Pmax + e->Tmax - 1;
+  uint32_t need = cfg->max_delay + 14 + (e->Tmax + 1) * e->B;
+  e->Rd = cfg->ring_length ? cfg->ring_length : ceil_div(need, e->B) * e->B;
+  BBX_REQUIRE(e->Rd >= cfg->max_delay + 14 + e->Tmax * e->B, "ring_length %u too short (need >= %u)", e->Rd,
+              cfg->max_delay + 14 + e->Tmax * e->B);
+  e->xstride = (e->Tmax + 1) * e->B;
+  e->paths.resize(e->n_paths);
+  for (uint32_t k = 0; k < e->n_paths; k++) {
+    PathState& p = e->paths[k];
+    if (e->mode == BBX_MODE_MIMO) {
+      p.output = k / e->n_in;
+      p.input = k % e->n_in;
+    } else if (e->mode == BBX_MODE_PER_CHANNEL) {
+      p.input = p.output = k;
+    }
+  }
+  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  BBX_CUDA_TRY(cudaEventCreate(&e->ev_start));
+  BBX_CUDA_TRY(cudaEventCreate(&e->ev_stop));
+  BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
+
+  const uint32_t B = e->B, N = 2 * B;
+  // twiddles exp(-2 pi i j / N), computed in double
+  {
+    std::vector<float2> tw(N);
+    const double PI = 3.14159265358979323846264338327950288;
+    for (uint32_t j = 0; j < N; j++) {
+      double a = -2.0 * PI * (double)j / (double)N;
+      tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->tw, sizeof(float2) * N));
+    BBX_CUDA_TRY(cudaMemcpy(e->tw, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+  }
+  size_t xin_bytes = sizeof(float) * (size_t)e->n_in * e->xstride;
+  for (int i = 0; i < 2; i++) {
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->xin[i], xin_bytes));
+    BBX_CUDA_TRY(cudaMemset(e->xin[i], 0, xin_bytes));
+  }
+  size_t fdl_bytes = sizeof(float2) * (size_t)e->n_in * e->R * B;
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->fdl, fdl_bytes));
+  BBX_CUDA_TRY(cudaMemset(e->fdl, 0, fdl_bytes));
+  size_t ybuf_bytes = sizeof(float) * (size_t)e->n_streams * e->Rd;
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->ybuf, ybuf_bytes));
+  BBX_CUDA_TRY(cudaMemset(e->ybuf, 0, ybuf_bytes));
+
+  // plan capacities
+  e->mac_occ = cfg->mac_ctas_per_sm ? std::min(cfg->mac_ctas_per_sm, 4u) : 2u;
+  e->max_ctas = kNumSMs * e->mac_occ;
+  uint32_t terms = (e->mode == BBX_MODE_MIMO) ? e->n_paths : e->n_paths;
+  e->max_jobs = 2 * e->n_streams + 1;
+  e->max_segs = e->max_ctas + 2 * terms + 8;
+  e->max_slots = e->max_ctas + e->max_jobs + 8;
+  if ((rc = alloc_plan(e, e->plan_first))) return rc;
+  if ((rc = alloc_plan(e, e->plan_steady))) return rc;
+  size_t ypart_bytes = sizeof(float2) * (size_t)e->Tmax * e->max_slots * B;
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->ypart, ypart_bytes));
+  BBX_CUDA_TRY(cudaMemset(e->ypart, 0, ypart_bytes));
+
+  // route tables
+  {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      size_t o = off;
+      off += (bytes + 255) & ~(size_t)255;
+      return o;
+    };
+    uint32_t ns = e->n_streams;
+    e->roff_first = take(sizeof(uint32_t) * (e->n_out + 1));
+    e->roff_stream = take(sizeof(uint32_t) * ns);
+    e->roff_gain = take(sizeof(float) * ns);
+    e->roff_dcur = take(sizeof(double) * ns);
+    e->roff_dold = take(sizeof(double) * ns);
+    e->roff_flags = take(sizeof(uint32_t) * ns);
+    e->route_bytes = off;
+    BBX_CUDA_TRY(cudaHostAlloc((void**)&e->h_route, off, cudaHostAllocDefault));
+    memset(e->h_route, 0, off);
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->d_route, off));
+  }
+  // PCM staging for the host-pointer process call (largest format both ways)
+  e->d_io_bytes = (size_t)e->Tmax * B * 8;
+  BBX_CUDA_TRY(cudaDeviceSynchronize());
+  *out = e;
+  return BBX_OK;
+}
+
+int bbx_engine_destroy(bbx_engine* e) {
+  if (!e) return BBX_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->tw);
+  cudaFree(e->xin[0]);
+  cudaFree(e->xin[1]);
+  cudaFree(e->fdl);
+  cudaFree(e->ypart);
+  cudaFree(e->ybuf);
+  cudaFree(e->d_in);
+  cudaFree(e->d_out);
+  cudaFree(e->flush_buf);
+  cudaFree(e->d_route);
+  cudaFreeHost(e->h_route);
+  for (MacPlan* pl : {&e->plan_first, &e->plan_steady}) {
+    cudaFree(pl->d_blob);
+    cudaFreeHost(pl->h_blob);
+  }
+  for (cudaEvent_t ev : e->mac_events) cudaEventDestroy(ev);
+  if (e->ev_start) cudaEventDestroy(e->ev_start);
+  if (e->ev_stop) cudaEventDestroy(e->ev_stop);
+  if (e->ev_upload) cudaEventDestroy(e->ev_upload);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return BBX_OK;
+}
+
+uint32_t bbx_engine_get_ring_length(const bbx_engine* e) { return e ? e->Rd : 0; }
+void* bbx_engine_get_stream(const bbx_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filter** out) {
+  BBX_REQUIRE(e && out, "bbx_filter_create: null argument");
+  BBX_REQUIRE(ir || length == 0, "bbx_filter_create: null impulse response");
+  const uint32_t B = e->B, N = 2 * B;
+  uint32_t P = std::max(1u, ceil_div(length, B));
+  BBX_REQUIRE(P <= e->Pmax, "impulse response of %u taps needs %u partitions, engine max_partitions is %u", length, P, e->Pmax);
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  // zero-padded windows [h[pB .. pB+B-1], 0^B]
+  std::vector<float> pad((size_t)P * N, 0.0f);
+  for (uint32_t i = 0; i < length; i++) pad[(size_t)(i / B) * N + (i % B)] = ir[i];
+  float* d_pad = nullptr;
+  BBX_CUDA_TRY(cudaMalloc((void**)&d_pad, sizeof(float) * pad.size()));
+  bbx_filter* f = new bbx_filter();
+  f->engine = e;
+  f->P = P;
+  f->H = nullptr;
+  BBX_CUDA_TRY(cudaMalloc((void**)&f->H, sizeof(float2) * (size_t)P * B));
+  BBX_CUDA_TRY(cudaMemcpyAsync(d_pad, pad.data(), sizeof(float) * pad.size(), cudaMemcpyHostToDevice, e->stream));
+  // H = R2C(window) / N : the only normalisation of the whole path, exact (power of two)
+  int rc = launch_rfft(B, d_pad, 0, N, f->H, 0, P, 0, e->tw, 1.0f / (float)N, 1, P, e->stream);
+  e->launches++;
+  cudaError_t se = cudaStreamSynchronize(e->stream);
+  cudaFree(d_pad);
+  if (rc || se != cudaSuccess) {
+    if (!rc) set_error("filter transform failed: %s", cudaGetErrorString(se));
+    cudaFree(f->H);
+    delete f;
+    return rc ? rc : BBX_ERR_CUDA;
+  }
+  *out = f;
+  return BBX_OK;
+}
+
+int bbx_filter_destroy(bbx_filter* f) {
+  if (!f) return BBX_OK;
+  cudaSetDevice(f->engine->device);
+  cudaStreamSynchronize(f->engine->stream);
+  cudaFree(f->H);
+  delete f;
+  return BBX_OK;
+}
+
+uint32_t bbx_filter_partitions(const bbx_filter* f) { return f ? f->P : 0; }
+
+int bbx_set_route(bbx_engine* e, uint32_t path, uint32_t input, uint32_t output, float gain) {
+  BBX_REQUIRE(e != nullptr, "bbx_set_route: null engine");
+  BBX_REQUIRE(e->mode == BBX_MODE_ROUTED, "bbx_set_route: engine is not in ROUTED mode");
+  BBX_REQUIRE(path < e->n_paths && input < e->n_in && output < e->n_out, "bbx_set_route: index out of range");
+  PathState& p = e->paths[path];
+  if (p.input != input) e->steady_dirty = true;
+  p.input = input;
+  p.output = output;
+  p.gain = gain;
+  e->route_dirty = true;
+  return BBX_OK;
+}
+
+int bbx_set_filter(bbx_engine* e, uint32_t path, const bbx_filter* filter, int crossfade, double delay) {
+  BBX_REQUIRE(e != nullptr, "bbx_set_filter: null engine");
+  BBX_REQUIRE(path < e->n_paths, "bbx_set_filter: path %u out of range", path);
+  BBX_REQUIRE(!filter || filter->engine == e, "bbx_set_filter: filter belongs to another engine");
+  BBX_REQUIRE(delay >= 0.0 && delay <= (double)e->cfg.max_delay, "bbx_set_filter: delay %g outside [0, max_delay=%u]", delay,
+              e->cfg.max_delay);
+  BBX_REQUIRE(e->mode != BBX_MODE_MIMO || delay == 0.0, "bbx_set_filter: MIMO mode has no per-path delay");
+  PathState& p = e->paths[path];
+  p.pend = filter;
+  p.pend_delay = delay;
+  p.xfade = crossfade != 0;
+  p.has_pending = true;
+  return BBX_OK;
+}
+
+int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
+                    int out_be, uint32_t out_channels, uint32_t nframes) {
+  BBX_REQUIRE(e && in && out, "bbx_process: null argument");
+  BBX_REQUIRE(infmt > FMT_UNKNOWN && infmt < FMT_COUNT && outfmt > FMT_UNKNOWN && outfmt < FMT_COUNT, "bbx_process: bad format");
+  BBX_REQUIRE(nframes > 0 && nframes % e->B == 0, "bbx_process: nframes %u is not a positive multiple of the block size %u",
+              nframes, e->B);
+  const uint32_t B = e->B, T = nframes / B;
+  BBX_REQUIRE(T <= e->Tmax, "bbx_process: %u blocks exceed max_blocks %u", T, e->Tmax);
+  BBX_REQUIRE(in_channels >= e->n_in && out_channels >= e->n_out, "bbx_process: too few channels in the PCM buffers");
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  int rc;
+  e->last_infmt = infmt;
+  e->last_outfmt = outfmt;
+
+  // ---- latch pending switches: they apply at this call's first block boundary ----
+  bool any_pending = false, any_xfade = false;
+  for (auto& p : e->paths)
+    if (p.has_pending) {
+      any_pending = true;
+      if (p.xfade) any_xfade = true;
+      else {  // hard switch: filter and delay jump now
+        if (p.cur != p.pend) e->steady_dirty = true;
+        p.cur = p.pend;
+        p.delay = p.pend_delay;
+        p.has_pending = false;
+        e->route_dirty = true;
+      }
+    }
+  uint32_t n_first = 0;
+  std::vector<std::vector<JobTerm>> jobs;
+  if (any_xfade) {
+    // transitional plan for block 0: old filters as the main jobs, new filters as extra jobs
+    make_jobs(e, false, jobs);
+    std::vector<uint32_t> xjob(e->n_streams, kNoJob);
+    if (e->mode == BBX_MODE_MIMO) {
+      for (uint32_t o = 0; o < e->n_out; o++) {
+        bool sw = false, differs = false;
+        std::vector<JobTerm> nj;
+        for (uint32_t i = 0; i < e->n_in; i++) {
+          const PathState& p = e->paths[(size_t)o * e->n_in + i];
+          const bbx_filter* f = p.has_pending ? p.pend : p.cur;
+          if (p.has_pending) {
+            sw = true;
+            if (p.pend != p.cur) differs = true;
+          }
+          if (f) nj.push_back({f, i});
+        }
+        if (sw) {
+          if (differs) {
+            xjob[o] = (uint32_t)jobs.size();
+            jobs.push_back(nj);
+          } else {
+            xjob[o] = kSameJob;
+          }
+        }
+      }
+    } else {
+      for (uint32_t k = 0; k < e->n_paths; k++) {
+        const PathState& p = e->paths[k];
+        if (!p.has_pending) continue;
+        if (p.pend == p.cur) xjob[k] = kSameJob;
+        else {
+          xjob[k] = (uint32_t)jobs.size();
+          std::vector<JobTerm> nj;
+          if (p.pend) nj.push_back({p.pend, p.input});
+          jobs.push_back(nj);
+        }
+      }
+    }
+    if ((rc = build_plan(e, e->plan_first, jobs, xjob))) return rc;
+    n_first = 1;
+    if ((rc = upload_routes(e, true))) return rc;
+    e->route_dirty = true;  // the steady-state tables follow after this call
+    // commit the crossfaded switches
+    for (auto& p : e->paths)
+      if (p.has_pending) {
+        if (p.cur != p.pend) e->steady_dirty = true;
+        p.cur = p.pend;
+        p.delay = p.pend_delay;
+        p.has_pending = false;
+      }
+  } else if (e->route_dirty) {
+    if ((rc = upload_routes(e, false))) return rc;
+    e->route_dirty = false;
+  }
+  (void)any_pending;
+  if (e->steady_dirty || !e->plan_steady.valid) {
+    make_jobs(e, false, jobs);
+    if ((rc = build_plan(e, e->plan_steady, jobs, std::vector<uint32_t>()))) return rc;
+    e->steady_dirty = false;
+  }
+
+  // ---- 1. PCM -> planar fp32 ----
+  {
+    PcmInArgs a;
+    a.pcm = (const uint8_t*)in;
+    a.fmt = infmt;
+    a.be = in_be;
+    a.in_channels = in_channels;
+    a.n_inputs = e->n_in;
+    a.B = B;
+    a.T = T;
+    a.xin_cur = e->xin[e->parity];
+    a.xin_prev = e->xin[e->parity ^ 1];
+    a.xstride = e->xstride;
+    a.prev_off = e->tprev * B;
+    dim3 grid((T + 1) * B / 32, ceil_div(e->n_in, 32));
+    k_pcm_in<<<grid, 256, 0, st>>>(a);
+    BBX_CUDA_TRY(cudaGetLastError());
+    e->launches++;
+  }
+  // ---- 2. forward transforms into the FDL ----
+  if ((rc = launch_rfft(B, e->xin[e->parity], e->xstride, B, e->fdl, (uint64_t)e->R * B, e->R, e->head, e->tw, 1.0f, e->n_in, T, st)))
+    return rc;
+  e->launches++;
+  // ---- 3. FDL multiply-accumulate ----
+  if (n_first) {
+    if ((rc = launch_mac(e, e->plan_first, 0, 1))) return rc;
+    if ((rc = launch_mac(e, e->plan_steady, 1, T - 1))) return rc;
+  } else {
+    if ((rc = launch_mac(e, e->plan_steady, 0, T))) return rc;
+  }
+  // ---- 4. inverse transforms, crossfade, delay ring ----
+  if ((rc = launch_irfft(e, T, n_first))) return rc;
+  e->launches++;
+  // ---- 5. delay read, mixdown, output format ----
+  {
+    PcmOutArgs a;
+    a.pcm = (uint8_t*)out;
+    a.fmt = outfmt;
+    a.be = out_be;
+    a.out_channels = out_channels;
+    a.n_outputs = e->n_out;
+    a.B = B;
+    a.T = T;
+    a.ybuf = e->ybuf;
+    a.Rd = e->Rd;
+    a.wpos0 = e->wpos;
+    a.fractional = e->cfg.fractional_delay;
+    a.rv = route_view(e);
+    dim3 grid(T * B / 32, ceil_div(e->n_out, 32));
+    k_pcm_out<<<grid, 256, 0, st>>>(a);
+    BBX_CUDA_TRY(cudaGetLastError());
+    e->launches++;
+  }
+  // ---- advance the state ----
+  e->head = (e->head + T) % e->R;
+  e->wpos = (e->wpos + T * B) % e->Rd;
+  e->parity ^= 1;
+  e->tprev = T;
+  return BBX_OK;
+}
+
+int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
+                int out_be, uint32_t out_channels, uint32_t nframes) {
+  BBX_REQUIRE(e && in && out, "bbx_process: null argument");
+  BBX_REQUIRE(infmt > FMT_UNKNOWN && infmt < FMT_COUNT && outfmt > FMT_UNKNOWN && outfmt < FMT_COUNT, "bbx_process: bad format");
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  size_t in_bytes = (size_t)nframes * in_channels * fmt_bytes(infmt);
+  size_t out_bytes = (size_t)nframes * out_channels * fmt_bytes(outfmt);
+  size_t need = std::max(in_bytes, out_bytes);
+  if (!e->d_in || e->d_io_bytes < need || !e->d_out) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_in);
+    cudaFree(e->d_out);
+    e->d_in = e->d_out = nullptr;
+    e->d_io_bytes = std::max(need, e->d_io_bytes);
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->d_in, e->d_io_bytes));
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->d_out, e->d_io_bytes));
+  }
+  BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in, in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+  if (out_channels > e->n_out)  // channels beyond n_outputs keep the caller's bytes
+    BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
+  int rc = bbx_process_dev(e, e->d_in, infmt, in_be, in_channels, e->d_out, outfmt, out_be, out_channels, nframes);
+  if (rc) return rc;
+  BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return BBX_OK;
+}
+
+int bbx_engine_sync(bbx_engine* e) {
+  BBX_REQUIRE(e != nullptr, "bbx_engine_sync: null engine");
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return BBX_OK;
+}
+
+int bbx_blockconvolver_convolve(bbx_engine* e, const float* in, float* out) {
+  BBX_REQUIRE(e && in && out, "bbx_blockconvolver_convolve: null argument");
+  BBX_REQUIRE(e->n_in == 1 && e->n_out == 1, "bbx_blockconvolver_convolve: engine must be single-channel");
+  return bbx_process(e, in, FMT_F32, 0, 1, out, FMT_F32, 0, 1, e->B);
+}
+
+int bbx_engine_timer_start(bbx_engine* e) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_start, e->stream));
+  return BBX_OK;
+}
+int bbx_engine_timer_stop(bbx_engine* e, float* elapsed_ms) {
+  BBX_REQUIRE(e && elapsed_ms, "null argument");
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_stop, e->stream));
+  BBX_CUDA_TRY(cudaEventSynchronize(e->ev_stop));
+  BBX_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e->ev_start, e->ev_stop));
+  return BBX_OK;
+}
+uint64_t bbx_engine_launch_count(const bbx_engine* e) { return e ? e->launches : 0; }
+
+int bbx_engine_profile_mac(bbx_engine* e, int enable) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->profile_mac = enable != 0;
+  e->mac_events_used = 0;
+  e->mac_ms_total = 0.0;
+  e->mac_launches = e->mac_units = e->mac_bytes = 0;
+  return BBX_OK;
+}
+
+int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint64_t* channel_blocks,
+                        uint64_t* algorithmic_bytes) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i + 1 < e->mac_events_used; i += 2) {
+    float ms = 0.f;
+    BBX_CUDA_TRY(cudaEventElapsedTime(&ms, e->mac_events[i], e->mac_events[i + 1]));
+    e->mac_ms_total += ms;
+  }
+  e->mac_events_used = 0;
+  if (total_ms) *total_ms = (float)e->mac_ms_total;
+  if (launches) *launches = e->mac_launches;
+  if (channel_blocks) *channel_blocks = e->mac_units;
+  if (algorithmic_bytes) *algorithmic_bytes = e->mac_bytes;
+  return BBX_OK;
+}
+
+int bbx_engine_flush_l2(bbx_engine* e, size_t bytes) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  bytes = (bytes + 15) & ~(size_t)15;
+  if (e->flush_bytes < bytes) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->flush_buf);
+    e->flush_buf = nullptr;
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->flush_buf, bytes));
+    e->flush_bytes = bytes;
+  }
+  k_flush<<<kNumSMs * 8, 256, 0, e->stream>>>(e->flush_buf, bytes / 16);
+  BBX_CUDA_TRY(cudaGetLastError());
+  return BBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+/* bbx.h -- C ABI of the B200-native partitioned-convolution engine (libbbx.so).
+ *
+ * This is the drop-in boundary for the bbcat-dsp convolution path: plain C, opaque
+ * handles, plain pointers and sizes.  Each entry point names the reference interface
+ * it replaces (paths relative to the bbcat-dsp tree).  Where the reference code is
+ * absent from the tree (BlockConvolver / Convolver / FFT, README:38-51) the entry
+ * point implements SURVEY.md 8.A.
+ *
+ * Conventions
+ *   - every function returning int returns BBX_OK (0) or a negative bbx_status;
+ *     bbx_last_error() gives the message of the last failure on the calling thread.
+ *   - "host" entry points take host pointers and copy through the GPU; "_dev" entry
+ *     points take device pointers on the current device and run on `stream`
+ *     (a cudaStream_t passed as void*, NULL = the legacy default stream).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with BBX_ERR_CUDA.
+ *   - sample formats carry the numeric values of SampleFormat_t
+ *     (src/SoundFormatConversions.h:20-37).
+ */
+#ifndef BBX_H
+#define BBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBX_VERSION 0x000100
+
+typedef enum {
+  BBX_OK = 0,
+  BBX_ERR_INVALID = -1,  /* bad argument / geometry */
+  BBX_ERR_CUDA = -2,     /* CUDA runtime failure (message holds the CUDA error string) */
+  BBX_ERR_NOMEM = -3,
+  BBX_ERR_STATE = -4,    /* call not valid in the object's current state */
+  BBX_ERR_UNSUPPORTED = -5
+} bbx_status;
+
+/* SampleFormat_t, src/SoundFormatConversions.h:20-37 (same numeric values) */
+typedef enum {
+  BBX_FMT_UNKNOWN = 0,
+  BBX_FMT_16BIT = 1,
+  BBX_FMT_24BIT = 2,
+  BBX_FMT_32BIT = 3,
+  BBX_FMT_FLOAT = 4,
+  BBX_FMT_DOUBLE = 5,
+  BBX_FMT_COUNT = 6
+} bbx_sample_format;
+
+/* ------------------------------------------------------------------------------------------
+ * library
+ * ---------------------------------------------------------------------------------------- */
+int bbx_version(void);
+const char* bbx_last_error(void);
+/* number of visible CUDA devices (0 and BBX_ERR_CUDA when the runtime cannot initialise) */
+int bbx_device_count(int* count);
+/* pinned host memory for bbx_process() I/O buffers (cudaHostAlloc / cudaFreeHost) */
+int bbx_host_alloc(void** ptr, size_t bytes);
+int bbx_host_free(void* ptr);
+/* block-contiguous channel shard of rank `rank` of `world`: pure host arithmetic */
+int bbx_shard_range(uint32_t nchannels, uint32_t rank, uint32_t world, uint32_t* first, uint32_t* count);
+
+/* ------------------------------------------------------------------------------------------
+ * a1/a2  GetBitsPerSample / GetBytesPerSample / BlockTransferSanityChecks
+ *        src/SoundFormatConversions.cpp:14-40, :59-93          (host integer logic, bit-exact)
+ * ---------------------------------------------------------------------------------------- */
+uint8_t bbx_get_bits_per_sample(int format);
+uint8_t bbx_get_bytes_per_sample(int format);
+/* returns 1 when the (clamped) transfer is non-empty and valid, else 0 */
+int bbx_block_transfer_sanity_checks(uint32_t* src_channel, uint32_t* src_channels, uint32_t* dst_channel,
+                                     uint32_t* dst_channels, uint32_t* nchannels, uint32_t* nframes,
+                                     int allowsinglechannel);
+
+/* ------------------------------------------------------------------------------------------
+ * a3-a7  TransferSamples / TransferSamplesLinear
+ *        src/SoundFormatConversions.cpp:151-198, :204-219 and the 2x2x6x6 converter table
+ *        src/SoundFormatRawConversions.cpp:4516-4869 (all 100 non-NULL entries), ditherer == NULL.
+ *        Invalid geometry or an Unknown format is a silent no-op returning BBX_OK, like the
+ *        reference (.cpp:160-166).  dst == src is allowed for the host form and gives the
+ *        out-of-place result; any other overlap is undefined (SoundFormatConversions.h:128-130).
+ * ---------------------------------------------------------------------------------------- */
+int bbx_transfer_samples(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
+                         void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
+                         uint32_t nchannels, uint32_t nframes);
+int bbx_transfer_samples_dev(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
+                             void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
+                             uint32_t nchannels, uint32_t nframes, void* stream);
+int bbx_transfer_samples_linear(const void* src, int srctype, void* dst, int dsttype, uint32_t nsamples);
+
+/* ------------------------------------------------------------------------------------------
+ * a8/a9  MixSamples<T> (src/SoundMixing.h:55-81) and MixSamples(..., Interpolator&, inc)
+ *        (src/SoundMixing.cpp:23-52, src/Interpolator.h:12-78).
+ *        interp_state = {target, current}; it is advanced nframes steps like the caller's
+ *        Interpolator object.  Products and sums are rounded separately (no FMA), so results
+ *        equal the reference build bit for bit.
+ * ---------------------------------------------------------------------------------------- */
+int bbx_mix_samples_f32(const float* src, uint32_t src_channel, uint32_t src_channels, float* dst,
+                        uint32_t dst_channel, uint32_t dst_channels, uint32_t nchannels, uint32_t nframes, float mul);
+int bbx_mix_samples_f64(const double* src, uint32_t src_channel, uint32_t src_channels, double* dst,
+                        uint32_t dst_channel, uint32_t dst_channels, uint32_t nchannels, uint32_t nframes, double mul);
+int bbx_mix_samples_interp(const float* src, uint32_t src_channel, uint32_t src_channels, float* dst,
+                           uint32_t dst_channel, uint32_t dst_channels, uint32_t nchannels, uint32_t nframes,
+                           float* interp_state, float inc);
+int bbx_mix_samples_f32_dev(const float* src, uint32_t src_channel, uint32_t src_channels, float* dst,
+                            uint32_t dst_channel, uint32_t dst_channels, uint32_t nchannels, uint32_t nframes,
+                            float mul, void* stream);
+int bbx_mix_samples_interp_dev(const float* src, uint32_t src_channel, uint32_t src_channels, float* dst,
+                               uint32_t dst_channel, uint32_t dst_channels, uint32_t nchannels, uint32_t nframes,
+                               float* interp_state_host, float inc, void* stream);
+/* Interpolator::operator+= applied nsteps times (src/Interpolator.h:55); host arithmetic */
+int bbx_interpolator_step(float* interp_state, float inc, uint32_t nsteps);
+
+/* ------------------------------------------------------------------------------------------
+ * a10  FractionalSample (float / double buffers) and FractionalSampleAdditionalDelayRequired
+ *      src/FractionalSample.cpp:249-341.  Batched: out[i] = FractionalSample(buffer, channel,
+ *      channels, length, pos[i]).  Double accumulation in tap order, bit-exact.
+ * ---------------------------------------------------------------------------------------- */
+uint32_t bbx_fractional_sample_additional_delay_required(void);
+int bbx_fractional_samples_f32(const float* buffer, uint32_t channel, uint32_t channels, uint32_t length,
+                               const double* pos, uint32_t n, double* out);
+int bbx_fractional_samples_f64(const double* buffer, uint32_t channel, uint32_t channels, uint32_t length,
+                               const double* pos, uint32_t n, double* out);
+int bbx_fractional_samples_f32_dev(const float* buffer, uint32_t channel, uint32_t channels, uint32_t length,
+                                   const double* pos, uint32_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11  SoundDelayBuffer  src/SoundDelayBuffer.h:23-95, src/SoundDelayBuffer.cpp:11-191
+ *      The ring lives in HBM, interleaved [length][channels] in `format`; src/dst are host
+ *      pointers.  Same clamping, wrap-split and return values as the reference.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bbx_delay bbx_delay;
+int bbx_delay_create(bbx_delay** out);
+int bbx_delay_destroy(bbx_delay* d);
+int bbx_delay_set_size(bbx_delay* d, uint32_t channels, uint32_t length, int format);
+uint32_t bbx_delay_get_channels(const bbx_delay* d);
+uint32_t bbx_delay_get_length(const bbx_delay* d);
+uint32_t bbx_delay_get_write_position(const bbx_delay* d);
+int bbx_delay_get_format(const bbx_delay* d);
+uint32_t bbx_delay_write_samples(bbx_delay* d, const void* src, int srcformat, uint32_t channel, uint32_t nchannels,
+                                 uint32_t nframes);
+int bbx_delay_increment_write_position(bbx_delay* d, uint32_t nframes);
+uint32_t bbx_delay_read_samples(bbx_delay* d, void* dst, int dstformat, uint32_t delay, uint32_t channel,
+                                uint32_t nchannels, uint32_t nframes);
+/* SoundDelayBuffer::ReadSample (.cpp:176-191) with the channel offset applied in SAMPLES */
+float bbx_delay_read_sample(bbx_delay* d, uint32_t channel, uint32_t delay);
+/* GetBuffer(): device pointer to the ring (format-native), NULL before SetSize */
+const void* bbx_delay_get_buffer_dev(const bbx_delay* d);
+/* copy the raw ring to host memory; returns bytes copied (0 on error) */
+uint32_t bbx_delay_copy_buffer(const bbx_delay* d, void* dst, uint32_t maxbytes);
+
+/* ------------------------------------------------------------------------------------------
+ * a12-a14  BlockConvolver / Convolver / FFT  (absent from the tree: README:38-51, 68-69;
+ *          behaviour = SURVEY.md 8.A)
+ *
+ * One engine = one multichannel convolver on one GPU.
+ *   PER_CHANNEL  path c: input c -> filter -> delay -> output c            (n_paths = n_inputs)
+ *   ROUTED       path p: input in(p) -> filter -> delay -> gain -> time-domain mix into out(p)
+ *   MIMO         path o*n_inputs+i: frequency-domain sum over i into output o, one C2R per output
+ * ---------------------------------------------------------------------------------------- */
+typedef enum { BBX_MODE_PER_CHANNEL = 0, BBX_MODE_ROUTED = 1, BBX_MODE_MIMO = 2 } bbx_mode;
+
+typedef struct {
+  int device;               /* CUDA device ordinal */
+  uint32_t block_size;      /* B: partition = block size, power of two, 64..4096 */
+  uint32_t max_partitions;  /* longest filter in partitions (P_max) */
+  uint32_t n_inputs;
+  uint32_t n_outputs;       /* PER_CHANNEL: ignored (= n_inputs) */
+  uint32_t n_paths;         /* ROUTED only; PER_CHANNEL = n_inputs, MIMO = n_inputs*n_outputs */
+  int mode;                 /* bbx_mode */
+  uint32_t max_blocks;      /* T_max: largest nframes/B accepted by one bbx_process call (>= 1) */
+  uint32_t max_delay;       /* ceil of the largest per-path delay in samples */
+  int fractional_delay;     /* 0: integer delays; 1: every delayed read goes through FractionalSample */
+  uint32_t ring_length;     /* delay ring length R per path in frames; 0 = choose (see _get_ring_length) */
+  uint32_t mac_ctas_per_sm; /* tuning: resident MAC CTAs per SM (0 = default) */
+  uint32_t reserved[7];
+} bbx_config;
+
+typedef struct bbx_engine bbx_engine;
+typedef struct bbx_filter bbx_filter;
+
+int bbx_engine_create(const bbx_config* cfg, bbx_engine** out);
+int bbx_engine_destroy(bbx_engine* e);
+/* R actually used for the per-path delay rings (the oracle must be run with the same R) */
+uint32_t bbx_engine_get_ring_length(const bbx_engine* e);
+/* stream the engine runs on (cudaStream_t as void*) */
+void* bbx_engine_get_stream(const bbx_engine* e);
+
+/* Filter object: H[p] = R2C_2B([h[pB .. pB+B-1], 0^B]), built on the device once, immutable,
+ * shareable between paths of the engine that created it. */
+int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filter** out);
+int bbx_filter_destroy(bbx_filter* f);
+uint32_t bbx_filter_partitions(const bbx_filter* f);
+
+/* ROUTED mode: connect path -> (input, output, gain).  Takes effect at the next bbx_process. */
+int bbx_set_route(bbx_engine* e, uint32_t path, uint32_t input, uint32_t output, float gain);
+/* Convolver::SelectFilter: latched, applied at the next block boundary (= first block of the
+ * next bbx_process call); filter and delay switch together; crossfade != 0 blends old and new
+ * over that one block with g_n = n/B.  filter == NULL silences the path. */
+int bbx_set_filter(bbx_engine* e, uint32_t path, const bbx_filter* filter, int crossfade, double delay_samples);
+
+/* Process nframes (a multiple of B, at most max_blocks*B) of interleaved PCM.
+ * in: [nframes][in_channels] in `infmt`, channels 0..n_inputs-1 are used.
+ * out: [nframes][out_channels] in `outfmt`, channels 0..n_outputs-1 are written.
+ * Host form: synchronous, includes H2D and D2H copies (pinned buffers avoid staging).
+ * _dev form: device pointers, asynchronous on the engine stream. */
+int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
+                int out_be, uint32_t out_channels, uint32_t nframes);
+int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
+                    int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
+int bbx_engine_sync(bbx_engine* e);
+
+/* Single-channel convenience = BlockConvolver::Convolve (README:38-39): path 0 of a
+ * PER_CHANNEL engine, one float block in, one float block out (host pointers). */
+int bbx_blockconvolver_convolve(bbx_engine* e, const float* in, float* out);
+
+/* ------------------------------------------------------------------------------------------
+ * measurement hooks (bench.py): CUDA-event timing on the engine stream, launch counting and
+ * the dominant kernel's (FDL MAC) accumulated device time.
+ * ---------------------------------------------------------------------------------------- */
+int bbx_engine_timer_start(bbx_engine* e);
+int bbx_engine_timer_stop(bbx_engine* e, float* elapsed_ms); /* synchronises the stream */
+uint64_t bbx_engine_launch_count(const bbx_engine* e);
+/* when enabled every MAC launch is bracketed by events; _mac_time sums them (synchronises) */
+int bbx_engine_profile_mac(bbx_engine* e, int enable);
+int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint64_t* channel_blocks,
+                        uint64_t* algorithmic_bytes);
+/* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
+int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBX_H */

@@ -1,0 +1,72 @@
+"""Adapter giving the CUDA product (through the C ABI) the same call surface as cpulibs.CpuLib, so one
+test body checks the oracle on CPU and libbbx on the GPU."""
+import numpy as np
+
+
+class GpuLib:
+    def __init__(self, bbx):
+        self.b = bbx
+
+    def bits_per_sample(self, fmt):
+        return self.b.GetBitsPerSample(fmt)
+
+    def bytes_per_sample(self, fmt):
+        return self.b.GetBytesPerSample(fmt)
+
+    def sanity(self, *a, allow=True):
+        return self.b.BlockTransferSanityChecks(*a, allowsinglechannel=allow)
+
+    def transfer(self, src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                 dst_channels, nchannels, nframes):
+        self.b.TransferSamples(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                               dst_channels, nchannels, nframes)
+
+    def transfer_linear(self, src, srctype, dst, dsttype, nsamples):
+        self.b.TransferSamplesLinear(src, srctype, dst, dsttype, nsamples)
+
+    def mix(self, src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul=1.0):
+        self.b.MixSamples(src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul)
+
+    def mix_interp(self, src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, state, inc):
+        self.b.MixSamples(src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes,
+                          interp=state, inc=inc)
+
+    def interp_step(self, state, inc, nsteps):
+        self.b.InterpolatorStep(state, inc, nsteps)
+
+    def frac_additional(self):
+        return self.b.FractionalSampleAdditionalDelayRequired()
+
+    def frac(self, buffer, channel, channels, length, pos):
+        return self.b.FractionalSample(buffer, channel, channels, length, np.asarray(pos, dtype=np.float64))
+
+    def delay(self):
+        return GpuDelay(self.b)
+
+
+class GpuDelay:
+    def __init__(self, b):
+        self.d = b.SoundDelayBuffer()
+
+    def close(self):
+        self.d.close()
+
+    def set_size(self, chans, length, fmt=4):
+        self.d.SetSize(chans, length, fmt)
+
+    channels = property(lambda s: s.d.GetChannels())
+    length = property(lambda s: s.d.GetLength())
+    write_position = property(lambda s: s.d.GetWritePosition())
+    format = property(lambda s: s.d.GetFormat())
+
+    def write(self, src, srcformat, channel, nchannels, nframes):
+        return self.d.WriteSamples(src, srcformat, channel, nchannels, nframes)
+
+    def increment(self, nframes):
+        self.d.IncrementWritePosition(nframes)
+
+    def read(self, dst, dstformat, delay, channel, nchannels, nframes):
+        return self.d.ReadSamples(dst, dstformat, delay, channel, nchannels, nframes)
+
+    def raw(self):
+        return self.d.raw()

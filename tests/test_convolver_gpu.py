@@ -1,0 +1,358 @@
+"""GPU tier (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle on the same seeded
+inputs (tolerance class: SNR >= 110 dB and max-abs <= 1e-5 x peak, BASELINE.json north_star), plus
+size-independent properties at BASELINE.json's full sizes.  Mirrors tests/test_convolver_oracle.py.
+"""
+import numpy as np
+import pytest
+
+import cpulibs as cl
+from convkit import GpuDriver, OracleDriver, interleave, make_ir, make_noise, run_float
+from parity import assert_float_parity, compare_float, s24_to_float
+
+pytestmark = pytest.mark.gpu
+
+
+def both(bbx, *a, **kw):
+    return GpuDriver(bbx, *a, **kw), OracleDriver(*a, **kw)
+
+
+@pytest.mark.parametrize("B", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_blockconvolver_all_block_sizes(bbx, orc, B):
+    """BlockConvolver::Convolve block by block, every supported partition size (T = 1)."""
+    L, nblk = 3 * B + 17, 7
+    h, x = make_ir(100 + B, L), make_noise(200 + B, nblk * B)
+    bc = bbx.BlockConvolver(B, 4)
+    bc.SetFilter(bc.CreateFilter(h))
+    y = np.concatenate([bc.Convolve(x[i * B:(i + 1) * B]) for i in range(nblk)])
+    bc.close()
+    f = orc.filter(h, B)
+    obc = orc.blockconv(B, 4)
+    obc.set_filter(f)
+    yo = np.concatenate([obc.convolve(x[i * B:(i + 1) * B]) for i in range(nblk)])
+    assert_float_parity(y, yo, "vs oracle")
+    assert_float_parity(y, orc.direct(x, h), "vs float64 direct")
+
+
+@pytest.mark.parametrize("name,B,L,nch,nblk", [("C1", 1024, 8192, 2, 24), ("C2-path", 256, 512, 8, 16), ("C4", 512, 4096, 4, 20)])
+def test_config_shapes_vs_oracle(bbx, orc, name, B, L, nch, nblk):
+    P = -(-L // B)
+    g, o = both(bbx, B, P, nch, max_blocks=8)
+    irs = [make_ir(2000 + c, L) for c in range(nch)]
+    xs = interleave([make_noise(1000 + c, nblk * B) for c in range(nch)])
+    for c in range(nch):
+        g.select(c, g.filter(irs[c]))
+        o.select(c, o.filter(irs[c]))
+    yg = run_float(g, xs, [B, 8 * B, 3 * B])  # ragged call sizes exercise the T-batched path and the state carry
+    yo = run_float(o, xs, [B, 8 * B, 3 * B])
+    g.close()
+    for c in range(nch):
+        assert_float_parity(yg[:, c], yo[:, c], "%s ch %d" % (name, c))
+
+
+def test_long_reverb_shape_vs_oracle_and_direct(bbx, orc):
+    """C3 shape at reduced channel count: 144000 taps, B = 512, P = 282, 6 channels, T up to 16."""
+    B, L, nch, nblk = 512, 144000, 6, 300
+    g, o = both(bbx, B, 282, nch, max_blocks=16)
+    irs = [make_ir(2000 + c, L) for c in range(nch)]
+    xs = [make_noise(1000 + c, nblk * B) for c in range(nch)]
+    for c in range(nch):
+        g.select(c, g.filter(irs[c]))
+        o.select(c, o.filter(irs[c]))
+    xi = interleave(xs)
+    yg = run_float(g, xi, [16 * B, B, 7 * B])
+    yo = run_float(o, xi, [16 * B, B, 7 * B])
+    g.close()
+    for c in range(nch):
+        assert_float_parity(yg[:, c], yo[:, c], "C3 ch %d vs oracle" % c)
+    n0 = nblk * B - 1024
+    assert_float_parity(yg[n0:, 2], orc.direct(xs[2], irs[2], n0=n0, count=1024), "C3 vs float64 direct window")
+
+
+def test_batching_invariance_bit_exact(bbx):
+    """T blocks in one call == the same blocks one call at a time, bit for bit (block/partition indexing)."""
+    B, L, nch, nblk = 256, 1500, 3, 12
+    irs = [make_ir(300 + c, L) for c in range(nch)]
+    xi = interleave([make_noise(310 + c, nblk * B) for c in range(nch)])
+    outs = []
+    for sizes in (B, 4 * B, [3 * B, B, 2 * B]):
+        g = GpuDriver(bbx, B, 6, nch, max_blocks=4, max_delay=40, fractional_delay=True)
+        for c in range(nch):
+            g.select(c, g.filter(irs[c]), delay=5.3 * c)
+        outs.append(run_float(g, xi, sizes))
+        g.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
+
+
+def test_zero_input_exact_zeros_and_null_filter(bbx):
+    B = 128
+    g = GpuDriver(bbx, B, 4, 2, max_blocks=2)
+    g.select(0, g.filter(make_ir(1, 500)))
+    y = run_float(g, np.zeros((4 * B, 2), dtype=np.float32), 2 * B)
+    assert not y.any()
+    x = interleave([make_noise(2, 4 * B), make_noise(3, 4 * B)])
+    y = run_float(g, x, 2 * B)
+    assert y[:, 0].any() and not y[:, 1].any()  # path 1 has no filter: silence
+    g.select(0, None)
+    y = run_float(g, x, 2 * B)
+    assert not y.any()
+    g.close()
+
+
+@pytest.mark.parametrize("B,L", [(64, 300), (512, 4096)])
+def test_delayed_impulse_ir(bbx, B, L):
+    P = -(-L // B)
+    nblk = P + 8
+    x = make_noise(1, nblk * B)
+    for tap in (0, B - 1, B, B + 1, L - 1):
+        h = np.zeros(L, dtype=np.float32)
+        h[tap] = 1.0
+        g = GpuDriver(bbx, B, P, 1, max_blocks=4)
+        g.select(0, g.filter(h))
+        y = run_float(g, x.reshape(-1, 1), 4 * B)[:, 0]
+        g.close()
+        want = np.concatenate([np.zeros(tap, dtype=np.float32), x])[: x.size]
+        assert_float_parity(y, want, "tap %d" % tap)
+
+
+def test_filter_switching_vs_oracle(bbx, orc):
+    """C4 shape: bank of IRs, a switch every few blocks, crossfaded and hard, fractional delays, s24 in/out."""
+    B, L, nch, nbank = 512, 4096, 4, 5
+    g, o = both(bbx, B, 8, nch, max_blocks=10, max_delay=64, fractional_delay=True)
+    assert g.ring_length == o.ring_length
+    bank = [[make_ir(2000 + 16 * c + k, L) for k in range(nbank)] for c in range(nch)]
+    gf = [[g.filter(h) for h in row] for row in bank]
+    of = [[o.filter(h) for h in row] for row in bank]
+    rng = np.random.default_rng(77)
+    pcm_g, pcm_o = [], []
+    for m in range(8):
+        nblk = 9 if m % 2 else 10  # 100 ms at 48 kHz = every 9th/10th block of 512
+        for c in range(nch):
+            k = (m + c) % nbank
+            d = 16 + 37.3 * ((m * 7 + c) % 11) / 11
+            xf = (m % 3 != 2)
+            if m == 0 or c != 3 or m % 2 == 0:  # channel 3 only switches on even m
+                g.select(c, gf[c][k], delay=d, crossfade=xf and m > 0)
+                o.select(c, of[c][k], delay=d, crossfade=xf and m > 0)
+        x = rng.uniform(-1, 1, (nblk * B, nch)).astype(np.float32)
+        pcm = np.zeros(x.size * 3, dtype=np.uint8)
+        orc.transfer(x.view(np.uint8).reshape(-1), cl.FMT_FLOAT, 0, 0, nch, pcm, cl.FMT_24, 0, 0, nch, nch, nblk * B)
+        pcm_g.append(g.process(pcm, cl.FMT_24, nch, cl.FMT_24, nch, nblk * B))
+        pcm_o.append(o.process(pcm, cl.FMT_24, nch, cl.FMT_24, nch, nblk * B))
+    g.close()
+    yg = s24_to_float(np.concatenate(pcm_g)).reshape(-1, nch)
+    yo = s24_to_float(np.concatenate(pcm_o)).reshape(-1, nch)
+    for c in range(nch):
+        r = compare_float(yg[:, c], yo[:, c])
+        # int24 outputs: equal as floats within tolerance, i.e. at most 1 LSB(24) apart where the float inputs
+        # to the converter differ by rounding
+        assert r["max_abs"] <= 2.0 ** -23 + 1e-9, r
+        assert (yg[:, c] != yo[:, c]).mean() < 0.02, "too many 1-LSB differences"
+
+
+def test_delay_only_crossfade_and_integer_mode(bbx):
+    B, L, nblk = 128, 400, 9
+    for frac in (False, True):
+        g, o = both(bbx, B, 4, 2, max_blocks=3, max_delay=50, fractional_delay=frac)
+        hs = [make_ir(5, L), make_ir(6, L)]
+        gf, of = [g.filter(h) for h in hs], [o.filter(h) for h in hs]
+        xi = interleave([make_noise(7, nblk * B), make_noise(8, nblk * B)])
+        ys = []
+        for d in (g, o):
+            fl = gf if d is g else of
+            d.select(0, fl[0], delay=3)
+            d.select(1, fl[1], delay=0)
+            a = run_float(d, xi[:3 * B], 3 * B)
+            d.select(0, fl[0], delay=41 if not frac else 40.6, crossfade=True)  # same filter, new delay
+            d.select(1, fl[1], delay=50, crossfade=False)                       # hard delay jump
+            b = run_float(d, xi[3 * B:], 3 * B)
+            ys.append(np.concatenate([a, b]))
+        g.close()
+        for c in range(2):
+            assert_float_parity(ys[0][:, c], ys[1][:, c], "delay switch frac=%s ch %d" % (frac, c))
+
+
+def test_routed_binaural_vs_oracle(bbx):
+    """C2 shape: 64 sources x 2 ears, 512-tap HRIRs, 256-sample blocks, per-path ITD delay and gain."""
+    B, L, nsrc, nblk = 256, 512, 64, 12
+    kw = dict(n_outputs=2, n_paths=2 * nsrc, mode=cl.MODE_ROUTED, max_blocks=4, max_delay=40)
+    g, o = both(bbx, B, 2, nsrc, **kw)
+    xi = interleave([make_noise(1000 + s, nblk * B) for s in range(nsrc)])
+    for s in range(nsrc):
+        for ear in range(2):
+            p = 2 * s + ear
+            h = make_ir(2000 + p, L)
+            gain = 0.05 + 0.01 * (p % 7)
+            delay = float((s * (1 + ear)) % 37)
+            for d in (g, o):
+                d.route(p, s, ear, gain)
+                d.select(p, d.filter(h), delay=delay)
+    yg, yo = run_float(g, xi, [4 * B, B]), run_float(o, xi, [4 * B, B])
+    g.close()
+    for ear in range(2):
+        assert_float_parity(yg[:, ear], yo[:, ear], "ear %d" % ear)
+
+
+def test_mimo_vs_oracle(bbx):
+    """C5 shape at reduced size: 8 x 8 matrix of 4096-tap IRs, B = 512, frequency-domain mixdown."""
+    B, L, nin, nout, nblk = 512, 4096, 8, 8, 12
+    g, o = both(bbx, B, 8, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=4)
+    xi = interleave([make_noise(1000 + i, nblk * B) for i in range(nin)])
+    for oo in range(nout):
+        for i in range(nin):
+            h = make_ir(2000 + 64 * oo + i, L)
+            for d in (g, o):
+                d.select(oo * nin + i, d.filter(h))
+    ya = [run_float(d, xi[:8 * B], 4 * B) for d in (g, o)]
+    # crossfade two entries of the matrix, hard-switch one
+    h2 = [make_ir(5000 + k, L) for k in range(3)]
+    for d in (g, o):
+        d.select(0 * nin + 1, d.filter(h2[0]), crossfade=True)
+        d.select(3 * nin + 2, d.filter(h2[1]), crossfade=True)
+        d.select(5 * nin + 5, d.filter(h2[2]), crossfade=False)
+    yb = [run_float(d, xi[8 * B:], 4 * B) for d in (g, o)]
+    g.close()
+    yg, yo = np.concatenate([ya[0], yb[0]]), np.concatenate([ya[1], yb[1]])
+    for oo in range(nout):
+        assert_float_parity(yg[:, oo], yo[:, oo], "MIMO out %d" % oo)
+
+
+def test_formats_in_out_and_extra_channels(bbx, orc):
+    """Every PCM format both ways (LE and BE); channels beyond n_inputs / n_outputs are ignored / preserved."""
+    B, L, nch, nblk = 64, 100, 2, 4
+    irs = [make_ir(90 + c, L) * 0.5 for c in range(nch)]
+    x = (interleave([make_noise(95 + c, nblk * B) for c in range(3)]) * 0.9).astype(np.float32)  # 3 in-channels
+    for fmt in (cl.FMT_16, cl.FMT_24, cl.FMT_32, cl.FMT_FLOAT, cl.FMT_DOUBLE):
+        for be in (False, True):
+            pcm = np.zeros(x.size * cl.FMT_BYTES[fmt], dtype=np.uint8)
+            orc.transfer(x.view(np.uint8).reshape(-1), cl.FMT_FLOAT, 0, 0, 3, pcm, fmt, be, 0, 3, 3, nblk * B)
+            outs = []
+            for mk in (lambda: GpuDriver(bbx, B, 2, nch, max_blocks=4), lambda: OracleDriver(B, 2, nch, max_blocks=4)):
+                d = mk()
+                for c in range(nch):
+                    d.select(c, d.filter(irs[c]))
+                out = np.full(nblk * B * 4 * cl.FMT_BYTES[fmt], 0x3C, dtype=np.uint8)  # 4 out-channels
+                if d.name == "gpu":
+                    d.eng.Convolve(pcm, fmt, 3, fmt, 4, nblk * B, be, be, out=out)
+                else:
+                    d.cv.process(pcm, fmt, 3, fmt, 4, nblk * B, be, be, out=out)
+                outs.append(out)
+                d.close()
+            a = outs[0].reshape(nblk * B, 4, -1)
+            b = outs[1].reshape(nblk * B, 4, -1)
+            assert (a[:, 2:] == 0x3C).all() and (b[:, 2:] == 0x3C).all()  # untouched channels
+            fa = np.zeros(nblk * B * 2, dtype=np.float64)
+            fb = np.zeros(nblk * B * 2, dtype=np.float64)
+            for arr, dst in ((a, fa), (b, fb)):
+                src = np.ascontiguousarray(arr[:, :2]).reshape(-1)
+                orc.transfer(src, fmt, be, 0, 2, dst.view(np.uint8), cl.FMT_DOUBLE, 0, 0, 2, 2, nblk * B)
+            lsb = {cl.FMT_16: 2.0 ** -15, cl.FMT_24: 2.0 ** -23}.get(fmt, 0.0)
+            r = compare_float(fa, fb)
+            assert r["max_abs"] <= lsb + 1e-5 * r["peak"], (fmt, be, r)
+
+
+def test_engine_argument_errors(bbx):
+    with pytest.raises(bbx.BbxError):
+        bbx.Convolver(100, 4, 2)  # not a power of two
+    eng = bbx.Convolver(64, 2, 2, max_blocks=2, max_delay=10)
+    with pytest.raises(bbx.BbxError):
+        eng.CreateFilter(np.zeros(64 * 3, dtype=np.float32))  # 3 partitions > max_partitions
+    f = eng.CreateFilter(np.ones(10, dtype=np.float32))
+    with pytest.raises(bbx.BbxError):
+        eng.SelectFilter(5, f)  # path out of range
+    with pytest.raises(bbx.BbxError):
+        eng.SelectFilter(0, f, delay=11.0)  # beyond max_delay
+    x = np.zeros((64 * 3, 2), dtype=np.float32)
+    with pytest.raises(bbx.BbxError):
+        eng.Convolve(x, cl.FMT_FLOAT, 2, cl.FMT_FLOAT, 2, 64 * 3)  # 3 blocks > max_blocks
+    with pytest.raises(bbx.BbxError):
+        eng.Convolve(x[:100], cl.FMT_FLOAT, 2, cl.FMT_FLOAT, 2, 100)  # not a multiple of B
+    eng.close()
+
+
+# ---- BASELINE.json full sizes: size-independent properties -------------------------------------------
+def test_full_size_c3_properties(bbx, orc):
+    """128 channels x 144000 taps, B = 512 (P = 282, ~300 MB of spectra + FDL):
+      - channel c convolved with a pure delay of c samples (impulse IR at tap 140000 + c) returns the input
+        delayed (no oracle needed),
+      - linearity: process(a x1 + b x2) == a process(x1) + b process(x2),
+      - channel-shard invariance: channels 16..31 alone (the 8-GPU shard of rank 1) are bit-identical,
+      - two spot channels with noise IRs against the float64 direct convolution on a window."""
+    B, L, nch, nblk, T = 512, 144000, 128, 320, 32
+    eng = GpuDriver(bbx, B, 282, nch, max_blocks=T)
+    taps = [140000 + c for c in range(nch)]
+    irs = {}
+    for c in range(nch):
+        if c in (5, 77):
+            irs[c] = make_ir(2000 + c, L)
+        else:
+            h = np.zeros(L, dtype=np.float32)
+            h[taps[c]] = 1.0
+            irs[c] = h
+        eng.select(c, eng.filter(irs[c]))
+    x1 = interleave([make_noise(1000 + c, nblk * B) for c in range(nch)])
+    y1 = run_float(eng, x1, T * B)
+    for c in range(0, nch, 9):
+        if c in (5, 77):
+            continue
+        want = np.concatenate([np.zeros(taps[c], dtype=np.float32), x1[:, c]])[: nblk * B]
+        assert_float_parity(y1[:, c], want, "pure delay ch %d" % c)
+    n0 = nblk * B - 512
+    for c in (5, 77):
+        assert_float_parity(y1[n0:, c], orc.direct(x1[:, c], irs[c], n0=n0, count=512), "noise IR ch %d" % c)
+    eng.close()
+
+    # linearity on a fresh engine state
+    x2 = interleave([make_noise(3000 + c, nblk * B) for c in range(nch)])
+    xs = (0.5 * x1 + 0.25 * x2).astype(np.float32)
+    outs = []
+    for x in (x2, xs):
+        e2 = GpuDriver(bbx, B, 282, nch, max_blocks=T)
+        for c in range(nch):
+            e2.select(c, e2.filter(irs[c]))
+        outs.append(run_float(e2, x, T * B))
+        e2.close()
+    lin = 0.5 * y1.astype(np.float64) + 0.25 * outs[0].astype(np.float64)
+    for c in (0, 5, 64, 77, 127):
+        assert_float_parity(outs[1][:, c], lin[:, c], "linearity ch %d" % c)
+
+    # shard invariance: rank 1 of 8 owns channels 16..31
+    first, count = bbx.shard_range(nch, 1, 8)
+    assert (first, count) == (16, 16)
+    e3 = GpuDriver(bbx, B, 282, count, max_blocks=T)
+    for c in range(count):
+        e3.select(c, e3.filter(irs[first + c]))
+    ys = run_float(e3, np.ascontiguousarray(x1[:, first:first + count]), T * B)
+    e3.close()
+    assert np.array_equal(ys.view(np.uint32), np.ascontiguousarray(y1[:, first:first + count]).view(np.uint32))
+
+
+def test_full_size_c5_mimo_property(bbx, orc):
+    """64 x 64 matrix of 4096-tap IRs (134 MB of spectra): a matrix of scaled pure delays makes every output a
+    known mix of delayed inputs; two noise-IR rows are checked against float64 direct sums on a window."""
+    B, L, nin, nout, nblk, T = 512, 4096, 64, 64, 24, 8
+    eng = GpuDriver(bbx, B, 8, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=T)
+    xi = interleave([make_noise(1000 + i, nblk * B) for i in range(nin)])
+    noise_rows = {3: {}, 40: {}}
+    for o in range(nout):
+        for i in range(nin):
+            if o in noise_rows:
+                h = make_ir(2000 + 64 * o + i, L) * 0.2
+                noise_rows[o][i] = h
+            else:
+                h = np.zeros(L, dtype=np.float32)
+                h[(37 * o + 11 * i) % L] = 1.0 / 64 if (o + i) % 2 == 0 else -1.0 / 64
+            eng.select(o * nin + i, eng.filter(h))
+    y = run_float(eng, xi, T * B)
+    eng.close()
+    for o in (0, 17, 63):
+        want = np.zeros(nblk * B)
+        for i in range(nin):
+            d = (37 * o + 11 * i) % L
+            s = 1.0 / 64 if (o + i) % 2 == 0 else -1.0 / 64
+            want += s * np.concatenate([np.zeros(d), xi[:, i].astype(np.float64)])[: nblk * B]
+        assert_float_parity(y[:, o], want, "MIMO delay matrix out %d" % o)
+    n0 = nblk * B - 256
+    for o, row in noise_rows.items():
+        want = sum(orc.direct(xi[:, i], row[i], n0=n0, count=256) for i in range(nin))
+        assert_float_parity(y[n0:, o], want, "MIMO noise row %d" % o)

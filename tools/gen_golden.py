@@ -1,0 +1,228 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE'S OWN CODE (oracle/_ref/libbbcref.so, compiled from
+/root/reference/src by oracle/Makefile) and, for the convolver (absent from the reference tree), from
+float64 direct convolution.  Run in the dev container only; the fixtures travel, the reference does not.
+
+    python tools/gen_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cpulibs as cl  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def special_floats():
+    v = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 1e-9, -1e-9, 3e-10, -3e-10, 0.99999994, -0.99999994, 2.0, -2.0,
+         2.0 ** -23, -2.0 ** -23, 1.5 * 2.0 ** -23, -1.5 * 2.0 ** -23, 0.123456789, -0.123456789,
+         2.0 ** -31, -2.0 ** -31, 2.0 ** -32, -2.0 ** -32, 1.0 - 2.0 ** -24, -(1.0 + 2.0 ** -23), 1e10, -1e10,
+         np.inf, -np.inf, 1e-40, -1e-40, 0.999999999, -0.999999999]
+    return np.array(v, dtype=np.float64)
+
+
+def gen_formats(ref):
+    rng = np.random.default_rng(20261018)
+    d = {}
+    sp64 = special_floats()
+    sp32 = sp64.astype(np.float32)
+    d["special_f32"] = sp32
+    d["special_f64"] = sp64
+    for srcname, src, sf in (("f32", sp32, cl.FMT_FLOAT), ("f64", sp64, cl.FMT_DOUBLE)):
+        for df in (cl.FMT_16, cl.FMT_24, cl.FMT_32, cl.FMT_FLOAT, cl.FMT_DOUBLE):
+            for be in (0, 1):
+                dst = np.zeros(src.size * cl.FMT_BYTES[df], dtype=np.uint8)
+                ref.transfer(src.view(np.uint8), sf, 0, 0, src.size, dst, df, be, 0, src.size, src.size, 1)
+                d["special_%s_to_%s_%s" % (srcname, cl.FMT_NAMES[df], "be" if be else "le")] = dst
+    # every table entry on random data, with a channel rectangle
+    nfr, sch, dch, nch, sc, dc = 23, 5, 6, 3, 1, 2
+    d["rect_geom"] = np.array([nfr, sch, dch, nch, sc, dc], dtype=np.uint32)
+    for sf in range(1, 6):
+        sb = cl.FMT_BYTES[sf]
+        if sf == cl.FMT_FLOAT:
+            raw = (rng.standard_normal(nfr * sch) * 0.6).astype("<f4").view(np.uint8)
+        elif sf == cl.FMT_DOUBLE:
+            raw = (rng.standard_normal(nfr * sch) * 0.6).astype("<f8").view(np.uint8)
+        else:
+            raw = rng.integers(0, 256, nfr * sch * sb, dtype=np.uint8)
+        raw = raw.copy()
+        for sbe in (0, 1):
+            src = raw.reshape(-1, sb)[:, ::-1].copy().reshape(-1) if sbe else raw
+            d["rect_src_%s_%s" % (cl.FMT_NAMES[sf], "be" if sbe else "le")] = src
+            for df in range(1, 6):
+                for dbe in (0, 1):
+                    dst = np.full(nfr * dch * cl.FMT_BYTES[df], 0xA5, dtype=np.uint8)
+                    ref.transfer(src, sf, sbe, sc, sch, dst, df, dbe, dc, dch, nch, nfr)
+                    d["rect_%s_%s_to_%s_%s" % (cl.FMT_NAMES[sf], "be" if sbe else "le", cl.FMT_NAMES[df],
+                                               "be" if dbe else "le")] = dst
+    # all 2^16 top patterns of int24 -> float -> int24 (the full 2^24 sweep runs live against _ref in tests)
+    v = (np.arange(0, 1 << 24, 251, dtype=np.int64) & 0xFFFFFF).astype(np.uint32)
+    b = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(-1)
+    f = np.zeros(v.size, dtype=np.float32)
+    ref.transfer(b, cl.FMT_24, 0, 0, v.size, f.view(np.uint8), cl.FMT_FLOAT, 0, 0, v.size, v.size, 1)
+    d["s24_sweep_bytes"] = b
+    d["s24_sweep_float"] = f
+    # sanity-check table
+    cases, results = [], []
+    for _ in range(400):
+        c = [int(rng.integers(0, 6)), int(rng.integers(0, 6)), int(rng.integers(0, 6)), int(rng.integers(0, 6)),
+             int(rng.choice([0, 1, 2, 3, 5, 0xFFFFFFFF])), int(rng.integers(0, 4))]
+        for allow in (0, 1):
+            ok, v = ref.sanity(*c, allow=bool(allow))
+            cases.append(c + [allow])
+            results.append([int(ok)] + list(v))
+    d["sanity_cases"] = np.array(cases, dtype=np.uint32)
+    d["sanity_results"] = np.array(results, dtype=np.uint32)
+    np.savez_compressed(os.path.join(OUT, "formats.npz"), **d)
+
+
+def gen_mix(ref):
+    rng = np.random.default_rng(31)
+    d = {}
+    nfr, sch, dch, nch, sc, dc = 19, 3, 4, 2, 1, 1
+    d["geom"] = np.array([nfr, sch, dch, nch, sc, dc], dtype=np.uint32)
+    for name, dt in (("f32", np.float32), ("f64", np.float64)):
+        src = rng.standard_normal(nfr * sch).astype(dt)
+        dst0 = rng.standard_normal(nfr * dch).astype(dt)
+        d["src_" + name] = src
+        d["dst0_" + name] = dst0
+        for mul in (0.5, 1.0, -0.333, 0.0):
+            dst = dst0.copy()
+            ref.mix(src, sc, sch, dst, dc, dch, nch, nfr, mul)
+            d["mix_%s_%g" % (name, mul)] = dst
+    # interpolated mixes: up-ramp, down-ramp, clamp at target, zero/zero no-op
+    src = d["src_f32"]
+    ramps = np.array([[1.0, 0.0, 0.25], [0.0, 1.0, 0.1], [0.3, 0.0, 0.07], [0.0, 0.0, 0.5], [0.5, 0.5, 0.1]],
+                     dtype=np.float32)
+    d["ramps"] = ramps
+    for i, (target, current, inc) in enumerate(ramps):
+        dst = d["dst0_f32"].copy()
+        st = np.array([target, current], dtype=np.float32)
+        ref.mix_interp(src, sc, sch, dst, dc, dch, nch, nfr, st, float(inc))
+        d["ramp_dst_%d" % i] = dst
+        d["ramp_state_%d" % i] = st
+    np.savez_compressed(os.path.join(OUT, "mix.npz"), **d)
+
+
+def gen_frac(ref):
+    rng = np.random.default_rng(47)
+    d = {}
+    # impulse scan: every coefficient of the 14 x 128 table is read back exactly once
+    length = 64
+    buf = np.zeros(length, dtype=np.float32)
+    buf[20] = 1.0
+    pos = 20.0 + np.arange(0, 15 * 128 + 64) / 128.0
+    d["impulse_pos"] = pos
+    d["impulse_out"] = ref.frac(buf, 0, 1, length, pos)
+    # random interleaved buffers, float and double
+    channels, length = 3, 97
+    bf = rng.standard_normal(channels * length).astype(np.float32)
+    bd = rng.standard_normal(channels * length).astype(np.float64)
+    pos = rng.uniform(0, length, 2000)
+    pos[:8] = [0.0, 0.5, 13.999, 14.0, length - 1e-9, length - 1.0, 1.0 / 128, 127.0 / 128]
+    d["rand_geom"] = np.array([channels, length], dtype=np.uint32)
+    d["rand_buf_f32"] = bf
+    d["rand_buf_f64"] = bd
+    d["rand_pos"] = pos
+    for ch in range(channels):
+        d["rand_out_f32_ch%d" % ch] = ref.frac(bf, ch, channels, length, pos)
+        d["rand_out_f64_ch%d" % ch] = ref.frac(bd, ch, channels, length, pos)
+    d["additional"] = np.array([ref.frac_additional()], dtype=np.uint32)
+    np.savez_compressed(os.path.join(OUT, "frac.npz"), **d)
+
+
+def delay_script(seed, n_ops=60):
+    """Deterministic random op sequence exercised against SoundDelayBuffer implementations."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(n_ops):
+        kind = rng.choice(["write", "inc", "read", "write", "read"])
+        if kind == "write":
+            ops.append(("write", int(rng.integers(1, 5)), int(rng.integers(0, 4)), int(rng.integers(1, 4)),
+                        int(rng.integers(1, 40))))
+        elif kind == "inc":
+            ops.append(("inc", int(rng.integers(0, 50))))
+        else:
+            ops.append(("read", int(rng.integers(1, 6)), int(rng.integers(0, 60)), int(rng.integers(0, 4)),
+                        int(rng.integers(1, 4)), int(rng.integers(1, 50))))
+    return ops
+
+
+def run_delay_script(lib, seed, chans=3, length=37, fmt=cl.FMT_FLOAT):
+    rng = np.random.default_rng(seed + 1000)
+    d = lib.delay()
+    d.set_size(chans, length, fmt)
+    trace = []
+    for op in delay_script(seed):
+        if op[0] == "write":
+            _, sfmt, ch, nch, nfr = op
+            n = nfr * min(nch, chans)  # upper bound of samples consumed
+            if sfmt >= cl.FMT_FLOAT:
+                src = (rng.standard_normal(nfr * chans) * 0.5).astype("<f4" if sfmt == cl.FMT_FLOAT else "<f8").view(np.uint8)
+            else:
+                src = rng.integers(0, 256, nfr * chans * cl.FMT_BYTES[sfmt], dtype=np.uint8)
+            got = d.write(src.copy(), sfmt, ch, nch, nfr)
+            trace.append(np.array([got], dtype=np.float64))
+            del n
+        elif op[0] == "inc":
+            d.increment(op[1])
+            trace.append(np.array([d.write_position], dtype=np.float64))
+        else:
+            _, dfmt, delay, ch, nch, nfr = op
+            dst = np.full(nfr * chans * cl.FMT_BYTES[dfmt], 0x5A, dtype=np.uint8)
+            got = d.read(dst, dfmt, delay, ch, nch, nfr)
+            trace.append(np.concatenate([[got], dst.astype(np.float64)]))
+    trace.append(d.raw().astype(np.float64))
+    d.close()
+    return np.concatenate(trace)
+
+
+def gen_delay(ref):
+    d = {}
+    for seed in (1, 2, 3):
+        for fmt in (cl.FMT_FLOAT, cl.FMT_16, cl.FMT_DOUBLE):
+            d["trace_seed%d_fmt%d" % (seed, fmt)] = run_delay_script(ref, seed, fmt=fmt)
+    np.savez_compressed(os.path.join(OUT, "delay.npz"), **d)
+
+
+def conv_case(seed, L, B, nblk, nch=1):
+    rng = np.random.default_rng(seed)
+    h = rng.standard_normal((nch, L)) * np.exp(-6.9 * np.arange(L) / L)
+    h /= np.sqrt((h ** 2).sum(axis=1, keepdims=True))
+    h = h.astype(np.float32)
+    x = rng.uniform(-1, 1, (nch, nblk * B)).astype(np.float32)
+    return h, x
+
+
+def gen_conv():
+    """float64 truth for the absent BlockConvolver: y = h * x by direct summation (numpy float64)."""
+    d = {}
+    cases = [(101, 8192, 1024, 12), (102, 512, 256, 10), (103, 4096, 512, 12), (104, 200, 64, 9), (105, 1000, 128, 11)]
+    d["cases"] = np.array(cases, dtype=np.uint32)
+    for seed, L, B, nblk in cases:
+        h, x = conv_case(seed, L, B, nblk)
+        y = np.convolve(x[0].astype(np.float64), h[0].astype(np.float64))[: nblk * B]
+        d["y_%d" % seed] = y
+    np.savez_compressed(os.path.join(OUT, "conv_truth.npz"), **d)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = cl.reference()
+    if ref is None:
+        sys.exit("oracle/_ref/libbbcref.so missing: run `make -C oracle` in the dev container first")
+    gen_formats(ref)
+    gen_mix(ref)
+    gen_frac(ref)
+    gen_delay(ref)
+    gen_conv()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
