@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the partitioned-convolution path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the configuration the metric / north_star targets are quoted on):
+128-channel long reverb, 3 s IR (144000 taps) at 48 kHz, 512-sample partitions (P = 282), distinct IR per
+channel, uniform white-noise input.  One "step" = one pass of the hot path over one batch of T = 64 blocks
+(32768 frames, 0.683 s of audio) for every channel of the rank, streaming semantics (every block-step
+re-streams the filter spectra and the FDL: 297.85 MB per 128-channel block-step, larger than the 126 MB L2,
+so no L2 flush is needed between iterations).
+
+  value  channel-seconds of audio per second, inputs resident in HBM, K steps timed with CUDA events on the
+         engine stream between barriers, max over ranks
+  e2e    the same metric through the C-ABI call bbx_process() with HOST (pinned) buffers: H2D and D2H copies
+         inside the timed region
+N > 1    weak scaling: every rank runs its own 128-channel shard (rank r = channels 128r .. 128r+127 of a
+         128N-channel renderer); channels are independent, so there is no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FS = 48000
+B = 512
+L = 144000
+P = (L + B - 1) // B  # 282
+NCH = 128
+T = 64
+K_BINS = B + 1
+# algorithmic bytes of one channel-block-step of the FDL MAC (fp32 in / fp32 out)
+BYTES_PER_CHANNEL_BLOCK = 16 * P * K_BINS + 16 * K_BINS + (4 + 4) * B  # 2,326,960
+WORKLOAD = "C3: 128-channel long reverb, 144000-tap IR (3 s @ 48 kHz), 512-sample partitions (P=282), f32 in/out"
+
+
+def make_ir(seed, n):
+    rng = np.random.default_rng(seed)
+    h = rng.standard_normal(n) * np.exp(-6.9 * np.arange(n) / n)
+    h /= np.sqrt((h ** 2).sum())
+    return h.astype(np.float32)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, n = [], None, set(), 0
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx, util = float(f[1]), float(f[2]), float(f[4])
+            except ValueError:
+                continue
+            n += 1
+            smax = mx
+            if util >= 50:
+                sm.append(clk)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": n, "samples_under_load": len(sm)}
+
+
+def cpu_convolver_rate(n_blocks, nthreads, want_seconds=None):
+    """Time the CPU oracle convolver (fp32 UPOLS, SURVEY.md 8.A, one worker per channel up to nthreads) on the
+    C3 workload for n_blocks block-steps.  Returns (channel-s/s, seconds, blocks)."""
+    import cpulibs
+    orc = cpulibs.oracle()
+    cv = orc.convolver(block=B, max_partitions=P, n_inputs=NCH, ring_len=4 * B, nthreads=nthreads)
+    filters = []
+    for c in range(NCH):
+        f = orc.filter(make_ir(2000 + c, L), B)
+        filters.append(f)
+        cv.set_filter(c, f, False, 0.0)
+    rng = np.random.default_rng(1000)
+    x = rng.uniform(-1, 1, (4 * B, NCH)).astype(np.float32)
+    cv.process(x, cpulibs.FMT_FLOAT, NCH, cpulibs.FMT_FLOAT, NCH, 4 * B)  # warm-up: page in spectra
+    done, t0 = 0, time.perf_counter()
+    while True:
+        cv.process(x, cpulibs.FMT_FLOAT, NCH, cpulibs.FMT_FLOAT, NCH, 4 * B)
+        done += 4
+        el = time.perf_counter() - t0
+        if done >= n_blocks or (want_seconds and el >= want_seconds):
+            break
+    return NCH * done * B / FS / el, el, done
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  BlockConvolver/Convolver are absent
+    from the mounted bbcat-dsp tree and FFTW is not installed, so this is the oracle port
+    (oracle/upols.c + convolver.c, OpenMP over channels) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    blocks_per_step = 8  # bounded sample of the 64-block step
+    import cpulibs
+    orc = cpulibs.oracle()
+    cv = orc.convolver(block=B, max_partitions=P, n_inputs=NCH, ring_len=4 * B, nthreads=cores)
+    keep = []
+    for c in range(NCH):
+        f = orc.filter(make_ir(2000 + c, L), B)
+        keep.append(f)
+        cv.set_filter(c, f, False, 0.0)
+    x = np.random.default_rng(1000).uniform(-1, 1, (blocks_per_step * B, NCH)).astype(np.float32)
+    for _ in range(args.warmup):
+        cv.process(x, cpulibs.FMT_FLOAT, NCH, cpulibs.FMT_FLOAT, NCH, blocks_per_step * B)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cv.process(x, cpulibs.FMT_FLOAT, NCH, cpulibs.FMT_FLOAT, NCH, blocks_per_step * B)
+    el = time.perf_counter() - t0
+    value = NCH * args.steps * blocks_per_step * B / FS / el
+    sample = "%d steps x %d blocks x %d channels of the C3 workload (step bounded from %d to %d blocks)" % (
+        args.steps, blocks_per_step, NCH, T, blocks_per_step)
+    line = {
+        "impl": "reference", "metric": "channel_seconds_per_second", "value": value, "unit": "channel-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "channels": NCH, "block": B, "partitions": P, "blocks_per_step": blocks_per_step,
+                   "note": "CPU port of the absent BlockConvolver/Convolver (own FFT, FFTW unavailable)"},
+        "cpu_baseline": {"value": value, "unit": "channel-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "channel-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--occ", type=int, default=0, help="MAC CTAs per SM (tuning)")
+    ap.add_argument("--blocks", type=int, default=T, help="blocks per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import bbcat_dsp_b200 as bbx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if bbx.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libbbx has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    nblk = args.blocks
+    warmup = max(3, args.warmup)
+
+    # ---- set up the rank's shard: 128 channels, distinct IRs, noise resident in HBM ----
+    eng = bbx.Convolver(B, P, NCH, max_blocks=nblk, device=local, mac_ctas_per_sm=args.occ)
+    for c in range(NCH):
+        eng.SelectFilter(c, eng.CreateFilter(make_ir(2000 + NCH * rank + c, L)))
+    frames = nblk * B
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1000 + rank)
+    x_dev = (torch.rand((frames, NCH), device="cuda", generator=g) * 2 - 1).contiguous()
+    y_dev = torch.empty((frames, NCH), device="cuda", dtype=torch.float32)
+    in_bytes = frames * NCH * 4
+    hin = bbx.PinnedBuffer(in_bytes)
+    hout = bbx.PinnedBuffer(in_bytes)
+    hin.array[:] = np.random.default_rng(1000 + rank).uniform(-1, 1, frames * NCH).astype(np.float32).view(np.uint8)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_dev():
+        eng.ConvolveDev(x_dev.data_ptr(), bbx.FMT_FLOAT, NCH, y_dev.data_ptr(), bbx.FMT_FLOAT, NCH, frames)
+
+    def step_host():
+        eng.ConvolveHostPtr(hin.ptr, bbx.FMT_FLOAT, NCH, hout.ptr, bbx.FMT_FLOAT, NCH, frames)
+
+    sampler = ClockSampler(local)
+    for _ in range(warmup):
+        step_dev()
+    eng.Sync()
+    if rank == 0:
+        sampler.start()
+
+    # ---- value: device-resident inputs ----
+    barrier()
+    eng.profile_mac(True)
+    l0 = eng.launch_count()
+    eng.timer_start()
+    for _ in range(args.steps):
+        step_dev()
+    ms = eng.timer_stop()
+    barrier()
+    launches = eng.launch_count() - l0
+    mac = eng.mac_time()
+    eng.profile_mac(False)
+    ms = max_over_ranks(ms)
+    audio_s = NCH * frames / FS  # channel-seconds per step per rank
+    value = world * audio_s * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through bbx_process ----
+    for _ in range(3):
+        step_host()
+    barrier()
+    eng.timer_start()
+    for _ in range(args.steps):
+        step_host()
+    ms_e2e = eng.timer_stop()
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
+    e2e = world * audio_s * args.steps / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-block latency, streaming T = 1 through the host API ----
+    latency = None
+    if not args.no_latency and rank == 0:
+        lat = []
+        nlat = 600
+        for i in range(nlat + 50):
+            t0 = time.perf_counter()
+            eng.ConvolveHostPtr(hin.ptr, bbx.FMT_FLOAT, NCH, hout.ptr, bbx.FMT_FLOAT, NCH, B)
+            if i >= 50:
+                lat.append(time.perf_counter() - t0)
+        lat = np.array(lat) * 1e6
+        latency = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "blocks": nlat,
+                   "block_period_us": 1e6 * B / FS, "mode": "T=1, bbx_process with pinned host buffers, host clock"}
+
+    # ---- roofline of the dominant kernel (k_fdl_mac), CUDA events around every launch in the timed region ----
+    peak, peak_src = peaks()
+    units_per_launch = mac["channel_blocks"] / max(1, mac["launches"])
+    alg_per_launch = BYTES_PER_CHANNEL_BLOCK * units_per_launch
+    mac_ms = mac["ms"] / max(1, mac["launches"])
+    achieved = alg_per_launch / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_channel_block"] * units_per_launch
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_fdl_mac", "launch_ms": mac_ms, "units_per_launch": units_per_launch,
+                "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
+                "mac_share_of_step": mac["ms"] / ms if ms > 0 else None}
+
+    # ---- CPU baseline on rank 0 at N = 1 (bounded sample of the same workload) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        rate, secs, blocks = cpu_convolver_rate(64, cores, want_seconds=20.0)
+        cpu = {"value": rate, "unit": "channel-s/s", "cores": cores, "kind": "port",
+               "sample": "%d block-steps x %d channels of the C3 workload in %.1f s (oracle UPOLS, OpenMP over channels, own FFT)" % (
+                   blocks, NCH, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": "channel_seconds_per_second", "value": value, "unit": "channel-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "channels_per_gpu": NCH, "total_channels": NCH * world, "block": B,
+                       "partitions": P, "blocks_per_step": nblk, "semantics": "streaming (T=1 algorithm per block-step)",
+                       "l2": "inputs larger than L2: 297.85 MB streamed per block-step vs 126 MB L2, no flush",
+                       "parallelism": "channel-sharded x%d, no collective" % world},
+            "x_realtime_per_channel": value / (NCH * world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "channel-s/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "latency": latency,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
