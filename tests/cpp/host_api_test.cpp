@@ -1,0 +1,80 @@
+// C++ host-side smoke of the drop-in headers (bbcat-dsp_b200/host/*.h), written the way reference client code
+// is written: TransferSamples / MixSamples / Interpolator / FractionalSample / SoundDelayBuffer / Convolver.
+// Built and run by tests/test_cpp_host.py on the GPU box; prints PASS and exits 0 on success.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "Convolver.h"
+#include "FractionalSample.h"
+#include "SoundDelayBuffer.h"
+#include "SoundMixing.h"
+
+using namespace bbcat;
+
+#define CHECK(cond)                                                   \
+  do {                                                                \
+    if (!(cond)) {                                                    \
+      fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      return 1;                                                       \
+    }                                                                 \
+  } while (0)
+
+int main() {
+  // TransferSamples: {1..6} 2ch -> channels 1-2 of 4 (reference known answer)
+  float src[6] = {1, 2, 3, 4, 5, 6}, dst[12] = {0};
+  TransferSamples(src, 0, 2, dst, 1, 4, 2, 3);
+  const float want[12] = {0, 1, 2, 0, 0, 3, 4, 0, 0, 5, 6, 0};
+  for (int i = 0; i < 12; i++) CHECK(dst[i] == want[i]);
+  // float -> 24-bit: +1.0 -> 7fffff, -1e-9 -> ffffff
+  float f[2] = {1.0f, -1e-9f};
+  uint8_t b[6];
+  TransferSamples(f, SampleFormat_Float, false, 0, 2, b, SampleFormat_24bit, false, 0, 2, 2, 1);
+  CHECK(b[0] == 0xff && b[1] == 0xff && b[2] == 0x7f && b[3] == 0xff && b[4] == 0xff && b[5] == 0xff);
+  // MixSamples with an Interpolator: gains 0, .25, .5 and the object ends at .75
+  float ones[3] = {1, 1, 1}, acc[3] = {0, 0, 0};
+  Interpolator interp(1.0f, 0.0f);
+  MixSamples(ones, 0, 1, acc, 0, 1, 1, 3, interp, 0.25f);
+  CHECK(acc[0] == 0.0f && acc[1] == 0.25f && acc[2] == 0.5f && (float)interp == 0.75f);
+  // FractionalSample KAT
+  std::vector<float> ring(64, 0.0f);
+  ring[20] = 1.0f;
+  CHECK(fabs(FractionalSample(&ring[0], 0, 1, 64, 28.0) - 9.976246356964e-01) < 1e-12);
+  CHECK(FractionalSampleAdditionalDelayRequired() == 14);
+  // SoundDelayBuffer
+  SoundDelayBuffer delay;
+  delay.SetSize(2, 8, SampleFormat_Float);
+  float frames[12];
+  for (int i = 0; i < 12; i++) frames[i] = (float)i;
+  CHECK(delay.WriteSamples(frames, 0, 2, 6) == 6);
+  delay.IncrementWritePosition(6);
+  float rd[8];
+  CHECK(delay.ReadSamples(rd, 4, 0, 2, 4) == 4);
+  CHECK(rd[0] == 4.0f && rd[7] == 11.0f);
+  // Convolver: 2 channels, pure-delay IRs, 3 blocks of 64
+  const uint_t B = 64;
+  Convolver conv(B, 2, 2, 3);
+  std::vector<float> ir0(100, 0.0f), ir1(100, 0.0f);
+  ir0[0] = 1.0f;
+  ir1[70] = 0.5f;
+  ConvolverFilter* f0 = conv.CreateFilter(&ir0[0], 100);
+  ConvolverFilter* f1 = conv.CreateFilter(&ir1[0], 100);
+  conv.SelectFilter(0, f0);
+  conv.SelectFilter(1, f1);
+  std::vector<float> x(3 * B * 2), y(3 * B * 2, 0.0f);
+  for (size_t i = 0; i < x.size(); i++) x[i] = (float)((i * 7919u) % 1000u) / 1000.0f - 0.5f;
+  conv.Convolve(&x[0], 2, &y[0], 2, 3 * B);
+  double err = 0;
+  for (uint_t n = 0; n < 3 * B; n++) {
+    err = fmax(err, fabs(y[2 * n] - x[2 * n]));
+    double w1 = n >= 70 ? 0.5 * x[2 * (n - 70) + 1] : 0.0;
+    err = fmax(err, fabs(y[2 * n + 1] - w1));
+  }
+  CHECK(err < 5e-6);
+  delete f0;
+  delete f1;
+  printf("PASS max_err=%g\n", err);
+  return 0;
+}
