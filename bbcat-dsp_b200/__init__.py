@@ -30,7 +30,8 @@ class BbxError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("block_size", u32), ("max_partitions", u32), ("n_inputs", u32),
                 ("n_outputs", u32), ("n_paths", u32), ("mode", C.c_int), ("max_blocks", u32), ("max_delay", u32),
-                ("fractional_delay", C.c_int), ("ring_length", u32), ("mac_ctas_per_sm", u32), ("reserved", u32 * 7)]
+                ("fractional_delay", C.c_int), ("ring_length", u32), ("mac_ctas_per_sm", u32), ("mac_l2_keep_16ths", u32),
+                ("mac_time_tile", u32), ("reserved", u32 * 5)]
 
 
 # every symbol include/bbx.h declares: name -> (restype, argtypes)
@@ -82,6 +83,7 @@ SYMBOLS = {
     "bbx_set_filter": (C.c_int, [vp, u32, vp, C.c_int, C.c_double]),
     "bbx_process": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
     "bbx_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
+    "bbx_process_async": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
     "bbx_engine_sync": (C.c_int, [vp]),
     "bbx_blockconvolver_convolve": (C.c_int, [vp, vp, vp]),
     "bbx_engine_timer_start": (C.c_int, [vp]),
@@ -283,7 +285,8 @@ class Convolver:
     """Multichannel partitioned convolver on one GPU (Convolver, README:43-44)."""
 
     def __init__(self, block_size, max_partitions, n_inputs, n_outputs=0, n_paths=0, mode=MODE_PER_CHANNEL,
-                 max_blocks=1, max_delay=0, fractional_delay=False, ring_length=0, device=0, mac_ctas_per_sm=0):
+                 max_blocks=1, max_delay=0, fractional_delay=False, ring_length=0, device=0, mac_ctas_per_sm=0,
+                 mac_l2_keep_16ths=0, mac_time_tile=0):
         cfg = Config()
         cfg.device = device
         cfg.block_size = block_size
@@ -297,6 +300,8 @@ class Convolver:
         cfg.fractional_delay = int(fractional_delay)
         cfg.ring_length = ring_length
         cfg.mac_ctas_per_sm = mac_ctas_per_sm
+        cfg.mac_l2_keep_16ths = mac_l2_keep_16ths
+        cfg.mac_time_tile = mac_time_tile
         h = vp()
         _check(lib().bbx_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -343,6 +348,12 @@ class Convolver:
     def ConvolveHostPtr(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes):
         """Raw host pointers (e.g. pinned buffers); synchronous, copies included."""
         _check(lib().bbx_process(self.h, vp(in_ptr), infmt, 0, in_channels, vp(out_ptr), outfmt, 0, out_channels, nframes))
+
+    def ConvolveHostPtrAsync(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes):
+        """Raw PINNED host pointers; returns after enqueueing (H2D, kernels, D2H on separate streams).  The buffers
+        must stay untouched until Sync()."""
+        _check(lib().bbx_process_async(self.h, vp(in_ptr), infmt, 0, in_channels, vp(out_ptr), outfmt, 0, out_channels,
+                                       nframes))
 
     def ConvolveDev(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes, in_be=False, out_be=False):
         """Device pointers (ints); asynchronous on the engine stream."""

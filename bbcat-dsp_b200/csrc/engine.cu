@@ -117,30 +117,58 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
-
-// acc += h * x for two packed complex bins; bin 0 of a row is (DC, Nyquist): two real products
-__device__ __forceinline__ void cmac2(float4& acc, const float4& h, const float4& x, bool bin0) {
-  const float u = bin0 ? x.y : x.x;  // operand of h.y in the "imaginary" lane
-  const float v = bin0 ? 0.f : x.y;  // cross terms vanish for the packed bin
-  acc.x = fmaf(h.x, x.x, acc.x);
-  acc.x = fmaf(-h.y, v, acc.x);
-  acc.y = fmaf(h.y, u, acc.y);
-  acc.y = fmaf(h.x, v, acc.y);
-  acc.z = fmaf(h.z, x.z, acc.z);
-  acc.z = fmaf(-h.w, x.w, acc.z);
-  acc.w = fmaf(h.z, x.w, acc.w);
-  acc.w = fmaf(h.w, x.z, acc.w);
+__device__ __forceinline__ float4 ld_policy(const float4* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float2 ld_stream2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
 }
 
-template <int U, int THREADS, int OCC>
+// One complex multiply-accumulate acc += h * x written as four FMAs whose coefficients depend on the
+// filter value only:  re += a*xr - b*xi ;  im += b*xr + c*xi  with (a, b, c) = (hr, hi, hr).
+// Bin 0 of a packed row holds (DC, Nyquist), two REAL spectra: there (a, b, c) = (hr, 0, hi) gives
+// re += hr*xr, im += hi*xi.  The selects cost two instructions per loaded h, not per FMA.
+// Every MAC kernel uses exactly this sequence, so their results are bit-identical.
+struct HCoef {
+  float a, b, c;
+};
+__device__ __forceinline__ HCoef hcoef(float hr, float hi, bool bin0) {
+  HCoef k;
+  k.a = hr;
+  k.b = bin0 ? 0.f : hi;
+  k.c = bin0 ? hi : hr;
+  return k;
+}
+__device__ __forceinline__ void cmac(float& re, float& im, const HCoef& k, float xr, float xi) {
+  re = fmaf(k.a, xr, re);
+  re = fmaf(-k.b, xi, re);
+  im = fmaf(k.b, xr, im);
+  im = fmaf(k.c, xi, im);
+}
+
+// ---- streaming form: one launch covers nt block-steps, every step re-streams H and the FDL ----
+template <int U, int THREADS, int OCC, bool POLICY>
 __global__ void __launch_bounds__(THREADS, OCC)
 k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float4* __restrict__ fdl,
-          float4* __restrict__ ypart, uint32_t halfB, uint32_t R, uint32_t head0, uint32_t t0, uint32_t slot_stride) {
+          float4* __restrict__ ypart, uint32_t halfB, uint32_t R, uint32_t head0, uint32_t t0, uint32_t slot_stride,
+          float l2_keep) {
   const uint32_t t = t0 + blockIdx.z;
   const uint32_t head = (head0 + t) % R;
   const uint32_t col = blockIdx.y * THREADS + threadIdx.x;
   const bool bin0 = (col == 0);
   const uint32_t sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
+  uint64_t pol = 0;
+  if (POLICY) {
+    // keep a fixed fraction of the lines resident in L2 across block-steps (the same H / FDL addresses are
+    // re-read every step), stream the rest with evict-first so they do not displace the resident set
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(l2_keep));
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (uint32_t si = sb; si < se; si++) {
     const MacSeg sg = segs[si];
@@ -156,24 +184,116 @@ k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
       for (int u = 0; u < U; u++) {
         int s = slot - u;
         s += (s >> 31) & (int)R;  // ring wrap, once per row
-        h[u] = ld_stream(hp + (uint64_t)u * halfB);
-        x[u] = __ldg(xbase + (uint64_t)s * halfB);
+        if (POLICY) {
+          h[u] = ld_policy(hp + (uint64_t)u * halfB, pol);
+          x[u] = ld_policy(xbase + (uint64_t)s * halfB, pol);
+        } else {
+          h[u] = ld_stream(hp + (uint64_t)u * halfB);
+          x[u] = __ldg(xbase + (uint64_t)s * halfB);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < U; u++) cmac2(acc, h[u], x[u], bin0);
+      for (int u = 0; u < U; u++) {
+        cmac(acc.x, acc.y, hcoef(h[u].x, h[u].y, bin0), x[u].x, x[u].y);
+        cmac(acc.z, acc.w, hcoef(h[u].z, h[u].w, false), x[u].z, x[u].w);
+      }
       hp += (uint64_t)U * halfB;
       slot -= U;
       if (slot < 0) slot += (int)R;
     }
     for (; p < sg.np; p++) {
-      float4 h = ld_stream(hp);
-      float4 x = __ldg(xbase + (uint64_t)slot * halfB);
-      cmac2(acc, h, x, bin0);
+      float4 h = POLICY ? ld_policy(hp, pol) : ld_stream(hp);
+      float4 x = POLICY ? ld_policy(xbase + (uint64_t)slot * halfB, pol) : __ldg(xbase + (uint64_t)slot * halfB);
+      cmac(acc.x, acc.y, hcoef(h.x, h.y, bin0), x.x, x.y);
+      cmac(acc.z, acc.w, hcoef(h.z, h.w, false), x.z, x.w);
       hp += halfB;
       slot -= 1;
       if (slot < 0) slot += (int)R;
     }
     if (sg.flags & 2u) ypart[((uint64_t)blockIdx.z * slot_stride + sg.slot) * halfB + col] = acc;
+  }
+}
+
+// ---- time-batched form: one CTA produces TT consecutive block-steps of its row range at once ----
+// Y_t[k] = sum_p H[p][k] X[s_t - p][k] for t = t_base .. t_base+TT-1 is a length-P FIR along the block axis:
+// H[p] is loaded once and applied to TT outputs, and the TT FDL rows it meets slide by one row per
+// partition, so the rows live in a register window rotated by static indexing (the p loop is unrolled TT
+// times).  Per partition a thread loads one complex of H and one of the FDL and issues 4*TT FMAs
+// (8 FMA per byte at TT = 32): the MAC becomes FP32-bound instead of HBM-bound.  Same plan, same per-output
+// FMA order as k_fdl_mac, hence bit-identical results.
+template <int TT, int THREADS, int PF>
+__global__ void __launch_bounds__(THREADS, 1)
+k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float2* __restrict__ fdl,
+             float2* __restrict__ ypart, uint32_t B, uint32_t R, uint32_t head0, uint32_t t0, uint32_t nt,
+             uint32_t ncoltiles, uint32_t slot_stride) {
+  static_assert(TT % PF == 0, "prefetch depth must divide the tile");
+  // blockIdx.x enumerates (column tile, t tile) so the CTAs that share H / FDL rows run in the same wave
+  const uint32_t coltile = blockIdx.x % ncoltiles, ttile = blockIdx.x / ncoltiles;
+  const uint32_t tbase = ttile * TT;                  // first block-step of this tile, relative to t0
+  const uint32_t s0 = (head0 + t0 + tbase) % R;       // its FDL slot
+  const uint32_t col = coltile * THREADS + threadIdx.x;
+  const bool bin0 = (col == 0);
+  const uint32_t sb = cta_seg_begin[blockIdx.y], se = cta_seg_begin[blockIdx.y + 1];
+  float2 acc[TT];
+#pragma unroll
+  for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
+  for (uint32_t si = sb; si < se; si++) {
+    const MacSeg sg = segs[si];
+    if (sg.flags & 1u) {
+#pragma unroll
+      for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
+    }
+    const float2* hp = reinterpret_cast<const float2*>(sg.H) + (uint64_t)sg.p0 * B + col;
+    const float2* xb = fdl + (uint64_t)sg.fdl_ch * R * B + col;
+    // FDL row met by output i at segment step q: base + i - q (mod R), base = s0 - p0
+    int base = (int)s0 - (int)(sg.p0 % R);
+    if (base < 0) base += (int)R;
+    float2 W[TT];  // W[e mod TT] = row base + e, e = i - q
+#pragma unroll
+    for (int e = 1; e < TT; e++) {
+      int r = base + e;
+      if (r >= (int)R) r -= (int)R;
+      W[e] = __ldg(xb + (uint64_t)r * B);
+    }
+    W[0] = make_float2(0.f, 0.f);
+    float2 hq[PF], xq[PF];
+    int prow = base;  // row of the next prefetch
+#pragma unroll
+    for (int j = 0; j < PF; j++) {
+      hq[j] = make_float2(0.f, 0.f);
+      xq[j] = make_float2(0.f, 0.f);
+      if ((uint32_t)j < sg.np) {
+        hq[j] = ld_stream2(hp + (uint64_t)j * B);
+        xq[j] = __ldg(xb + (uint64_t)prow * B);
+        prow = prow ? prow - 1 : (int)R - 1;
+      }
+    }
+    for (uint32_t qb = 0; qb < sg.np; qb += TT) {
+#pragma unroll
+      for (int u = 0; u < TT; u++) {
+        const uint32_t q = qb + u;
+        if (q < sg.np) {
+          const float2 h = hq[u % PF];
+          W[(TT - u) % TT] = xq[u % PF];
+          if (q + PF < sg.np) {
+            hq[u % PF] = ld_stream2(hp + (uint64_t)(q + PF) * B);
+            xq[u % PF] = __ldg(xb + (uint64_t)prow * B);
+            prow = prow ? prow - 1 : (int)R - 1;
+          }
+          const HCoef k = hcoef(h.x, h.y, bin0);
+#pragma unroll
+          for (int i = 0; i < TT; i++) {
+            const float2 x = W[(i - u + TT) % TT];
+            cmac(acc[i].x, acc[i].y, k, x.x, x.y);
+          }
+        }
+      }
+    }
+    if (sg.flags & 2u) {
+#pragma unroll
+      for (int i = 0; i < TT; i++)
+        if (tbase + i < nt) ypart[((uint64_t)(tbase + i) * slot_stride + sg.slot) * B + col] = acc[i];
+    }
   }
 }
 
@@ -412,9 +532,15 @@ struct bbx_engine {
   float2* fdl = nullptr;
   float2* ypart = nullptr;
   float* ybuf = nullptr;
-  uint8_t* d_in = nullptr;
-  uint8_t* d_out = nullptr;
+  // host-pointer path: double-buffered PCM staging, copies on their own streams so that the H2D of call
+  // n+1 and the D2H of call n-1 overlap the kernels of call n
+  uint8_t* d_in[2] = {nullptr, nullptr};
+  uint8_t* d_out[2] = {nullptr, nullptr};
   size_t d_io_bytes = 0;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_join_in = nullptr, ev_join_out = nullptr;
+  uint64_t host_calls = 0;
   float4* flush_buf = nullptr;
   size_t flush_bytes = 0;
   // route tables (device blob + pinned staging)
@@ -434,6 +560,8 @@ struct bbx_engine {
   cudaEvent_t ev_upload = nullptr;  // last H2D copy out of the pinned plan/route staging
   bool upload_pending = false;
   uint32_t mac_occ = 2;
+  float mac_l2_keep = 0.f;       // fraction of H / FDL lines given L2 evict-last priority by the streaming MAC
+  uint32_t mac_time_tile = 0;    // TT of the time-batched MAC (0 = streaming kernel only)
   uint64_t launches = 0;
   bool profile_mac = false;
   std::vector<cudaEvent_t> mac_events;  // pairs
@@ -499,13 +627,38 @@ void launch_mac_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cu
   const MacSeg* segs = pl.segs();
   const uint32_t* cta = pl.cta_seg_begin();
   const float4* fdl = (const float4*)e->fdl;
+  const float keep = e->mac_l2_keep;
+#define BBX_MAC_LAUNCH(U, OCC)                                                                                            \
+  do {                                                                                                                    \
+    if (keep > 0.f)                                                                                                       \
+      k_fdl_mac<U, THREADS, OCC, true><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep); \
+    else                                                                                                                  \
+      k_fdl_mac<U, THREADS, OCC, false><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep); \
+  } while (0)
   // resident CTAs per SM <-> loads in flight per thread: fewer, fatter CTAs unroll deeper
   switch (e->mac_occ) {
-    case 1: k_fdl_mac<16, THREADS, 1><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
-    case 2: k_fdl_mac<8, THREADS, 2><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
-    case 3: k_fdl_mac<6, THREADS, 3><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
-    default: k_fdl_mac<4, THREADS, 4><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots); break;
+    case 1: BBX_MAC_LAUNCH(16, 1); break;
+    case 2: BBX_MAC_LAUNCH(8, 2); break;
+    case 3: BBX_MAC_LAUNCH(6, 3); break;
+    default: BBX_MAC_LAUNCH(4, 4); break;
   }
+#undef BBX_MAC_LAUNCH
+}
+
+template <int TT, int THREADS>
+void launch_mac_tb_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cudaStream_t st) {
+  const uint32_t ncol = e->B / THREADS, ntile = ceil_div(nt, TT);
+  dim3 grid(ncol * ntile, pl.n_ctas);
+  float2* yp = e->ypart + (uint64_t)t0 * e->max_slots * e->B;
+  k_fdl_mac_tb<TT, THREADS, 4><<<grid, THREADS, 0, st>>>(pl.segs(), pl.cta_seg_begin(), e->fdl, yp, e->B, e->R, e->head, t0, nt,
+                                                        ncol, e->max_slots);
+}
+
+template <int TT>
+void launch_mac_tb(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cudaStream_t st) {
+  if (e->B >= 256) launch_mac_tb_t<TT, 256>(e, pl, t0, nt, st);
+  else if (e->B == 128) launch_mac_tb_t<TT, 128>(e, pl, t0, nt, st);
+  else launch_mac_tb_t<TT, 64>(e, pl, t0, nt, st);
 }
 
 int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
@@ -523,7 +676,11 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     BBX_CUDA_TRY(cudaEventRecord(ev0, st));
   }
   const uint32_t halfB = e->B / 2;
-  if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
+  const uint32_t tb = e->mac_time_tile;  // 0: streaming only
+  if (tb && nt >= tb / 2) {
+    if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
+    else launch_mac_tb<16>(e, pl, t0, nt, st);
+  } else if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
   else if (halfB == 128) launch_mac_t<128>(e, pl, t0, nt, st);
   else if (halfB == 64) launch_mac_t<64>(e, pl, t0, nt, st);
   else launch_mac_t<32>(e, pl, t0, nt, st);
@@ -786,6 +943,15 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     }
   }
   BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+    BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
+    BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming));
+  }
+  BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join_in, cudaEventDisableTiming));
+  BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join_out, cudaEventDisableTiming));
   BBX_CUDA_TRY(cudaEventCreate(&e->ev_start));
   BBX_CUDA_TRY(cudaEventCreate(&e->ev_stop));
   BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
@@ -817,6 +983,8 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   // plan capacities
   e->mac_occ = cfg->mac_ctas_per_sm ? std::min(cfg->mac_ctas_per_sm, 4u) : 2u;
   e->max_ctas = kNumSMs * e->mac_occ;
+  e->mac_l2_keep = std::min(cfg->mac_l2_keep_16ths, 16u) / 16.0f;
+  e->mac_time_tile = (cfg->mac_time_tile == 16 || cfg->mac_time_tile == 32) ? cfg->mac_time_tile : 0;
   uint32_t terms = (e->mode == BBX_MODE_MIMO) ? e->n_paths : e->n_paths;
   e->max_jobs = 2 * e->n_streams + 1;
   e->max_segs = e->max_ctas + 2 * terms + 8;
@@ -847,8 +1015,6 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     memset(e->h_route, 0, off);
     BBX_CUDA_TRY(cudaMalloc((void**)&e->d_route, off));
   }
-  // PCM staging for the host-pointer process call (largest format both ways)
-  e->d_io_bytes = (size_t)e->Tmax * B * 8;
   BBX_CUDA_TRY(cudaDeviceSynchronize());
   *out = e;
   return BBX_OK;
@@ -858,14 +1024,25 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (!e) return BBX_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->s_in) cudaStreamSynchronize(e->s_in);
+  if (e->s_out) cudaStreamSynchronize(e->s_out);
   cudaFree(e->tw);
   cudaFree(e->xin[0]);
   cudaFree(e->xin[1]);
   cudaFree(e->fdl);
   cudaFree(e->ypart);
   cudaFree(e->ybuf);
-  cudaFree(e->d_in);
-  cudaFree(e->d_out);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(e->d_in[i]);
+    cudaFree(e->d_out[i]);
+    if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+    if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+    if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
+  }
+  if (e->ev_join_in) cudaEventDestroy(e->ev_join_in);
+  if (e->ev_join_out) cudaEventDestroy(e->ev_join_out);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
   cudaFree(e->flush_buf);
   cudaFree(e->d_route);
   cudaFreeHost(e->h_route);
@@ -1111,37 +1288,64 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   return BBX_OK;
 }
 
-int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
-                int out_be, uint32_t out_channels, uint32_t nframes) {
+int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
+                      int out_be, uint32_t out_channels, uint32_t nframes) {
   BBX_REQUIRE(e && in && out, "bbx_process: null argument");
   BBX_REQUIRE(infmt > FMT_UNKNOWN && infmt < FMT_COUNT && outfmt > FMT_UNKNOWN && outfmt < FMT_COUNT, "bbx_process: bad format");
   BBX_CUDA_TRY(cudaSetDevice(e->device));
   size_t in_bytes = (size_t)nframes * in_channels * fmt_bytes(infmt);
   size_t out_bytes = (size_t)nframes * out_channels * fmt_bytes(outfmt);
   size_t need = std::max(in_bytes, out_bytes);
-  if (!e->d_in || e->d_io_bytes < need || !e->d_out) {
-    cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_in);
-    cudaFree(e->d_out);
-    e->d_in = e->d_out = nullptr;
+  if (!e->d_in[0] || e->d_io_bytes < need) {
+    BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
+    BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
     e->d_io_bytes = std::max(need, e->d_io_bytes);
-    BBX_CUDA_TRY(cudaMalloc((void**)&e->d_in, e->d_io_bytes));
-    BBX_CUDA_TRY(cudaMalloc((void**)&e->d_out, e->d_io_bytes));
+    for (int i = 0; i < 2; i++) {
+      cudaFree(e->d_in[i]);
+      cudaFree(e->d_out[i]);
+      e->d_in[i] = e->d_out[i] = nullptr;
+      BBX_CUDA_TRY(cudaMalloc((void**)&e->d_in[i], e->d_io_bytes));
+      BBX_CUDA_TRY(cudaMalloc((void**)&e->d_out[i], e->d_io_bytes));
+    }
   }
-  BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in, in, in_bytes, cudaMemcpyHostToDevice, e->stream));
-  if (out_channels > e->n_out)  // channels beyond n_outputs keep the caller's bytes
-    BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
-  int rc = bbx_process_dev(e, e->d_in, infmt, in_be, in_channels, e->d_out, outfmt, out_be, out_channels, nframes);
+  const int k = (int)(e->host_calls & 1);
+  e->host_calls++;
+  // H2D on the input-copy stream, once the kernels of call n-2 have finished reading this staging buffer
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
+  BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
+  if (out_channels > e->n_out) {
+    // channels beyond n_outputs keep the caller's bytes: seed the output staging with them
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_d2h[k], 0));
+    BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out[k], out, out_bytes, cudaMemcpyHostToDevice, e->s_in));
+  }
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_h2d[k], e->s_in));
+  // kernels on the engine stream
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[k], 0));
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_d2h[k], 0));
+  int rc = bbx_process_dev(e, e->d_in[k], infmt, in_be, in_channels, e->d_out[k], outfmt, out_be, out_channels, nframes);
   if (rc) return rc;
-  BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
-  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_comp[k], e->stream));
+  // D2H on the output-copy stream
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_comp[k], 0));
+  BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out[k], out_bytes, cudaMemcpyDeviceToHost, e->s_out));
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_d2h[k], e->s_out));
   return BBX_OK;
 }
 
 int bbx_engine_sync(bbx_engine* e) {
   BBX_REQUIRE(e != nullptr, "bbx_engine_sync: null engine");
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
   return BBX_OK;
+}
+
+int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
+                int out_be, uint32_t out_channels, uint32_t nframes) {
+  int rc = bbx_process_async(e, in, infmt, in_be, in_channels, out, outfmt, out_be, out_channels, nframes);
+  if (rc) return rc;
+  return bbx_engine_sync(e);
 }
 
 int bbx_blockconvolver_convolve(bbx_engine* e, const float* in, float* out) {
@@ -1152,11 +1356,21 @@ int bbx_blockconvolver_convolve(bbx_engine* e, const float* in, float* out) {
 
 int bbx_engine_timer_start(bbx_engine* e) {
   BBX_REQUIRE(e != nullptr, "null engine");
-  BBX_CUDA_TRY(cudaEventRecord(e->ev_start, e->stream));
+  // nothing of the timed region may start before the start event: drain, record, and fence the other streams
+  int rc = bbx_engine_sync(e);
+  if (rc) return rc;
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_start, e->s_in));
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_start, 0));
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_start, 0));
   return BBX_OK;
 }
 int bbx_engine_timer_stop(bbx_engine* e, float* elapsed_ms) {
   BBX_REQUIRE(e && elapsed_ms, "null argument");
+  // the stop event follows everything enqueued on the copy streams and the engine stream
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_join_in, e->s_in));
+  BBX_CUDA_TRY(cudaEventRecord(e->ev_join_out, e->s_out));
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join_in, 0));
+  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join_out, 0));
   BBX_CUDA_TRY(cudaEventRecord(e->ev_stop, e->stream));
   BBX_CUDA_TRY(cudaEventSynchronize(e->ev_stop));
   BBX_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e->ev_start, e->ev_stop));

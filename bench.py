@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--occ", type=int, default=0, help="MAC CTAs per SM (tuning)")
+    ap.add_argument("--l2keep", type=int, default=0, help="sixteenths of H/FDL lines kept L2-resident (streaming MAC)")
+    ap.add_argument("--tile", type=int, default=0, help="time-batched MAC tile (0 = streaming kernel, 16 or 32)")
     ap.add_argument("--blocks", type=int, default=T, help="blocks per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true")
@@ -217,7 +219,8 @@ def main():
     warmup = max(3, args.warmup)
 
     # ---- set up the rank's shard: 128 channels, distinct IRs, noise resident in HBM ----
-    eng = bbx.Convolver(B, P, NCH, max_blocks=nblk, device=local, mac_ctas_per_sm=args.occ)
+    eng = bbx.Convolver(B, P, NCH, max_blocks=nblk, device=local, mac_ctas_per_sm=args.occ,
+                        mac_l2_keep_16ths=args.l2keep, mac_time_tile=args.tile)
     for c in range(NCH):
         eng.SelectFilter(c, eng.CreateFilter(make_ir(2000 + NCH * rank + c, L)))
     frames = nblk * B
@@ -226,9 +229,12 @@ def main():
     x_dev = (torch.rand((frames, NCH), device="cuda", generator=g) * 2 - 1).contiguous()
     y_dev = torch.empty((frames, NCH), device="cuda", dtype=torch.float32)
     in_bytes = frames * NCH * 4
-    hin = bbx.PinnedBuffer(in_bytes)
-    hout = bbx.PinnedBuffer(in_bytes)
-    hin.array[:] = np.random.default_rng(1000 + rank).uniform(-1, 1, frames * NCH).astype(np.float32).view(np.uint8)
+    # two pinned buffer pairs: the asynchronous host API overlaps the copies of one step with the kernels of the next
+    hins = [bbx.PinnedBuffer(in_bytes) for _ in range(2)]
+    houts = [bbx.PinnedBuffer(in_bytes) for _ in range(2)]
+    for i, h in enumerate(hins):
+        h.array[:] = np.random.default_rng(1000 + rank + 17 * i).uniform(-1, 1, frames * NCH).astype(np.float32).view(np.uint8)
+    hin, hout = hins[0], houts[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,8 +252,8 @@ def main():
     def step_dev():
         eng.ConvolveDev(x_dev.data_ptr(), bbx.FMT_FLOAT, NCH, y_dev.data_ptr(), bbx.FMT_FLOAT, NCH, frames)
 
-    def step_host():
-        eng.ConvolveHostPtr(hin.ptr, bbx.FMT_FLOAT, NCH, hout.ptr, bbx.FMT_FLOAT, NCH, frames)
+    def step_host(i):
+        eng.ConvolveHostPtrAsync(hins[i & 1].ptr, bbx.FMT_FLOAT, NCH, houts[i & 1].ptr, bbx.FMT_FLOAT, NCH, frames)
 
     sampler = ClockSampler(local)
     for _ in range(warmup):
@@ -273,13 +279,14 @@ def main():
     value = world * audio_s * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through bbx_process ----
-    for _ in range(3):
-        step_host()
+    for i in range(4):
+        step_host(i)
+    eng.Sync()
     barrier()
     eng.timer_start()
-    for _ in range(args.steps):
-        step_host()
-    ms_e2e = eng.timer_stop()
+    for i in range(args.steps):
+        step_host(i)
+    ms_e2e = eng.timer_stop()  # covers the last D2H copy
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
     e2e = world * audio_s * args.steps / (ms_e2e * 1e-3)

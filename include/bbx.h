@@ -173,8 +173,10 @@ typedef struct {
   uint32_t max_delay;       /* ceil of the largest per-path delay in samples */
   int fractional_delay;     /* 0: integer delays; 1: every delayed read goes through FractionalSample */
   uint32_t ring_length;     /* delay ring length R per path in frames; 0 = choose (see _get_ring_length) */
-  uint32_t mac_ctas_per_sm; /* tuning: resident MAC CTAs per SM (0 = default) */
-  uint32_t reserved[7];
+  uint32_t mac_ctas_per_sm; /* tuning: resident MAC CTAs per SM (0 = default 2) */
+  uint32_t mac_l2_keep_16ths; /* tuning: sixteenths of the H/FDL lines kept L2-resident by the streaming MAC (0 = none) */
+  uint32_t mac_time_tile;   /* 0: streaming MAC only; 16 or 32: calls with enough blocks use the time-batched MAC */
+  uint32_t reserved[5];
 } bbx_config;
 
 typedef struct bbx_engine bbx_engine;
@@ -209,6 +211,11 @@ int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in
                 int out_be, uint32_t out_channels, uint32_t nframes);
 int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
                     int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
+/* Host pointers, asynchronous: returns once the H2D copy, the kernels and the D2H copy are enqueued (copies on
+ * their own streams, staging double-buffered), so consecutive calls overlap transfer and compute.  `in` and
+ * `out` must stay valid and untouched until bbx_engine_sync(); use pinned buffers (bbx_host_alloc). */
+int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
+                      int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
 int bbx_engine_sync(bbx_engine* e);
 
 /* Single-channel convenience = BlockConvolver::Convolve (README:38-39): path 0 of a

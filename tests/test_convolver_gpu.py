@@ -84,6 +84,66 @@ def test_batching_invariance_bit_exact(bbx):
     assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
 
 
+@pytest.mark.parametrize("kw", [dict(mac_time_tile=16), dict(mac_time_tile=32), dict(mac_l2_keep_16ths=5),
+                                dict(mac_ctas_per_sm=1), dict(mac_ctas_per_sm=4)])
+def test_mac_variants_bit_identical(bbx, kw):
+    """Every MAC kernel variant (time-batched TT = 16 / 32, L2-residency hints, other unroll / occupancy) uses the
+    same plan and the same per-output FMA order as the default streaming kernel: outputs must be bit-identical,
+    including across a crossfaded filter switch, ragged call sizes and a MIMO matrix."""
+    B, L, nch, nblk = 512, 20000, 5, 76
+    irs = [make_ir(400 + c, L) for c in range(nch + 1)]
+    xi = interleave([make_noise(410 + c, nblk * B) for c in range(nch)])
+    outs = []
+    for extra in ({}, kw):
+        g = GpuDriver(bbx, B, 40, nch, max_blocks=40, max_delay=30, fractional_delay=True, **extra)
+        fl = [g.filter(h) for h in irs]
+        for c in range(nch):
+            g.select(c, fl[c], delay=2.5 * c)
+        a = run_float(g, xi[:46 * B], [40 * B, 6 * B])
+        g.select(2, fl[nch], delay=11.25, crossfade=True)
+        b = run_float(g, xi[46 * B:], [23 * B, 7 * B])
+        outs.append(np.concatenate([a, b]))
+        g.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    # MIMO: several terms per job accumulate in registers across segments
+    nin, nout, Lm = 6, 3, 3000
+    xm = interleave([make_noise(500 + i, 36 * B) for i in range(nin)])
+    outs = []
+    for extra in ({}, kw):
+        g = GpuDriver(bbx, B, 6, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=36, **extra)
+        for o in range(nout):
+            for i in range(nin):
+                g.select(o * nin + i, g.filter(make_ir(600 + o * nin + i, Lm)))
+        outs.append(run_float(g, xm, 36 * B))
+        g.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+def test_async_host_pipeline_matches_sync(bbx):
+    """bbx_process_async with double-buffered pinned I/O == the synchronous call, bit for bit."""
+    B, L, nch, nblk, T = 256, 3000, 4, 24, 4
+    irs = [make_ir(700 + c, L) for c in range(nch)]
+    xi = interleave([make_noise(710 + c, nblk * B) for c in range(nch)])
+    g = GpuDriver(bbx, B, 12, nch, max_blocks=T)
+    for c in range(nch):
+        g.select(c, g.filter(irs[c]))
+    want = run_float(g, xi, T * B)
+    g.close()
+    g = GpuDriver(bbx, B, 12, nch, max_blocks=T)
+    for c in range(nch):
+        g.select(c, g.filter(irs[c]))
+    nbytes = T * B * nch * 4
+    hin = [bbx.PinnedBuffer(nbytes) for _ in range(nblk // T)]
+    hout = [bbx.PinnedBuffer(nbytes) for _ in range(nblk // T)]
+    for i in range(nblk // T):
+        hin[i].array[:] = xi[i * T * B:(i + 1) * T * B].reshape(-1).view(np.uint8)
+        g.eng.ConvolveHostPtrAsync(hin[i].ptr, cl.FMT_FLOAT, nch, hout[i].ptr, cl.FMT_FLOAT, nch, T * B)
+    g.eng.Sync()
+    got = np.concatenate([h.array.view(np.float32).reshape(T * B, nch).copy() for h in hout])
+    g.close()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_zero_input_exact_zeros_and_null_filter(bbx):
     B = 128
     g = GpuDriver(bbx, B, 4, 2, max_blocks=2)
