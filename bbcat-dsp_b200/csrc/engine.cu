@@ -221,12 +221,26 @@ k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
 // times).  Per partition a thread loads one complex of H and one of the FDL and issues 4*TT FMAs
 // (8 FMA per byte at TT = 32): the MAC becomes FP32-bound instead of HBM-bound.  Same plan, same per-output
 // FMA order as k_fdl_mac, hence bit-identical results.
-template <int TT, int THREADS, int PF>
-__global__ void __launch_bounds__(THREADS, 1)
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Operands are staged through shared memory with cp.async: every thread copies the H and FDL values of its own
+// column NST-1 partitions ahead and reads them back itself (no block barrier), and cp.async.wait_group gives
+// the "at most N groups pending" wait that register-target loads cannot express (their scoreboards only count to
+// zero, which collapses a deep software pipeline to a depth of one; see profiles/r01 notes in DESIGN.md).
+template <int TT, int THREADS, int NST>
+__global__ void __launch_bounds__(THREADS, (TT <= 16) ? 2 : 1)
 k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float2* __restrict__ fdl,
              float2* __restrict__ ypart, uint32_t B, uint32_t R, uint32_t head0, uint32_t t0, uint32_t nt,
              uint32_t ncoltiles, uint32_t slot_stride) {
-  static_assert(TT % PF == 0, "prefetch depth must divide the tile");
+  static_assert(TT % NST == 0, "stage count must divide the tile so that stage indices are static");
+  __shared__ float2 stage[NST][2][THREADS];
   // blockIdx.x enumerates (column tile, t tile) so the CTAs that share H / FDL rows run in the same wave
   const uint32_t coltile = blockIdx.x % ncoltiles, ttile = blockIdx.x / ncoltiles;
   const uint32_t tbase = ttile * TT;                  // first block-step of this tile, relative to t0
@@ -234,6 +248,8 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
   const uint32_t col = coltile * THREADS + threadIdx.x;
   const bool bin0 = (col == 0);
   const uint32_t sb = cta_seg_begin[blockIdx.y], se = cta_seg_begin[blockIdx.y + 1];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&stage[0][0][threadIdx.x]);
+  constexpr uint32_t kStageBytes = 2 * THREADS * sizeof(float2);
   float2 acc[TT];
 #pragma unroll
   for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
@@ -248,6 +264,17 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
     // FDL row met by output i at segment step q: base + i - q (mod R), base = s0 - p0
     int base = (int)s0 - (int)(sg.p0 % R);
     if (base < 0) base += (int)R;
+    int prow = base;  // FDL row of the next step to be staged
+    // stage the first NST-1 steps (one commit group per step, empty past the end so the count stays uniform)
+#pragma unroll
+    for (int j = 0; j < NST - 1; j++) {
+      if ((uint32_t)j < sg.np) {
+        cp_async8(sbase + j * kStageBytes, hp + (uint64_t)j * B);
+        cp_async8(sbase + j * kStageBytes + THREADS * sizeof(float2), xb + (uint64_t)prow * B);
+        prow = prow ? prow - 1 : (int)R - 1;
+      }
+      cp_async_commit();
+    }
     float2 W[TT];  // W[e mod TT] = row base + e, e = i - q
 #pragma unroll
     for (int e = 1; e < TT; e++) {
@@ -256,30 +283,23 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
       W[e] = __ldg(xb + (uint64_t)r * B);
     }
     W[0] = make_float2(0.f, 0.f);
-    float2 hq[PF], xq[PF];
-    int prow = base;  // row of the next prefetch
-#pragma unroll
-    for (int j = 0; j < PF; j++) {
-      hq[j] = make_float2(0.f, 0.f);
-      xq[j] = make_float2(0.f, 0.f);
-      if ((uint32_t)j < sg.np) {
-        hq[j] = ld_stream2(hp + (uint64_t)j * B);
-        xq[j] = __ldg(xb + (uint64_t)prow * B);
-        prow = prow ? prow - 1 : (int)R - 1;
-      }
-    }
     for (uint32_t qb = 0; qb < sg.np; qb += TT) {
 #pragma unroll
       for (int u = 0; u < TT; u++) {
         const uint32_t q = qb + u;
         if (q < sg.np) {
-          const float2 h = hq[u % PF];
-          W[(TT - u) % TT] = xq[u % PF];
-          if (q + PF < sg.np) {
-            hq[u % PF] = ld_stream2(hp + (uint64_t)(q + PF) * B);
-            xq[u % PF] = __ldg(xb + (uint64_t)prow * B);
+          // stage step q + NST - 1 into the slot freed by step q - 1
+          const uint32_t qn = q + NST - 1;
+          const int sn = (u + NST - 1) % NST;
+          if (qn < sg.np) {
+            cp_async8(sbase + sn * kStageBytes, hp + (uint64_t)qn * B);
+            cp_async8(sbase + sn * kStageBytes + THREADS * sizeof(float2), xb + (uint64_t)prow * B);
             prow = prow ? prow - 1 : (int)R - 1;
           }
+          cp_async_commit();
+          cp_async_wait<NST - 1>();  // step q has landed
+          const float2 h = stage[u % NST][0][threadIdx.x];
+          W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
           const HCoef k = hcoef(h.x, h.y, bin0);
 #pragma unroll
           for (int i = 0; i < TT; i++) {
@@ -289,6 +309,7 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
         }
       }
     }
+    cp_async_wait<0>();
     if (sg.flags & 2u) {
 #pragma unroll
       for (int i = 0; i < TT; i++)
@@ -650,7 +671,7 @@ void launch_mac_tb_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt,
   const uint32_t ncol = e->B / THREADS, ntile = ceil_div(nt, TT);
   dim3 grid(ncol * ntile, pl.n_ctas);
   float2* yp = e->ypart + (uint64_t)t0 * e->max_slots * e->B;
-  k_fdl_mac_tb<TT, THREADS, 4><<<grid, THREADS, 0, st>>>(pl.segs(), pl.cta_seg_begin(), e->fdl, yp, e->B, e->R, e->head, t0, nt,
+  k_fdl_mac_tb<TT, THREADS, 8><<<grid, THREADS, 0, st>>>(pl.segs(), pl.cta_seg_begin(), e->fdl, yp, e->B, e->R, e->head, t0, nt,
                                                         ncol, e->max_slots);
 }
 
