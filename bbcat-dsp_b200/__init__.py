@@ -91,6 +91,7 @@ SYMBOLS = {
     "bbx_engine_launch_count": (u64, [vp]),
     "bbx_engine_profile_mac": (C.c_int, [vp, C.c_int]),
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+    "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
 }
 
@@ -382,6 +383,10 @@ class Convolver:
         ms, n, units, nbytes = C.c_float(0), u64(0), u64(0), u64(0)
         _check(lib().bbx_engine_mac_time(self.h, C.byref(ms), C.byref(n), C.byref(units), C.byref(nbytes)))
         return {"ms": ms.value, "launches": n.value, "channel_blocks": units.value, "algorithmic_bytes": nbytes.value}
+
+    def set_tuning(self, ctas_per_sm=0, l2_keep_16ths=0, time_tile=0):
+        """0 = leave as is; time_tile=1 forces the streaming MAC, l2_keep_16ths > 16 switches the hints off."""
+        _check(lib().bbx_engine_set_tuning(self.h, ctas_per_sm, l2_keep_16ths, time_tile))
 
     def flush_l2(self, nbytes=256 << 20):
         _check(lib().bbx_engine_flush_l2(self.h, nbytes))

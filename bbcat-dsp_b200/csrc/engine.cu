@@ -250,6 +250,8 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
   const uint32_t sb = cta_seg_begin[blockIdx.y], se = cta_seg_begin[blockIdx.y + 1];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&stage[0][0][threadIdx.x]);
   constexpr uint32_t kStageBytes = 2 * THREADS * sizeof(float2);
+  constexpr uint32_t kXOff = THREADS * sizeof(float2);
+  const uint32_t row_bytes = B * (uint32_t)sizeof(float2);
   float2 acc[TT];
 #pragma unroll
   for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
@@ -259,45 +261,68 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
 #pragma unroll
       for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
     }
-    const float2* hp = reinterpret_cast<const float2*>(sg.H) + (uint64_t)sg.p0 * B + col;
-    const float2* xb = fdl + (uint64_t)sg.fdl_ch * R * B + col;
+    // byte pointers: one 32x32+64 multiply-add per address
+    const char* hp = reinterpret_cast<const char*>(reinterpret_cast<const float2*>(sg.H) + (uint64_t)sg.p0 * B + col);
+    const char* xb = reinterpret_cast<const char*>(fdl + (uint64_t)sg.fdl_ch * R * B + col);
     // FDL row met by output i at segment step q: base + i - q (mod R), base = s0 - p0
-    int base = (int)s0 - (int)(sg.p0 % R);
-    if (base < 0) base += (int)R;
-    int prow = base;  // FDL row of the next step to be staged
+    uint32_t base = s0 + R - (sg.p0 % R);
+    if (base >= R) base -= R;
+    uint32_t prow = base;  // FDL row of the next step to be staged
     // stage the first NST-1 steps (one commit group per step, empty past the end so the count stays uniform)
 #pragma unroll
     for (int j = 0; j < NST - 1; j++) {
       if ((uint32_t)j < sg.np) {
-        cp_async8(sbase + j * kStageBytes, hp + (uint64_t)j * B);
-        cp_async8(sbase + j * kStageBytes + THREADS * sizeof(float2), xb + (uint64_t)prow * B);
-        prow = prow ? prow - 1 : (int)R - 1;
+        cp_async8(sbase + j * kStageBytes, hp + (uint64_t)j * row_bytes);
+        cp_async8(sbase + j * kStageBytes + kXOff, xb + (uint64_t)prow * row_bytes);
+        prow = prow ? prow - 1 : R - 1;
       }
       cp_async_commit();
     }
     float2 W[TT];  // W[e mod TT] = row base + e, e = i - q
 #pragma unroll
     for (int e = 1; e < TT; e++) {
-      int r = base + e;
-      if (r >= (int)R) r -= (int)R;
-      W[e] = __ldg(xb + (uint64_t)r * B);
+      uint32_t r = base + e;
+      if (r >= R) r -= R;
+      W[e] = __ldg(reinterpret_cast<const float2*>(xb + (uint64_t)r * row_bytes));
     }
     W[0] = make_float2(0.f, 0.f);
-    for (uint32_t qb = 0; qb < sg.np; qb += TT) {
+    uint32_t qb = 0;
+    // fast path: whole groups of TT steps whose look-ahead stays inside the segment, no per-step checks
+    for (; qb + TT + NST - 1 <= sg.np; qb += TT) {
+#pragma unroll
+      for (int u = 0; u < TT; u++) {
+        const uint32_t qn = qb + u + NST - 1;
+        const int sn = (u + NST - 1) % NST;
+        cp_async8(sbase + sn * kStageBytes, hp + (uint64_t)qn * row_bytes);
+        cp_async8(sbase + sn * kStageBytes + kXOff, xb + (uint64_t)prow * row_bytes);
+        prow = prow ? prow - 1 : R - 1;
+        cp_async_commit();
+        cp_async_wait<NST - 1>();  // step qb + u has landed
+        const float2 h = stage[u % NST][0][threadIdx.x];
+        W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
+        const HCoef k = hcoef(h.x, h.y, bin0);
+#pragma unroll
+        for (int i = 0; i < TT; i++) {
+          const float2 x = W[(i - u + TT) % TT];
+          cmac(acc[i].x, acc[i].y, k, x.x, x.y);
+        }
+      }
+    }
+    // tail: same steps with bound checks
+    for (; qb < sg.np; qb += TT) {
 #pragma unroll
       for (int u = 0; u < TT; u++) {
         const uint32_t q = qb + u;
         if (q < sg.np) {
-          // stage step q + NST - 1 into the slot freed by step q - 1
           const uint32_t qn = q + NST - 1;
           const int sn = (u + NST - 1) % NST;
           if (qn < sg.np) {
-            cp_async8(sbase + sn * kStageBytes, hp + (uint64_t)qn * B);
-            cp_async8(sbase + sn * kStageBytes + THREADS * sizeof(float2), xb + (uint64_t)prow * B);
-            prow = prow ? prow - 1 : (int)R - 1;
+            cp_async8(sbase + sn * kStageBytes, hp + (uint64_t)qn * row_bytes);
+            cp_async8(sbase + sn * kStageBytes + kXOff, xb + (uint64_t)prow * row_bytes);
+            prow = prow ? prow - 1 : R - 1;
           }
           cp_async_commit();
-          cp_async_wait<NST - 1>();  // step q has landed
+          cp_async_wait<NST - 1>();
           const float2 h = stage[u % NST][0][threadIdx.x];
           W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
           const HCoef k = hcoef(h.x, h.y, bin0);
@@ -580,9 +605,9 @@ struct bbx_engine {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_upload = nullptr;  // last H2D copy out of the pinned plan/route staging
   bool upload_pending = false;
-  uint32_t mac_occ = 2;
+  uint32_t mac_occ = 1;          // resident streaming-MAC CTAs per SM; the plan has 148 * mac_occ row ranges
   float mac_l2_keep = 0.f;       // fraction of H / FDL lines given L2 evict-last priority by the streaming MAC
-  uint32_t mac_time_tile = 0;    // TT of the time-batched MAC (0 = streaming kernel only)
+  uint32_t mac_time_tile = 16;   // TT of the time-batched MAC (0 = streaming kernel only)
   uint64_t launches = 0;
   bool profile_mac = false;
   std::vector<cudaEvent_t> mac_events;  // pairs
@@ -756,7 +781,7 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
   } else {
     // even split of the flattened row space; small problems get fewer, fatter CTAs
     const uint32_t min_rows = 4;
-    uint32_t G = std::min(e->max_ctas, std::max(1u, total / min_rows));
+    uint32_t G = std::min(kNumSMs * e->mac_occ, std::max(1u, total / min_rows));
     uint32_t rpc = ceil_div(total, G);
     G = ceil_div(total, rpc);
     uint32_t nseg = 0, nslot = 0, row = 0, cur_cta = 0;
@@ -910,6 +935,14 @@ RouteView route_view(const bbx_engine* e) {
 
 bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
+// 0 always means "leave as is" (library default at creation)
+void apply_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile) {
+  if (ctas_per_sm) e->mac_occ = std::min(ctas_per_sm, 4u);
+  if (l2_keep_16ths) e->mac_l2_keep = (l2_keep_16ths > 16u) ? 0.f : l2_keep_16ths / 16.0f;  // > 16: hints off
+  if (time_tile) e->mac_time_tile = (time_tile == 16 || time_tile == 32) ? time_tile : 0;     // 1: streaming only
+  e->steady_dirty = true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1002,10 +1035,8 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   BBX_CUDA_TRY(cudaMemset(e->ybuf, 0, ybuf_bytes));
 
   // plan capacities
-  e->mac_occ = cfg->mac_ctas_per_sm ? std::min(cfg->mac_ctas_per_sm, 4u) : 2u;
-  e->max_ctas = kNumSMs * e->mac_occ;
-  e->mac_l2_keep = std::min(cfg->mac_l2_keep_16ths, 16u) / 16.0f;
-  e->mac_time_tile = (cfg->mac_time_tile == 16 || cfg->mac_time_tile == 32) ? cfg->mac_time_tile : 0;
+  e->max_ctas = kNumSMs * 4;  // capacity for every tuning; the plan uses kNumSMs * mac_occ of them
+  apply_tuning(e, cfg->mac_ctas_per_sm, cfg->mac_l2_keep_16ths, cfg->mac_time_tile);
   uint32_t terms = (e->mode == BBX_MODE_MIMO) ? e->n_paths : e->n_paths;
   e->max_jobs = 2 * e->n_streams + 1;
   e->max_segs = e->max_ctas + 2 * terms + 8;
@@ -1423,6 +1454,13 @@ int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint
   if (launches) *launches = e->mac_launches;
   if (channel_blocks) *channel_blocks = e->mac_units;
   if (algorithmic_bytes) *algorithmic_bytes = e->mac_bytes;
+  return BBX_OK;
+}
+
+int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  apply_tuning(e, ctas_per_sm, l2_keep_16ths, time_tile);
   return BBX_OK;
 }
 

@@ -7,14 +7,19 @@
 Workload (BASELINE.json configs[2], the configuration the metric / north_star targets are quoted on):
 128-channel long reverb, 3 s IR (144000 taps) at 48 kHz, 512-sample partitions (P = 282), distinct IR per
 channel, uniform white-noise input.  One "step" = one pass of the hot path over one batch of T = 64 blocks
-(32768 frames, 0.683 s of audio) for every channel of the rank, streaming semantics (every block-step
-re-streams the filter spectra and the FDL: 297.85 MB per 128-channel block-step, larger than the 126 MB L2,
-so no L2 flush is needed between iterations).
+(32768 frames, 0.683 s of audio) for every channel of the rank.  Per step the working set (148 MB of filter
+spectra + 181 MB of FDL + 147 MB of partial sums) is larger than the 126 MB L2, so no L2 flush is needed
+between iterations.
 
   value  channel-seconds of audio per second, inputs resident in HBM, K steps timed with CUDA events on the
-         engine stream between barriers, max over ranks
-  e2e    the same metric through the C-ABI call bbx_process() with HOST (pinned) buffers: H2D and D2H copies
-         inside the timed region
+         engine streams between barriers, max over ranks.  The engine's default path: calls with >= 8 blocks run
+         the time-batched FDL MAC (k_fdl_mac_tb, FP32-bound), shorter calls the streaming MAC (k_fdl_mac, HBM-bound).
+  e2e    the same metric through the C-ABI call bbx_process_async() with HOST (pinned) buffers: the H2D copy of
+         the step's input and the D2H copy of its output are inside the timed region (copy streams overlap them
+         with the kernels of the neighbouring steps)
+  roofline            the dominant kernel of the timed region (k_fdl_mac_tb): FP32 FMA rate against the SIMT peak
+  roofline_streaming  the streaming MAC (k_fdl_mac) timed in the same run: algorithmic HBM bytes against the
+                      measured HBM peak -- the roofline BASELINE.json's north_star names
 N > 1    weak scaling: every rank runs its own 128-channel shard (rank r = channels 128r .. 128r+127 of a
          128N-channel renderer); channels are independent, so there is no data-path collective.
 """
@@ -41,6 +46,7 @@ T = 64
 K_BINS = B + 1
 # algorithmic bytes of one channel-block-step of the FDL MAC (fp32 in / fp32 out)
 BYTES_PER_CHANNEL_BLOCK = 16 * P * K_BINS + 16 * K_BINS + (4 + 4) * B  # 2,326,960
+FLOPS_PER_CHANNEL_BLOCK = 8 * P * K_BINS  # 1,157,328 (complex MAC = 4 FMA = 8 flop)
 WORKLOAD = "C3: 128-channel long reverb, 144000-tap IR (3 s @ 48 kHz), 512-sample partitions (P=282), f32 in/out"
 
 
@@ -193,8 +199,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--occ", type=int, default=0, help="MAC CTAs per SM (tuning)")
-    ap.add_argument("--l2keep", type=int, default=0, help="sixteenths of H/FDL lines kept L2-resident (streaming MAC)")
-    ap.add_argument("--tile", type=int, default=0, help="time-batched MAC tile (0 = streaming kernel, 16 or 32)")
+    ap.add_argument("--l2keep", type=int, default=0, help="sixteenths of H/FDL lines kept L2-resident (streaming MAC), 0 = default")
+    ap.add_argument("--tile", type=int, default=0, help="time-batched MAC tile: 0 = default (16), 1 = streaming kernel only, 16, 32")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the streaming-MAC roofline pass")
     ap.add_argument("--blocks", type=int, default=T, help="blocks per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true")
@@ -306,24 +313,68 @@ def main():
         latency = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "blocks": nlat,
                    "block_period_us": 1e6 * B / FS, "mode": "T=1, bbx_process with pinned host buffers, host clock"}
 
-    # ---- roofline of the dominant kernel (k_fdl_mac), CUDA events around every launch in the timed region ----
+    # ---- roofline of the dominant kernel of the timed region, CUDA events around every MAC launch ----
     peak, peak_src = peaks()
     units_per_launch = mac["channel_blocks"] / max(1, mac["launches"])
-    alg_per_launch = BYTES_PER_CHANNEL_BLOCK * units_per_launch
     mac_ms = mac["ms"] / max(1, mac["launches"])
-    achieved = alg_per_launch / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
-    traffic = None
+    traffic_tb = traffic_stream = None
     tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_channel_block"] * units_per_launch
+            traffic_stream = tj["dram_bytes_per_channel_block"]
+            traffic_tb = tj.get("tb_dram_bytes_per_channel_block")
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_fdl_mac", "launch_ms": mac_ms, "units_per_launch": units_per_launch,
-                "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
-                "mac_share_of_step": mac["ms"] / ms if ms > 0 else None}
+            pass
+    batched = args.tile != 1
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s: 148 SMs x 128 FMA lanes x 2 flop x max SM clock
+    if batched:
+        tflops = FLOPS_PER_CHANNEL_BLOCK * units_per_launch / (mac_ms * 1e-3) / 1e12 if mac_ms > 0 else 0.0
+        roofline = {"bound": "fp32", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
+                    "traffic": traffic_tb * units_per_launch if traffic_tb else None,
+                    "kernel": "k_fdl_mac_tb<16,256,8>" if args.tile in (0, 16) else "k_fdl_mac_tb<32,256,8>",
+                    "launch_ms": mac_ms, "units_per_launch": units_per_launch,
+                    "flops_per_launch": FLOPS_PER_CHANNEL_BLOCK * units_per_launch,
+                    "peak_source": "nominal SIMT FP32: 148 SM x 128 lanes x 2 flop x %.0f MHz (no FP32 figure in MEASURED_PEAKS.json)" % sm_max,
+                    "note": "time-batched MAC: H[p] is loaded once per 16 block-steps, 4 FMA per loaded byte -> bound by the "
+                            "FP32 pipe, not HBM; the hbm roofline of the streaming kernel is in roofline_streaming",
+                    "hbm_equivalent_GBps": BYTES_PER_CHANNEL_BLOCK * units_per_launch / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
+                    "mac_share_of_step": mac["ms"] / ms if ms > 0 else None}
+    else:
+        achieved = BYTES_PER_CHANNEL_BLOCK * units_per_launch / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic_stream * units_per_launch if traffic_stream else None, "kernel": "k_fdl_mac",
+                    "launch_ms": mac_ms, "units_per_launch": units_per_launch,
+                    "algorithmic_bytes_per_launch": BYTES_PER_CHANNEL_BLOCK * units_per_launch, "peak_source": peak_src,
+                    "mac_share_of_step": mac["ms"] / ms if ms > 0 else None}
+
+    # ---- the streaming MAC in the same run (the HBM-bound kernel the north_star roofline is about) ----
+    roofline_streaming = None
+    if batched and not args.no_streaming:
+        eng.set_tuning(time_tile=1)
+        ks = max(3, min(args.steps, 40))
+        for _ in range(3):
+            step_dev()
+        barrier()
+        eng.profile_mac(True)
+        eng.timer_start()
+        for _ in range(ks):
+            step_dev()
+        ms_s = max_over_ranks(eng.timer_stop())
+        barrier()
+        mac_s = eng.mac_time()
+        eng.profile_mac(False)
+        eng.set_tuning(time_tile=args.tile or 16)
+        upl = mac_s["channel_blocks"] / max(1, mac_s["launches"])
+        lms = mac_s["ms"] / max(1, mac_s["launches"])
+        ach = BYTES_PER_CHANNEL_BLOCK * upl / (lms * 1e-3) / 1e9 if lms > 0 else 0.0
+        roofline_streaming = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "traffic": traffic_stream * upl if traffic_stream else None, "kernel": "k_fdl_mac",
+                              "launch_ms": lms, "units_per_launch": upl,
+                              "algorithmic_bytes_per_launch": BYTES_PER_CHANNEL_BLOCK * upl, "peak_source": peak_src,
+                              "value_streaming": world * audio_s * ks / (ms_s * 1e-3), "steps": ks,
+                              "mac_share_of_step": mac_s["ms"] / ms_s if ms_s > 0 else None}
 
     # ---- CPU baseline on rank 0 at N = 1 (bounded sample of the same workload) ----
     cpu = None
@@ -340,11 +391,12 @@ def main():
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "channels_per_gpu": NCH, "total_channels": NCH * world, "block": B,
-                       "partitions": P, "blocks_per_step": nblk, "semantics": "streaming (T=1 algorithm per block-step)",
-                       "l2": "inputs larger than L2: 297.85 MB streamed per block-step vs 126 MB L2, no flush",
+                       "partitions": P, "blocks_per_step": nblk,
+                       "mac": "time-batched (tile 16)" if args.tile in (0, 16) else ("streaming" if args.tile == 1 else "time-batched (tile %d)" % args.tile),
+                       "l2": "inputs larger than L2: 148 MB spectra + 181 MB FDL + partial sums per step vs 126 MB L2, no flush",
                        "parallelism": "channel-sharded x%d, no collective" % world},
             "x_realtime_per_channel": value / (NCH * world),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_streaming": roofline_streaming, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "channel-s/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "latency": latency,

@@ -173,9 +173,10 @@ typedef struct {
   uint32_t max_delay;       /* ceil of the largest per-path delay in samples */
   int fractional_delay;     /* 0: integer delays; 1: every delayed read goes through FractionalSample */
   uint32_t ring_length;     /* delay ring length R per path in frames; 0 = choose (see _get_ring_length) */
-  uint32_t mac_ctas_per_sm; /* tuning: resident MAC CTAs per SM (0 = default 2) */
-  uint32_t mac_l2_keep_16ths; /* tuning: sixteenths of the H/FDL lines kept L2-resident by the streaming MAC (0 = none) */
-  uint32_t mac_time_tile;   /* 0: streaming MAC only; 16 or 32: calls with enough blocks use the time-batched MAC */
+  /* tuning knobs; 0 = library default */
+  uint32_t mac_ctas_per_sm;   /* streaming MAC: resident CTAs per SM, 1..4 (default 1: 148 row ranges) */
+  uint32_t mac_l2_keep_16ths; /* streaming MAC: sixteenths of the H/FDL lines kept L2-resident, 1..16; > 16 = hints off (default) */
+  uint32_t mac_time_tile;     /* 16 or 32: calls with >= tile/2 blocks use the time-batched MAC (default 16); 1 = streaming MAC only */
   uint32_t reserved[5];
 } bbx_config;
 
@@ -233,6 +234,8 @@ uint64_t bbx_engine_launch_count(const bbx_engine* e);
 int bbx_engine_profile_mac(bbx_engine* e, int enable);
 int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint64_t* channel_blocks,
                         uint64_t* algorithmic_bytes);
+/* change the tuning knobs of bbx_config at run time (0 = leave as is); takes effect at the next call */
+int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile);
 /* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
 

@@ -84,11 +84,11 @@ def test_batching_invariance_bit_exact(bbx):
     assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
 
 
-@pytest.mark.parametrize("kw", [dict(mac_time_tile=16), dict(mac_time_tile=32), dict(mac_l2_keep_16ths=5),
-                                dict(mac_ctas_per_sm=1), dict(mac_ctas_per_sm=4)])
+@pytest.mark.parametrize("kw", [dict(mac_time_tile=1), dict(mac_time_tile=32), dict(mac_time_tile=1, mac_l2_keep_16ths=5),
+                                dict(mac_time_tile=1, mac_ctas_per_sm=2)])
 def test_mac_variants_bit_identical(bbx, kw):
-    """Every MAC kernel variant (time-batched TT = 16 / 32, L2-residency hints, other unroll / occupancy) uses the
-    same plan and the same per-output FMA order as the default streaming kernel: outputs must be bit-identical,
+    """Every MAC kernel variant (streaming, time-batched TT = 16 (default) / 32, L2-residency hints, other unroll
+    depth) uses the same plan and the same per-output FMA order: outputs must be bit-identical to the default,
     including across a crossfaded filter switch, ragged call sizes and a MIMO matrix."""
     B, L, nch, nblk = 512, 20000, 5, 76
     irs = [make_ir(400 + c, L) for c in range(nch + 1)]
