@@ -157,7 +157,7 @@ template <int U, int THREADS, int OCC, bool POLICY>
 __global__ void __launch_bounds__(THREADS, OCC)
 k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float4* __restrict__ fdl,
           float4* __restrict__ ypart, uint32_t halfB, uint32_t R, uint32_t head0, uint32_t t0, uint32_t slot_stride,
-          float l2_keep) {
+          float l2_keep, int policy_x) {
   const uint32_t t = t0 + blockIdx.z;
   const uint32_t head = (head0 + t) % R;
   const uint32_t col = blockIdx.y * THREADS + threadIdx.x;
@@ -177,19 +177,24 @@ k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
     const float4* xbase = fdl + (uint64_t)sg.fdl_ch * R * halfB + col;
     int slot = (int)head - (int)sg.p0;  // p0 < R
     if (slot < 0) slot += (int)R;
-    uint32_t p = 0;
-    for (; p + U <= sg.np; p += U) {
+    // U rows per iteration, all 2U loads issued before the first FMA; rows past the end of a short segment are
+    // predicated off and contribute h = x = 0 (acc += 0 exactly), so short filters keep their loads in flight
+    for (uint32_t p = 0; p < sg.np; p += U) {
       float4 h[U], x[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         int s = slot - u;
         s += (s >> 31) & (int)R;  // ring wrap, once per row
-        if (POLICY) {
-          h[u] = ld_policy(hp + (uint64_t)u * halfB, pol);
-          x[u] = ld_policy(xbase + (uint64_t)s * halfB, pol);
-        } else {
-          h[u] = ld_stream(hp + (uint64_t)u * halfB);
-          x[u] = __ldg(xbase + (uint64_t)s * halfB);
+        h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p + u < sg.np) {
+          if (POLICY) {
+            h[u] = ld_policy(hp + (uint64_t)u * halfB, pol);
+            x[u] = policy_x ? ld_policy(xbase + (uint64_t)s * halfB, pol) : __ldg(xbase + (uint64_t)s * halfB);
+          } else {
+            h[u] = ld_stream(hp + (uint64_t)u * halfB);
+            x[u] = __ldg(xbase + (uint64_t)s * halfB);
+          }
         }
       }
 #pragma unroll
@@ -199,15 +204,6 @@ k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
       }
       hp += (uint64_t)U * halfB;
       slot -= U;
-      if (slot < 0) slot += (int)R;
-    }
-    for (; p < sg.np; p++) {
-      float4 h = POLICY ? ld_policy(hp, pol) : ld_stream(hp);
-      float4 x = POLICY ? ld_policy(xbase + (uint64_t)slot * halfB, pol) : __ldg(xbase + (uint64_t)slot * halfB);
-      cmac(acc.x, acc.y, hcoef(h.x, h.y, bin0), x.x, x.y);
-      cmac(acc.z, acc.w, hcoef(h.z, h.w, false), x.z, x.w);
-      hp += halfB;
-      slot -= 1;
       if (slot < 0) slot += (int)R;
     }
     if (sg.flags & 2u) ypart[((uint64_t)blockIdx.z * slot_stride + sg.slot) * halfB + col] = acc;
@@ -550,7 +546,7 @@ struct MacPlan {
   size_t blob_bytes = 0;
   // offsets inside the blob
   size_t off_segs = 0, off_cta = 0, off_first = 0, off_count = 0, off_xjob = 0;
-  uint32_t n_ctas = 0, n_slots = 0, n_jobs = 0, total_rows = 0;
+  uint32_t n_ctas = 0, n_slots = 0, n_jobs = 0, total_rows = 0, n_terms = 0;
   bool valid = false;
   const MacSeg* segs() const { return (const MacSeg*)(d_blob + off_segs); }
   const uint32_t* cta_seg_begin() const { return (const uint32_t*)(d_blob + off_cta); }
@@ -606,7 +602,7 @@ struct bbx_engine {
   cudaEvent_t ev_upload = nullptr;  // last H2D copy out of the pinned plan/route staging
   bool upload_pending = false;
   uint32_t mac_occ = 1;          // resident streaming-MAC CTAs per SM; the plan has 148 * mac_occ row ranges
-  float mac_l2_keep = 0.f;       // fraction of H / FDL lines given L2 evict-last priority by the streaming MAC
+  float mac_l2_keep = 3.f / 16;  // fraction of H / FDL lines given L2 evict-last priority by the streaming MAC
   uint32_t mac_time_tile = 16;   // TT of the time-batched MAC (0 = streaming kernel only)
   uint64_t launches = 0;
   bool profile_mac = false;
@@ -674,12 +670,15 @@ void launch_mac_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cu
   const uint32_t* cta = pl.cta_seg_begin();
   const float4* fdl = (const float4*)e->fdl;
   const float keep = e->mac_l2_keep;
+  // FDL rows are read once per step only when every input feeds one path; shared inputs (ROUTED fan-out, MIMO)
+  // re-read them within the step and must keep normal L2 priority
+  const int px = (e->mode == BBX_MODE_PER_CHANNEL) ? 1 : 0;
 #define BBX_MAC_LAUNCH(U, OCC)                                                                                            \
   do {                                                                                                                    \
     if (keep > 0.f)                                                                                                       \
-      k_fdl_mac<U, THREADS, OCC, true><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep); \
+      k_fdl_mac<U, THREADS, OCC, true><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
     else                                                                                                                  \
-      k_fdl_mac<U, THREADS, OCC, false><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep); \
+      k_fdl_mac<U, THREADS, OCC, false><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
   } while (0)
   // resident CTAs per SM <-> loads in flight per thread: fewer, fatter CTAs unroll deeper
   switch (e->mac_occ) {
@@ -722,8 +721,9 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     BBX_CUDA_TRY(cudaEventRecord(ev0, st));
   }
   const uint32_t halfB = e->B / 2;
+  // the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters
   const uint32_t tb = e->mac_time_tile;  // 0: streaming only
-  if (tb && nt >= tb / 2) {
+  if (tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb) {
     if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
     else launch_mac_tb<16>(e, pl, t0, nt, st);
   } else if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
@@ -758,9 +758,14 @@ int mark_upload(bbx_engine* e) {
 
 // Build a MAC plan from a job list into plan.h_blob (pinned) and enqueue its upload.
 int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm>>& jobs, const std::vector<uint32_t>& xjob) {
-  uint32_t total = 0;
+  uint32_t total = 0, nterms = 0;
   for (auto& j : jobs)
-    for (auto& tm : j) total += tm.f ? tm.f->P : 0;
+    for (auto& tm : j)
+      if (tm.f) {
+        total += tm.f->P;
+        nterms++;
+      }
+  pl.n_terms = nterms;
   {
     int wrc = wait_uploads(e);
     if (wrc) return wrc;

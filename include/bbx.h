@@ -175,8 +175,8 @@ typedef struct {
   uint32_t ring_length;     /* delay ring length R per path in frames; 0 = choose (see _get_ring_length) */
   /* tuning knobs; 0 = library default */
   uint32_t mac_ctas_per_sm;   /* streaming MAC: resident CTAs per SM, 1..4 (default 1: 148 row ranges) */
-  uint32_t mac_l2_keep_16ths; /* streaming MAC: sixteenths of the H/FDL lines kept L2-resident, 1..16; > 16 = hints off (default) */
-  uint32_t mac_time_tile;     /* 16 or 32: calls with >= tile/2 blocks use the time-batched MAC (default 16); 1 = streaming MAC only */
+  uint32_t mac_l2_keep_16ths; /* streaming MAC: sixteenths of the H/FDL lines kept L2-resident, 1..16 (default 3); > 16 = hints off */
+  uint32_t mac_time_tile;     /* 16 or 32: calls with >= tile/2 blocks and filters of >= 2*tile partitions use the time-batched MAC (default 16); 1 = streaming MAC only */
   uint32_t reserved[5];
 } bbx_config;
 
