@@ -139,7 +139,7 @@ def cpu_convolver_rate(n_blocks, nthreads, want_seconds=None):
         cv.process(x, cpulibs.FMT_FLOAT, NCH, cpulibs.FMT_FLOAT, NCH, 4 * B)
         done += 4
         el = time.perf_counter() - t0
-        if done >= n_blocks or (want_seconds and el >= want_seconds):
+        if done >= n_blocks and (not want_seconds or el >= want_seconds):
             break
     return NCH * done * B / FS / el, el, done
 
@@ -394,7 +394,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
-        rate, secs, blocks = cpu_convolver_rate(64, cores, want_seconds=20.0)
+        rate, secs, blocks = cpu_convolver_rate(64, cores, want_seconds=12.0)
         cpu = {"value": rate, "unit": "channel-s/s", "cores": cores, "kind": "port",
                "sample": "%d block-steps x %d channels of the C3 workload in %.1f s (oracle UPOLS, OpenMP over channels, own FFT)" % (
                    blocks, NCH, secs)}
