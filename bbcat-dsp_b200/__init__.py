@@ -72,6 +72,13 @@ SYMBOLS = {
     "bbx_delay_read_sample": (C.c_float, [vp, u32, u32]),
     "bbx_delay_get_buffer_dev": (vp, [vp]),
     "bbx_delay_copy_buffer": (u32, [vp, vp, u32]),
+    "bbx_mlb_create": (C.c_int, [u32, u32, C.POINTER(vp)]),
+    "bbx_mlb_destroy": (C.c_int, [vp]),
+    "bbx_mlb_get_channels": (u32, [vp]),
+    "bbx_mlb_get_layers": (u32, [vp]),
+    "bbx_mlb_get_available_frames": (u32, [vp]),
+    "bbx_mlb_write_layer": (C.c_int, [vp, u32, vp, u32, u32, u32, u32, u32]),
+    "bbx_mlb_read_buffer": (u32, [vp, u32, vp, u32, u32, u32, u32, C.c_int]),
     "bbx_engine_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
     "bbx_engine_destroy": (C.c_int, [vp]),
     "bbx_engine_get_ring_length": (u32, [vp]),
@@ -260,6 +267,38 @@ class SoundDelayBuffer:
         if got != n:
             raise BbxError("bbx_delay_copy_buffer returned %d of %d bytes" % (got, n))
         return out
+
+
+# ---- next row: MultilayerBuffer (src/MultilayerBuffer.h) -------------------------------------
+class MultilayerBuffer:
+    def __init__(self, channels, layers):
+        h = vp()
+        _check(lib().bbx_mlb_create(channels, layers, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_mlb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def GetChannels(self):
+        return lib().bbx_mlb_get_channels(self.h)
+
+    def GetLayers(self):
+        return lib().bbx_mlb_get_layers(self.h)
+
+    def GetAvailableFrames(self):
+        return lib().bbx_mlb_get_available_frames(self.h)
+
+    def WriteLayer(self, layer, src, srcchannel, nsrcchannels, ndstchannel, nchannels, nframes):
+        _check(lib().bbx_mlb_write_layer(self.h, layer, _p(src), srcchannel, nsrcchannels, ndstchannel,
+                                         nchannels & 0xFFFFFFFF, nframes))
+
+    def ReadBuffer(self, srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, overwrite=True):
+        return lib().bbx_mlb_read_buffer(self.h, srcchannel, _p(dst), dstchannel, ndstchannels, nchannels & 0xFFFFFFFF,
+                                         nframes, int(overwrite))
 
 
 # ---- a12-a14 ------------------------------------------------------------------------------

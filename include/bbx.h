@@ -224,6 +224,24 @@ int bbx_engine_sync(bbx_engine* e);
 int bbx_blockconvolver_convolve(bbx_engine* e, const float* in, float* out);
 
 /* ------------------------------------------------------------------------------------------
+ * next row  MultilayerBuffer<float>  src/MultilayerBuffer.h:19-431
+ *      Output collection bus in HBM for renderers with different block sizes: every layer mixes
+ *      (MixSamples) its blocks at its own write position; frames written by ALL layers can be read
+ *      (TransferSamples when overwrite != 0, MixSamples otherwise) and are then shifted out.
+ *      src / dst are host pointers.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bbx_mlb bbx_mlb;
+int bbx_mlb_create(uint32_t channels, uint32_t layers, bbx_mlb** out);
+int bbx_mlb_destroy(bbx_mlb* m);
+uint32_t bbx_mlb_get_channels(const bbx_mlb* m);
+uint32_t bbx_mlb_get_layers(const bbx_mlb* m);
+uint32_t bbx_mlb_get_available_frames(const bbx_mlb* m);
+int bbx_mlb_write_layer(bbx_mlb* m, uint32_t layer, const float* src, uint32_t srcchannel, uint32_t nsrcchannels,
+                        uint32_t dstchannel, uint32_t nchannels, uint32_t nframes);
+uint32_t bbx_mlb_read_buffer(bbx_mlb* m, uint32_t srcchannel, float* dst, uint32_t dstchannel, uint32_t ndstchannels,
+                             uint32_t nchannels, uint32_t nframes, int overwrite);
+
+/* ------------------------------------------------------------------------------------------
  * measurement hooks (bench.py): CUDA-event timing on the engine stream, launch counting and
  * the dominant kernel's (FDL MAC) accumulated device time.
  * ---------------------------------------------------------------------------------------- */

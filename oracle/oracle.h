@@ -83,6 +83,16 @@ unsigned orc_delay_read_samples(orc_delay* d, void* dst, int dstformat, unsigned
                                 unsigned nchannels, unsigned nframes);
 unsigned orc_delay_copy_buffer(const orc_delay* d, void* dst, unsigned maxbytes);
 
+/* ---- multilayer.c : MultilayerBuffer.h ("next" row) ---- */
+typedef struct orc_mlb orc_mlb;
+orc_mlb* orc_mlb_create(unsigned channels, unsigned layers);
+void orc_mlb_destroy(orc_mlb* m);
+void orc_mlb_write_layer(orc_mlb* m, unsigned layer, const float* src, unsigned srcchannel, unsigned nsrcchannels,
+                         unsigned dstchannel, unsigned nchannels, unsigned nframes);
+unsigned orc_mlb_available_frames(const orc_mlb* m);
+unsigned orc_mlb_read_buffer(orc_mlb* m, unsigned srcchannel, float* dst, unsigned dstchannel, unsigned ndstchannels,
+                             unsigned nchannels, unsigned nframes, int overwrite);
+
 /* ---- fft.c : own FFT (FFTW stand-in, unnormalised both directions) ---- */
 /* complex in-place FFT of n (power of two) interleaved float pairs; inverse != 0 conjugates the kernel */
 void orc_cfft(float* data, unsigned n, int inverse);

@@ -72,6 +72,11 @@ class CpuLib:
         self._dl_inc = fn("delay_increment_write_position", None, [vp, u32])
         self._dl_read = fn("delay_read_samples", u32, [vp, vp, C.c_int, u32, u32, u32, u32])
         self._dl_copy = fn("delay_copy_buffer", u32, [vp, vp, u32])
+        self._mlb_create = fn("mlb_create", vp, [u32, u32])
+        self._mlb_destroy = fn("mlb_destroy", None, [vp])
+        self._mlb_write = fn("mlb_write_layer", None, [vp, u32, vp, u32, u32, u32, u32, u32])
+        self._mlb_avail = fn("mlb_available_frames", u32, [vp])
+        self._mlb_read = fn("mlb_read_buffer", u32, [vp, u32, vp, u32, u32, u32, u32, C.c_int])
 
     # ---- formats ----
     def bits_per_sample(self, fmt):
@@ -126,6 +131,31 @@ class CpuLib:
     # ---- delay buffer ----
     def delay(self):
         return CpuDelay(self)
+
+    # ---- MultilayerBuffer<float> ----
+    def multilayer(self, channels, layers):
+        return CpuMultilayer(self, channels, layers)
+
+
+class CpuMultilayer:
+    def __init__(self, lib, channels, layers):
+        self.l = lib
+        self.h = lib._mlb_create(channels, layers)
+
+    def close(self):
+        if self.h:
+            self.l._mlb_destroy(self.h)
+            self.h = None
+
+    def write_layer(self, layer, src, srcchannel, nsrcchannels, dstchannel, nchannels, nframes):
+        self.l._mlb_write(self.h, layer, _ptr(src), srcchannel, nsrcchannels, dstchannel, nchannels & 0xFFFFFFFF, nframes)
+
+    def available(self):
+        return self.l._mlb_avail(self.h)
+
+    def read(self, srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, overwrite=True):
+        return self.l._mlb_read(self.h, srcchannel, _ptr(dst), dstchannel, ndstchannels, nchannels & 0xFFFFFFFF, nframes,
+                                int(overwrite))
 
 
 class CpuDelay:

@@ -43,6 +43,26 @@ class GpuLib:
     def delay(self):
         return GpuDelay(self.b)
 
+    def multilayer(self, channels, layers):
+        return GpuMultilayer(self.b, channels, layers)
+
+
+class GpuMultilayer:
+    def __init__(self, b, channels, layers):
+        self.m = b.MultilayerBuffer(channels, layers)
+
+    def close(self):
+        self.m.close()
+
+    def write_layer(self, layer, src, srcchannel, nsrcchannels, dstchannel, nchannels, nframes):
+        self.m.WriteLayer(layer, src, srcchannel, nsrcchannels, dstchannel, nchannels, nframes)
+
+    def available(self):
+        return self.m.GetAvailableFrames()
+
+    def read(self, srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, overwrite=True):
+        return self.m.ReadBuffer(srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, overwrite)
+
 
 class GpuDelay:
     def __init__(self, b):

@@ -111,7 +111,8 @@ def c4(steps):
         for c in range(nch):
             eng.SelectFilter(c, bank[c][(m + c) % nbank], delay=16 + 37.3 * ((m * 7 + c) % 11) / 11, crossfade=m > 0)
         # switch every 100 ms: block index ceil(m * 4800 / 512)
-        return -(-(m + 1) * 4800 // 512) - (-(m * 4800) // 512)
+        cd = lambda a: -(-a // 512)
+        return cd((m + 1) * 4800) - cd(m * 4800)
 
     r = {"config": "C4 32ch dynamic IR: bank of 16 IRs/ch (4096 taps), select every 100 ms with crossfade + fractional "
                    "delay, B=512, s24 in/out", "channels": nch}
