@@ -83,19 +83,23 @@ __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
 // k_rfft : windows of 2B floats -> packed spectra
 // ------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(M / 4) k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride,
-                                                float2* __restrict__ dst, uint64_t dst_ch_stride, uint32_t R,
-                                                uint32_t slot0, const float2* __restrict__ tw, float scale) {
-  __shared__ float2 s[M];
-  const uint32_t ch = blockIdx.x, t = blockIdx.y;
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
+k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, float2* __restrict__ dst, uint64_t dst_ch_stride,
+       uint32_t R, uint32_t slot0, const float2* __restrict__ tw, float scale, uint32_t nch) {
+  constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
+  __shared__ float2 smem[FPB][MP];
+  float2* s = smem[threadIdx.y];
+  const int tid = threadIdx.x;
+  const uint32_t chq = blockIdx.x * FPB + threadIdx.y, t = blockIdx.y;
+  const bool active = chq < nch;
+  const uint32_t ch = active ? chq : nch - 1;  // idle transforms of the last CTA recompute a valid one, stores masked
   const float2* win = reinterpret_cast<const float2*>(src + ch * ch_stride + (uint64_t)t * win_stride);
-  constexpr int Q = M / 4;
 #pragma unroll
-  for (int h = 0; h < 4; h++) s[threadIdx.x + h * Q] = win[threadIdx.x + h * Q];
+  for (int h = 0; h < RAD; h++) s[PAD(tid + h * NT)] = win[tid + h * NT];
   __syncthreads();
-  cfft_smem<M, false>(s, tw);
+  cfft_smem<M, false>(s, tw, tid);
   const uint32_t slot = (slot0 + t) % R;
-  rfft_split_store<M>(s, tw, dst + ch * dst_ch_stride + (uint64_t)slot * M, scale);
+  rfft_split_store<M>(s, tw, dst + ch * dst_ch_stride + (uint64_t)slot * M, scale, tid, active);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -351,11 +355,11 @@ struct PlanView {
 template <int M>
 __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, uint32_t first, uint32_t count,
                                              float2* __restrict__ x, float2* __restrict__ s,
-                                             const float2* __restrict__ tw, float (&o)[4]) {
-  constexpr int Q = M / 4;
+                                             const float2* __restrict__ tw, int tid, float (&o)[FftCfg<M>::R]) {
+  constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT;
 #pragma unroll
-  for (int h = 0; h < 4; h++) {
-    const int k = threadIdx.x + h * Q;
+  for (int h = 0; h < RAD; h++) {
+    const int k = tid + h * NT;
     float2 a = make_float2(0.f, 0.f);
     for (uint32_t sl = 0; sl < count; sl++) {  // fixed order: deterministic sums
       float2 v = ypart_t[(uint64_t)(first + sl) * M + k];
@@ -365,13 +369,13 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
     x[k] = a;
   }
   __syncthreads();
-  irfft_unsplit<M>(x, tw, s);
+  irfft_unsplit<M>(x, tw, s, tid);
   __syncthreads();
-  cfft_smem<M, true>(s, tw);
-  // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(j + hQ) + {0,1}, h < 2
+  cfft_smem<M, true>(s, tw, tid);
+  // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(tid + h NT) + {0,1}, h < R/2
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    float2 z = s[M / 2 + threadIdx.x + h * Q];
+  for (int h = 0; h < RAD / 2; h++) {
+    float2 z = s[PAD(M / 2 + tid + h * NT)];
     o[2 * h] = z.x;
     o[2 * h + 1] = z.y;
   }
@@ -379,48 +383,57 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
 }
 
 template <int M>
-__global__ void __launch_bounds__(M / 4) k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk,
-                                                 PlanView steady, uint32_t n_first, const float2* __restrict__ tw,
-                                                 float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0) {
-  extern __shared__ float2 k_irfft_smem[];  // 2M float2: summed spectrum + FFT workspace (64 KB at M = 4096)
-  float2* x = k_irfft_smem;
-  float2* s = k_irfft_smem + M;
-  constexpr int Q = M / 4;
-  const uint32_t stream = blockIdx.x, t = blockIdx.y;
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
+k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
+        const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams) {
+  constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
+  extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
+  float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
+  float2* s = x + M;
+  const int tid = threadIdx.x;
+  const uint32_t sq = blockIdx.x * FPB + threadIdx.y, t = blockIdx.y;
+  const bool active = sq < n_streams;
+  const uint32_t stream = active ? sq : n_streams - 1;
   const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
   const PlanView pv = first ? first_blk : steady;
   const float2* ypart_t = ypart + (uint64_t)t * slot_stride * M;
-  float o[4];
-  job_to_block<M>(ypart_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, o);
+  float o[RAD];
+  job_to_block<M>(ypart_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
+  // the crossfade decision must be uniform across the CTA (block-wide barriers inside job_to_block):
+  // every transform of the CTA runs the second pass when any of them needs it
   const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
+  const int any_x = __syncthreads_or(xj != kNoJob && xj != kSameJob);
+  float o2[RAD];
+  if (any_x) {
+    const bool mine = (xj != kNoJob && xj != kSameJob);
+    job_to_block<M>(ypart_t, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw, tid, o2);
+  }
   if (xj != kNoJob) {
-    float o2[4];
     if (xj == kSameJob) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) o2[i] = o[i];
-    } else {
-      job_to_block<M>(ypart_t, pv.job_slot_first[xj], pv.job_slot_count[xj], x, s, tw, o2);
+      for (int i = 0; i < RAD; i++) o2[i] = o[i];
     }
     // out = (1-g) o_f + g o_f', g_n = n/B  (MixSamples + Interpolator ramp, sampled before the step)
     const float inc = 1.0f / (float)M;
 #pragma unroll
-    for (int h = 0; h < 2; h++)
+    for (int h = 0; h < RAD / 2; h++)
 #pragma unroll
       for (int c = 0; c < 2; c++) {
-        const uint32_t n = 2 * (threadIdx.x + h * Q) + c;
+        const uint32_t n = 2 * (tid + h * NT) + c;
         const float g = __fmul_rn((float)n, inc);
         const float a = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
         const float b = __fmul_rn(g, o2[2 * h + c]);
         o[2 * h + c] = __fadd_rn(a, b);
       }
   }
+  if (!active) return;
   float* ring = ybuf + (uint64_t)stream * Rd;
   const uint32_t w = (wpos0 + t * (uint32_t)M) % Rd;
 #pragma unroll
-  for (int h = 0; h < 2; h++)
+  for (int h = 0; h < RAD / 2; h++)
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-      const uint32_t n = 2 * (threadIdx.x + h * Q) + c;
+      const uint32_t n = 2 * (tid + h * NT) + c;
       uint32_t idx = w + n;
       if (idx >= Rd) idx -= Rd;
       ring[idx] = o[2 * h + c];
@@ -618,7 +631,9 @@ namespace {
 template <int M>
 void launch_rfft_t(const float* src, uint64_t ch_stride, uint32_t win_stride, float2* dst, uint64_t dst_ch_stride, uint32_t R,
                    uint32_t slot0, const float2* tw, float scale, uint32_t nch, uint32_t T, cudaStream_t st) {
-  k_rfft<M><<<dim3(nch, T), M / 4, 0, st>>>(src, ch_stride, win_stride, dst, dst_ch_stride, R, slot0, tw, scale);
+  constexpr int FPB = FftCfg<M>::FPB;
+  k_rfft<M><<<dim3(ceil_div(nch, FPB), T), dim3(FftCfg<M>::NT, FPB), 0, st>>>(src, ch_stride, win_stride, dst, dst_ch_stride, R,
+                                                                              slot0, tw, scale, nch);
 }
 
 int launch_rfft(uint32_t B, const float* src, uint64_t ch_stride, uint32_t win_stride, float2* dst, uint64_t dst_ch_stride,
@@ -639,10 +654,11 @@ int launch_rfft(uint32_t B, const float* src, uint64_t ch_stride, uint32_t win_s
 
 template <int M>
 void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, cudaStream_t st) {
-  constexpr size_t smem = 2 * sizeof(float2) * M;
+  constexpr int FPB = FftCfg<M>::FPB;
+  constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_irfft<M><<<dim3(e->n_streams, T), M / 4, smem, st>>>(e->ypart, e->max_slots, e->plan_first.view(), e->plan_steady.view(),
-                                                      n_first, e->tw, e->ybuf, e->Rd, e->wpos);
+  k_irfft<M><<<dim3(ceil_div(e->n_streams, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
+      e->ypart, e->max_slots, e->plan_first.view(), e->plan_steady.view(), n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams);
 }
 
 int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first) {

@@ -7,9 +7,14 @@
 //
 // A real transform of N = 2B points is one complex FFT of M = B points on z[n] = x[2n] + i x[2n+1]
 // plus an even/odd split.  The complex FFT is a Stockham autosort (natural order in and out, no bit
-// reversal), radix-4 passes with one radix-2 pass when log2(M) is odd, M/4 threads, data in shared
-// memory, twiddles read from a table computed in double precision on the host
+// reversal) with the data in shared memory between passes and R values per thread in registers:
+//   M = 64, 512, 4096 (powers of 8): radix-8 passes, M/8 threads per transform
+//   other powers of two            : radix-4 passes (+ one radix-2 pass), M/4 threads per transform
+// Several transforms share a CTA (threadIdx.y) so that small sizes still launch 128-256 threads.
+// Twiddles come from a table computed in double precision on the host
 // (tw[j] = exp(-2 pi i j / N), j < N; the M-point twiddle exp(-2 pi i j / M) is tw[2j]).
+// Shared-memory indices are padded by one element per eight (PAD) so that the stride-R stores of the
+// first passes are bank-conflict free.
 //
 // Spectra are stored PACKED: B complex values per row, bin 0 holds (X[0].re, X[B].re) -- DC and
 // Nyquist are both real for real input -- so a row is exactly 8B bytes (4 KB at B = 512).
@@ -25,67 +30,136 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 d) {
+  return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+}
 
-// Complex FFT of M points held in smem `s` (float2[M]); blockDim.x == M/4 threads take part.
-// INV = false: kernel exp(-i...), INV = true: exp(+i...).  Result in `s`, natural order.
-// Ends with a __syncthreads().
+template <int M>
+struct FftCfg {
+  static constexpr int R = (M == 64 || M == 512 || M == 4096) ? 8 : 4;  // values per thread
+  static constexpr int NT = M / R;                                     // threads per transform
+  static constexpr int FPB = (NT >= 256) ? 1 : ((256 / NT) > 16 ? 16 : (256 / NT));  // transforms per CTA
+  static constexpr int MP = M + M / 8;                                  // padded smem elements per transform
+};
+__device__ __forceinline__ int PAD(int i) { return i + (i >> 3); }
+
+// 4-point DFT, outputs in natural order
+template <bool INV>
+__device__ __forceinline__ void fft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = mul_mi<INV>(csub(v1, v3));
+  v0 = cadd(a0, a2);
+  v1 = cadd(a1, a3);
+  v2 = csub(a0, a2);
+  v3 = csub(a1, a3);
+}
+
+// 8-point DFT (decimation in frequency: even outputs from the sums, odd outputs from the twiddled
+// differences), outputs in natural order
+template <bool INV>
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+  constexpr float S = 0.70710678118654752440f;
+  float2 b0 = cadd(v[0], v[4]), b1 = cadd(v[1], v[5]), b2 = cadd(v[2], v[6]), b3 = cadd(v[3], v[7]);
+  float2 c0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+  // c_n = d_n * W8^n, W8 = exp(-+ i pi/4): W8^1 = (1 -+ i)/sqrt2, W8^2 = -+ i, W8^3 = (-1 -+ i)/sqrt2
+  float2 c1 = INV ? make_float2(S * (d1.x - d1.y), S * (d1.x + d1.y)) : make_float2(S * (d1.x + d1.y), S * (d1.y - d1.x));
+  float2 c2 = mul_mi<INV>(d2);
+  float2 c3 = INV ? make_float2(-S * (d3.x + d3.y), S * (d3.x - d3.y)) : make_float2(S * (d3.y - d3.x), -S * (d3.x + d3.y));
+  fft4<INV>(b0, b1, b2, b3);
+  fft4<INV>(c0, c1, c2, c3);
+  v[0] = b0;
+  v[1] = c0;
+  v[2] = b1;
+  v[3] = c1;
+  v[4] = b2;
+  v[5] = c2;
+  v[6] = b3;
+  v[7] = c3;
+}
+
+// Complex FFT of M points held in smem `s` (padded, FftCfg<M>::MP float2); threads tid = 0..NT-1 of one
+// transform take part, every thread of the CTA must call it (block-wide barriers).  Result in `s`,
+// natural order.  Ends with a __syncthreads().
 template <int M, bool INV>
-__device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* __restrict__ tw) {
-  constexpr int Q = M / 4;
-  const int j = threadIdx.x;
+__device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* __restrict__ tw, int tid) {
+  constexpr int R = FftCfg<M>::R, NT = FftCfg<M>::NT;
+  const int j = tid;
   int Ns = 1;
+  if (R == 8) {
 #pragma unroll 1
-  for (; Ns * 4 <= M; Ns *= 4) {
-    const int k = j & (Ns - 1);
-    float2 v0 = s[j], v1 = s[j + Q], v2 = s[j + 2 * Q], v3 = s[j + 3 * Q];
-    if (Ns > 1) {
-      // exp(-2 pi i r k / (4 Ns)) = tw_M[r k M/(4 Ns)] = tw[2 r k M/(4 Ns)]
-      const int stride = 2 * (M / (4 * Ns));
-      float2 w1 = __ldg(&tw[k * stride]), w2 = __ldg(&tw[2 * k * stride]), w3 = __ldg(&tw[3 * k * stride]);
-      if (INV) {
-        w1.y = -w1.y;
-        w2.y = -w2.y;
-        w3.y = -w3.y;
+    for (; Ns * 8 <= M; Ns *= 8) {
+      const int k = j & (Ns - 1);
+      float2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) v[r] = s[PAD(j + r * NT)];
+      if (Ns > 1) {
+        const int stride = 2 * (M / (8 * Ns));  // tw index of exp(-2 pi i k / (8 Ns))
+#pragma unroll
+        for (int r = 1; r < 8; r++) {
+          float2 w = __ldg(&tw[r * k * stride]);
+          if (INV) w.y = -w.y;
+          v[r] = cmul(v[r], w);
+        }
       }
-      v1 = cmul(v1, w1);
-      v2 = cmul(v2, w2);
-      v3 = cmul(v3, w3);
-    }
-    float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), d = csub(v1, v3);
-    // forward: (v1 - v3) * (-i) = (d.y, -d.x); inverse: * (+i) = (-d.y, d.x)
-    float2 a3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-    const int j0 = ((j - k) << 2) + k;
-    __syncthreads();
-    s[j0] = cadd(a0, a2);
-    s[j0 + Ns] = cadd(a1, a3);
-    s[j0 + 2 * Ns] = csub(a0, a2);
-    s[j0 + 3 * Ns] = csub(a1, a3);
-    __syncthreads();
-  }
-  if (Ns < M) {
-    // one radix-2 pass left (Ns == M/2): each thread does two butterflies
-    float2 r[4];
+      fft8<INV>(v);
+      const int j0 = ((j - k) << 3) + k;
+      __syncthreads();
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int jj = j + h * Q;  // jj < M/2
-      const int k = jj & (Ns - 1);
-      float2 v0 = s[jj], v1 = s[jj + M / 2];
-      float2 w = __ldg(&tw[2 * k * (M / (2 * Ns))]);
-      if (INV) w.y = -w.y;
-      v1 = cmul(v1, w);
-      r[2 * h] = cadd(v0, v1);
-      r[2 * h + 1] = csub(v0, v1);
+      for (int r = 0; r < 8; r++) s[PAD(j0 + r * Ns)] = v[r];
+      __syncthreads();
     }
-    __syncthreads();
+  } else {
+#pragma unroll 1
+    for (; Ns * 4 <= M; Ns *= 4) {
+      const int k = j & (Ns - 1);
+      float2 v0 = s[PAD(j)], v1 = s[PAD(j + NT)], v2 = s[PAD(j + 2 * NT)], v3 = s[PAD(j + 3 * NT)];
+      if (Ns > 1) {
+        const int stride = 2 * (M / (4 * Ns));
+        float2 w1 = __ldg(&tw[k * stride]), w2 = __ldg(&tw[2 * k * stride]), w3 = __ldg(&tw[3 * k * stride]);
+        if (INV) {
+          w1.y = -w1.y;
+          w2.y = -w2.y;
+          w3.y = -w3.y;
+        }
+        v1 = cmul(v1, w1);
+        v2 = cmul(v2, w2);
+        v3 = cmul(v3, w3);
+      }
+      fft4<INV>(v0, v1, v2, v3);
+      const int j0 = ((j - k) << 2) + k;
+      __syncthreads();
+      s[PAD(j0)] = v0;
+      s[PAD(j0 + Ns)] = v1;
+      s[PAD(j0 + 2 * Ns)] = v2;
+      s[PAD(j0 + 3 * Ns)] = v3;
+      __syncthreads();
+    }
+    if (Ns < M) {
+      // one radix-2 pass left (Ns == M/2): each thread does two butterflies
+      float2 r[4];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int jj = j + h * Q;
-      const int k = jj & (Ns - 1);
-      const int j0 = ((jj - k) << 1) + k;
-      s[j0] = r[2 * h];
-      s[j0 + Ns] = r[2 * h + 1];
+      for (int h = 0; h < 2; h++) {
+        const int jj = j + h * NT;  // jj < M/2
+        const int k = jj & (Ns - 1);
+        float2 v0 = s[PAD(jj)], v1 = s[PAD(jj + M / 2)];
+        float2 w = __ldg(&tw[2 * k * (M / (2 * Ns))]);
+        if (INV) w.y = -w.y;
+        v1 = cmul(v1, w);
+        r[2 * h] = cadd(v0, v1);
+        r[2 * h + 1] = csub(v0, v1);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int jj = j + h * NT;
+        const int k = jj & (Ns - 1);
+        const int j0 = ((jj - k) << 1) + k;
+        s[PAD(j0)] = r[2 * h];
+        s[PAD(j0 + Ns)] = r[2 * h + 1];
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -94,40 +168,37 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
 //   X[k] = E + w^k O,  E = (Z[k] + conj Z[M-k])/2,  O = -i (Z[k] - conj Z[M-k])/2,  w = exp(-2 pi i / 2M)
 template <int M>
 __device__ __forceinline__ void rfft_split_store(const float2* __restrict__ s, const float2* __restrict__ tw,
-                                                 float2* __restrict__ out, float scale) {
-  constexpr int Q = M / 4;
-  const int j = threadIdx.x;
+                                                 float2* __restrict__ out, float scale, int tid, bool active) {
+  constexpr int R = FftCfg<M>::R, NT = FftCfg<M>::NT;
 #pragma unroll
-  for (int h = 0; h < 4; h++) {
-    const int k = j + h * Q;  // 0 .. M-1
+  for (int h = 0; h < R; h++) {
+    const int k = tid + h * NT;  // 0 .. M-1
     float2 x;
     if (k == 0) {
       float2 z0 = s[0];
       x = make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
     } else {
-      float2 a = s[k], b = s[M - k];
+      float2 a = s[PAD(k)], b = s[PAD(M - k)];
       float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
       float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
       float2 o = make_float2(d.y, -d.x);
       float2 t = cmul(o, __ldg(&tw[k]));
       x = cadd(e, t);
     }
-    out[k] = make_float2(x.x * scale, x.y * scale);
+    if (active) out[k] = make_float2(x.x * scale, x.y * scale);
   }
 }
 
-// Inverse split: packed half spectrum X (M complex, already summed) -> Z in smem such that
-// IFFT_M(Z) = (y[2n] + i y[2n+1]) * 2M-scaling of an unnormalised c2r.
+// Inverse split: packed half spectrum X (M complex, already summed, unpadded smem `x`) -> Z in padded
+// smem `s` such that IFFT_M(Z) = (y[2n] + i y[2n+1]) of an unnormalised c2r.
 //   Z[k] = (X[k] + conj X[M-k]) + i conj(w^k) (X[k] - conj X[M-k])
-// `x` is a smem copy of the packed spectrum; result written to `s` (distinct array).
 template <int M>
 __device__ __forceinline__ void irfft_unsplit(const float2* __restrict__ x, const float2* __restrict__ tw,
-                                              float2* __restrict__ s) {
-  constexpr int Q = M / 4;
-  const int j = threadIdx.x;
+                                              float2* __restrict__ s, int tid) {
+  constexpr int R = FftCfg<M>::R, NT = FftCfg<M>::NT;
 #pragma unroll
-  for (int h = 0; h < 4; h++) {
-    const int k = j + h * Q;
+  for (int h = 0; h < R; h++) {
+    const int k = tid + h * NT;
     float2 z;
     if (k == 0) {
       float2 p = x[0];  // (DC, Nyquist)
@@ -141,7 +212,7 @@ __device__ __forceinline__ void irfft_unsplit(const float2* __restrict__ x, cons
       float2 t = cmul(d, w);
       z = make_float2(e.x - t.y, e.y + t.x);
     }
-    s[k] = z;
+    s[PAD(k)] = z;
   }
 }
 
