@@ -48,6 +48,7 @@ struct PcmInArgs {
   const float* xin_prev;  // previous call's buffer
   uint32_t xstride;
   uint32_t prev_off;      // offset of the previous call's last block inside xin_prev rows
+  int fast;               // little-endian, base and frame stride aligned to the sample size: typed loads
 };
 
 __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
       uint32_t fl = warp + 8 * i, c = c0 + lane;
       uint32_t frame = f0 + fl - a.B;
       float v = 0.f;
-      if (c < a.n_inputs) v = load_as_f32(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps, a.fmt, a.be != 0);
+      if (c < a.n_inputs) v = load_as_f32(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps, a.fmt, a.be != 0, a.fast != 0);
       tile[fl][lane] = v;
     }
     __syncthreads();
@@ -361,10 +362,18 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
   for (int h = 0; h < RAD; h++) {
     const int k = tid + h * NT;
     float2 a = make_float2(0.f, 0.f);
-    for (uint32_t sl = 0; sl < count; sl++) {  // fixed order: deterministic sums
-      float2 v = ypart_t[(uint64_t)(first + sl) * M + k];
-      a.x += v.x;
-      a.y += v.y;
+    // fixed slot order (deterministic sums); four loads in flight per step
+    for (uint32_t sl = 0; sl < count; sl += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        v[q] = (sl + q < count) ? ypart_t[(uint64_t)(first + sl + q) * M + k] : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (sl + q < count) {
+          a.x += v[q].x;
+          a.y += v[q].y;
+        }
     }
     x[k] = a;
   }
@@ -450,6 +459,8 @@ struct RouteView {
   const double* delay_cur;     // per stream, delay in force after this call's first block boundary
   const double* delay_old;     // per stream, delay before it
   const uint32_t* dflags;      // per stream, bit0: crossfade old->cur over the first block
+  const uint32_t* idelay_cur;  // per stream, (uint32)delay mod Rd for the integer-delay mode
+  const uint32_t* idelay_old;
 };
 
 struct PcmOutArgs {
@@ -461,18 +472,22 @@ struct PcmOutArgs {
   const float* ybuf;
   uint32_t Rd, wpos0;
   int fractional;
+  int fast;  // typed stores (see PcmInArgs::fast)
   RouteView rv;
 };
 
 __device__ __forceinline__ float delayed_read(const float* __restrict__ ring, uint32_t Rd, uint32_t w, uint32_t n, double d,
-                                              int fractional) {
+                                              uint32_t di, int fractional) {
   if (fractional) {
     // FractionalSample(ring, 0, 1, Rd, fmod((w + n + Rd) - d, Rd))   (src/FractionalSample.cpp:312-341)
     const double pos = fmod((double)(w + n + Rd) - d, (double)Rd);
     return __double2float_rn(fractional_sample_dev<float>(ring, 0, 1, Rd, pos));
   }
-  const uint32_t di = (uint32_t)d % Rd;  // ring[(w + n - d) mod R]   (src/SoundDelayBuffer.cpp:141)
-  return ring[(w + n + Rd - di) % Rd];
+  // ring[(w + n - d) mod R] with d = (uint)delay mod R precomputed on the host   (src/SoundDelayBuffer.cpp:141)
+  uint32_t idx = w + n + Rd - di;  // w < Rd, n < B <= Rd, di < Rd  ->  idx < 3 Rd
+  if (idx >= Rd) idx -= Rd;
+  if (idx >= Rd) idx -= Rd;
+  return ring[idx];
 }
 
 __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
@@ -495,9 +510,10 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
         const float gain = a.rv.gain[st];
         if (!(gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
         const float* ring = a.ybuf + (uint64_t)st * a.Rd;
-        float v = delayed_read(ring, a.Rd, w, n, a.rv.delay_cur[st], a.fractional);
+        const double dc = a.fractional ? a.rv.delay_cur[st] : 0.0;
+        float v = delayed_read(ring, a.Rd, w, n, dc, a.rv.idelay_cur[st], a.fractional);
         if (t == 0 && (a.rv.dflags[st] & 1u)) {
-          const float vo = delayed_read(ring, a.Rd, w, n, a.rv.delay_old[st], a.fractional);
+          const float vo = delayed_read(ring, a.Rd, w, n, a.rv.delay_old[st], a.rv.idelay_old[st], a.fractional);
           const float g = __fmul_rn((float)n, inc);
           v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
         }
@@ -514,7 +530,7 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
     const uint32_t fl = warp + 8 * i, o = c0 + lane;
     if (o >= a.n_outputs) continue;
     const uint32_t frame = f0 + fl;
-    store_from_f32(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0);
+    store_from_f32(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0, a.fast != 0);
   }
 }
 
@@ -601,7 +617,8 @@ struct bbx_engine {
   // route tables (device blob + pinned staging)
   uint8_t* h_route = nullptr;
   uint8_t* d_route = nullptr;
-  size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0;
+  size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0,
+         roff_icur = 0, roff_iold = 0;
   bool route_dirty = true;
   // plans
   MacPlan plan_first, plan_steady;
@@ -913,12 +930,15 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
   double* dcur = (double*)(e->h_route + e->roff_dcur);
   double* dold = (double*)(e->h_route + e->roff_dold);
   uint32_t* flags = (uint32_t*)(e->h_route + e->roff_flags);
+  uint32_t* icur = (uint32_t*)(e->h_route + e->roff_icur);
+  uint32_t* iold = (uint32_t*)(e->h_route + e->roff_iold);
   if (e->mode == BBX_MODE_MIMO) {
     for (uint32_t o = 0; o < e->n_out; o++) {
       ofirst[o] = o;
       rstream[o] = o;
       gain[o] = 1.0f;
       dcur[o] = dold[o] = 0.0;
+      icur[o] = iold[o] = 0;
       flags[o] = 0;
     }
     ofirst[e->n_out] = e->n_out;
@@ -936,6 +956,8 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
       bool sw = first_block_transition && p.has_pending;
       dcur[k] = sw ? p.pend_delay : p.delay;
       dold[k] = p.delay;
+      icur[k] = (uint32_t)dcur[k] % e->Rd;
+      iold[k] = (uint32_t)dold[k] % e->Rd;
       flags[k] = (sw && p.xfade && p.pend_delay != p.delay) ? 1u : 0u;
     }
   }
@@ -951,6 +973,8 @@ RouteView route_view(const bbx_engine* e) {
   v.delay_cur = (const double*)(e->d_route + e->roff_dcur);
   v.delay_old = (const double*)(e->d_route + e->roff_dold);
   v.dflags = (const uint32_t*)(e->d_route + e->roff_flags);
+  v.idelay_cur = (const uint32_t*)(e->d_route + e->roff_icur);
+  v.idelay_old = (const uint32_t*)(e->d_route + e->roff_iold);
   return v;
 }
 
@@ -1083,6 +1107,8 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     e->roff_dcur = take(sizeof(double) * ns);
     e->roff_dold = take(sizeof(double) * ns);
     e->roff_flags = take(sizeof(uint32_t) * ns);
+    e->roff_icur = take(sizeof(uint32_t) * ns);
+    e->roff_iold = take(sizeof(uint32_t) * ns);
     e->route_bytes = off;
     BBX_CUDA_TRY(cudaHostAlloc((void**)&e->h_route, off, cudaHostAllocDefault));
     memset(e->h_route, 0, off);
@@ -1314,6 +1340,10 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     a.xin_prev = e->xin[e->parity ^ 1];
     a.xstride = e->xstride;
     a.prev_off = e->tprev * B;
+    {
+      const uint32_t bps = fmt_bytes(infmt);
+      a.fast = (!in_be && bps != 3 && ((uintptr_t)in % bps) == 0) ? 1 : 0;  // frame stride = in_channels * bps is aligned too
+    }
     dim3 grid((T + 1) * B / 32, ceil_div(e->n_in, 32));
     k_pcm_in<<<grid, 256, 0, st>>>(a);
     BBX_CUDA_TRY(cudaGetLastError());
@@ -1347,6 +1377,10 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     a.Rd = e->Rd;
     a.wpos0 = e->wpos;
     a.fractional = e->cfg.fractional_delay;
+    {
+      const uint32_t bps = fmt_bytes(outfmt);
+      a.fast = (!out_be && bps != 3 && ((uintptr_t)out % bps) == 0) ? 1 : 0;
+    }
     a.rv = route_view(e);
     dim3 grid(T * B / 32, ceil_div(e->n_out, 32));
     k_pcm_out<<<grid, 256, 0, st>>>(a);
