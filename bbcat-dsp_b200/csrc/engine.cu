@@ -157,6 +157,25 @@ __device__ __forceinline__ void cmac(float& re, float& im, const HCoef& k, float
   im = fmaf(k.c, xi, im);
 }
 
+// The same complex MAC as two packed FP32x2 FMAs (Blackwell FFMA2: one instruction, two lanes):
+//   (re, im) += (a, b) * xr ;  (re, im) += (-b, c) * xi
+// ptxas folds the scalar broadcast and the swapped / negated pair into FFMA2 operand modifiers, so the pair
+// (k1, k2) costs no extra registers for ordinary bins.  Each lane is an IEEE fma: bit-identical to cmac().
+struct HCoef2 {
+  float2 k1, k2;
+};
+__device__ __forceinline__ HCoef2 hcoef2(float hr, float hi, bool bin0) {
+  HCoef2 k;
+  const float b = bin0 ? 0.f : hi, c = bin0 ? hi : hr;
+  k.k1 = make_float2(hr, b);
+  k.k2 = make_float2(-b, c);
+  return k;
+}
+__device__ __forceinline__ void cmac_x2(float2& acc, const HCoef2& k, float2 x) {
+  acc = __ffma2_rn(k.k1, make_float2(x.x, x.x), acc);
+  acc = __ffma2_rn(k.k2, make_float2(x.y, x.y), acc);
+}
+
 // ---- streaming form: one launch covers nt block-steps, every step re-streams H and the FDL ----
 template <int U, int THREADS, int OCC, bool POLICY>
 __global__ void __launch_bounds__(THREADS, OCC)
@@ -301,12 +320,9 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
         cp_async_wait<NST - 1>();  // step qb + u has landed
         const float2 h = stage[u % NST][0][threadIdx.x];
         W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
-        const HCoef k = hcoef(h.x, h.y, bin0);
+        const HCoef2 k = hcoef2(h.x, h.y, bin0);
 #pragma unroll
-        for (int i = 0; i < TT; i++) {
-          const float2 x = W[(i - u + TT) % TT];
-          cmac(acc[i].x, acc[i].y, k, x.x, x.y);
-        }
+        for (int i = 0; i < TT; i++) cmac_x2(acc[i], k, W[(i - u + TT) % TT]);
       }
     }
     // tail: same steps with bound checks
@@ -326,12 +342,9 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
           cp_async_wait<NST - 1>();
           const float2 h = stage[u % NST][0][threadIdx.x];
           W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
-          const HCoef k = hcoef(h.x, h.y, bin0);
+          const HCoef2 k = hcoef2(h.x, h.y, bin0);
 #pragma unroll
-          for (int i = 0; i < TT; i++) {
-            const float2 x = W[(i - u + TT) % TT];
-            cmac(acc[i].x, acc[i].y, k, x.x, x.y);
-          }
+          for (int i = 0; i < TT; i++) cmac_x2(acc[i], k, W[(i - u + TT) % TT]);
         }
       }
     }
