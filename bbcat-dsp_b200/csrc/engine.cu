@@ -135,57 +135,40 @@ __device__ __forceinline__ float2 ld_stream2(const float2* p) {
   return r;
 }
 
-// One complex multiply-accumulate acc += h * x written as four FMAs whose coefficients depend on the
-// filter value only:  re += a*xr - b*xi ;  im += b*xr + c*xi  with (a, b, c) = (hr, hi, hr).
-// Bin 0 of a packed row holds (DC, Nyquist), two REAL spectra: there (a, b, c) = (hr, 0, hi) gives
-// re += hr*xr, im += hi*xi.  The selects cost two instructions per loaded h, not per FMA.
-// Every MAC kernel uses exactly this sequence, so their results are bit-identical.
-struct HCoef {
-  float a, b, c;
-};
-__device__ __forceinline__ HCoef hcoef(float hr, float hi, bool bin0) {
-  HCoef k;
-  k.a = hr;
-  k.b = bin0 ? 0.f : hi;
-  k.c = bin0 ? hi : hr;
-  return k;
-}
-__device__ __forceinline__ void cmac(float& re, float& im, const HCoef& k, float xr, float xi) {
-  re = fmaf(k.a, xr, re);
-  re = fmaf(-k.b, xi, re);
-  im = fmaf(k.b, xr, im);
-  im = fmaf(k.c, xi, im);
+// One complex multiply-accumulate acc += h * x: four FMAs in a fixed order (every MAC kernel uses exactly this
+// sequence per output, so their results are bit-identical):
+//   re = fma(hr, xr, re); re = fma(-hi, xi, re); im = fma(hi, xr, im); im = fma(hr, xi, im)
+//
+// Bin 0 of a packed row holds (DC, Nyquist), two REAL spectra.  The MAC kernels do not special-case it: column 0
+// runs the generic complex MAC, whose real part is G = sum DCh DCx - sum Nqh Nqx, and the Nyquist sum
+// N = sum Nqh Nqx is accumulated separately (one extra FMA per row in the streaming kernel, k_nyq_mac next to the
+// time-batched kernel; same order, same fma).  k_irfft restores bin 0 = (G + N, N).  This keeps selects and
+// register-pair shuffles out of the hot loops (profiles/: ALU pipe 45 % -> see DESIGN.md).
+__device__ __forceinline__ void cmac(float& re, float& im, float hr, float hi, float xr, float xi) {
+  re = fmaf(hr, xr, re);
+  re = fmaf(-hi, xi, re);
+  im = fmaf(hi, xr, im);
+  im = fmaf(hr, xi, im);
 }
 
 // The same complex MAC as two packed FP32x2 FMAs (Blackwell FFMA2: one instruction, two lanes):
-//   (re, im) += (a, b) * xr ;  (re, im) += (-b, c) * xi
-// ptxas folds the scalar broadcast and the swapped / negated pair into FFMA2 operand modifiers, so the pair
-// (k1, k2) costs no extra registers for ordinary bins.  Each lane is an IEEE fma: bit-identical to cmac().
-struct HCoef2 {
-  float2 k1, k2;
-};
-__device__ __forceinline__ HCoef2 hcoef2(float hr, float hi, bool bin0) {
-  HCoef2 k;
-  const float b = bin0 ? 0.f : hi, c = bin0 ? hi : hr;
-  k.k1 = make_float2(hr, b);
-  k.k2 = make_float2(-b, c);
-  return k;
-}
-__device__ __forceinline__ void cmac_x2(float2& acc, const HCoef2& k, float2 x) {
-  acc = __ffma2_rn(k.k1, make_float2(x.x, x.x), acc);
-  acc = __ffma2_rn(k.k2, make_float2(x.y, x.y), acc);
+//   (re, im) += (hr, hi) * xr ;  (re, im) += (-hi, hr) * xi
+// ptxas folds the scalar broadcast and the swapped / negated pair into FFMA2 operand modifiers, so no extra
+// registers or moves are needed.  Each lane is an IEEE fma: bit-identical to cmac().
+__device__ __forceinline__ void cmac_x2(float2& acc, float2 h, float2 x) {
+  acc = __ffma2_rn(h, make_float2(x.x, x.x), acc);
+  acc = __ffma2_rn(make_float2(-h.y, h.x), make_float2(x.y, x.y), acc);
 }
 
 // ---- streaming form: one launch covers nt block-steps, every step re-streams H and the FDL ----
 template <int U, int THREADS, int OCC, bool POLICY>
 __global__ void __launch_bounds__(THREADS, OCC)
 k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float4* __restrict__ fdl,
-          float4* __restrict__ ypart, uint32_t halfB, uint32_t R, uint32_t head0, uint32_t t0, uint32_t slot_stride,
-          float l2_keep, int policy_x) {
+          float4* __restrict__ ypart, float* __restrict__ nyq_part, uint32_t halfB, uint32_t R, uint32_t head0,
+          uint32_t t0, uint32_t slot_stride, float l2_keep, int policy_x) {
   const uint32_t t = t0 + blockIdx.z;
   const uint32_t head = (head0 + t) % R;
   const uint32_t col = blockIdx.y * THREADS + threadIdx.x;
-  const bool bin0 = (col == 0);
   const uint32_t sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
   uint64_t pol = 0;
   if (POLICY) {
@@ -194,9 +177,13 @@ k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
     asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(l2_keep));
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nacc = 0.f;  // Nyquist sum of the row's first slot; only column 0's copy is meaningful
   for (uint32_t si = sb; si < se; si++) {
     const MacSeg sg = segs[si];
-    if (sg.flags & 1u) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sg.flags & 1u) {
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      nacc = 0.f;
+    }
     const float4* hp = sg.H + (uint64_t)sg.p0 * halfB + col;
     const float4* xbase = fdl + (uint64_t)sg.fdl_ch * R * halfB + col;
     int slot = (int)head - (int)sg.p0;  // p0 < R
@@ -223,14 +210,18 @@ k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        cmac(acc.x, acc.y, hcoef(h[u].x, h[u].y, bin0), x[u].x, x[u].y);
-        cmac(acc.z, acc.w, hcoef(h[u].z, h[u].w, false), x[u].z, x[u].w);
+        cmac(acc.x, acc.y, h[u].x, h[u].y, x[u].x, x[u].y);
+        cmac(acc.z, acc.w, h[u].z, h[u].w, x[u].z, x[u].w);
+        nacc = fmaf(h[u].y, x[u].y, nacc);
       }
       hp += (uint64_t)U * halfB;
       slot -= U;
       if (slot < 0) slot += (int)R;
     }
-    if (sg.flags & 2u) ypart[((uint64_t)blockIdx.z * slot_stride + sg.slot) * halfB + col] = acc;
+    if (sg.flags & 2u) {
+      ypart[((uint64_t)blockIdx.z * slot_stride + sg.slot) * halfB + col] = acc;
+      if (col == 0) nyq_part[(uint64_t)blockIdx.z * slot_stride + sg.slot] = nacc;
+    }
   }
 }
 
@@ -266,7 +257,6 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
   const uint32_t tbase = ttile * TT;                  // first block-step of this tile, relative to t0
   const uint32_t s0 = (head0 + t0 + tbase) % R;       // its FDL slot
   const uint32_t col = coltile * THREADS + threadIdx.x;
-  const bool bin0 = (col == 0);
   const uint32_t sb = cta_seg_begin[blockIdx.y], se = cta_seg_begin[blockIdx.y + 1];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&stage[0][0][threadIdx.x]);
   constexpr uint32_t kStageBytes = 2 * THREADS * sizeof(float2);
@@ -320,9 +310,8 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
         cp_async_wait<NST - 1>();  // step qb + u has landed
         const float2 h = stage[u % NST][0][threadIdx.x];
         W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
-        const HCoef2 k = hcoef2(h.x, h.y, bin0);
 #pragma unroll
-        for (int i = 0; i < TT; i++) cmac_x2(acc[i], k, W[(i - u + TT) % TT]);
+        for (int i = 0; i < TT; i++) cmac_x2(acc[i], h, W[(i - u + TT) % TT]);
       }
     }
     // tail: same steps with bound checks
@@ -342,9 +331,8 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
           cp_async_wait<NST - 1>();
           const float2 h = stage[u % NST][0][threadIdx.x];
           W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
-          const HCoef2 k = hcoef2(h.x, h.y, bin0);
 #pragma unroll
-          for (int i = 0; i < TT; i++) cmac_x2(acc[i], k, W[(i - u + TT) % TT]);
+          for (int i = 0; i < TT; i++) cmac_x2(acc[i], h, W[(i - u + TT) % TT]);
         }
       }
     }
@@ -354,6 +342,36 @@ k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_s
       for (int i = 0; i < TT; i++)
         if (tbase + i < nt) ypart[((uint64_t)(tbase + i) * slot_stride + sg.slot) * B + col] = acc[i];
     }
+  }
+}
+
+// Nyquist sums next to the time-batched MAC: N[t][run] = sum over the run's rows of Nqh[p] * Nqx[s_t - p] (the
+// imaginary parts of column 0), p ascending, one fma per row -- the same sequence the streaming kernel runs inline.
+// One warp per (row range, tile of 32 block-steps), lane = block-step.
+__global__ void __launch_bounds__(32)
+k_nyq_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float2* __restrict__ fdl,
+          float* __restrict__ nyq_part, uint32_t B, uint32_t R, uint32_t head0, uint32_t t0, uint32_t nt, uint32_t slot_stride) {
+  const uint32_t tq = blockIdx.y * 32 + threadIdx.x;
+  const bool active = tq < nt;
+  const uint32_t t = active ? tq : nt - 1;
+  const uint32_t s_t = (head0 + t0 + t) % R;
+  const uint32_t sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
+  float acc = 0.f;
+  for (uint32_t si = sb; si < se; si++) {
+    const MacSeg sg = segs[si];
+    if (sg.flags & 1u) acc = 0.f;
+    const float2* hcol = reinterpret_cast<const float2*>(sg.H) + (uint64_t)sg.p0 * B;
+    const float2* xb = fdl + (uint64_t)sg.fdl_ch * R * B;
+    uint32_t row = s_t + R - (sg.p0 % R);
+    if (row >= R) row -= R;
+#pragma unroll 8
+    for (uint32_t p = 0; p < sg.np; p++) {
+      const float h = __ldg(&hcol[(uint64_t)p * B]).y;
+      const float x = __ldg(&xb[(uint64_t)row * B]).y;
+      acc = fmaf(h, x, acc);
+      row = row ? row - 1 : R - 1;
+    }
+    if ((sg.flags & 2u) && active) nyq_part[(uint64_t)t * slot_stride + sg.slot] = acc;
   }
 }
 
@@ -367,9 +385,10 @@ struct PlanView {
 };
 
 template <int M>
-__device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, uint32_t first, uint32_t count,
-                                             float2* __restrict__ x, float2* __restrict__ s,
-                                             const float2* __restrict__ tw, int tid, float (&o)[FftCfg<M>::R]) {
+__device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, const float* __restrict__ nyq_t,
+                                             uint32_t first, uint32_t count, float2* __restrict__ x,
+                                             float2* __restrict__ s, const float2* __restrict__ tw, int tid,
+                                             float (&o)[FftCfg<M>::R]) {
   constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT;
 #pragma unroll
   for (int h = 0; h < RAD; h++) {
@@ -387,6 +406,12 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
           a.x += v[q].x;
           a.y += v[q].y;
         }
+    }
+    if (k == 0) {
+      // bin 0: the MAC kernels left G = DC - N in the real part; add the Nyquist sum back (same slot order)
+      float n = 0.f;
+      for (uint32_t sl = 0; sl < count; sl++) n += nyq_t[first + sl];
+      a = make_float2(a.x + n, n);
     }
     x[k] = a;
   }
@@ -407,7 +432,8 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
 template <int M>
 __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
 k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
-        const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams) {
+        const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
+        const float* __restrict__ nyq_part) {
   constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
   extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
   float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
@@ -419,8 +445,9 @@ k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_b
   const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
   const PlanView pv = first ? first_blk : steady;
   const float2* ypart_t = ypart + (uint64_t)t * slot_stride * M;
+  const float* nyq_t = nyq_part + (uint64_t)t * slot_stride;
   float o[RAD];
-  job_to_block<M>(ypart_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
+  job_to_block<M>(ypart_t, nyq_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
   // the crossfade decision must be uniform across the CTA (block-wide barriers inside job_to_block):
   // every transform of the CTA runs the second pass when any of them needs it
   const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
@@ -428,7 +455,7 @@ k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_b
   float o2[RAD];
   if (any_x) {
     const bool mine = (xj != kNoJob && xj != kSameJob);
-    job_to_block<M>(ypart_t, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw, tid, o2);
+    job_to_block<M>(ypart_t, nyq_t, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw, tid, o2);
   }
   if (xj != kNoJob) {
     if (xj == kSameJob) {
@@ -615,6 +642,7 @@ struct bbx_engine {
   float* xin[2] = {nullptr, nullptr};
   float2* fdl = nullptr;
   float2* ypart = nullptr;
+  float* nyq_part = nullptr;  // [Tmax][max_slots] Nyquist partial sums (see cmac)
   float* ybuf = nullptr;
   // host-pointer path: double-buffered PCM staging, copies on their own streams so that the H2D of call
   // n+1 and the D2H of call n-1 overlap the kernels of call n
@@ -688,7 +716,8 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, cudaStream_t st
   constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_irfft<M><<<dim3(ceil_div(e->n_streams, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
-      e->ypart, e->max_slots, e->plan_first.view(), e->plan_steady.view(), n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams);
+      e->ypart, e->max_slots, e->plan_first.view(), e->plan_steady.view(), n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams,
+      e->nyq_part);
 }
 
 int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first) {
@@ -712,6 +741,7 @@ void launch_mac_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cu
   const uint32_t halfB = e->B / 2;
   dim3 grid(pl.n_ctas, halfB / THREADS, nt);
   float4* yp = (float4*)e->ypart + (uint64_t)t0 * e->max_slots * halfB;
+  float* nq = e->nyq_part + (uint64_t)t0 * e->max_slots;
   const MacSeg* segs = pl.segs();
   const uint32_t* cta = pl.cta_seg_begin();
   const float4* fdl = (const float4*)e->fdl;
@@ -722,9 +752,9 @@ void launch_mac_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cu
 #define BBX_MAC_LAUNCH(U, OCC)                                                                                            \
   do {                                                                                                                    \
     if (keep > 0.f)                                                                                                       \
-      k_fdl_mac<U, THREADS, OCC, true><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
+      k_fdl_mac<U, THREADS, OCC, true><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, nq, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
     else                                                                                                                  \
-      k_fdl_mac<U, THREADS, OCC, false><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
+      k_fdl_mac<U, THREADS, OCC, false><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, nq, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
   } while (0)
   // resident CTAs per SM <-> loads in flight per thread: fewer, fatter CTAs unroll deeper
   switch (e->mac_occ) {
@@ -743,6 +773,7 @@ void launch_mac_tb_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt,
   float2* yp = e->ypart + (uint64_t)t0 * e->max_slots * e->B;
   k_fdl_mac_tb<TT, THREADS, 8><<<grid, THREADS, 0, st>>>(pl.segs(), pl.cta_seg_begin(), e->fdl, yp, e->B, e->R, e->head, t0, nt,
                                                         ncol, e->max_slots);
+
 }
 
 template <int TT>
@@ -769,9 +800,11 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
   const uint32_t halfB = e->B / 2;
   // the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters
   const uint32_t tb = e->mac_time_tile;  // 0: streaming only
+  bool used_tb = false;
   if (tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb) {
     if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
     else launch_mac_tb<16>(e, pl, t0, nt, st);
+    used_tb = true;
   } else if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
   else if (halfB == 128) launch_mac_t<128>(e, pl, t0, nt, st);
   else if (halfB == 64) launch_mac_t<64>(e, pl, t0, nt, st);
@@ -779,6 +812,14 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
   BBX_CUDA_TRY(cudaGetLastError());
   if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
   e->launches++;
+  if (used_tb) {
+    // Nyquist sums of column 0 (the streaming kernel accumulates them inline)
+    k_nyq_mac<<<dim3(pl.n_ctas, ceil_div(nt, 32)), 32, 0, st>>>(pl.segs(), pl.cta_seg_begin(), e->fdl,
+                                                               e->nyq_part + (uint64_t)t0 * e->max_slots, e->B, e->R, e->head,
+                                                               t0, nt, e->max_slots);
+    BBX_CUDA_TRY(cudaGetLastError());
+    e->launches++;
+  }
   e->mac_launches++;
   e->mac_units += (uint64_t)e->n_streams * nt;
   // 16 P K + 16 K + (bytes_in + bytes_out) B per channel-block, K = B + 1
@@ -1104,6 +1145,8 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   size_t ypart_bytes = sizeof(float2) * (size_t)e->Tmax * e->max_slots * B;
   BBX_CUDA_TRY(cudaMalloc((void**)&e->ypart, ypart_bytes));
   BBX_CUDA_TRY(cudaMemset(e->ypart, 0, ypart_bytes));
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->nyq_part, sizeof(float) * (size_t)e->Tmax * e->max_slots));
+  BBX_CUDA_TRY(cudaMemset(e->nyq_part, 0, sizeof(float) * (size_t)e->Tmax * e->max_slots));
 
   // route tables
   {
@@ -1143,6 +1186,7 @@ int bbx_engine_destroy(bbx_engine* e) {
   cudaFree(e->xin[1]);
   cudaFree(e->fdl);
   cudaFree(e->ypart);
+  cudaFree(e->nyq_part);
   cudaFree(e->ybuf);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_in[i]);
