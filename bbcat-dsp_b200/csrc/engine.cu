@@ -364,7 +364,7 @@ k_nyq_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_
     const float2* xb = fdl + (uint64_t)sg.fdl_ch * R * B;
     uint32_t row = s_t + R - (sg.p0 % R);
     if (row >= R) row -= R;
-#pragma unroll 8
+#pragma unroll 16
     for (uint32_t p = 0; p < sg.np; p++) {
       const float h = __ldg(&hcol[(uint64_t)p * B]).y;
       const float x = __ldg(&xb[(uint64_t)row * B]).y;
@@ -650,6 +650,8 @@ struct bbx_engine {
   uint8_t* d_out[2] = {nullptr, nullptr};
   size_t d_io_bytes = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_aux = nullptr;  // side stream: k_nyq_mac runs next to the time-batched MAC
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   cudaEvent_t ev_join_in = nullptr, ev_join_out = nullptr;
   uint64_t host_calls = 0;
@@ -795,16 +797,27 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     }
     ev0 = e->mac_events[e->mac_events_used++];
     ev1 = e->mac_events[e->mac_events_used++];
-    BBX_CUDA_TRY(cudaEventRecord(ev0, st));
   }
   const uint32_t halfB = e->B / 2;
   // the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters
   const uint32_t tb = e->mac_time_tile;  // 0: streaming only
-  bool used_tb = false;
-  if (tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb) {
+  const bool use_tb = tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb;
+  if (use_tb) {
+    // Nyquist sums of column 0 (the streaming kernel accumulates them inline): a few hundred latency-bound warps,
+    // forked onto the side stream so they run underneath the MAC instead of after it
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
+    k_nyq_mac<<<dim3(pl.n_ctas, ceil_div(nt, 32)), 32, 0, e->s_aux>>>(pl.segs(), pl.cta_seg_begin(), e->fdl,
+                                                                     e->nyq_part + (uint64_t)t0 * e->max_slots, e->B, e->R,
+                                                                     e->head, t0, nt, e->max_slots);
+    BBX_CUDA_TRY(cudaGetLastError());
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_join, e->s_aux));
+    e->launches++;
+  }
+  if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+  if (use_tb) {
     if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
     else launch_mac_tb<16>(e, pl, t0, nt, st);
-    used_tb = true;
   } else if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
   else if (halfB == 128) launch_mac_t<128>(e, pl, t0, nt, st);
   else if (halfB == 64) launch_mac_t<64>(e, pl, t0, nt, st);
@@ -812,14 +825,7 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
   BBX_CUDA_TRY(cudaGetLastError());
   if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
   e->launches++;
-  if (used_tb) {
-    // Nyquist sums of column 0 (the streaming kernel accumulates them inline)
-    k_nyq_mac<<<dim3(pl.n_ctas, ceil_div(nt, 32)), 32, 0, st>>>(pl.segs(), pl.cta_seg_begin(), e->fdl,
-                                                               e->nyq_part + (uint64_t)t0 * e->max_slots, e->B, e->R, e->head,
-                                                               t0, nt, e->max_slots);
-    BBX_CUDA_TRY(cudaGetLastError());
-    e->launches++;
-  }
+  if (use_tb) BBX_CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
   e->mac_launches++;
   e->mac_units += (uint64_t)e->n_streams * nt;
   // 16 P K + 16 K + (bytes_in + bytes_out) B per channel-block, K = B + 1
@@ -1098,6 +1104,9 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
   BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
+  BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) {
     BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
     BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
@@ -1181,6 +1190,7 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
+  if (e->s_aux) cudaStreamSynchronize(e->s_aux);
   cudaFree(e->tw);
   cudaFree(e->xin[0]);
   cudaFree(e->xin[1]);
@@ -1199,6 +1209,9 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->ev_join_out) cudaEventDestroy(e->ev_join_out);
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
+  if (e->s_aux) cudaStreamDestroy(e->s_aux);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   cudaFree(e->flush_buf);
   cudaFree(e->d_route);
   cudaFreeHost(e->h_route);
