@@ -616,6 +616,7 @@ struct MacPlan {
   // offsets inside the blob
   size_t off_segs = 0, off_cta = 0, off_first = 0, off_count = 0, off_xjob = 0;
   uint32_t n_ctas = 0, n_slots = 0, n_jobs = 0, total_rows = 0, n_terms = 0;
+  uint32_t occ = 1;  // streaming-MAC variant this plan was cut for (CTAs per SM <-> unroll depth)
   bool valid = false;
   const MacSeg* segs() const { return (const MacSeg*)(d_blob + off_segs); }
   const uint32_t* cta_seg_begin() const { return (const uint32_t*)(d_blob + off_cta); }
@@ -759,7 +760,7 @@ void launch_mac_t(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, cu
       k_fdl_mac<U, THREADS, OCC, false><<<grid, THREADS, 0, st>>>(segs, cta, fdl, yp, nq, halfB, e->R, e->head, t0, e->max_slots, keep, px); \
   } while (0)
   // resident CTAs per SM <-> loads in flight per thread: fewer, fatter CTAs unroll deeper
-  switch (e->mac_occ) {
+  switch (pl.occ) {
     case 1: BBX_MAC_LAUNCH(16, 1); break;
     case 2: BBX_MAC_LAUNCH(8, 2); break;
     case 3: BBX_MAC_LAUNCH(6, 3); break;
@@ -879,7 +880,10 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
   } else {
     // even split of the flattened row space; small problems get fewer, fatter CTAs
     const uint32_t min_rows = 4;
-    uint32_t G = std::min(kNumSMs * e->mac_occ, std::max(1u, total / min_rows));
+    // short filters (<= 8 partitions per term, e.g. the 64x64 MIMO matrix) cannot fill a 16-deep unroll: cut the
+    // plan for two resident CTAs per SM with 8 rows in flight each instead
+    pl.occ = (nterms && total / nterms <= 8 && e->mac_occ < 2) ? 2u : e->mac_occ;
+    uint32_t G = std::min(kNumSMs * pl.occ, std::max(1u, total / min_rows));
     uint32_t rpc = ceil_div(total, G);
     G = ceil_div(total, rpc);
     uint32_t nseg = 0, nslot = 0, row = 0, cur_cta = 0;
@@ -1488,6 +1492,20 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   }
   const int k = (int)(e->host_calls & 1);
   e->host_calls++;
+  if (nframes / e->B < 8) {
+    // short (real-time) calls: nothing to overlap, so keep copy -> kernels -> copy on the engine stream and skip the
+    // cross-stream events (latency path); ordering against earlier pipelined calls via their events
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[k], 0));
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_d2h[k], 0));
+    BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    if (out_channels > e->n_out) BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out[k], out, out_bytes, cudaMemcpyHostToDevice, e->stream));
+    int rc1 = bbx_process_dev(e, e->d_in[k], infmt, in_be, in_channels, e->d_out[k], outfmt, out_be, out_channels, nframes);
+    if (rc1) return rc1;
+    BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out[k], out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_comp[k], e->stream));
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_d2h[k], e->stream));
+    return BBX_OK;
+  }
   // H2D on the input-copy stream, once the kernels of call n-2 have finished reading this staging buffer
   BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
   BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
