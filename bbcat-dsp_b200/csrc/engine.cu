@@ -1492,20 +1492,6 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   }
   const int k = (int)(e->host_calls & 1);
   e->host_calls++;
-  if (nframes / e->B < 8) {
-    // short (real-time) calls: nothing to overlap, so keep copy -> kernels -> copy on the engine stream and skip the
-    // cross-stream events (latency path); ordering against earlier pipelined calls via their events
-    BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[k], 0));
-    BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_d2h[k], 0));
-    BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->stream));
-    if (out_channels > e->n_out) BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out[k], out, out_bytes, cudaMemcpyHostToDevice, e->stream));
-    int rc1 = bbx_process_dev(e, e->d_in[k], infmt, in_be, in_channels, e->d_out[k], outfmt, out_be, out_channels, nframes);
-    if (rc1) return rc1;
-    BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out[k], out_bytes, cudaMemcpyDeviceToHost, e->stream));
-    BBX_CUDA_TRY(cudaEventRecord(e->ev_comp[k], e->stream));
-    BBX_CUDA_TRY(cudaEventRecord(e->ev_d2h[k], e->stream));
-    return BBX_OK;
-  }
   // H2D on the input-copy stream, once the kernels of call n-2 have finished reading this staging buffer
   BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
   BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
