@@ -31,7 +31,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("block_size", u32), ("max_partitions", u32), ("n_inputs", u32),
                 ("n_outputs", u32), ("n_paths", u32), ("mode", C.c_int), ("max_blocks", u32), ("max_delay", u32),
                 ("fractional_delay", C.c_int), ("ring_length", u32), ("mac_ctas_per_sm", u32), ("mac_l2_keep_16ths", u32),
-                ("mac_time_tile", u32), ("reserved", u32 * 5)]
+                ("mac_time_tile", u32), ("mimo_tensor", u32), ("reserved", u32 * 4)]
 
 
 # every symbol include/bbx.h declares: name -> (restype, argtypes)
@@ -100,6 +100,7 @@ SYMBOLS = {
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
+    "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -326,7 +327,7 @@ class Convolver:
 
     def __init__(self, block_size, max_partitions, n_inputs, n_outputs=0, n_paths=0, mode=MODE_PER_CHANNEL,
                  max_blocks=1, max_delay=0, fractional_delay=False, ring_length=0, device=0, mac_ctas_per_sm=0,
-                 mac_l2_keep_16ths=0, mac_time_tile=0):
+                 mac_l2_keep_16ths=0, mac_time_tile=0, mimo_tensor=0):
         cfg = Config()
         cfg.device = device
         cfg.block_size = block_size
@@ -342,6 +343,7 @@ class Convolver:
         cfg.mac_ctas_per_sm = mac_ctas_per_sm
         cfg.mac_l2_keep_16ths = mac_l2_keep_16ths
         cfg.mac_time_tile = mac_time_tile
+        cfg.mimo_tensor = mimo_tensor
         h = vp()
         _check(lib().bbx_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -426,6 +428,12 @@ class Convolver:
     def set_tuning(self, ctas_per_sm=0, l2_keep_16ths=0, time_tile=0):
         """0 = leave as is; time_tile=1 forces the streaming MAC, l2_keep_16ths > 16 switches the hints off."""
         _check(lib().bbx_engine_set_tuning(self.h, ctas_per_sm, l2_keep_16ths, time_tile))
+
+    def tensor_status(self):
+        """(launches of the tensor-core MIMO kernel so far, device status word: 0 = ok)."""
+        n, st = u64(0), C.c_int(0)
+        _check(lib().bbx_engine_tensor_status(self.h, C.byref(n), C.byref(st)))
+        return n.value, st.value
 
     def flush_l2(self, nbytes=256 << 20):
         _check(lib().bbx_engine_flush_l2(self.h, nbytes))

@@ -28,6 +28,7 @@
 #include "fft.cuh"
 #include "formats.cuh"
 #include "fracsample.cuh"
+#include "mimo_tc.cuh"
 
 namespace bbx {
 
@@ -407,8 +408,9 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
           a.y += v[q].y;
         }
     }
-    if (k == 0) {
+    if (k == 0 && nyq_t) {
       // bin 0: the MAC kernels left G = DC - N in the real part; add the Nyquist sum back (same slot order)
+      // (nyq_t == NULL: the tensor-core MIMO path writes bin 0 = (DC, Nyquist) directly)
       float n = 0.f;
       for (uint32_t sl = 0; sl < count; sl++) n += nyq_t[first + sl];
       a = make_float2(a.x + n, n);
@@ -445,7 +447,7 @@ k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_b
   const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
   const PlanView pv = first ? first_blk : steady;
   const float2* ypart_t = ypart + (uint64_t)t * slot_stride * M;
-  const float* nyq_t = nyq_part + (uint64_t)t * slot_stride;
+  const float* nyq_t = nyq_part ? nyq_part + (uint64_t)t * slot_stride : nullptr;
   float o[RAD];
   job_to_block<M>(ypart_t, nyq_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
   // the crossfade decision must be uniform across the CTA (block-wide barriers inside job_to_block):
@@ -685,6 +687,20 @@ struct bbx_engine {
   double mac_ms_total = 0.0;
   uint64_t mac_launches = 0, mac_units = 0, mac_bytes = 0;
   int last_infmt = FMT_F32, last_outfmt = FMT_F32;
+  // MIMO on the tensor cores (mimo_tc.cuh): bin-major operand copies and a one-slot-per-output plan view
+  bool tc_on = false;          // buffers exist (MIMO mode, max_blocks >= tc_min_blocks, not disabled)
+  bool tc_dirty = true;        // Hpack must be rebuilt from the current filter matrix
+  uint32_t tc_min_blocks = 16; // calls with fewer blocks use the streaming SIMT MAC
+  uint32_t tc_P2 = 1, tc_P2log = 0, tc_G = 0, tc_nog = 0, tc_W = 0;
+  float4* tc_hpack = nullptr;
+  float2* tc_xb = nullptr;
+  const float2** tc_ftab_h = nullptr;  // pinned staging [n_out][n_in]
+  const float2** tc_ftab_d = nullptr;
+  uint32_t* tc_fparts_h = nullptr;
+  uint32_t* tc_fparts_d = nullptr;
+  uint32_t* tc_view = nullptr;  // device: first[n_out] | count[n_out] | xjob[n_out]
+  int* tc_status = nullptr;
+  uint64_t tc_launches = 0;
 };
 
 namespace {
@@ -713,26 +729,37 @@ int launch_rfft(uint32_t B, const float* src, uint64_t ch_stride, uint32_t win_s
   return BBX_OK;
 }
 
+// view of the tensor-core MIMO result: output o = slot o, one slot per job, no crossfade
+PlanView tc_plan_view(const bbx_engine* e) {
+  PlanView v;
+  v.job_slot_first = e->tc_view;
+  v.job_slot_count = e->tc_view + e->n_out;
+  v.xjob = e->tc_view + 2 * (size_t)e->n_out;
+  return v;
+}
+
 template <int M>
-void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, cudaStream_t st) {
+void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaStream_t st) {
   constexpr int FPB = FftCfg<M>::FPB;
   constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const PlanView first = tc ? tc_plan_view(e) : e->plan_first.view();
+  const PlanView steady = tc ? tc_plan_view(e) : e->plan_steady.view();
   k_irfft<M><<<dim3(ceil_div(e->n_streams, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
-      e->ypart, e->max_slots, e->plan_first.view(), e->plan_steady.view(), n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams,
-      e->nyq_part);
+      e->ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams,
+      tc ? nullptr : e->nyq_part);
 }
 
-int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first) {
+int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc = false) {
   cudaStream_t st = e->stream;
   switch (e->B) {
-    case 64: launch_irfft_t<64>(e, T, n_first, st); break;
-    case 128: launch_irfft_t<128>(e, T, n_first, st); break;
-    case 256: launch_irfft_t<256>(e, T, n_first, st); break;
-    case 512: launch_irfft_t<512>(e, T, n_first, st); break;
-    case 1024: launch_irfft_t<1024>(e, T, n_first, st); break;
-    case 2048: launch_irfft_t<2048>(e, T, n_first, st); break;
-    case 4096: launch_irfft_t<4096>(e, T, n_first, st); break;
+    case 64: launch_irfft_t<64>(e, T, n_first, tc, st); break;
+    case 128: launch_irfft_t<128>(e, T, n_first, tc, st); break;
+    case 256: launch_irfft_t<256>(e, T, n_first, tc, st); break;
+    case 512: launch_irfft_t<512>(e, T, n_first, tc, st); break;
+    case 1024: launch_irfft_t<1024>(e, T, n_first, tc, st); break;
+    case 2048: launch_irfft_t<2048>(e, T, n_first, tc, st); break;
+    case 4096: launch_irfft_t<4096>(e, T, n_first, tc, st); break;
     default: set_error("unsupported block size %u", e->B); return BBX_ERR_UNSUPPORTED;
   }
   BBX_CUDA_TRY(cudaGetLastError());
@@ -1044,6 +1071,118 @@ RouteView route_view(const bbx_engine* e) {
 
 bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
+// ---- MIMO on the tensor cores ----
+int tc_alloc(bbx_engine* e) {
+  uint32_t P2 = 1, lg = 0;
+  while (P2 < e->Pmax) {
+    P2 <<= 1;
+    lg++;
+  }
+  e->tc_P2 = P2;
+  e->tc_P2log = lg;
+  const uint32_t Kc = ceil_div(e->n_in * P2, (uint32_t)kTcChunk) * kTcChunk;  // complex K, padded to whole chunks
+  e->tc_G = Kc / 2;
+  e->tc_nog = ceil_div(e->n_out, 64u);
+  e->tc_W = P2 - 1 + ceil_div(e->Tmax, (uint32_t)kTcNmax) * kTcNmax;
+  const size_t hbytes = sizeof(float4) * (size_t)e->tc_nog * e->B * e->tc_G * 64;
+  const size_t xbytes = sizeof(float2) * (size_t)e->B * e->n_in * e->tc_W;
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_hpack, hbytes));
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_xb, xbytes));
+  BBX_CUDA_TRY(cudaMemset(e->tc_xb, 0, xbytes));
+  const size_t npaths = (size_t)e->n_out * e->n_in;
+  BBX_CUDA_TRY(cudaHostAlloc((void**)&e->tc_ftab_h, sizeof(float2*) * npaths, cudaHostAllocDefault));
+  BBX_CUDA_TRY(cudaHostAlloc((void**)&e->tc_fparts_h, sizeof(uint32_t) * npaths, cudaHostAllocDefault));
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_ftab_d, sizeof(float2*) * npaths));
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_fparts_d, sizeof(uint32_t) * npaths));
+  std::vector<uint32_t> view(3 * (size_t)e->n_out);
+  for (uint32_t o = 0; o < e->n_out; o++) {
+    view[o] = o;
+    view[e->n_out + o] = 1;
+    view[2 * (size_t)e->n_out + o] = kNoJob;
+  }
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_view, sizeof(uint32_t) * view.size()));
+  BBX_CUDA_TRY(cudaMemcpy(e->tc_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
+  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_status, sizeof(int)));
+  BBX_CUDA_TRY(cudaMemset(e->tc_status, 0, sizeof(int)));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  e->tc_on = true;
+  e->tc_dirty = true;
+  return BBX_OK;
+}
+
+// rebuild the bin-major filter operand from the current filter matrix
+int tc_pack_filters(bbx_engine* e) {
+  int rc = wait_uploads(e);
+  if (rc) return rc;
+  const size_t npaths = (size_t)e->n_out * e->n_in;
+  for (size_t k = 0; k < npaths; k++) {
+    const bbx_filter* f = e->paths[k].cur;
+    e->tc_ftab_h[k] = f ? f->H : nullptr;
+    e->tc_fparts_h[k] = f ? f->P : 0;
+  }
+  BBX_CUDA_TRY(cudaMemcpyAsync(e->tc_ftab_d, e->tc_ftab_h, sizeof(float2*) * npaths, cudaMemcpyHostToDevice, e->stream));
+  BBX_CUDA_TRY(cudaMemcpyAsync(e->tc_fparts_d, e->tc_fparts_h, sizeof(uint32_t) * npaths, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = mark_upload(e))) return rc;
+  k_mimo_pack_h<<<dim3(e->B / 32, e->tc_G, e->tc_nog), 256, 0, e->stream>>>(e->tc_ftab_d, e->tc_fparts_d, e->tc_hpack, e->B, e->n_in,
+                                                                        e->n_out, e->tc_P2log, e->tc_G);
+  BBX_CUDA_TRY(cudaGetLastError());
+  e->launches++;
+  e->tc_dirty = false;
+  return BBX_OK;
+}
+
+// the T block-steps of one call: FDL rows -> bin-major X, then one GEMM per bin
+int launch_mimo_tc(bbx_engine* e, uint32_t T) {
+  cudaStream_t st = e->stream;
+  uint32_t N = 16, Nlog = 4;
+  while (N < T && N < (uint32_t)kTcNmax) {
+    N <<= 1;
+    Nlog++;
+  }
+  const uint32_t ntiles = ceil_div(T, N);
+  k_mimo_pack_x<<<dim3(e->B / 32, ceil_div(e->tc_W, 32u), e->n_in), 256, 0, st>>>(e->fdl, e->tc_xb, e->B, e->R, e->head, e->n_in,
+                                                                              e->tc_P2, T, e->tc_W);
+  BBX_CUDA_TRY(cudaGetLastError());
+  e->launches++;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e->profile_mac) {
+    if (e->mac_events_used + 2 > e->mac_events.size()) {
+      size_t old = e->mac_events.size();
+      e->mac_events.resize(old + 64);
+      for (size_t i = old; i < e->mac_events.size(); i++) BBX_CUDA_TRY(cudaEventCreate(&e->mac_events[i]));
+    }
+    ev0 = e->mac_events[e->mac_events_used++];
+    ev1 = e->mac_events[e->mac_events_used++];
+  }
+  MimoTcArgs a;
+  a.hpack = e->tc_hpack;
+  a.xb = e->tc_xb;
+  a.ypart = e->ypart;
+  a.status = e->tc_status;
+  a.B = e->B;
+  a.n_in = e->n_in;
+  a.n_out = e->n_out;
+  a.P2log = e->tc_P2log;
+  a.G = e->tc_G;
+  a.W = e->tc_W;
+  a.T = T;
+  a.N = N;
+  a.Nlog = Nlog;
+  a.slot_stride = e->max_slots;
+  if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+  k_mimo_tc<<<dim3(e->B / kTcBins, e->tc_nog, ntiles), kTcThreads, kTcSmemBytes, st>>>(a);
+  BBX_CUDA_TRY(cudaGetLastError());
+  if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
+  e->launches++;
+  e->tc_launches++;
+  e->mac_launches++;
+  e->mac_units += (uint64_t)e->n_streams * T;
+  const uint64_t K = e->B + 1;
+  e->mac_bytes += (uint64_t)T * (16ull * e->plan_steady.total_rows * K + 16ull * K * e->n_streams +
+                                 (uint64_t)e->B * (fmt_bytes(e->last_infmt) * e->n_in + fmt_bytes(e->last_outfmt) * e->n_out));
+  return BBX_OK;
+}
+
 // 0 always means "leave as is" (library default at creation)
 void apply_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile) {
   if (ctas_per_sm) e->mac_occ = std::min(ctas_per_sm, 4u);
@@ -1161,6 +1300,16 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   BBX_CUDA_TRY(cudaMalloc((void**)&e->nyq_part, sizeof(float) * (size_t)e->Tmax * e->max_slots));
   BBX_CUDA_TRY(cudaMemset(e->nyq_part, 0, sizeof(float) * (size_t)e->Tmax * e->max_slots));
 
+  // MIMO: tensor-core operands (time-batched calls only)
+  if (e->mode == BBX_MODE_MIMO && cfg->mimo_tensor != 1 && e->Tmax >= e->tc_min_blocks && e->B >= 64) {
+    uint32_t P2 = 1;
+    while (P2 < e->Pmax) P2 <<= 1;
+    // longer sums than kTcMaxK complex terms stay on the exact-fp32 SIMT MAC (accumulator truncation, mimo_tc.cuh)
+    if ((uint64_t)e->n_in * P2 <= kTcMaxK) {
+      if ((rc = tc_alloc(e))) return rc;
+    }
+  }
+
   // route tables
   {
     size_t off = 0;
@@ -1217,6 +1366,14 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   cudaFree(e->flush_buf);
+  cudaFree(e->tc_hpack);
+  cudaFree(e->tc_xb);
+  cudaFree(e->tc_ftab_d);
+  cudaFree(e->tc_fparts_d);
+  cudaFree(e->tc_view);
+  cudaFree(e->tc_status);
+  if (e->tc_ftab_h) cudaFreeHost(e->tc_ftab_h);
+  if (e->tc_fparts_h) cudaFreeHost(e->tc_fparts_h);
   cudaFree(e->d_route);
   cudaFreeHost(e->h_route);
   for (MacPlan* pl : {&e->plan_first, &e->plan_steady}) {
@@ -1398,6 +1555,12 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     make_jobs(e, false, jobs);
     if ((rc = build_plan(e, e->plan_steady, jobs, std::vector<uint32_t>()))) return rc;
     e->steady_dirty = false;
+    e->tc_dirty = true;
+  }
+  // MIMO calls of >= tc_min_blocks blocks without a crossfade in flight run the per-bin GEMM on the tensor cores
+  const bool use_tc = e->tc_on && n_first == 0 && T >= e->tc_min_blocks && e->plan_steady.total_rows > 0;
+  if (use_tc && e->tc_dirty) {
+    if ((rc = tc_pack_filters(e))) return rc;
   }
 
   // ---- 1. PCM -> planar fp32 ----
@@ -1428,14 +1591,16 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     return rc;
   e->launches++;
   // ---- 3. FDL multiply-accumulate ----
-  if (n_first) {
+  if (use_tc) {
+    if ((rc = launch_mimo_tc(e, T))) return rc;
+  } else if (n_first) {
     if ((rc = launch_mac(e, e->plan_first, 0, 1))) return rc;
     if ((rc = launch_mac(e, e->plan_steady, 1, T - 1))) return rc;
   } else {
     if ((rc = launch_mac(e, e->plan_steady, 0, T))) return rc;
   }
   // ---- 4. inverse transforms, crossfade, delay ring ----
-  if ((rc = launch_irfft(e, T, n_first))) return rc;
+  if ((rc = launch_irfft(e, T, n_first, use_tc))) return rc;
   e->launches++;
   // ---- 5. delay read, mixdown, output format ----
   {
@@ -1590,6 +1755,18 @@ int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_
   BBX_REQUIRE(e != nullptr, "null engine");
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   apply_tuning(e, ctas_per_sm, l2_keep_16ths, time_tile);
+  return BBX_OK;
+}
+
+int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (launches) *launches = e->tc_launches;
+  if (status) {
+    *status = 0;
+    if (e->tc_status) BBX_CUDA_TRY(cudaMemcpy(status, e->tc_status, sizeof(int), cudaMemcpyDeviceToHost));
+  }
   return BBX_OK;
 }
 

@@ -177,7 +177,8 @@ typedef struct {
   uint32_t mac_ctas_per_sm;   /* streaming MAC: resident CTAs per SM, 1..4 (default 1: 148 row ranges) */
   uint32_t mac_l2_keep_16ths; /* streaming MAC: sixteenths of the H/FDL lines kept L2-resident, 1..16 (default 3); > 16 = hints off */
   uint32_t mac_time_tile;     /* 16 or 32: calls with >= tile/2 blocks and filters of >= 2*tile partitions use the time-batched MAC (default 16); 1 = streaming MAC only */
-  uint32_t reserved[5];
+  uint32_t mimo_tensor;       /* MIMO mode: 0 = calls of >= 16 blocks run the per-bin complex GEMM on the tensor cores (3xTF32, tcgen05); 1 = SIMT MAC only */
+  uint32_t reserved[4];
 } bbx_config;
 
 typedef struct bbx_engine bbx_engine;
@@ -254,6 +255,9 @@ int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint
                         uint64_t* algorithmic_bytes);
 /* change the tuning knobs of bbx_config at run time (0 = leave as is); takes effect at the next call */
 int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile);
+/* tensor-core MIMO path: number of k_mimo_tc launches so far and the device status word (0 = ok; non-zero =
+ * a barrier wait timed out inside the kernel, results invalid).  Synchronises the stream. */
+int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status);
 /* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
 
