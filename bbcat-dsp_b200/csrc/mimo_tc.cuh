@@ -18,8 +18,9 @@
 //   Xb[k][i][w] float2           w = t + p': block t - p of this call (negative = history) -> W = P2-1+Tcap
 // One CTA owns kTcBins adjacent bins (their 8-byte output writes fill one 32-byte sector in L2) and walks K in chunks
 // of 16 complex: all 256 threads convert the chunk (hi/lo split, sign/swap expansion) into the canonical
-// no-swizzle K-major core-matrix layout in shared memory, then one thread issues the 12 tcgen05.mma of the
-// chunk; tcgen05.commit on a per-stage mbarrier releases the stage for re-use (4 stages).
+// no-swizzle K-major core-matrix layout in shared memory and arrive on the stage's "full" mbarrier; a ninth
+// warp waits for it and issues the 12 tcgen05.mma of the chunk; tcgen05.commit on the stage's "empty" mbarrier
+// releases it for re-use (4 stages).  No block-wide barrier in the main loop.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -27,7 +28,8 @@
 
 namespace bbx {
 
-static constexpr int kTcThreads = 256;
+static constexpr int kTcProducers = 256;            // warps 0..7: operand conversion + epilogue
+static constexpr int kTcThreads = kTcProducers + 32;  // warp 8: one elected lane issues the MMAs
 static constexpr int kTcBins = 4;      // adjacent bins per CTA
 static constexpr int kTcStages = 4;
 static constexpr int kTcChunk = 16;    // complex K elements per stage = 32 tf32 = 4 MMA k-steps
@@ -103,15 +105,17 @@ __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
+// v = hi + lo with hi = v rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa to the
+// sign-magnitude pattern and clear the 13 low bits; cvt.rna.tf32.f32 compiles to a ~6-instruction sequence with
+// NaN handling on sm_100a, this is two).  v - hi is exact; the remainder gets the half-ulp only: the tensor core
+// ignores the 13 low bits of a TF32 operand, which completes the rounding.
+__device__ __forceinline__ void split(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = __uint_as_float(__float_as_uint(v - hi) + 0x1000u);
 }
 
-__device__ __forceinline__ void split(float v, float& hi, float& lo) {
-  hi = tf32_rna(v);
-  lo = tf32_rna(v - hi);  // v - hi is exact; the remainder keeps 11 of its <= 13 significant bits
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ float4 ld_stream4(const float4* p) {
@@ -137,13 +141,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   const uint32_t N = a.N, Nlog = a.Nlog;
   const uint32_t smem0 = smem_u32(tc_smem);
   float* tile = reinterpret_cast<float*>(tc_smem + kTcStages * kTcStageBytes);
-  const uint32_t bar0 = smem0 + kTcStages * kTcStageBytes + kTcTileBytes;  // empty[0..NST-1], full[0..1]
-  const uint32_t bar_full = bar0 + 8 * kTcStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + kTcStages * kTcStageBytes + kTcTileBytes + 8 * (kTcStages + 2));
+  // mbarriers: full[NST] (256 producer arrivals), empty[NST] (tcgen05.commit), acc_full[2] (commit), acc_empty[2] (256)
+  const uint32_t bar_full = smem0 + kTcStages * kTcStageBytes + kTcTileBytes;
+  const uint32_t bar_empty = bar_full + 8 * kTcStages;
+  const uint32_t bar_accf = bar_empty + 8 * kTcStages;
+  const uint32_t bar_acce = bar_accf + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + kTcStages * kTcStageBytes + kTcTileBytes + 8 * (2 * kTcStages + 4));
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTcStages + 2; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s));
+    for (int s = 0; s < kTcStages; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "n"(kTcProducers));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_empty + 8 * s));
+    }
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_accf + 8 * b));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_acce + 8 * b), "n"(kTcProducers));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -154,154 +169,199 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-
-  // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 @17, M >> 4 @24
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
-
   const uint32_t nchunk = a.G / (kTcChunk / 2);
-  const uint32_t total = kTcBins * nchunk;
-  // A producer: this thread owns output o of the group and K groups gq, gq + 4 of every chunk
-  const uint32_t ao = tid & 63, agq = tid >> 6;
-  const float4* hp = a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64 + ao;
-  // B producer: items e = tid + 256 r, e -> (pair member, column t, K group)
-  const uint32_t nbr = N >> 4;  // items per thread: 16 N / 256
-  const uint32_t P2m = (1u << a.P2log) - 1;
-
-  float4 ra[2];
-  float2 rb[4];
-  auto load_chunk = [&](uint32_t it) {
-    const uint32_t j = it / nchunk, c = it - j * nchunk;
-#pragma unroll
-    for (int q = 0; q < 2; q++) ra[q] = ld_stream4(hp + ((uint64_t)j * a.G + c * 8 + agq + 4 * q) * 64);
-    const float2* xk = a.xb + (uint64_t)(kb + j) * a.n_in * a.W + t0;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      rb[r] = make_float2(0.f, 0.f);
-      if ((uint32_t)r < nbr) {
-        const uint32_t e = tid + 256 * r;
-        const uint32_t jl = ((e >> (1 + Nlog)) << 1) | (e & 1), t = (e >> 1) & (N - 1);
-        const uint32_t jj = c * kTcChunk + jl, i = jj >> a.P2log, pp = jj & P2m;
-        if (i < a.n_in) rb[r] = __ldg(xk + (uint64_t)i * a.W + t + pp);
-      }
-    }
-  };
-
   bool ok = true;
-  // drain the accumulator set of bin j: sum its three tiles, pair (re, im) through the smem tile, store 8 bytes
-  // per (t, output).  The four bins of a CTA fill one 32-byte sector within microseconds: L2 merges the writes.
-  auto drain_bin = [&](uint32_t j) {
-    const uint32_t b = j & 1;
-    __syncthreads();  // the previous drain's readers are done with the tile
-    if (ok && !mbar_wait(bar_full + 8 * b, (j >> 1) & 1)) ok = false;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t q = warp & 3, h = warp >> 2;
-    const uint32_t m = 32 * q + lane, cc = m >> 6, o = m & 63;
-    for (uint32_t cg = h; cg < (N >> 4); cg += 2) {
-      uint32_t r[kTcAccTiles][16];
+
+  if (warp == kTcProducers / 32) {
+    // ================= MMA issuer: one lane =================
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 @17, M >> 4 @24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+      uint32_t s = 0, ph = 0;
+      for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
+        // accumulator set j & 1: tiles 0..2 take the hi*hi products by k-step mod 3, tile 3 the small terms
+        const uint32_t d = tmem + (j & 1) * kTcAccTiles * kTcNmax;
+        if (j >= 2 && ok && !mbar_wait(bar_acce + 8 * (j & 1), ((j >> 1) - 1) & 1)) ok = false;  // set drained
+        uint32_t rot = 0, ks = 0;
+        for (uint32_t c = 0; c < nchunk; c++) {
+          if (ok && !mbar_wait(bar_full + 8 * s, ph)) ok = false;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sA = smem0 + s * kTcStageBytes, sB = sA + 2 * kTcAHalf;
 #pragma unroll
-      for (uint32_t z = 0; z < kTcAccTiles; z++) {
-        const uint32_t taddr = tmem + ((32 * q) << 16) + (b * kTcAccTiles + z) * kTcNmax + cg * 16;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[z][0]), "=r"(r[z][1]), "=r"(r[z][2]), "=r"(r[z][3]), "=r"(r[z][4]), "=r"(r[z][5]), "=r"(r[z][6]),
-              "=r"(r[z][7]), "=r"(r[z][8]), "=r"(r[z][9]), "=r"(r[z][10]), "=r"(r[z][11]), "=r"(r[z][12]), "=r"(r[z][13]),
-              "=r"(r[z][14]), "=r"(r[z][15])
-            : "r"(taddr));
+          for (int k8 = 0; k8 < kTcChunk / 4; k8++) {
+            const uint64_t a_hi = make_desc(sA + k8 * 2 * (kTcRows * 16), kTcRows * 16, 128);
+            const uint64_t a_lo = make_desc(sA + kTcAHalf + k8 * 2 * (kTcRows * 16), kTcRows * 16, 128);
+            const uint64_t b_hi = make_desc(sB + k8 * 2 * (N * 16), N * 16, 128);
+            const uint64_t b_lo = make_desc(sB + kTcBHalf + k8 * 2 * (N * 16), N * 16, 128);
+            mma_tf32(d + 3 * kTcNmax, a_lo, b_hi, idesc, ks ? 1u : 0u);
+            mma_tf32(d + 3 * kTcNmax, a_hi, b_lo, idesc, 1u);
+            mma_tf32(d + rot * kTcNmax, a_hi, b_hi, idesc, ks >= 3u ? 1u : 0u);
+            rot = rot == 2 ? 0 : rot + 1;
+            ks++;
+          }
+          commit(bar_empty + 8 * s);
+          if (c + 1 == nchunk) commit(bar_accf + 8 * (j & 1));
+          if (++s == kTcStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
       }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int u = 0; u < 16; u++) {
-        const uint32_t t = cg * 16 + u;
-        const float v = ((__uint_as_float(r[0][u]) + __uint_as_float(r[1][u])) + __uint_as_float(r[2][u])) + __uint_as_float(r[3][u]);
-        tile[(t * 2 + cc) * 64 + o] = v;
-      }
+      if (!ok) atomicExch(a.status, 2);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    for (uint32_t idx = tid; idx < N * 64; idx += kTcThreads) {
-      const uint32_t oo = idx & 63, t = idx >> 6;
-      const uint32_t og_o = og * 64 + oo, tt = t0 + t;
-      if (tt < a.T && og_o < a.n_out)
-        a.ypart[((uint64_t)tt * a.slot_stride + og_o) * a.B + kb + j] = make_float2(tile[(t * 2) * 64 + oo], tile[(t * 2 + 1) * 64 + oo]);
-    }
-  };
-  const uint32_t cdrain = nchunk > 1 ? 1u : 0u;  // chunk of bin j after which bin j-1 is drained
-  load_chunk(0);
-  for (uint32_t it = 0; it < total; it++) {
-    const uint32_t s = it % kTcStages;
-    const uint32_t j = it / nchunk, c = it - j * nchunk;
-    const uint32_t sA = smem0 + s * kTcStageBytes, sB = sA + 2 * kTcAHalf;
-    if (it >= kTcStages) {
-      // the MMAs that read this stage kTcStages chunks ago have completed
-      if (ok && !mbar_wait(bar0 + 8 * s, ((it / kTcStages) - 1) & 1)) ok = false;
-    }
-    // ---- A: raw (a0, b0, a1, b1) = two complex of output ao -> rows ao (re) and 64 + ao (im), hi and lo ----
-    const float4 ca0 = ra[0], ca1 = ra[1];
-    const float2 cb0 = rb[0], cb1 = rb[1], cb2 = rb[2], cb3 = rb[3];
-    if (it + 1 < total) load_chunk(it + 1);  // next chunk's global loads fly under this chunk's conversion
-    const bool bin0 = (kb + j) == 0;         // packed bin 0 = (DC, Nyquist): two real products, no cross terms
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const float4 v = q ? ca1 : ca0;
-      float ah0, al0, bh0, bl0, ah1, al1, bh1, bl1;
-      split(v.x, ah0, al0);
-      split(v.y, bh0, bl0);
-      split(v.z, ah1, al1);
-      split(v.w, bh1, bl1);
-      const uint32_t off = (agq + 4 * q) * (kTcRows * 16) + ao * 16;
-      if (!bin0) {
-        st_shared4(sA + off, ah0, -bh0, ah1, -bh1);
-        st_shared4(sA + off + 64 * 16, bh0, ah0, bh1, ah1);
-        st_shared4(sA + kTcAHalf + off, al0, -bl0, al1, -bl1);
-        st_shared4(sA + kTcAHalf + off + 64 * 16, bl0, al0, bl1, al1);
-      } else {
-        st_shared4(sA + off, ah0, 0.f, ah1, 0.f);
-        st_shared4(sA + off + 64 * 16, 0.f, bh0, 0.f, bh1);
-        st_shared4(sA + kTcAHalf + off, al0, 0.f, al1, 0.f);
-        st_shared4(sA + kTcAHalf + off + 64 * 16, 0.f, bl0, 0.f, bl1);
-      }
-    }
-    // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo ----
+  } else {
+    // ================= producers (256 threads) =================
+    // A: this thread owns output ao of the group and K groups agq, agq + 4 of every chunk; the packed operand is
+    // linear in (bin, chunk): 512 float4 per chunk
+    const uint32_t ao = tid & 63, agq = tid >> 6;
+    const float4* hp = a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64 + (uint64_t)agq * 64 + ao;
+    const uint32_t offA = agq * (kTcRows * 16) + ao * 16;
+    // B: items e = tid + 256 r -> (pair member, column t, K group)
+    const uint32_t nbr = N >> 4;
+    const uint32_t P2m = (1u << a.P2log) - 1;
+    uint32_t offB[4], jlB[4], tB[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      if ((uint32_t)r < nbr) {
-        const float2 v = r == 0 ? cb0 : r == 1 ? cb1 : r == 2 ? cb2 : cb3;
-        const uint32_t e = tid + 256 * r;
-        const uint32_t kg = e >> (1 + Nlog), t = (e >> 1) & (N - 1);
-        const uint32_t off = kg * (N * 16) + t * 16 + (e & 1) * 8;
-        float xh, xl, yh, yl;
-        split(v.x, xh, xl);
-        split(v.y, yh, yl);
-        st_shared2(sB + off, xh, yh);
-        st_shared2(sB + kTcBHalf + off, xl, yl);
-      }
+      const uint32_t e = tid + 256 * r;
+      const uint32_t kg = e >> (1 + Nlog);
+      tB[r] = (e >> 1) & (N - 1);
+      jlB[r] = (kg << 1) | (e & 1);
+      offB[r] = kg * (N * 16) + tB[r] * 16 + (e & 1) * 8;
     }
-    // generic-proxy writes -> visible to the tensor core (async proxy), then hand the stage to the issuer
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d = tmem + (j & 1) * kTcAccTiles * kTcNmax;  // tiles 0..2: hi*hi by k-step mod 3, tile 3: small terms
-      uint32_t rot = (c * (kTcChunk / 4)) % 3;
+    const float2* xk0 = a.xb + (uint64_t)kb * a.n_in * a.W + t0;
+    const uint64_t xbin = (uint64_t)a.n_in * a.W;
+
+    float4 ra[2][2];
+    float2 rb[2][4];
+    uint32_t lj = 0, lc = 0;  // (bin, chunk) of the next load
+    auto load_chunk = [&](float4(&qa)[2], float2(&qb)[4]) {
+      if (lj < (uint32_t)kTcBins) {
+        qa[0] = ld_stream4(hp);
+        qa[1] = ld_stream4(hp + 4 * 64);
+        hp += 8 * 64;
+        const float2* xk = xk0 + lj * xbin;
 #pragma unroll
-      for (int k8 = 0; k8 < kTcChunk / 4; k8++) {
-        const uint64_t a_hi = make_desc(sA + k8 * 2 * (kTcRows * 16), kTcRows * 16, 128);
-        const uint64_t a_lo = make_desc(sA + kTcAHalf + k8 * 2 * (kTcRows * 16), kTcRows * 16, 128);
-        const uint64_t b_hi = make_desc(sB + k8 * 2 * (N * 16), N * 16, 128);
-        const uint64_t b_lo = make_desc(sB + kTcBHalf + k8 * 2 * (N * 16), N * 16, 128);
-        mma_tf32(d + 3 * kTcNmax, a_lo, b_hi, idesc, (c | (uint32_t)k8) ? 1u : 0u);
-        mma_tf32(d + 3 * kTcNmax, a_hi, b_lo, idesc, 1u);
-        mma_tf32(d + rot * kTcNmax, a_hi, b_hi, idesc, (c * (kTcChunk / 4) + (uint32_t)k8 >= 3u) ? 1u : 0u);
-        rot = rot == 2 ? 0 : rot + 1;
+        for (int r = 0; r < 4; r++) {
+          qb[r] = make_float2(0.f, 0.f);
+          if ((uint32_t)r < nbr) {
+            const uint32_t jj = lc * kTcChunk + jlB[r], i = jj >> a.P2log, pp = jj & P2m;
+            if (i < a.n_in) qb[r] = __ldg(xk + (uint64_t)i * a.W + tB[r] + pp);
+          }
+        }
+        if (++lc == nchunk) {
+          lc = 0;
+          lj++;
+        }
       }
-      commit(bar0 + 8 * s);
-      if (c + 1 == nchunk) commit(bar_full + 8 * (j & 1));
-    }
-    if (j > 0 && c == cdrain) drain_bin(j - 1);
+    };
+
+    // drain the accumulator set of bin j: sum its four tiles, pair (re, im) through the smem tile, store 8 bytes
+    // per (t, output).  The four bins of a CTA fill one 32-byte sector within microseconds: L2 merges the writes.
+    auto drain_bin = [&](uint32_t j) {
+      const uint32_t b = j & 1;
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");  // the previous drain's readers are done with the tile
+      if (ok && !mbar_wait(bar_accf + 8 * b, (j >> 1) & 1)) ok = false;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t q = warp & 3, h = warp >> 2;
+      const uint32_t m = 32 * q + lane, cc = m >> 6, o = m & 63;
+      for (uint32_t cg = h; cg < (N >> 4); cg += 2) {
+        uint32_t r[kTcAccTiles][16];
+#pragma unroll
+        for (uint32_t z = 0; z < kTcAccTiles; z++) {
+          const uint32_t taddr = tmem + ((32 * q) << 16) + (b * kTcAccTiles + z) * kTcNmax + cg * 16;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[z][0]), "=r"(r[z][1]), "=r"(r[z][2]), "=r"(r[z][3]), "=r"(r[z][4]), "=r"(r[z][5]), "=r"(r[z][6]),
+                "=r"(r[z][7]), "=r"(r[z][8]), "=r"(r[z][9]), "=r"(r[z][10]), "=r"(r[z][11]), "=r"(r[z][12]), "=r"(r[z][13]),
+                "=r"(r[z][14]), "=r"(r[z][15])
+              : "r"(taddr));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+          const uint32_t t = cg * 16 + u;
+          const float v = ((__uint_as_float(r[0][u]) + __uint_as_float(r[1][u])) + __uint_as_float(r[2][u])) + __uint_as_float(r[3][u]);
+          tile[(t * 2 + cc) * 64 + o] = v;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acce + 8 * b);  // this thread's reads of the set are complete
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");
+      for (uint32_t idx = tid; idx < N * 64; idx += kTcProducers) {
+        const uint32_t oo = idx & 63, t = idx >> 6;
+        const uint32_t og_o = og * 64 + oo, tt = t0 + t;
+        if (tt < a.T && og_o < a.n_out)
+          a.ypart[((uint64_t)tt * a.slot_stride + og_o) * a.B + kb + j] = make_float2(tile[(t * 2) * 64 + oo], tile[(t * 2 + 1) * 64 + oo]);
+      }
+    };
+
+    uint32_t s = 0, ph = 0, it = 0;
+    auto produce = [&](float4(&qa)[2], float2(&qb)[4], uint32_t j) {
+      const uint32_t sA = smem0 + s * kTcStageBytes, sB = sA + 2 * kTcAHalf;
+      if (it >= (uint32_t)kTcStages) {
+        // the MMAs that read this stage kTcStages chunks ago have completed
+        if (ok && !mbar_wait(bar_empty + 8 * s, ph ^ 1)) ok = false;
+      }
+      const bool bin0 = (kb + j) == 0;  // packed bin 0 = (DC, Nyquist): two real products, no cross terms
+      // ---- A: raw (a0, b0, a1, b1) = two complex of output ao -> rows ao (re) and 64 + ao (im), hi and lo ----
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const float4 v = qa[q];
+        float ah0, al0, bh0, bl0, ah1, al1, bh1, bl1;
+        split(v.x, ah0, al0);
+        split(v.y, bh0, bl0);
+        split(v.z, ah1, al1);
+        split(v.w, bh1, bl1);
+        const uint32_t off = offA + q * 4 * (kTcRows * 16);
+        if (!bin0) {
+          st_shared4(sA + off, ah0, -bh0, ah1, -bh1);
+          st_shared4(sA + off + 64 * 16, bh0, ah0, bh1, ah1);
+          st_shared4(sA + kTcAHalf + off, al0, -bl0, al1, -bl1);
+          st_shared4(sA + kTcAHalf + off + 64 * 16, bl0, al0, bl1, al1);
+        } else {
+          st_shared4(sA + off, ah0, 0.f, ah1, 0.f);
+          st_shared4(sA + off + 64 * 16, 0.f, bh0, 0.f, bh1);
+          st_shared4(sA + kTcAHalf + off, al0, 0.f, al1, 0.f);
+          st_shared4(sA + kTcAHalf + off + 64 * 16, 0.f, bl0, 0.f, bl1);
+        }
+      }
+      // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo ----
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if ((uint32_t)r < nbr) {
+          float xh, xl, yh, yl;
+          split(qb[r].x, xh, xl);
+          split(qb[r].y, yh, yl);
+          st_shared2(sB + offB[r], xh, yh);
+          st_shared2(sB + kTcBHalf + offB[r], xl, yl);
+        }
+      }
+      load_chunk(qa, qb);  // refill this register set: the chunk two iterations ahead
+      // generic-proxy writes -> visible to the tensor core (async proxy), then hand the stage to the issuer
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + 8 * s);
+      if (++s == kTcStages) {
+        s = 0;
+        ph ^= 1;
+      }
+      it++;
+    };
+
+    load_chunk(ra[0], rb[0]);
+    load_chunk(ra[1], rb[1]);
+    const uint32_t cdrain = nchunk > 1 ? 1u : 0u;  // chunk of bin j after which bin j-1 is drained
+    uint32_t par = 0;
+    for (uint32_t j = 0; j < (uint32_t)kTcBins; j++)
+      for (uint32_t c = 0; c < nchunk; c++) {
+        if (par == 0) produce(ra[0], rb[0], j);
+        else produce(ra[1], rb[1], j);
+        par ^= 1;
+        if (j > 0 && c == cdrain) drain_bin(j - 1);
+      }
+    drain_bin(kTcBins - 1);
+    if (!ok && tid == 0) atomicExch(a.status, 1);
   }
-  drain_bin(kTcBins - 1);
-  if (!ok && tid == 0) atomicExch(a.status, 1);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
