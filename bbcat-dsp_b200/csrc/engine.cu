@@ -692,6 +692,7 @@ struct bbx_engine {
   bool tc_dirty = true;        // Hpack must be rebuilt from the current filter matrix
   uint32_t tc_min_blocks = 16; // calls with fewer blocks use the streaming SIMT MAC
   uint32_t tc_P2 = 1, tc_P2log = 0, tc_G = 0, tc_nog = 0, tc_W = 0;
+  uint64_t tc_xbin = 0;
   float4* tc_hpack = nullptr;
   float2* tc_xb = nullptr;
   const float2** tc_ftab_h = nullptr;  // pinned staging [n_out][n_in]
@@ -1083,9 +1084,11 @@ int tc_alloc(bbx_engine* e) {
   const uint32_t Kc = ceil_div(e->n_in * P2, (uint32_t)kTcChunk) * kTcChunk;  // complex K, padded to whole chunks
   e->tc_G = Kc / 2;
   e->tc_nog = ceil_div(e->n_out, 64u);
-  e->tc_W = P2 - 1 + ceil_div(e->Tmax, (uint32_t)kTcNmax) * kTcNmax;
+  // row length: history + columns, plus one element so the 16-byte TMA runs of the last column stay inside; even
+  e->tc_W = (P2 + ceil_div(e->Tmax, (uint32_t)kTcNmax) * kTcNmax + 1) & ~1u;
   const size_t hbytes = sizeof(float4) * (size_t)e->tc_nog * e->B * e->tc_G * 64;
-  const size_t xbytes = sizeof(float2) * (size_t)e->B * e->n_in * e->tc_W;
+  e->tc_xbin = (uint64_t)(Kc >> lg) * e->tc_W;  // inputs padded (zero rows) to the padded K
+  const size_t xbytes = 2 * sizeof(float2) * (size_t)e->B * e->tc_xbin;  // hi part, then lo part
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_hpack, hbytes));
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_xb, xbytes));
   BBX_CUDA_TRY(cudaMemset(e->tc_xb, 0, xbytes));
@@ -1104,7 +1107,9 @@ int tc_alloc(bbx_engine* e) {
   BBX_CUDA_TRY(cudaMemcpy(e->tc_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_status, sizeof(int)));
   BBX_CUDA_TRY(cudaMemset(e->tc_status, 0, sizeof(int)));
-  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   e->tc_on = true;
   e->tc_dirty = true;
   return BBX_OK;
@@ -1140,8 +1145,8 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
     Nlog++;
   }
   const uint32_t ntiles = ceil_div(T, N);
-  k_mimo_pack_x<<<dim3(e->B / 32, ceil_div(e->tc_W, 32u), e->n_in), 256, 0, st>>>(e->fdl, e->tc_xb, e->B, e->R, e->head, e->n_in,
-                                                                              e->tc_P2, T, e->tc_W);
+  k_mimo_pack_x<<<dim3(e->B / 32, ceil_div(e->tc_W, 32u), e->n_in), 256, 0, st>>>(e->fdl, e->tc_xb, e->B, e->R, e->head, e->tc_xbin,
+                                                                              (uint64_t)e->B * e->tc_xbin, e->tc_P2, T, e->tc_W);
   BBX_CUDA_TRY(cudaGetLastError());
   e->launches++;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1166,11 +1171,14 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   a.G = e->tc_G;
   a.W = e->tc_W;
   a.T = T;
-  a.N = N;
-  a.Nlog = Nlog;
   a.slot_stride = e->max_slots;
+  a.xbin = e->tc_xbin;
+  a.xlo = (uint64_t)e->B * e->tc_xbin;
   if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
-  k_mimo_tc<<<dim3(e->B / kTcBins, e->tc_nog, ntiles), kTcThreads, kTcSmemBytes, st>>>(a);
+  const dim3 grid(e->B / kTcBins, e->tc_nog, ntiles);
+  if (Nlog == 4) k_mimo_tc<4><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+  else if (Nlog == 5) k_mimo_tc<5><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+  else k_mimo_tc<6><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
   BBX_CUDA_TRY(cudaGetLastError());
   if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
   e->launches++;

@@ -15,12 +15,16 @@
 //   Hpack[og][k][g][64] float4   g indexes pairs of complex K elements j = 2g, 2g+1;  j = i*P2 + p',
 //                                 p' = P2-1-p (partition order reversed so a column of B is a contiguous
 //                                 run of the time axis), P2 = power of two >= P, K padded to 16 with zeros
-//   Xb[k][i][w] float2           w = t + p': block t - p of this call (negative = history) -> W = P2-1+Tcap
+//   Xb[k][i][w] float2           w = t + p': block t - p of this call (negative = history) -> W = P2-1+Tcap;
+//                                 inputs padded with zero rows up to the padded K
 // One CTA owns kTcBins adjacent bins (their 8-byte output writes fill one 32-byte sector in L2) and walks K in chunks
-// of 16 complex: all 256 threads convert the chunk (hi/lo split, sign/swap expansion) into the canonical
-// no-swizzle K-major core-matrix layout in shared memory and arrive on the stage's "full" mbarrier; a ninth
-// warp waits for it and issues the 12 tcgen05.mma of the chunk; tcgen05.commit on the stage's "empty" mbarrier
-// releases it for re-use (4 stages).  No block-wide barrier in the main loop.
+// of 16 complex in three decoupled pipelines (mbarriers only, no block-wide barrier in the main loop):
+//   loader warp   TMA bulk copies (cp.async.bulk) of the chunk's raw H and FDL runs into a raw smem ring
+//   2 x 8 producer warps (alternating chunks)  raw H -> hi/lo split + sign/swap expansion -> A tile into TENSOR MEMORY (tcgen05.st); raw FDL
+//                 (already split by k_mimo_pack_x) -> B tile in shared memory (canonical no-swizzle K-major layout)
+//   4 epilogue warps  accumulators (TMEM) -> sum of the four tiles -> (re, im) pairs -> HBM
+//   MMA warp      one lane issues the 12 tcgen05.mma (A from TMEM, B from smem) of the chunk; tcgen05.commit
+//                 releases the stage
 #pragma once
 
 #include <cuda_runtime.h>
@@ -28,25 +32,42 @@
 
 namespace bbx {
 
-static constexpr int kTcProducers = 256;            // warps 0..7: operand conversion + epilogue
-static constexpr int kTcThreads = kTcProducers + 32;  // warp 8: one elected lane issues the MMAs
+static constexpr int kTcGroups = 2;        // producer groups: group g converts chunks it = g (mod 2), so the fences and
+                                          // barrier waits of one chunk overlap the arithmetic of the next
+static constexpr int kTcProducers = 256;  // threads per group (8 warps); warps 0..15 produce
+static constexpr int kTcWarpEpi = 16;     // warps 16..19: accumulator read-out (warp & 3 = TMEM lane quarter)
+static constexpr int kTcEpiThreads = 128;
+static constexpr int kTcWarpMma = 20;     // one elected lane issues the MMAs
+static constexpr int kTcWarpLoad = 21;    // one elected lane issues the TMA bulk copies
+static constexpr int kTcThreads = 704;
 static constexpr int kTcBins = 4;      // adjacent bins per CTA
-static constexpr int kTcStages = 4;
+static constexpr int kTcStages = 3;    // converted operand stages: A in TMEM, B in shared memory
+static constexpr int kTcRawStages = 4; // raw operand stages (TMA bulk copies from HBM)
 static constexpr int kTcChunk = 16;    // complex K elements per stage = 32 tf32 = 4 MMA k-steps
 static constexpr int kTcRows = 128;    // accumulator rows: 64 outputs x (re, im)
 static constexpr int kTcNmax = 64;     // columns (block-steps) per accumulator tile
-static constexpr uint32_t kTcAHalf = kTcRows * kTcChunk * 2 * 4;          // 16 KB: A_hi (then A_lo)
 static constexpr uint32_t kTcBHalf = kTcNmax * kTcChunk * 2 * 4;          // 8 KB:  B_hi (then B_lo)
-static constexpr uint32_t kTcStageBytes = 2 * kTcAHalf + 2 * kTcBHalf;    // 48 KB
+static constexpr uint32_t kTcStageBytes = 2 * kTcBHalf;                   // 16 KB of shared memory per stage
 static constexpr uint32_t kTcTileBytes = kTcNmax * 2 * 64 * 4;            // 32 KB: epilogue tile [t][re/im][o]
-static constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + kTcTileBytes + 128;  // + barriers
-// TMEM: two accumulator sets (bins alternate, so a set drains while the other fills) of four 64-column tiles.
+// raw stage: 8 KB of packed H (64 outputs x 16 complex) + the FDL runs of the chunk: (16 / P2) input rows of
+// N + P2 complex (P2 < 16) or one row of N + 16, hi and lo parts; worst case P2 = 1: 2 x 16 x 66 x 8 bytes
+static constexpr uint32_t kTcRawStageBytes = 8192 + 2 * 16 * 66 * 8;
+static constexpr uint32_t kTcOffTile = kTcStages * kTcStageBytes;
+static constexpr uint32_t kTcOffRaw = kTcOffTile + kTcTileBytes;
+static constexpr uint32_t kTcOffBar = kTcOffRaw + kTcRawStages * kTcRawStageBytes;
+static constexpr uint32_t kTcSmemBytes = kTcOffBar + 256;
+// TMEM (512 columns x 128 lanes): columns 0..255 = four 64-column accumulator tiles, columns 256..511 = the A
+// operand ring (per stage 32 columns of A_hi and 32 of A_lo: row = lane, K along columns).  A never touches
+// shared memory: the producers write it with tcgen05.st, the MMA reads it from TMEM ([a-tmem] operand form), which
+// takes 2/3 of the operand traffic off the shared-memory pipe (the bottleneck of the SS form, profiles/).
 // The tensor core truncates the fp32 accumulator on every MMA, a bias that grows with the number of sequential
 // accumulations (one tile for everything: 109 dB SNR at K = 512 complex).  The hi*hi products therefore rotate
 // over three tiles (k-step mod 3) and the small lo*hi / hi*lo terms have their own tile, so the dominant sums see
 // K/12 accumulations instead of 3K/4; the epilogue adds the four tiles in fp32 round-to-nearest.
-static constexpr uint32_t kTcAccTiles = 4;
-static constexpr uint32_t kTcTmemCols = 512;                              // 2 x 4 x 64
+static constexpr uint32_t kTcAccTiles = 5;
+static constexpr uint32_t kTcAccCols = kTcAccTiles * kTcNmax;             // 320
+static constexpr uint32_t kTcAStageCols = 4 * kTcChunk;                   // 64: A_hi | A_lo
+static constexpr uint32_t kTcTmemCols = 512;
 static constexpr uint32_t kTcMaxK = 1024;                                 // complex K verified against the tolerance
 
 struct MimoTcArgs {
@@ -54,7 +75,9 @@ struct MimoTcArgs {
   const float2* xb;
   float2* ypart;     // [t][slot_stride][B], slot = output
   int* status;       // set non-zero when a barrier wait times out (never hang the device)
-  uint32_t B, n_in, n_out, P2log, G /* float4 K groups = Kc/2 */, W, T, N /* 16, 32 or 64 */, Nlog, slot_stride;
+  uint32_t B, n_in, n_out, P2log, G /* float4 K groups = Kc/2 */, W, T, slot_stride;
+  uint64_t xbin;     // float2 elements per bin of xb = (inputs padded to whole chunks) * W
+  uint64_t xlo;      // float2 elements from the hi part of xb to the lo part (same layout)
 };
 
 namespace tc {
@@ -84,11 +107,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-// bounded wait: returns false after ~1e6 polls
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+// bounded wait: returns false after ~1e6 polls (never hang the device); one poll on the fast path
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
   for (int spin = 0; spin < (1 << 20); spin++)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -98,6 +125,36 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// A operand in tensor memory, B through a shared-memory descriptor
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 8 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void st_tmem8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
+// 16 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void st_tmem16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
 }
 
@@ -124,6 +181,22 @@ __device__ __forceinline__ float4 ld_stream4(const float4* p) {
   return r;
 }
 
+__device__ __forceinline__ float4 ld_shared4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ float2 ld_shared2(uint32_t addr) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr) : "memory");
+  return r;
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned addresses and size)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void st_shared4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -133,20 +206,86 @@ __device__ __forceinline__ void st_shared2(uint32_t addr, float a, float b) {
 
 }  // namespace tc
 
+namespace tc {
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// B tile descriptors (SWIZZLE_NONE, K-major): high word = SBO 128 bytes | version 1, low word = LBO (N * 16 bytes)
+// | address >> 4: advancing a descriptor is one 32-bit add on the low word
+static constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+template <uint32_t N>
+static constexpr uint32_t kDescLo = ((N * 16u) >> 4) << 16;
+
+template <bool ACC>
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t idesc) {
+  const uint64_t db = ((uint64_t)kDescHi << 32) | desc_lo;
+  if (ACC)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc)
+        : "memory");
+}
+
+// the 12 MMAs of one chunk (4 k-steps of 8); FIRST = first chunk of a bin (accumulators start from zero)
+template <uint32_t N, bool FIRST>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tA, uint32_t blo, uint32_t rot0) {
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 @17, M >> 4 @24
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+#pragma unroll
+  for (int k8 = 0; k8 < kTcChunk / 4; k8++) {
+    const uint32_t a_hi = tA + k8 * 8, a_lo = a_hi + 2 * kTcChunk;
+    const uint32_t b_hi = blo + k8 * ((2 * N * 16) >> 4), b_lo = b_hi + (kTcBHalf >> 4);
+    uint32_t r = rot0 + k8;
+    r = r >= 3 ? r - 3 : r;
+    const uint32_t d_hh = tmem + r * kTcNmax;
+    if (FIRST && k8 == 0) {
+      mma_ts<false>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
+      mma_ts<false>(tmem + 4 * kTcNmax, a_hi, b_lo, idesc);
+    } else {
+      mma_ts<true>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
+      mma_ts<true>(tmem + 4 * kTcNmax, a_hi, b_lo, idesc);
+    }
+    if (FIRST && k8 < 3) mma_ts<false>(d_hh, a_hi, b_hi, idesc);
+    else mma_ts<true>(d_hh, a_hi, b_hi, idesc);
+  }
+}
+
+}  // namespace tc
+
+template <int NLOG>
 __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   using namespace tc;
+  constexpr uint32_t N = 1u << NLOG;  // columns of the accumulator tile = block-steps per CTA
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t kb = blockIdx.x * kTcBins, og = blockIdx.y, t0 = blockIdx.z * a.N;
-  const uint32_t N = a.N, Nlog = a.Nlog;
+  const uint32_t kb = blockIdx.x * kTcBins, og = blockIdx.y, t0 = blockIdx.z * N;
   const uint32_t smem0 = smem_u32(tc_smem);
-  float* tile = reinterpret_cast<float*>(tc_smem + kTcStages * kTcStageBytes);
-  // mbarriers: full[NST] (256 producer arrivals), empty[NST] (tcgen05.commit), acc_full[2] (commit), acc_empty[2] (256)
-  const uint32_t bar_full = smem0 + kTcStages * kTcStageBytes + kTcTileBytes;
+  float* tile = reinterpret_cast<float*>(tc_smem + kTcOffTile);
+  const uint32_t raw0 = smem0 + kTcOffRaw;
+  // mbarriers: full[NST] (producer arrivals), empty[NST] (tcgen05.commit), acc_full (commit), acc_empty (epilogue
+  // threads), raw_full[RD] (loader + TMA bytes), raw_empty[RD] (producers)
+  const uint32_t bar_full = smem0 + kTcOffBar;
   const uint32_t bar_empty = bar_full + 8 * kTcStages;
   const uint32_t bar_accf = bar_empty + 8 * kTcStages;
-  const uint32_t bar_acce = bar_accf + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + kTcStages * kTcStageBytes + kTcTileBytes + 8 * (2 * kTcStages + 4));
+  const uint32_t bar_acce = bar_accf + 8;
+  const uint32_t bar_rawf = bar_acce + 8;
+  const uint32_t bar_rawe = bar_rawf + 8 * kTcRawStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + kTcOffBar + 8 * (2 * kTcStages + 2 + 2 * kTcRawStages));
 
   if (tid == 0) {
 #pragma unroll
@@ -154,10 +293,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "n"(kTcProducers));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_empty + 8 * s));
     }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_accf));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_acce), "n"(kTcEpiThreads));
 #pragma unroll
-    for (int b = 0; b < 2; b++) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_accf + 8 * b));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_acce + 8 * b), "n"(kTcProducers));
+    for (int d = 0; d < kTcRawStages; d++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_rawf + 8 * d));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_rawe + 8 * d), "n"(kTcProducers));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -170,197 +311,229 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const uint32_t nchunk = a.G / (kTcChunk / 2);
+  const uint32_t P2log = a.P2log, P2 = 1u << P2log, P2m = P2 - 1;
+  // raw B segment of one chunk: ninp input rows of seg complex each (rounded to 16 bytes), once for hi, once for lo
+  const uint32_t ninp = P2log < 4 ? (16u >> P2log) : 1u;
+  const uint32_t seg = P2log < 4 ? ((N + P2) & ~1u) : N + 16;
+  const uint32_t bhalf = ninp * seg * 8;  // bytes of the hi (or lo) part
   bool ok = true;
 
-  if (warp == kTcProducers / 32) {
-    // ================= MMA issuer: one lane =================
-    if (lane == 0) {
-      // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 @17, M >> 4 @24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
-      uint32_t s = 0, ph = 0;
+  if (warp == kTcWarpLoad) {
+    // ================= loader: one lane issues the bulk copies (TMA) of the raw operands =================
+    {
+      uint32_t d = 0, ph = 0, it = 0;
+      const uint32_t bytes = 8192 + 2 * bhalf;
       for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
-        // accumulator set j & 1: tiles 0..2 take the hi*hi products by k-step mod 3, tile 3 the small terms
-        const uint32_t d = tmem + (j & 1) * kTcAccTiles * kTcNmax;
-        if (j >= 2 && ok && !mbar_wait(bar_acce + 8 * (j & 1), ((j >> 1) - 1) & 1)) ok = false;  // set drained
-        uint32_t rot = 0, ks = 0;
-        for (uint32_t c = 0; c < nchunk; c++) {
-          if (ok && !mbar_wait(bar_full + 8 * s, ph)) ok = false;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sA = smem0 + s * kTcStageBytes, sB = sA + 2 * kTcAHalf;
-#pragma unroll
-          for (int k8 = 0; k8 < kTcChunk / 4; k8++) {
-            const uint64_t a_hi = make_desc(sA + k8 * 2 * (kTcRows * 16), kTcRows * 16, 128);
-            const uint64_t a_lo = make_desc(sA + kTcAHalf + k8 * 2 * (kTcRows * 16), kTcRows * 16, 128);
-            const uint64_t b_hi = make_desc(sB + k8 * 2 * (N * 16), N * 16, 128);
-            const uint64_t b_lo = make_desc(sB + kTcBHalf + k8 * 2 * (N * 16), N * 16, 128);
-            mma_tf32(d + 3 * kTcNmax, a_lo, b_hi, idesc, ks ? 1u : 0u);
-            mma_tf32(d + 3 * kTcNmax, a_hi, b_lo, idesc, 1u);
-            mma_tf32(d + rot * kTcNmax, a_hi, b_hi, idesc, ks >= 3u ? 1u : 0u);
-            rot = rot == 2 ? 0 : rot + 1;
-            ks++;
+        const char* asrc = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb + j) * a.G) * 64);
+        const float2* xrow = a.xb + (uint64_t)(kb + j) * a.xbin + t0;
+        for (uint32_t c = 0; c < nchunk; c++, it++) {
+          if (it >= (uint32_t)kTcRawStages) {
+            if (ok && !mbar_wait(bar_rawe + 8 * d, ph ^ 1)) ok = false;
           }
-          commit(bar_empty + 8 * s);
-          if (c + 1 == nchunk) commit(bar_accf + 8 * (j & 1));
-          if (++s == kTcStages) {
-            s = 0;
+          if (elect_one()) {
+            const uint32_t dst = raw0 + d * kTcRawStageBytes, bar = bar_rawf + 8 * d;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            bulk_g2s(dst, asrc + (uint64_t)c * 8192, 8192, bar);
+            // chunk c starts at complex K index 16 c = (input i0, reversed partition pp0)
+            const uint32_t i0 = P2log < 4 ? c * ninp : (c >> (P2log - 4)), pp0 = P2log < 4 ? 0u : ((c << 4) & P2m);
+            for (uint32_t il = 0; il < ninp; il++) {
+              const float2* src = xrow + (uint64_t)(i0 + il) * a.W + pp0;
+              bulk_g2s(dst + 8192 + il * seg * 8, src, seg * 8, bar);
+              bulk_g2s(dst + 8192 + bhalf + il * seg * 8, src + a.xlo, seg * 8, bar);
+            }
+          }
+          __syncwarp();
+          if (++d == kTcRawStages) {
+            d = 0;
             ph ^= 1;
           }
         }
       }
-      if (!ok) atomicExch(a.status, 2);
+      if (!ok && lane == 0) atomicExch(a.status, 3);
     }
-  } else {
-    // ================= producers (256 threads) =================
-    // A: this thread owns output ao of the group and K groups agq, agq + 4 of every chunk; the packed operand is
-    // linear in (bin, chunk): 512 float4 per chunk
-    const uint32_t ao = tid & 63, agq = tid >> 6;
-    const float4* hp = a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64 + (uint64_t)agq * 64 + ao;
-    const uint32_t offA = agq * (kTcRows * 16) + ao * 16;
-    // B: items e = tid + 256 r -> (pair member, column t, K group)
-    const uint32_t nbr = N >> 4;
-    const uint32_t P2m = (1u << a.P2log) - 1;
-    uint32_t offB[4], jlB[4], tB[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const uint32_t e = tid + 256 * r;
-      const uint32_t kg = e >> (1 + Nlog);
-      tB[r] = (e >> 1) & (N - 1);
-      jlB[r] = (kg << 1) | (e & 1);
-      offB[r] = kg * (N * 16) + tB[r] * 16 + (e & 1) * 8;
-    }
-    const float2* xk0 = a.xb + (uint64_t)kb * a.n_in * a.W + t0;
-    const uint64_t xbin = (uint64_t)a.n_in * a.W;
-
-    float4 ra[2][2];
-    float2 rb[2][4];
-    uint32_t lj = 0, lc = 0;  // (bin, chunk) of the next load
-    auto load_chunk = [&](float4(&qa)[2], float2(&qb)[4]) {
-      if (lj < (uint32_t)kTcBins) {
-        qa[0] = ld_stream4(hp);
-        qa[1] = ld_stream4(hp + 4 * 64);
-        hp += 8 * 64;
-        const float2* xk = xk0 + lj * xbin;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          qb[r] = make_float2(0.f, 0.f);
-          if ((uint32_t)r < nbr) {
-            const uint32_t jj = lc * kTcChunk + jlB[r], i = jj >> a.P2log, pp = jj & P2m;
-            if (i < a.n_in) qb[r] = __ldg(xk + (uint64_t)i * a.W + tB[r] + pp);
-          }
+  } else if (warp == kTcWarpMma) {
+    // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+    // accumulator tiles 0..2 take the hi*hi products by k-step mod 3, tiles 3 and 4 the small lo*hi / hi*lo terms
+    // (consecutive MMAs never accumulate into the same tile)
+    const uint32_t blo0 = kDescLo<N> + (smem0 >> 4);  // low descriptor word of stage 0's B_hi tile
+    uint32_t s = 0, ph = 0;
+    for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
+      if (j >= 1 && ok && !mbar_wait(bar_acce, (j - 1) & 1)) ok = false;  // the previous bin has been read out
+      uint32_t rot0 = 0;
+      for (uint32_t c = 0; c < nchunk; c++) {
+        if (ok && !mbar_wait(bar_full + 8 * s, ph)) ok = false;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t tA = tmem + kTcAccCols + s * kTcAStageCols;
+          const uint32_t blo = blo0 + s * (kTcStageBytes >> 4);
+          if (c == 0) issue_chunk<N, true>(tmem, tA, blo, rot0);
+          else issue_chunk<N, false>(tmem, tA, blo, rot0);
+          commit(bar_empty + 8 * s);
+          if (c + 1 == nchunk) commit(bar_accf);
         }
-        if (++lc == nchunk) {
-          lc = 0;
-          lj++;
+        __syncwarp();
+        rot0 = rot0 == 2 ? 0 : rot0 + 1;  // 4 k-steps per chunk: (rot0 + 4) mod 3
+        if (++s == kTcStages) {
+          s = 0;
+          ph ^= 1;
         }
       }
-    };
-
-    // drain the accumulator set of bin j: sum its four tiles, pair (re, im) through the smem tile, store 8 bytes
-    // per (t, output).  The four bins of a CTA fill one 32-byte sector within microseconds: L2 merges the writes.
-    auto drain_bin = [&](uint32_t j) {
-      const uint32_t b = j & 1;
-      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");  // the previous drain's readers are done with the tile
-      if (ok && !mbar_wait(bar_accf + 8 * b, (j >> 1) & 1)) ok = false;
+    }
+    if (!ok && lane == 0) atomicExch(a.status, 2);
+  } else if (warp >= kTcWarpEpi && warp < kTcWarpEpi + 4) {
+    // ================= epilogue (4 warps, one per TMEM lane quarter) =================
+    // read out the accumulators of bin j: sum the four tiles, release them, pair (re, im) through the smem tile,
+    // store 8 bytes per (t, output).  The four bins of a CTA fill one 32-byte sector within microseconds: L2 merges.
+    const uint32_t q = warp & 3, et = tid - kTcWarpEpi * 32;
+    const uint32_t m = 32 * q + lane, cc = m >> 6, o = m & 63;
+    for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
+      if (ok && !mbar_wait(bar_accf, j & 1)) ok = false;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t q = warp & 3, h = warp >> 2;
-      const uint32_t m = 32 * q + lane, cc = m >> 6, o = m & 63;
-      for (uint32_t cg = h; cg < (N >> 4); cg += 2) {
-        uint32_t r[kTcAccTiles][16];
-#pragma unroll
+#pragma unroll 1
+      for (uint32_t cg = 0; cg < (N >> 4); cg++) {
+        // (((t0 + t1) + t2) + t3) + t4, one tile in flight (few registers: 704 threads share the register file)
+        float v[16];
+#pragma unroll 1
         for (uint32_t z = 0; z < kTcAccTiles; z++) {
-          const uint32_t taddr = tmem + ((32 * q) << 16) + (b * kTcAccTiles + z) * kTcNmax + cg * 16;
+          uint32_t r[16];
+          const uint32_t taddr = tmem + ((32 * q) << 16) + z * kTcNmax + cg * 16;
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[z][0]), "=r"(r[z][1]), "=r"(r[z][2]), "=r"(r[z][3]), "=r"(r[z][4]), "=r"(r[z][5]), "=r"(r[z][6]),
-                "=r"(r[z][7]), "=r"(r[z][8]), "=r"(r[z][9]), "=r"(r[z][10]), "=r"(r[z][11]), "=r"(r[z][12]), "=r"(r[z][13]),
-                "=r"(r[z][14]), "=r"(r[z][15])
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
               : "r"(taddr));
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-          const uint32_t t = cg * 16 + u;
-          const float v = ((__uint_as_float(r[0][u]) + __uint_as_float(r[1][u])) + __uint_as_float(r[2][u])) + __uint_as_float(r[3][u]);
-          tile[(t * 2 + cc) * 64 + o] = v;
+          for (int u = 0; u < 16; u++) v[u] = z == 0 ? __uint_as_float(r[u]) : v[u] + __uint_as_float(r[u]);
         }
+#pragma unroll
+        for (int u = 0; u < 16; u++) tile[((cg * 16 + u) * 2 + cc) * 64 + o] = v[u];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar_acce + 8 * b);  // this thread's reads of the set are complete
-      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");
-      for (uint32_t idx = tid; idx < N * 64; idx += kTcProducers) {
+      mbar_arrive(bar_acce);  // this thread's reads of the accumulators are complete: the next bin may start
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
+      for (uint32_t idx = et; idx < N * 64; idx += kTcEpiThreads) {
         const uint32_t oo = idx & 63, t = idx >> 6;
         const uint32_t og_o = og * 64 + oo, tt = t0 + t;
         if (tt < a.T && og_o < a.n_out)
           a.ypart[((uint64_t)tt * a.slot_stride + og_o) * a.B + kb + j] = make_float2(tile[(t * 2) * 64 + oo], tile[(t * 2 + 1) * 64 + oo]);
       }
-    };
-
-    uint32_t s = 0, ph = 0, it = 0;
-    auto produce = [&](float4(&qa)[2], float2(&qb)[4], uint32_t j) {
-      const uint32_t sA = smem0 + s * kTcStageBytes, sB = sA + 2 * kTcAHalf;
-      if (it >= (uint32_t)kTcStages) {
-        // the MMAs that read this stage kTcStages chunks ago have completed
-        if (ok && !mbar_wait(bar_empty + 8 * s, ph ^ 1)) ok = false;
-      }
-      const bool bin0 = (kb + j) == 0;  // packed bin 0 = (DC, Nyquist): two real products, no cross terms
-      // ---- A: raw (a0, b0, a1, b1) = two complex of output ao -> rows ao (re) and 64 + ao (im), hi and lo ----
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");  // tile free for the next bin
+    }
+    if (!ok && lane == 0) atomicExch(a.status, 4);
+  } else if (warp < kTcGroups * kTcProducers / 32) {
+    // ================= producers (2 groups of 8 warps): raw operands (smem) -> A tile (TMEM), B tile (smem) =====
+    // A lives in tensor memory (row = lane, K along columns): warp w owns TMEM lanes 32 (w & 3) .. + 31 = rows m of
+    // the expanded matrix (m < 64: re of output m, m >= 64: im of output m - 64) and K columns 16 h .. 16 h + 15,
+    // h = bit 2 of the warp index
+    const uint32_t grp = warp >> 3, gtid = tid & (kTcProducers - 1);
+    const uint32_t q = warp & 3, half = (warp >> 2) & 1;
+    const uint32_t m = 32 * q + lane, ao = m & 63;
+    const bool im_row = (q >> 1) != 0;  // warp-uniform
+    const uint32_t srcA = (4 * half * 64 + ao) * 16;                   // raw [g][o] float4, g = 4 half .. 4 half + 3
+    const uint32_t dstA = ((32 * q) << 16) + kTcAccCols + 16 * half;  // + stage * kTcAStageCols (+ 32 for lo)
+    // B (pre-split by k_mimo_pack_x): items e = tid + 256 r -> (pair member, column t, K group); 16 N complex per chunk
+    constexpr int NBR = 16 * N / kTcProducers;  // 4, 2, 1
+    uint32_t offB[NBR], srcB[NBR];
 #pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const float4 v = qa[q];
-        float ah0, al0, bh0, bl0, ah1, al1, bh1, bl1;
-        split(v.x, ah0, al0);
-        split(v.y, bh0, bl0);
-        split(v.z, ah1, al1);
-        split(v.w, bh1, bl1);
-        const uint32_t off = offA + q * 4 * (kTcRows * 16);
-        if (!bin0) {
-          st_shared4(sA + off, ah0, -bh0, ah1, -bh1);
-          st_shared4(sA + off + 64 * 16, bh0, ah0, bh1, ah1);
-          st_shared4(sA + kTcAHalf + off, al0, -bl0, al1, -bl1);
-          st_shared4(sA + kTcAHalf + off + 64 * 16, bl0, al0, bl1, al1);
+    for (int r = 0; r < NBR; r++) {
+      const uint32_t e = gtid + kTcProducers * r;
+      const uint32_t kg = (e >> (1 + NLOG)) & 7, t = (e >> 1) & (N - 1), jl = (kg << 1) | (e & 1);
+      offB[r] = kg * (N * 16) + t * 16 + (e & 1) * 8;
+      // element (local K index jl, column t) of the raw segment: row jl / P2, position t + p'
+      srcB[r] = 8192 + 8 * ((P2log < 4) ? (jl >> P2log) * seg + (jl & P2m) + t : jl + t);
+    }
+
+    // this group's chunks: it = grp, grp + 2, ...; stage it mod NST, raw slot it mod RD, phases from the wrap counts
+    const uint32_t total = kTcBins * nchunk;
+    uint32_t s = grp % kTcStages, ph = 0, d = grp % kTcRawStages, phd = 0;
+    uint32_t cnext = grp;  // chunk index inside the bin, to find the bin of `it`
+    uint32_t j = 0;
+    for (uint32_t it = grp; it < total; it += kTcGroups) {
+      while (cnext >= nchunk) {
+        cnext -= nchunk;
+        j++;
+      }
+      cnext += kTcGroups;
+      {
+        // ---- raw operands of this chunk (landed by TMA) -> registers; release the raw slot at once ----
+        const uint32_t raw = raw0 + d * kTcRawStageBytes;
+        if (ok && !mbar_wait(bar_rawf + 8 * d, phd)) ok = false;
+        float4 qa[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) qa[g] = ld_shared4(raw + srcA + g * 1024);
+        float2 qh[NBR], ql[NBR];
+#pragma unroll
+        for (int r = 0; r < NBR; r++) {
+          qh[r] = ld_shared2(raw + srcB[r]);
+          ql[r] = ld_shared2(raw + srcB[r] + bhalf);
+        }
+        mbar_arrive(bar_rawe + 8 * d);
+        d += kTcGroups;
+        if (d >= (uint32_t)kTcRawStages) {
+          d -= kTcRawStages;
+          phd ^= 1;
+        }
+        // ---- A: eight complex (a_i, b_i) of output ao -> 16 K columns of row m: re row (a, -b), im row (b, a) ----
+        float hi[16], lo[16];
+        const bool bin0 = (kb + j) == 0;  // packed bin 0 = (DC, Nyquist): two real products, no cross terms
+        if (!im_row) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            split(qa[g].x, hi[4 * g], lo[4 * g]);
+            split(-qa[g].y, hi[4 * g + 1], lo[4 * g + 1]);
+            split(qa[g].z, hi[4 * g + 2], lo[4 * g + 2]);
+            split(-qa[g].w, hi[4 * g + 3], lo[4 * g + 3]);
+          }
+          if (bin0) {
+#pragma unroll
+            for (int u = 1; u < 16; u += 2) hi[u] = lo[u] = 0.f;
+          }
         } else {
-          st_shared4(sA + off, ah0, 0.f, ah1, 0.f);
-          st_shared4(sA + off + 64 * 16, 0.f, bh0, 0.f, bh1);
-          st_shared4(sA + kTcAHalf + off, al0, 0.f, al1, 0.f);
-          st_shared4(sA + kTcAHalf + off + 64 * 16, 0.f, bl0, 0.f, bl1);
-        }
-      }
-      // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo ----
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        if ((uint32_t)r < nbr) {
-          float xh, xl, yh, yl;
-          split(qb[r].x, xh, xl);
-          split(qb[r].y, yh, yl);
-          st_shared2(sB + offB[r], xh, yh);
-          st_shared2(sB + kTcBHalf + offB[r], xl, yl);
+          for (int g = 0; g < 4; g++) {
+            split(qa[g].y, hi[4 * g], lo[4 * g]);
+            split(qa[g].x, hi[4 * g + 1], lo[4 * g + 1]);
+            split(qa[g].w, hi[4 * g + 2], lo[4 * g + 2]);
+            split(qa[g].z, hi[4 * g + 3], lo[4 * g + 3]);
+          }
+          if (bin0) {
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+              hi[u + 1] = hi[u];
+              lo[u + 1] = lo[u];
+              hi[u] = lo[u] = 0.f;
+            }
+          }
+        }
+        // ---- the MMAs that read this stage kTcStages chunks ago have completed ----
+        if (it >= (uint32_t)kTcStages) {
+          if (ok && !mbar_wait(bar_empty + 8 * s, ph ^ 1)) ok = false;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        st_tmem16(tmem + dstA + s * kTcAStageCols, hi);
+        st_tmem16(tmem + dstA + s * kTcAStageCols + 2 * kTcChunk, lo);
+        // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo ----
+        const uint32_t sB = smem0 + s * kTcStageBytes;
+#pragma unroll
+        for (int r = 0; r < NBR; r++) {
+          st_shared2(sB + offB[r], qh[r].x, qh[r].y);
+          st_shared2(sB + kTcBHalf + offB[r], ql[r].x, ql[r].y);
+        }
+        // TMEM stores complete, smem writes visible to the tensor core (async proxy); hand the stage to the issuer
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_full + 8 * s);
+        s += kTcGroups;
+        if (s >= (uint32_t)kTcStages) {
+          s -= kTcStages;
+          ph ^= 1;
         }
       }
-      load_chunk(qa, qb);  // refill this register set: the chunk two iterations ahead
-      // generic-proxy writes -> visible to the tensor core (async proxy), then hand the stage to the issuer
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_full + 8 * s);
-      if (++s == kTcStages) {
-        s = 0;
-        ph ^= 1;
-      }
-      it++;
-    };
-
-    load_chunk(ra[0], rb[0]);
-    load_chunk(ra[1], rb[1]);
-    const uint32_t cdrain = nchunk > 1 ? 1u : 0u;  // chunk of bin j after which bin j-1 is drained
-    uint32_t par = 0;
-    for (uint32_t j = 0; j < (uint32_t)kTcBins; j++)
-      for (uint32_t c = 0; c < nchunk; c++) {
-        if (par == 0) produce(ra[0], rb[0], j);
-        else produce(ra[1], rb[1], j);
-        par ^= 1;
-        if (j > 0 && c == cdrain) drain_bin(j - 1);
-      }
-    drain_bin(kTcBins - 1);
-    if (!ok && tid == 0) atomicExch(a.status, 1);
+    }
+    if (!ok && gtid == 0) atomicExch(a.status, 1);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -369,11 +542,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTcTmemCols));
 }
 
-// Xb[k][i][w] = FDL[i][slot of block (w - (P2-1))][k] for w < P2-1+T, zero for the padding columns.
+// Xb[k][i][w] = FDL[i][slot of block (w - (P2-1))][k] for w < P2-1+T, zero for the padding columns; written as
+// its TF32 hi part and (xlo elements further) its lo part, so the GEMM kernel only copies the B operand.
 // 32 x 32 tile transpose (k <-> w) through shared memory, one input per blockIdx.z.
 __global__ void __launch_bounds__(256) k_mimo_pack_x(const float2* __restrict__ fdl, float2* __restrict__ xb, uint32_t B,
-                                                     uint32_t R, uint32_t head, uint32_t n_in, uint32_t P2, uint32_t T,
-                                                     uint32_t W) {
+                                                     uint32_t R, uint32_t head, uint64_t xbin, uint64_t xlo, uint32_t P2,
+                                                     uint32_t T, uint32_t W) {
   __shared__ float2 tile[32][33];
   const uint32_t k0 = blockIdx.x * 32, w0 = blockIdx.y * 32, i = blockIdx.z;
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -393,7 +567,15 @@ __global__ void __launch_bounds__(256) k_mimo_pack_x(const float2* __restrict__ 
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const uint32_t kl = ty + 8 * r, w = w0 + tx;
-    if (w < W) xb[((uint64_t)(k0 + kl) * n_in + i) * W + w] = tile[tx][kl];
+    if (w < W) {
+      const float2 v = tile[tx][kl];
+      float2 h, l;
+      tc::split(v.x, h.x, l.x);
+      tc::split(v.y, h.y, l.y);
+      const uint64_t at = (uint64_t)(k0 + kl) * xbin + (uint64_t)i * W + w;
+      xb[at] = h;
+      xb[at + xlo] = l;
+    }
   }
 }
 

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) k_probe(const float* __restrict__ A, cons
   for (int idx = tid; idx < K * N; idx += 128) {
     int k = idx / N, n = idx % N;
     int off = (k / 8) * (N / 4) * 32 + (n / 4) * 32 + (k % 8) * 4 + (n % 4);
-    if (mode == 1) off = (k / 4) * (N / 8) * 32 + (n / 8) * 32 + (n % 8) * 4 + (k % 4);  // K-major like A
+    if (mode == 1 || mode == 3) off = (k / 4) * (N / 8) * 32 + (n / 8) * 32 + (n % 8) * 4 + (k % 4);  // K-major like A
     sB[off] = B[idx];
   }
   if (tid == 0) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) k_probe(const float* __restrict__ A, cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // make the generic-proxy smem writes visible to the async proxy (tensor core reads)
@@ -75,7 +75,37 @@ __global__ void __launch_bounds__(128) k_probe(const float* __restrict__ A, cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base;
 
-  if (mode == 2) {
+  if (mode == 3) {
+    // A operand in TMEM: row = lane, K along columns (one 32-bit column per tf32 element), written with tcgen05.st
+    // at columns 128 .. 128+K-1 (the accumulator uses columns 0 .. 127)
+    const int row = warp * 32 + (tid & 31);
+    for (int c = 0; c < K; c++) {
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 128u + (uint32_t)c;
+      uint32_t v = __float_as_uint(A[row * K + c]);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(M >> 4) << 24);
+      const uint32_t b0 = smem_u32(sB);
+      for (int j = 0; j < K / 8; j++) {
+        const uint64_t db = make_desc(b0 + j * 2 * (N / 8) * 128, (N / 8) * 128, 128);
+        const uint32_t acc = j > 0 ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+            :
+            : "r"(tmem), "r"(tmem + 128u + (uint32_t)(j * 8)), "l"(db), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+  } else if (mode == 2) {
     // no MMA: write a pattern into TMEM with tcgen05.st and read it back below (checks the ld path / addressing)
     for (int c0 = 0; c0 < N; c0 += 32) {
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
@@ -139,7 +169,7 @@ __global__ void __launch_bounds__(128) k_probe(const float* __restrict__ A, cons
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
 int main(int argc, char** argv) {
@@ -163,7 +193,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
   int rc = 1;
-  for (int mode = 0; mode < 3; mode++) {
+  for (int mode = 0; mode < 4; mode++) {
     cudaMemset(dS, 0, 4);
     cudaMemset(dC, 0, C.size() * 4);
     k_probe<<<1, 128>>>(dA, dB, dC, dS, mode);
@@ -182,7 +212,7 @@ int main(int argc, char** argv) {
     }
     printf("mode=%d cuda=%s status=%d maxerr=%g bad=%d nonzero=%d  C[0..3]=%g %g %g %g  C[129]=%g R[0..3]=%g %g %g %g R[129]=%g\n", mode,
            cudaGetErrorString(e), st, maxerr, bad, nz, C[0], C[1], C[2], C[3], C[129], R[0], R[1], R[2], R[3], R[129]);
-    if (mode == 0 && e == cudaSuccess && st == 1 && bad == 0) rc = 0;
+    if (mode == 1 && e == cudaSuccess && st == 1 && bad == 0) rc = 0;
     if (e != cudaSuccess) break;
   }
   return rc;
