@@ -1107,9 +1107,9 @@ int tc_alloc(bbx_engine* e) {
   BBX_CUDA_TRY(cudaMemcpy(e->tc_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_status, sizeof(int)));
   BBX_CUDA_TRY(cudaMemset(e->tc_status, 0, sizeof(int)));
-  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax));
+  BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax));
   e->tc_on = true;
   e->tc_dirty = true;
   return BBX_OK;
@@ -1175,10 +1175,20 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   a.xbin = e->tc_xbin;
   a.xlo = (uint64_t)e->B * e->tc_xbin;
   if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+  // raw ring: 8 KB of H + hi and lo FDL runs per chunk (see mimo_tc.cuh); as many stages as fit, an even number
+  {
+    const uint32_t ninp = e->tc_P2log < 4 ? (16u >> e->tc_P2log) : 1u;
+    const uint32_t seg = e->tc_P2log < 4 ? ((N + e->tc_P2) & ~1u) : N + 16;
+    a.raw_stage_bytes = (8192 + 2 * ninp * seg * 8 + 127) & ~127u;
+    uint32_t nst = (kTcSmemMax - kTcOffRaw) / a.raw_stage_bytes;
+    nst = std::min(nst, (uint32_t)kTcRawStagesMax) & ~1u;
+    a.raw_stages = nst;
+  }
+  const uint32_t smem = kTcOffRaw + a.raw_stages * a.raw_stage_bytes;
   const dim3 grid(e->B / kTcBins, e->tc_nog, ntiles);
-  if (Nlog == 4) k_mimo_tc<4><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
-  else if (Nlog == 5) k_mimo_tc<5><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
-  else k_mimo_tc<6><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+  if (Nlog == 4) k_mimo_tc<4><<<grid, kTcThreads, smem, st>>>(a);
+  else if (Nlog == 5) k_mimo_tc<5><<<grid, kTcThreads, smem, st>>>(a);
+  else k_mimo_tc<6><<<grid, kTcThreads, smem, st>>>(a);
   BBX_CUDA_TRY(cudaGetLastError());
   if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
   e->launches++;

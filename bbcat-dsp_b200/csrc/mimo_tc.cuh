@@ -41,8 +41,8 @@ static constexpr int kTcWarpMma = 20;     // one elected lane issues the MMAs
 static constexpr int kTcWarpLoad = 21;    // one elected lane issues the TMA bulk copies
 static constexpr int kTcThreads = 704;
 static constexpr int kTcBins = 4;      // adjacent bins per CTA
-static constexpr int kTcStages = 3;    // converted operand stages: A in TMEM, B in shared memory
-static constexpr int kTcRawStages = 4; // raw operand stages (TMA bulk copies from HBM)
+static constexpr int kTcStages = 4;    // converted operand stages: A in TMEM, B in shared memory
+static constexpr int kTcRawStagesMax = 8; // raw operand stages (TMA bulk copies from HBM): as many as fit, even
 static constexpr int kTcChunk = 16;    // complex K elements per stage = 32 tf32 = 4 MMA k-steps
 static constexpr int kTcRows = 128;    // accumulator rows: 64 outputs x (re, im)
 static constexpr int kTcNmax = 64;     // columns (block-steps) per accumulator tile
@@ -50,12 +50,12 @@ static constexpr uint32_t kTcBHalf = kTcNmax * kTcChunk * 2 * 4;          // 8 K
 static constexpr uint32_t kTcStageBytes = 2 * kTcBHalf;                   // 16 KB of shared memory per stage
 static constexpr uint32_t kTcTileBytes = kTcNmax * 2 * 64 * 4;            // 32 KB: epilogue tile [t][re/im][o]
 // raw stage: 8 KB of packed H (64 outputs x 16 complex) + the FDL runs of the chunk: (16 / P2) input rows of
-// N + P2 complex (P2 < 16) or one row of N + 16, hi and lo parts; worst case P2 = 1: 2 x 16 x 66 x 8 bytes
-static constexpr uint32_t kTcRawStageBytes = 8192 + 2 * 16 * 66 * 8;
+// N + P2 complex (P2 < 16) or one row of N + 16, hi and lo parts.  Its size depends on (P2, N): the host passes
+// the stage size and the number of stages that fit (MimoTcArgs::raw_stage_bytes / raw_stages).
 static constexpr uint32_t kTcOffTile = kTcStages * kTcStageBytes;
-static constexpr uint32_t kTcOffRaw = kTcOffTile + kTcTileBytes;
-static constexpr uint32_t kTcOffBar = kTcOffRaw + kTcRawStages * kTcRawStageBytes;
-static constexpr uint32_t kTcSmemBytes = kTcOffBar + 256;
+static constexpr uint32_t kTcOffBar = kTcOffTile + kTcTileBytes;
+static constexpr uint32_t kTcOffRaw = kTcOffBar + 256;
+static constexpr uint32_t kTcSmemMax = 227 * 1024;
 // TMEM (512 columns x 128 lanes): columns 0..255 = four 64-column accumulator tiles, columns 256..511 = the A
 // operand ring (per stage 32 columns of A_hi and 32 of A_lo: row = lane, K along columns).  A never touches
 // shared memory: the producers write it with tcgen05.st, the MMA reads it from TMEM ([a-tmem] operand form), which
@@ -64,8 +64,8 @@ static constexpr uint32_t kTcSmemBytes = kTcOffBar + 256;
 // accumulations (one tile for everything: 109 dB SNR at K = 512 complex).  The hi*hi products therefore rotate
 // over three tiles (k-step mod 3) and the small lo*hi / hi*lo terms have their own tile, so the dominant sums see
 // K/12 accumulations instead of 3K/4; the epilogue adds the four tiles in fp32 round-to-nearest.
-static constexpr uint32_t kTcAccTiles = 5;
-static constexpr uint32_t kTcAccCols = kTcAccTiles * kTcNmax;             // 320
+static constexpr uint32_t kTcAccTiles = 4;
+static constexpr uint32_t kTcAccCols = kTcAccTiles * kTcNmax;             // 256
 static constexpr uint32_t kTcAStageCols = 4 * kTcChunk;                   // 64: A_hi | A_lo
 static constexpr uint32_t kTcTmemCols = 512;
 static constexpr uint32_t kTcMaxK = 1024;                                 // complex K verified against the tolerance
@@ -78,6 +78,7 @@ struct MimoTcArgs {
   uint32_t B, n_in, n_out, P2log, G /* float4 K groups = Kc/2 */, W, T, slot_stride;
   uint64_t xbin;     // float2 elements per bin of xb = (inputs padded to whole chunks) * W
   uint64_t xlo;      // float2 elements from the hi part of xb to the lo part (same layout)
+  uint32_t raw_stage_bytes, raw_stages;  // raw ring geometry (stages: even, <= kTcRawStagesMax)
 };
 
 namespace tc {
@@ -253,13 +254,9 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tA, uint32_t
     uint32_t r = rot0 + k8;
     r = r >= 3 ? r - 3 : r;
     const uint32_t d_hh = tmem + r * kTcNmax;
-    if (FIRST && k8 == 0) {
-      mma_ts<false>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
-      mma_ts<false>(tmem + 4 * kTcNmax, a_hi, b_lo, idesc);
-    } else {
-      mma_ts<true>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
-      mma_ts<true>(tmem + 4 * kTcNmax, a_hi, b_lo, idesc);
-    }
+    if (FIRST && k8 == 0) mma_ts<false>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
+    else mma_ts<true>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
+    mma_ts<true>(tmem + 3 * kTcNmax, a_hi, b_lo, idesc);
     if (FIRST && k8 < 3) mma_ts<false>(d_hh, a_hi, b_hi, idesc);
     else mma_ts<true>(d_hh, a_hi, b_hi, idesc);
   }
@@ -284,8 +281,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   const uint32_t bar_accf = bar_empty + 8 * kTcStages;
   const uint32_t bar_acce = bar_accf + 8;
   const uint32_t bar_rawf = bar_acce + 8;
-  const uint32_t bar_rawe = bar_rawf + 8 * kTcRawStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + kTcOffBar + 8 * (2 * kTcStages + 2 + 2 * kTcRawStages));
+  const uint32_t bar_rawe = bar_rawf + 8 * kTcRawStagesMax;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + kTcOffBar + 8 * (2 * kTcStages + 2 + 2 * kTcRawStagesMax));
+  const uint32_t RD = a.raw_stages, RSB = a.raw_stage_bytes;
 
   if (tid == 0) {
 #pragma unroll
@@ -296,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_accf));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_acce), "n"(kTcEpiThreads));
 #pragma unroll
-    for (int d = 0; d < kTcRawStages; d++) {
+    for (int d = 0; d < kTcRawStagesMax; d++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_rawf + 8 * d));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_rawe + 8 * d), "n"(kTcProducers));
     }
@@ -327,11 +325,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         const char* asrc = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb + j) * a.G) * 64);
         const float2* xrow = a.xb + (uint64_t)(kb + j) * a.xbin + t0;
         for (uint32_t c = 0; c < nchunk; c++, it++) {
-          if (it >= (uint32_t)kTcRawStages) {
+          if (it >= RD) {
             if (ok && !mbar_wait(bar_rawe + 8 * d, ph ^ 1)) ok = false;
           }
           if (elect_one()) {
-            const uint32_t dst = raw0 + d * kTcRawStageBytes, bar = bar_rawf + 8 * d;
+            const uint32_t dst = raw0 + d * RSB, bar = bar_rawf + 8 * d;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             bulk_g2s(dst, asrc + (uint64_t)c * 8192, 8192, bar);
             // chunk c starts at complex K index 16 c = (input i0, reversed partition pp0)
@@ -343,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
             }
           }
           __syncwarp();
-          if (++d == kTcRawStages) {
+          if (++d == RD) {
             d = 0;
             ph ^= 1;
           }
@@ -353,8 +351,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     }
   } else if (warp == kTcWarpMma) {
     // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
-    // accumulator tiles 0..2 take the hi*hi products by k-step mod 3, tiles 3 and 4 the small lo*hi / hi*lo terms
-    // (consecutive MMAs never accumulate into the same tile)
+    // accumulator tiles 0..2 take the hi*hi products by k-step mod 3, tile 3 the small lo*hi / hi*lo terms
     const uint32_t blo0 = kDescLo<N> + (smem0 >> 4);  // low descriptor word of stage 0's B_hi tile
     uint32_t s = 0, ph = 0;
     for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
@@ -391,7 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (uint32_t cg = 0; cg < (N >> 4); cg++) {
-        // (((t0 + t1) + t2) + t3) + t4, one tile in flight (few registers: 704 threads share the register file)
+        // ((t0 + t1) + t2) + t3, one tile in flight (few registers: 704 threads share the register file)
         float v[16];
 #pragma unroll 1
         for (uint32_t z = 0; z < kTcAccTiles; z++) {
@@ -447,7 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
 
     // this group's chunks: it = grp, grp + 2, ...; stage it mod NST, raw slot it mod RD, phases from the wrap counts
     const uint32_t total = kTcBins * nchunk;
-    uint32_t s = grp % kTcStages, ph = 0, d = grp % kTcRawStages, phd = 0;
+    uint32_t s = grp % kTcStages, ph = 0, d = grp % RD, phd = 0;
     uint32_t cnext = grp;  // chunk index inside the bin, to find the bin of `it`
     uint32_t j = 0;
     for (uint32_t it = grp; it < total; it += kTcGroups) {
@@ -458,7 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       cnext += kTcGroups;
       {
         // ---- raw operands of this chunk (landed by TMA) -> registers; release the raw slot at once ----
-        const uint32_t raw = raw0 + d * kTcRawStageBytes;
+        const uint32_t raw = raw0 + d * RSB;
         if (ok && !mbar_wait(bar_rawf + 8 * d, phd)) ok = false;
         float4 qa[4];
 #pragma unroll
@@ -471,8 +468,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         }
         mbar_arrive(bar_rawe + 8 * d);
         d += kTcGroups;
-        if (d >= (uint32_t)kTcRawStages) {
-          d -= kTcRawStages;
+        if (d >= RD) {
+          d -= RD;
           phd ^= 1;
         }
         // ---- A: eight complex (a_i, b_i) of output ao -> 16 K columns of row m: re row (a, -b), im row (b, a) ----
