@@ -31,7 +31,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("block_size", u32), ("max_partitions", u32), ("n_inputs", u32),
                 ("n_outputs", u32), ("n_paths", u32), ("mode", C.c_int), ("max_blocks", u32), ("max_delay", u32),
                 ("fractional_delay", C.c_int), ("ring_length", u32), ("mac_ctas_per_sm", u32), ("mac_l2_keep_16ths", u32),
-                ("mac_time_tile", u32), ("mimo_tensor", u32), ("reserved", u32 * 4)]
+                ("mac_time_tile", u32), ("mimo_tensor", u32), ("mimo_shard_world", u32), ("mimo_shard_rank", u32), ("reserved", u32 * 2)]
 
 
 # every symbol include/bbx.h declares: name -> (restype, argtypes)
@@ -101,6 +101,11 @@ SYMBOLS = {
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
     "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
+    "bbx_comm_available": (C.c_int, []),
+    "bbx_comm_unique_id": (C.c_int, [C.POINTER(u8)]),
+    "bbx_comm_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(u8), C.c_int, C.POINTER(vp)]),
+    "bbx_comm_destroy": (C.c_int, [vp]),
+    "bbx_engine_set_comm": (C.c_int, [vp, vp]),
 }
 
 _lib = None
@@ -327,7 +332,7 @@ class Convolver:
 
     def __init__(self, block_size, max_partitions, n_inputs, n_outputs=0, n_paths=0, mode=MODE_PER_CHANNEL,
                  max_blocks=1, max_delay=0, fractional_delay=False, ring_length=0, device=0, mac_ctas_per_sm=0,
-                 mac_l2_keep_16ths=0, mac_time_tile=0, mimo_tensor=0):
+                 mac_l2_keep_16ths=0, mac_time_tile=0, mimo_tensor=0, mimo_shard_world=0, mimo_shard_rank=0):
         cfg = Config()
         cfg.device = device
         cfg.block_size = block_size
@@ -344,6 +349,8 @@ class Convolver:
         cfg.mac_l2_keep_16ths = mac_l2_keep_16ths
         cfg.mac_time_tile = mac_time_tile
         cfg.mimo_tensor = mimo_tensor
+        cfg.mimo_shard_world = mimo_shard_world
+        cfg.mimo_shard_rank = mimo_shard_rank
         h = vp()
         _check(lib().bbx_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -351,6 +358,8 @@ class Convolver:
         self.mode = mode
         self.n_inputs = n_inputs
         self.n_outputs = n_inputs if mode == MODE_PER_CHANNEL else n_outputs
+        if mimo_shard_world > 1:
+            self.n_outputs = n_outputs // mimo_shard_world  # PCM channels written by this rank
         self.n_paths = n_inputs if mode == MODE_PER_CHANNEL else (n_inputs * n_outputs if mode == MODE_MIMO else n_paths)
         self.max_blocks = max(1, max_blocks)
         self.ring_length = lib().bbx_engine_get_ring_length(h)
@@ -429,6 +438,11 @@ class Convolver:
         """0 = leave as is; time_tile=1 forces the streaming MAC, l2_keep_16ths > 16 switches the hints off."""
         _check(lib().bbx_engine_set_tuning(self.h, ctas_per_sm, l2_keep_16ths, time_tile))
 
+    def SetComm(self, comm):
+        """Attach the communicator of the input-sharded MIMO engine (None detaches)."""
+        _check(lib().bbx_engine_set_comm(self.h, comm.h if comm is not None else None))
+        self._comm = comm
+
     def tensor_status(self):
         """(launches of the tensor-core MIMO kernel so far, device status word: 0 = ok)."""
         n, st = u64(0), C.c_int(0)
@@ -437,6 +451,29 @@ class Convolver:
 
     def flush_l2(self, nbytes=256 << 20):
         _check(lib().bbx_engine_flush_l2(self.h, nbytes))
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the other ranks receive it out of band)."""
+    buf = (u8 * 128)()
+    _check(lib().bbx_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """Communicator of the input-sharded MIMO engine (NCCL, loaded at run time by libbbx)."""
+
+    def __init__(self, world, rank, unique_id, device=0):
+        assert len(unique_id) == 128
+        buf = (u8 * 128).from_buffer_copy(unique_id)
+        h = vp()
+        _check(lib().bbx_comm_create(world, rank, buf, device, C.byref(h)))
+        self.h, self.world, self.rank = h, world, rank
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_comm_destroy(self.h)
+            self.h = None
 
 
 class BlockConvolver:

@@ -386,7 +386,7 @@ struct PlanView {
 };
 
 template <int M>
-__device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, const float* __restrict__ nyq_t,
+__device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, const float* __restrict__ nyq_t, uint64_t s_stride,
                                              uint32_t first, uint32_t count, float2* __restrict__ x,
                                              float2* __restrict__ s, const float2* __restrict__ tw, int tid,
                                              float (&o)[FftCfg<M>::R]) {
@@ -400,7 +400,7 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
       float2 v[4];
 #pragma unroll
       for (int q = 0; q < 4; q++)
-        v[q] = (sl + q < count) ? ypart_t[(uint64_t)(first + sl + q) * M + k] : make_float2(0.f, 0.f);
+        v[q] = (sl + q < count) ? ypart_t[(uint64_t)(first + sl + q) * s_stride + k] : make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; q++)
         if (sl + q < count) {
@@ -435,7 +435,9 @@ template <int M>
 __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
 k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
         const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
-        const float* __restrict__ nyq_part) {
+        const float* __restrict__ nyq_part, uint64_t t_stride, uint64_t s_stride, uint32_t stream0) {
+  // spectrum of (block t, slot s) at ypart + t * t_stride + s * s_stride (the MAC kernels: t_stride = slot_stride * M,
+  // s_stride = M; after the sharded reduce-scatter: [slot][t][M]); streams stream0 .. stream0 + n_streams - 1
   constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
   extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
   float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
@@ -443,13 +445,13 @@ k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_b
   const int tid = threadIdx.x;
   const uint32_t sq = blockIdx.x * FPB + threadIdx.y, t = blockIdx.y;
   const bool active = sq < n_streams;
-  const uint32_t stream = active ? sq : n_streams - 1;
+  const uint32_t stream = stream0 + (active ? sq : n_streams - 1);
   const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
   const PlanView pv = first ? first_blk : steady;
-  const float2* ypart_t = ypart + (uint64_t)t * slot_stride * M;
+  const float2* ypart_t = ypart + (uint64_t)t * t_stride;
   const float* nyq_t = nyq_part ? nyq_part + (uint64_t)t * slot_stride : nullptr;
   float o[RAD];
-  job_to_block<M>(ypart_t, nyq_t, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
+  job_to_block<M>(ypart_t, nyq_t, s_stride, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
   // the crossfade decision must be uniform across the CTA (block-wide barriers inside job_to_block):
   // every transform of the CTA runs the second pass when any of them needs it
   const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
@@ -457,7 +459,7 @@ k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_b
   float o2[RAD];
   if (any_x) {
     const bool mine = (xj != kNoJob && xj != kSameJob);
-    job_to_block<M>(ypart_t, nyq_t, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw, tid, o2);
+    job_to_block<M>(ypart_t, nyq_t, s_stride, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw, tid, o2);
   }
   if (xj != kNoJob) {
     if (xj == kSameJob) {
@@ -581,6 +583,35 @@ __global__ void k_flush(float4* p, size_t n) {
     p[i] = make_float4(1.f, 2.f, 3.f, 4.f);
 }
 
+// Input-sharded MIMO: this rank's partial output spectra, job by job (slots summed in fixed order, bin 0 restored to
+// (DC, Nyquist)), into the reduce-scatter send buffer [output][t][B] -- one contiguous chunk per destination rank.
+__global__ void __launch_bounds__(256) k_gather_spectra(const float2* __restrict__ ypart, const float* __restrict__ nyq_part,
+                                                        uint32_t slot_stride, PlanView pv, float2* __restrict__ send, uint32_t B,
+                                                        uint32_t T) {
+  const uint32_t o = blockIdx.x, t = blockIdx.y;
+  const uint32_t first = pv.job_slot_first[o], count = pv.job_slot_count[o];
+  const float2* yt = ypart + (uint64_t)t * slot_stride * B;
+  for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) {
+    float2 a = make_float2(0.f, 0.f);
+    for (uint32_t sl = 0; sl < count; sl++) {
+      const float2 v = yt[(uint64_t)(first + sl) * B + k];
+      a.x += v.x;
+      a.y += v.y;
+    }
+    if (k == 0 && nyq_part) {
+      float n = 0.f;
+      for (uint32_t sl = 0; sl < count; sl++) n += nyq_part[(uint64_t)t * slot_stride + first + sl];
+      a = make_float2(a.x + n, n);
+    }
+    send[((uint64_t)o * T + t) * B + k] = a;
+  }
+}
+
+// comm.cu
+int comm_reduce_scatter_f32(bbx_comm* c, const float* send, float* recv, size_t recvcount, cudaStream_t st);
+int comm_world(const bbx_comm* c);
+int comm_rank(const bbx_comm* c);
+
 }  // namespace bbx
 
 using namespace bbx;
@@ -687,6 +718,13 @@ struct bbx_engine {
   double mac_ms_total = 0.0;
   uint64_t mac_launches = 0, mac_units = 0, mac_bytes = 0;
   int last_infmt = FMT_F32, last_outfmt = FMT_F32;
+  // input-sharded MIMO (bbx_config::mimo_shard_*): partial spectra -> reduce-scatter -> local outputs only
+  uint32_t sh_world = 1, sh_rank = 0, sh_o0 = 0, sh_nloc = 0;  // local outputs [sh_o0, sh_o0 + sh_nloc)
+  uint32_t n_out_pcm = 0;                                      // channels written by bbx_process (= sh_nloc when sharded)
+  bbx_comm* comm = nullptr;
+  float2* sh_send = nullptr;  // [n_out][T][B]
+  float2* sh_recv = nullptr;  // [sh_nloc][T][B]
+  uint32_t* sh_view = nullptr;  // device: first[n_out] | count[n_out] | xjob[n_out], first[o] = o - sh_o0
   // MIMO on the tensor cores (mimo_tc.cuh): bin-major operand copies and a one-slot-per-output plan view
   bool tc_on = false;          // buffers exist (MIMO mode, max_blocks >= tc_min_blocks, not disabled)
   bool tc_dirty = true;        // Hpack must be rebuilt from the current filter matrix
@@ -739,16 +777,32 @@ PlanView tc_plan_view(const bbx_engine* e) {
   return v;
 }
 
+PlanView shard_plan_view(const bbx_engine* e) {
+  PlanView v;
+  v.job_slot_first = e->sh_view;
+  v.job_slot_count = e->sh_view + e->n_out;
+  v.xjob = e->sh_view + 2 * (size_t)e->n_out;
+  return v;
+}
+
 template <int M>
 void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaStream_t st) {
   constexpr int FPB = FftCfg<M>::FPB;
   constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e->sh_world > 1 || e->comm) {
+    // reduced spectra of the local outputs, [local output][t][M]
+    const PlanView v = shard_plan_view(e);
+    k_irfft<M><<<dim3(ceil_div(e->sh_nloc, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
+        e->sh_recv, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
+        e->sh_o0);
+    return;
+  }
   const PlanView first = tc ? tc_plan_view(e) : e->plan_first.view();
   const PlanView steady = tc ? tc_plan_view(e) : e->plan_steady.view();
   k_irfft<M><<<dim3(ceil_div(e->n_streams, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
       e->ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams,
-      tc ? nullptr : e->nyq_part);
+      tc ? nullptr : e->nyq_part, (uint64_t)e->max_slots * M, (uint64_t)M, 0u);
 }
 
 int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc = false) {
@@ -1034,6 +1088,8 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
       flags[o] = 0;
     }
     ofirst[e->n_out] = e->n_out;
+    // sharded: PCM channel c of this rank is output sh_o0 + c
+    for (uint32_t c = 0; c < e->n_out_pcm && e->n_out_pcm < e->n_out; c++) rstream[c] = e->sh_o0 + c;
   } else {
     uint32_t n = 0;
     for (uint32_t o = 0; o < e->n_out; o++) {
@@ -1244,7 +1300,18 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     e->n_out = cfg->n_outputs;
     e->n_paths = e->n_in * e->n_out;
     e->n_streams = e->n_out;
+    if (cfg->mimo_shard_world > 1) {
+      BBX_REQUIRE(cfg->mimo_shard_rank < cfg->mimo_shard_world, "mimo_shard_rank %u out of range", cfg->mimo_shard_rank);
+      BBX_REQUIRE(e->n_out % cfg->mimo_shard_world == 0, "n_outputs %u is not a multiple of mimo_shard_world %u", e->n_out,
+                  cfg->mimo_shard_world);
+      e->sh_world = cfg->mimo_shard_world;
+      e->sh_rank = cfg->mimo_shard_rank;
+    }
   }
+  BBX_REQUIRE(e->mode == BBX_MODE_MIMO || cfg->mimo_shard_world <= 1, "mimo_shard_world needs MIMO mode");
+  e->sh_nloc = e->n_out / e->sh_world;
+  e->sh_o0 = e->sh_rank * e->sh_nloc;
+  e->n_out_pcm = (e->sh_world > 1) ? e->sh_nloc : e->n_out;
   e->Tmax = std::max(1u, cfg->max_blocks);
   e->R = e->Pmax + e->Tmax - 1;
   uint32_t need = cfg->max_delay + 14 + (e->Tmax + 1) * e->B;
@@ -1318,6 +1385,19 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   BBX_CUDA_TRY(cudaMalloc((void**)&e->nyq_part, sizeof(float) * (size_t)e->Tmax * e->max_slots));
   BBX_CUDA_TRY(cudaMemset(e->nyq_part, 0, sizeof(float) * (size_t)e->Tmax * e->max_slots));
 
+  if (e->sh_world > 1) {
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->sh_send, sizeof(float2) * (size_t)e->n_out * e->Tmax * B));
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->sh_recv, sizeof(float2) * (size_t)e->sh_nloc * e->Tmax * B));
+    std::vector<uint32_t> view(3 * (size_t)e->n_out);
+    for (uint32_t o = 0; o < e->n_out; o++) {
+      view[o] = (o >= e->sh_o0 && o < e->sh_o0 + e->sh_nloc) ? o - e->sh_o0 : 0u;
+      view[e->n_out + o] = 1;
+      view[2 * (size_t)e->n_out + o] = kNoJob;
+    }
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->sh_view, sizeof(uint32_t) * view.size()));
+    BBX_CUDA_TRY(cudaMemcpy(e->sh_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
+  }
+
   // MIMO: tensor-core operands (time-batched calls only)
   if (e->mode == BBX_MODE_MIMO && cfg->mimo_tensor != 1 && e->Tmax >= e->tc_min_blocks && e->B >= 64) {
     uint32_t P2 = 1;
@@ -1384,6 +1464,9 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   cudaFree(e->flush_buf);
+  cudaFree(e->sh_send);
+  cudaFree(e->sh_recv);
+  cudaFree(e->sh_view);
   cudaFree(e->tc_hpack);
   cudaFree(e->tc_xb);
   cudaFree(e->tc_ftab_d);
@@ -1474,6 +1557,8 @@ int bbx_set_filter(bbx_engine* e, uint32_t path, const bbx_filter* filter, int c
   BBX_REQUIRE(delay >= 0.0 && delay <= (double)e->cfg.max_delay, "bbx_set_filter: delay %g outside [0, max_delay=%u]", delay,
               e->cfg.max_delay);
   BBX_REQUIRE(e->mode != BBX_MODE_MIMO || delay == 0.0, "bbx_set_filter: MIMO mode has no per-path delay");
+  BBX_REQUIRE(!(e->sh_world > 1 || e->comm) || !crossfade,
+              "bbx_set_filter: the input-sharded MIMO engine switches filters without crossfade");
   PathState& p = e->paths[path];
   p.pend = filter;
   p.pend_delay = delay;
@@ -1490,7 +1575,8 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
               nframes, e->B);
   const uint32_t B = e->B, T = nframes / B;
   BBX_REQUIRE(T <= e->Tmax, "bbx_process: %u blocks exceed max_blocks %u", T, e->Tmax);
-  BBX_REQUIRE(in_channels >= e->n_in && out_channels >= e->n_out, "bbx_process: too few channels in the PCM buffers");
+  BBX_REQUIRE(in_channels >= e->n_in && out_channels >= e->n_out_pcm, "bbx_process: too few channels in the PCM buffers");
+  BBX_REQUIRE(e->sh_world <= 1 || e->comm, "bbx_process: the input-sharded MIMO engine needs bbx_engine_set_comm()");
   BBX_CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
   int rc;
@@ -1617,6 +1703,15 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   } else {
     if ((rc = launch_mac(e, e->plan_steady, 0, T))) return rc;
   }
+  // ---- 3b. input-sharded MIMO: sum the partial spectra over the ranks, keep the local outputs ----
+  if (e->sh_world > 1 || e->comm) {
+    const PlanView pv = use_tc ? tc_plan_view(e) : e->plan_steady.view();
+    k_gather_spectra<<<dim3(e->n_out, T), 256, 0, st>>>(e->ypart, use_tc ? nullptr : e->nyq_part, e->max_slots, pv, e->sh_send, B, T);
+    BBX_CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    if ((rc = comm_reduce_scatter_f32(e->comm, (const float*)e->sh_send, (float*)e->sh_recv, (size_t)e->sh_nloc * T * B * 2, st)))
+      return rc;
+  }
   // ---- 4. inverse transforms, crossfade, delay ring ----
   if ((rc = launch_irfft(e, T, n_first, use_tc))) return rc;
   e->launches++;
@@ -1627,7 +1722,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     a.fmt = outfmt;
     a.be = out_be;
     a.out_channels = out_channels;
-    a.n_outputs = e->n_out;
+    a.n_outputs = e->n_out_pcm;
     a.B = B;
     a.T = T;
     a.ybuf = e->ybuf;
@@ -1639,7 +1734,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
       a.fast = (!out_be && bps != 3 && ((uintptr_t)out % bps) == 0) ? 1 : 0;
     }
     a.rv = route_view(e);
-    dim3 grid(T * B / 32, ceil_div(e->n_out, 32));
+    dim3 grid(T * B / 32, ceil_div(e->n_out_pcm, 32));
     k_pcm_out<<<grid, 256, 0, st>>>(a);
     BBX_CUDA_TRY(cudaGetLastError());
     e->launches++;
@@ -1678,7 +1773,7 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   // H2D on the input-copy stream, once the kernels of call n-2 have finished reading this staging buffer
   BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
   BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
-  if (out_channels > e->n_out) {
+  if (out_channels > e->n_out_pcm) {
     // channels beyond n_outputs keep the caller's bytes: seed the output staging with them
     BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_d2h[k], 0));
     BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out[k], out, out_bytes, cudaMemcpyHostToDevice, e->s_in));
@@ -1773,6 +1868,31 @@ int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_
   BBX_REQUIRE(e != nullptr, "null engine");
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   apply_tuning(e, ctas_per_sm, l2_keep_16ths, time_tile);
+  return BBX_OK;
+}
+
+int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_REQUIRE(e->mode == BBX_MODE_MIMO, "bbx_engine_set_comm: only the MIMO engine has a collective");
+  BBX_REQUIRE(!c || ((uint32_t)comm_world(c) == e->sh_world && (uint32_t)comm_rank(c) == e->sh_rank),
+              "bbx_engine_set_comm: communicator (rank %d of %d) does not match the engine (rank %u of %u)", comm_rank(c),
+              comm_world(c), e->sh_rank, e->sh_world);
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (c && !e->sh_send) {
+    // world == 1 with a communicator: the sharded code path on one GPU (tests)
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->sh_send, sizeof(float2) * (size_t)e->n_out * e->Tmax * e->B));
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->sh_recv, sizeof(float2) * (size_t)e->sh_nloc * e->Tmax * e->B));
+    std::vector<uint32_t> view(3 * (size_t)e->n_out);
+    for (uint32_t o = 0; o < e->n_out; o++) {
+      view[o] = o;
+      view[e->n_out + o] = 1;
+      view[2 * (size_t)e->n_out + o] = kNoJob;
+    }
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->sh_view, sizeof(uint32_t) * view.size()));
+    BBX_CUDA_TRY(cudaMemcpy(e->sh_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
+  }
+  e->comm = c;
   return BBX_OK;
 }
 

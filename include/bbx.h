@@ -178,7 +178,13 @@ typedef struct {
   uint32_t mac_l2_keep_16ths; /* streaming MAC: sixteenths of the H/FDL lines kept L2-resident, 1..16 (default 3); > 16 = hints off */
   uint32_t mac_time_tile;     /* 16 or 32: calls with >= tile/2 blocks and filters of >= 2*tile partitions use the time-batched MAC (default 16); 1 = streaming MAC only */
   uint32_t mimo_tensor;       /* MIMO mode: 0 = calls of >= 16 blocks run the per-bin complex GEMM on the tensor cores (3xTF32, tcgen05); 1 = SIMT MAC only */
-  uint32_t reserved[4];
+  /* MIMO, input-sharded over several GPUs: this engine holds n_inputs of the inputs and ALL n_outputs
+   * outputs of the matrix; after the MAC the partial output spectra are summed over the ranks with one NCCL
+   * reduce-scatter per call and rank r converts outputs [r n_outputs / world, (r+1) n_outputs / world) to PCM
+   * (bbx_process writes n_outputs / world channels).  0 or 1 = not sharded.  Needs bbx_engine_set_comm(). */
+  uint32_t mimo_shard_world;
+  uint32_t mimo_shard_rank;
+  uint32_t reserved[2];
 } bbx_config;
 
 typedef struct bbx_engine bbx_engine;
@@ -219,6 +225,16 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
 int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
                       int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
 int bbx_engine_sync(bbx_engine* e);
+
+/* Communicator for the input-sharded MIMO engine: a thin handle over an NCCL communicator (libnccl is loaded at run
+ * time).  Rank 0 creates the 128-byte id and distributes it out of band; every rank then calls bbx_comm_create. */
+typedef struct bbx_comm bbx_comm;
+int bbx_comm_available(void); /* 1 when libnccl.so.2 can be loaded */
+int bbx_comm_unique_id(uint8_t* id128);
+int bbx_comm_create(int world, int rank, const uint8_t* id128, int device, bbx_comm** out);
+int bbx_comm_destroy(bbx_comm* c);
+/* attach the communicator (world and rank must match bbx_config::mimo_shard_*); the engine does not own it */
+int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c);
 
 /* Single-channel convenience = BlockConvolver::Convolve (README:38-39): path 0 of a
  * PER_CHANNEL engine, one float block in, one float block out (host pointers). */

@@ -140,14 +140,72 @@ def c5(steps):
     return r
 
 
+def c5_sharded(steps):
+    """C5 input-sharded over the ranks of a torchrun launch (one process per GPU): rank g holds 64 / world inputs and
+    all 64 outputs; per call one ncclReduceScatter of the partial output spectra (16.8 MB at T = 64); rank g converts
+    64 / world outputs.  Device time = max over ranks between barriers; prints on rank 0.
+
+        python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+            tools/bench_configs.py --configs C5S
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    B, L, nin, nout, T = 512, 4096, 64, 64, 64
+    uid = [bbx.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = bbx.Comm(world, rank, uid[0], device=local)
+    i0, ni = bbx.shard_range(nin, rank, world)
+    eng = bbx.Convolver(B, 8, ni, n_outputs=nout, mode=bbx.MODE_MIMO, max_blocks=T, mimo_shard_world=world,
+                        mimo_shard_rank=rank, device=local)
+    eng.SetComm(comm)
+    for o in range(nout):
+        for i in range(ni):
+            eng.SelectFilter(o * ni + i, eng.CreateFilter(make_ir(2000 + 64 * o + i0 + i, L)))
+    nloc = nout // world
+    frames = T * B
+    x = (torch.rand(frames * ni, device="cuda") * 2 - 1).view(torch.uint8)
+    y = torch.empty(frames * nloc * 4, dtype=torch.uint8, device="cuda")
+    for _ in range(5):
+        eng.ConvolveDev(x.data_ptr(), 4, ni, y.data_ptr(), 4, nloc, frames)
+    eng.Sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.timer_start()
+    for _ in range(steps):
+        eng.ConvolveDev(x.data_ptr(), 4, ni, y.data_ptr(), 4, nloc, frames)
+    ms = eng.timer_stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    r = {"config": "C5 MIMO 64 x 64, 4096 taps, B=512, f32, input-sharded over %d GPU(s), ncclReduceScatter of %d MB per "
+                   "step" % (world, nout * T * B * 8 >> 20), "channels": nout, "n_gpus": world,
+         "channel_s_per_s": nout * steps * frames / FS / (ms * 1e-3), "ms_per_step": ms / steps, "blocks_per_step": T}
+    eng.close()
+    comm.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return r if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C1,C2,C4,C5")
     ap.add_argument("--steps", type=int, default=200)
     args = ap.parse_args()
-    fns = {"C1": c1, "C2": c2, "C4": c4, "C5": c5}
+    fns = {"C1": c1, "C2": c2, "C4": c4, "C5": c5, "C5S": c5_sharded}
     for name in args.configs.split(","):
-        print(json.dumps({name: fns[name](args.steps)}))
+        r = fns[name](args.steps)
+        if r is not None:
+            print(json.dumps({name: r}))
 
 
 if __name__ == "__main__":
