@@ -35,6 +35,7 @@ namespace bbx {
 static constexpr uint32_t kNoJob = 0xFFFFFFFFu;
 static constexpr uint32_t kSameJob = 0xFFFFFFFEu;  // crossfade a stream with itself (delay-only switch)
 static constexpr int kNumSMs = 148;
+__host__ __device__ __forceinline__ uint32_t ceil_div_dev(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------
 // k_pcm_in
@@ -102,6 +103,54 @@ k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, f
   cfft_smem<M, false>(s, tw, tid);
   const uint32_t slot = (slot0 + t) % R;
   rfft_split_store<M>(s, tw, dst + ch * dst_ch_stride + (uint64_t)slot * M, scale, tid, active);
+}
+
+// Radix-8 sizes: persistent CTAs loop over (channel group, block) items with their twiddles in registers, the next
+// item's window prefetched into registers, the first pass straight from those registers, and (for M = 512) one named
+// barrier per transform instead of the block barrier.
+template <int M>
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
+k_rfft8(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, float2* __restrict__ dst, uint64_t dst_ch_stride,
+        uint32_t R, uint32_t slot0, const float2* __restrict__ tw, float scale, uint32_t nch, uint32_t T) {
+  constexpr int NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
+  __shared__ float2 smem[FPB][MP];
+  float2* s = smem[threadIdx.y];
+  const int tid = threadIdx.x;
+  Tw8<M> tw8;
+  load_tw8<M>(tw8, tw, tid);
+  const uint32_t nchg = ceil_div_dev(nch, (uint32_t)FPB), nitems = nchg * T;
+  auto window = [&](uint32_t item, uint32_t& ch, uint32_t& t, bool& active) {
+    t = item / nchg;
+    const uint32_t chq = (item - t * nchg) * FPB + threadIdx.y;
+    active = chq < nch;
+    ch = active ? chq : nch - 1;  // idle transforms of a last group recompute a valid one, stores masked
+    return reinterpret_cast<const float2*>(src + ch * ch_stride + (uint64_t)t * win_stride);
+  };
+  uint32_t item = blockIdx.x, ch = 0, t = 0;
+  bool active = false;
+  float2 vn[8];
+  if (item < nitems) {
+    const float2* win = window(item, ch, t, active);
+#pragma unroll
+    for (int r = 0; r < 8; r++) vn[r] = win[tid + r * NT];
+  }
+  for (; item < nitems; item += gridDim.x) {
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = vn[r];
+    const uint32_t ch_c = ch, t_c = t;
+    const bool active_c = active;
+    if (item + gridDim.x < nitems) {
+      const float2* win = window(item + gridDim.x, ch, t, active);
+#pragma unroll
+      for (int r = 0; r < 8; r++) vn[r] = win[tid + r * NT];
+    }
+    fft_bar<M>();  // the previous item's split stage is done with the workspace
+    pass8_first<M, false>(v, s, tid);
+    passes8_rest<M, false>(s, tw8, tid);
+    const uint32_t slot = (slot0 + t_c) % R;
+    rfft_split_store8<M>(s, tw8, dst + ch_c * dst_ch_stride + (uint64_t)slot * M, scale, tid, active_c);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -493,6 +542,121 @@ k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_b
     }
 }
 
+// Radix-8 sizes: same contract as job_to_block, with cached twiddles, all of a slot's partial loads in flight at once,
+// the inverse split and the first pass in registers, per-transform barriers.
+template <int M>
+__device__ __forceinline__ void job_to_block8(const float2* __restrict__ ypart_t, const float* __restrict__ nyq_t, uint64_t s_stride,
+                                              uint32_t first, uint32_t count, float2* __restrict__ x, float2* __restrict__ s,
+                                              const Tw8<M>& tw8, int tid, float (&o)[8]) {
+  constexpr int NT = M / 8;
+  float2 a[8];
+#pragma unroll
+  for (int h = 0; h < 8; h++) a[h] = make_float2(0.f, 0.f);
+  for (uint32_t sl = 0; sl < count; sl++) {  // fixed slot order (deterministic sums)
+    const float2* row = ypart_t + (uint64_t)(first + sl) * s_stride;
+    float2 v[8];
+#pragma unroll
+    for (int h = 0; h < 8; h++) v[h] = row[tid + h * NT];
+#pragma unroll
+    for (int h = 0; h < 8; h++) {
+      a[h].x += v[h].x;
+      a[h].y += v[h].y;
+    }
+  }
+  if (tid == 0 && nyq_t) {
+    // bin 0: the MAC kernels left G = DC - N in the real part; add the Nyquist sum back (same slot order)
+    float n = 0.f;
+    for (uint32_t sl = 0; sl < count; sl++) n += nyq_t[first + sl];
+    a[0] = make_float2(a[0].x + n, n);
+  }
+#pragma unroll
+  for (int h = 0; h < 8; h++) x[tid + h * NT] = a[h];
+  fft_bar<M>();  // x complete; also: every thread of the transform is past its reads of s from the previous job
+  float2 v[8];
+  irfft_unsplit8<M>(x, tw8, v, tid);
+  pass8_first<M, true>(v, s, tid);
+  passes8_rest<M, true>(s, tw8, tid);
+  // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(tid + h NT) + {0,1}, h < 4
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    float2 z = s[PAD(M / 2 + tid + h * NT)];
+    o[2 * h] = z.x;
+    o[2 * h + 1] = z.y;
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
+k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
+         const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
+         const float* __restrict__ nyq_part, uint64_t t_stride, uint64_t s_stride, uint32_t stream0, uint32_t T) {
+  constexpr int RAD = 8, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
+  extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
+  float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
+  float2* s = x + M;
+  const int tid = threadIdx.x;
+  Tw8<M> tw8;
+  load_tw8<M>(tw8, tw, tid);
+  const uint32_t nsg = ceil_div_dev(n_streams, (uint32_t)FPB), nitems = nsg * T;
+  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const uint32_t t = item / nsg, sq = (item - t * nsg) * FPB + threadIdx.y;
+    const bool active = sq < n_streams;
+    const uint32_t stream = stream0 + (active ? sq : n_streams - 1);
+    const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
+    const PlanView pv = first ? first_blk : steady;
+    const float2* ypart_t = ypart + (uint64_t)t * t_stride;
+    const float* nyq_t = nyq_part ? nyq_part + (uint64_t)t * slot_stride : nullptr;
+    float o[RAD];
+    job_to_block8<M>(ypart_t, nyq_t, s_stride, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw8, tid, o);
+    const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
+    // the barriers inside job_to_block8 span one transform (M = 512) or the CTA: the decision to run the second
+    // pass is made CTA-uniform so that both cases are safe
+    const int any_x = __syncthreads_or(xj != kNoJob && xj != kSameJob);
+    float o2[RAD];
+    if (any_x) {
+      const bool mine = (xj != kNoJob && xj != kSameJob);
+      job_to_block8<M>(ypart_t, nyq_t, s_stride, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw8,
+                       tid, o2);
+    }
+    if (xj != kNoJob) {
+      if (xj == kSameJob) {
+#pragma unroll
+        for (int i = 0; i < RAD; i++) o2[i] = o[i];
+      }
+      // out = (1-g) o_f + g o_f', g_n = n/B  (MixSamples + Interpolator ramp, sampled before the step)
+      const float inc = 1.0f / (float)M;
+#pragma unroll
+      for (int h = 0; h < RAD / 2; h++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const uint32_t n = 2 * (tid + h * NT) + c;
+          const float g = __fmul_rn((float)n, inc);
+          const float a = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
+          const float b = __fmul_rn(g, o2[2 * h + c]);
+          o[2 * h + c] = __fadd_rn(a, b);
+        }
+    }
+    if (active) {
+      float* ring = ybuf + (uint64_t)stream * Rd;
+      const uint32_t w = (wpos0 + t * (uint32_t)M) % Rd;
+#pragma unroll
+      for (int h = 0; h < RAD / 2; h++) {
+        const uint32_t n = 2 * (tid + h * NT);
+        uint32_t idx = w + n;  // w and n are even, Rd is a multiple of the block size: the pair never straddles the wrap
+        if (idx >= Rd) idx -= Rd;
+        if ((Rd & 1u) == 0 && (w & 1u) == 0) {
+          *reinterpret_cast<float2*>(ring + idx) = make_float2(o[2 * h], o[2 * h + 1]);
+        } else {
+          ring[idx] = o[2 * h];
+          uint32_t i1 = idx + 1;
+          if (i1 >= Rd) i1 -= Rd;
+          ring[i1] = o[2 * h + 1];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_pcm_out : delay read + mixdown + format conversion
 // ------------------------------------------------------------------------------------------
@@ -744,10 +908,26 @@ struct bbx_engine {
 
 namespace {
 
+// persistent grid of the radix-8 kernels: enough CTAs to fill the machine, never more than there are items
+template <typename K>
+uint32_t persistent_grid(K kernel, int threads, size_t smem, uint32_t nitems) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return std::max(1u, std::min(nitems, (uint32_t)(kNumSMs * per_sm)));
+}
+
 template <int M>
 void launch_rfft_t(const float* src, uint64_t ch_stride, uint32_t win_stride, float2* dst, uint64_t dst_ch_stride, uint32_t R,
                    uint32_t slot0, const float2* tw, float scale, uint32_t nch, uint32_t T, cudaStream_t st) {
   constexpr int FPB = FftCfg<M>::FPB;
+  if constexpr (FftCfg<M>::R == 8) {
+    static uint32_t per_sm_grid = 0;  // occupancy query once per size
+    if (!per_sm_grid) per_sm_grid = persistent_grid(k_rfft8<M>, FftCfg<M>::NT * FPB, 0, 1u << 30);
+    const uint32_t nitems = ceil_div(nch, FPB) * T;
+    k_rfft8<M><<<std::min(nitems, per_sm_grid), dim3(FftCfg<M>::NT, FPB), 0, st>>>(src, ch_stride, win_stride, dst, dst_ch_stride, R,
+                                                                                  slot0, tw, scale, nch, T);
+    return;
+  }
   k_rfft<M><<<dim3(ceil_div(nch, FPB), T), dim3(FftCfg<M>::NT, FPB), 0, st>>>(src, ch_stride, win_stride, dst, dst_ch_stride, R,
                                                                               slot0, tw, scale, nch);
 }
@@ -793,6 +973,14 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaSt
   if (e->sh_world > 1 || e->comm) {
     // reduced spectra of the local outputs, [local output][t][M]
     const PlanView v = shard_plan_view(e);
+    if constexpr (FftCfg<M>::R == 8) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft8<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      const uint32_t nitems = ceil_div(e->sh_nloc, FPB) * T;
+      k_irfft8<M><<<std::min(nitems, (uint32_t)kNumSMs * 2), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
+          e->sh_recv, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
+          e->sh_o0, T);
+      return;
+    }
     k_irfft<M><<<dim3(ceil_div(e->sh_nloc, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
         e->sh_recv, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
         e->sh_o0);
@@ -800,6 +988,18 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaSt
   }
   const PlanView first = tc ? tc_plan_view(e) : e->plan_first.view();
   const PlanView steady = tc ? tc_plan_view(e) : e->plan_steady.view();
+  if constexpr (FftCfg<M>::R == 8) {
+    static uint32_t per_sm_grid = 0;
+    if (!per_sm_grid) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft8<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      per_sm_grid = persistent_grid(k_irfft8<M>, FftCfg<M>::NT * FPB, smem, 1u << 30);
+    }
+    const uint32_t nitems = ceil_div(e->n_streams, FPB) * T;
+    k_irfft8<M><<<std::min(nitems, per_sm_grid), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
+        e->ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams, tc ? nullptr : e->nyq_part,
+        (uint64_t)e->max_slots * M, (uint64_t)M, 0u, T);
+    return;
+  }
   k_irfft<M><<<dim3(ceil_div(e->n_streams, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
       e->ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams,
       tc ? nullptr : e->nyq_part, (uint64_t)e->max_slots * M, (uint64_t)M, 0u);

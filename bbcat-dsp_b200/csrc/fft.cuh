@@ -163,6 +163,127 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
   }
 }
 
+// ---- radix-8 sizes (M = 64, 512, 4096): persistent-kernel building blocks ----
+// A thread's twiddles depend on its index only, not on the transform, so a CTA that loops over many transforms
+// loads them once into registers: tw8.w[p][r-1] = exp(-2 pi i r k / (8 Ns)) for pass p+1 (Ns = 8^(p+1),
+// k = j mod Ns) and tw8.ws[h] = exp(-2 pi i (j + h NT) / 2M) for the real-transform split stage.
+template <int M>
+struct Tw8 {
+  static constexpr int NP = (M == 64) ? 1 : (M == 512) ? 2 : 3;  // twiddled passes (the first pass has none)
+  float2 w[NP][7];
+  float2 ws[8];
+};
+
+template <int M>
+__device__ __forceinline__ void load_tw8(Tw8<M>& t, const float2* __restrict__ tw, int j) {
+  constexpr int NT = M / 8;
+  int Ns = 8;
+#pragma unroll
+  for (int p = 0; p < Tw8<M>::NP; p++) {
+    const int k = j & (Ns - 1), stride = 2 * (M / (8 * Ns));
+#pragma unroll
+    for (int r = 1; r < 8; r++) t.w[p][r - 1] = __ldg(&tw[r * k * stride]);
+    Ns *= 8;
+  }
+#pragma unroll
+  for (int h = 0; h < 8; h++) t.ws[h] = __ldg(&tw[j + h * NT]);
+}
+
+// barrier over the NT threads of one transform (threadIdx.y): a named barrier when they are whole warps and the CTA
+// holds several transforms, otherwise the block barrier (every transform of the CTA runs the same sequence)
+template <int M>
+__device__ __forceinline__ void fft_bar() {
+  constexpr int NT = M / 8;
+  if (NT % 32 == 0 && FftCfg<M>::FPB > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.y), "n"(NT) : "memory");
+  else __syncthreads();
+}
+
+// first pass (Ns = 1, no twiddles) on values already in registers (v[r] = element j + r NT), result to smem
+template <int M, bool INV>
+__device__ __forceinline__ void pass8_first(float2 (&v)[8], float2* __restrict__ s, int j) {
+  fft8<INV>(v);
+#pragma unroll
+  for (int r = 0; r < 8; r++) s[PAD(8 * j + r)] = v[r];
+  fft_bar<M>();
+}
+
+// pass with Ns = NS > 1 (smem -> smem), ends with a barrier
+template <int M, bool INV, int NS>
+__device__ __forceinline__ void pass8(float2* __restrict__ s, const float2 (&w)[7], int j) {
+  constexpr int NT = M / 8;
+  const int k = j & (NS - 1);
+  float2 v[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) v[r] = s[PAD(j + r * NT)];
+#pragma unroll
+  for (int r = 1; r < 8; r++) {
+    float2 ww = w[r - 1];
+    if (INV) ww.y = -ww.y;
+    v[r] = cmul(v[r], ww);
+  }
+  fft8<INV>(v);
+  const int j0 = ((j - k) << 3) + k;
+  fft_bar<M>();
+#pragma unroll
+  for (int r = 0; r < 8; r++) s[PAD(j0 + r * NS)] = v[r];
+  fft_bar<M>();
+}
+
+// all passes after the first
+template <int M, bool INV>
+__device__ __forceinline__ void passes8_rest(float2* __restrict__ s, const Tw8<M>& t, int j) {
+  pass8<M, INV, 8>(s, t.w[0], j);
+  if constexpr (M >= 512) pass8<M, INV, 64>(s, t.w[1], j);
+  if constexpr (M >= 4096) pass8<M, INV, 512>(s, t.w[2], j);
+}
+
+// forward split with cached twiddles (same arithmetic as rfft_split_store)
+template <int M>
+__device__ __forceinline__ void rfft_split_store8(const float2* __restrict__ s, const Tw8<M>& t, float2* __restrict__ out,
+                                                  float scale, int tid, bool active) {
+  constexpr int NT = M / 8;
+#pragma unroll
+  for (int h = 0; h < 8; h++) {
+    const int k = tid + h * NT;
+    float2 x;
+    if (k == 0) {
+      float2 z0 = s[0];
+      x = make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
+    } else {
+      float2 a = s[PAD(k)], b = s[PAD(M - k)];
+      float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+      float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+      float2 o = make_float2(d.y, -d.x);
+      x = cadd(e, cmul(o, t.ws[h]));
+    }
+    if (active) out[k] = make_float2(x.x * scale, x.y * scale);
+  }
+}
+
+// inverse split into registers: v[h] = Z[tid + h NT] (same arithmetic as irfft_unsplit), x = summed packed spectrum
+template <int M>
+__device__ __forceinline__ void irfft_unsplit8(const float2* __restrict__ x, const Tw8<M>& t, float2 (&v)[8], int tid) {
+  constexpr int NT = M / 8;
+#pragma unroll
+  for (int h = 0; h < 8; h++) {
+    const int k = tid + h * NT;
+    float2 z;
+    if (k == 0) {
+      float2 p = x[0];
+      z = make_float2(p.x + p.y, p.x - p.y);
+    } else {
+      float2 a = x[k], b = x[M - k];
+      float2 e = make_float2(a.x + b.x, a.y - b.y);
+      float2 d = make_float2(a.x - b.x, a.y + b.y);
+      float2 w = t.ws[h];
+      w.y = -w.y;
+      float2 tt = cmul(d, w);
+      z = make_float2(e.x - tt.y, e.y + tt.x);
+    }
+    v[h] = z;
+  }
+}
+
 // Forward split: Z = FFT_M(z) in smem -> packed half spectrum X (M complex) of the 2M-point real
 // transform, scaled by `scale`, written to global `out` (coalesced float2).
 //   X[k] = E + w^k O,  E = (Z[k] + conj Z[M-k])/2,  O = -i (Z[k] - conj Z[M-k])/2,  w = exp(-2 pi i / 2M)
