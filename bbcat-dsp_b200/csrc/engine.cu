@@ -660,15 +660,21 @@ k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_
 // ------------------------------------------------------------------------------------------
 // k_pcm_out : delay read + mixdown + format conversion
 // ------------------------------------------------------------------------------------------
+// one routed path in mixdown order (ascending stream per output == MixSamples call order), everything k_pcm_out
+// needs about it in one place
+struct RouteEntry {
+  uint32_t stream;  // delay ring of the path
+  float gain;
+  uint32_t icur, iold;  // (uint32)delay mod Rd for the integer-delay mode: in force after / before this call's first block boundary
+  uint32_t flags;       // bit0: crossfade old->cur over the first block
+  uint32_t pad;
+  double dcur, dold;    // the same delays in samples (fractional mode)
+};
+static_assert(sizeof(RouteEntry) == 40, "RouteEntry layout");
+
 struct RouteView {
-  const uint32_t* out_first;   // [n_outputs+1] CSR over outputs
-  const uint32_t* route_stream;  // ascending stream index per output
-  const float* gain;           // per stream
-  const double* delay_cur;     // per stream, delay in force after this call's first block boundary
-  const double* delay_old;     // per stream, delay before it
-  const uint32_t* dflags;      // per stream, bit0: crossfade old->cur over the first block
-  const uint32_t* idelay_cur;  // per stream, (uint32)delay mod Rd for the integer-delay mode
-  const uint32_t* idelay_old;
+  const uint32_t* out_first;  // [n_outputs+1] CSR over outputs
+  const RouteEntry* entry;    // per route
 };
 
 struct PcmOutArgs {
@@ -698,13 +704,26 @@ __device__ __forceinline__ float delayed_read(const float* __restrict__ ring, ui
   return ring[idx];
 }
 
+static constexpr uint32_t kPcmOutCache = 64;  // routes of one 32-output tile kept in shared memory
+
 __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
   __shared__ float tile[32][33];
+  __shared__ uint32_t s_first[33];
+  __shared__ RouteEntry s_rt[kPcmOutCache];
   const uint32_t f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t t = f0 / a.B;               // a tile lies inside one block (B % 32 == 0)
   const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
   const float inc = 1.0f / (float)a.B;
+  // the tile's slice of the route tables -> shared memory (two dependent loads per CTA instead of a chain of table
+  // lookups per sample); tiles with more than kPcmOutCache routes read the entries from global memory
+  const uint32_t no = min(32u, a.n_outputs - c0);
+  if (threadIdx.x <= no) s_first[threadIdx.x] = a.rv.out_first[c0 + threadIdx.x];
+  __syncthreads();
+  const uint32_t r0 = s_first[0], nr = s_first[no] - r0;
+  const bool cached = nr <= kPcmOutCache;
+  if (cached && threadIdx.x < nr) s_rt[threadIdx.x] = a.rv.entry[r0 + threadIdx.x];
+  __syncthreads();
   // phase 1: lanes over frames (ring reads are contiguous), one output channel per warp pass
 #pragma unroll 1
   for (int i = 0; i < 4; i++) {
@@ -712,20 +731,18 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
     float bus = 0.f;
     if (o < a.n_outputs) {
       const uint32_t n = f0 + lane - t * a.B;  // frame inside the block
-      const uint32_t rb = a.rv.out_first[o], re = a.rv.out_first[o + 1];
+      const uint32_t rb = s_first[cl], re = s_first[cl + 1];
       for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
-        const uint32_t st = a.rv.route_stream[r];
-        const float gain = a.rv.gain[st];
-        if (!(gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
-        const float* ring = a.ybuf + (uint64_t)st * a.Rd;
-        const double dc = a.fractional ? a.rv.delay_cur[st] : 0.0;
-        float v = delayed_read(ring, a.Rd, w, n, dc, a.rv.idelay_cur[st], a.fractional);
-        if (t == 0 && (a.rv.dflags[st] & 1u)) {
-          const float vo = delayed_read(ring, a.Rd, w, n, a.rv.delay_old[st], a.rv.idelay_old[st], a.fractional);
+        const RouteEntry en = cached ? s_rt[r - r0] : a.rv.entry[r];
+        if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
+        const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
+        float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
+        if (t == 0 && (en.flags & 1u)) {
+          const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
           const float g = __fmul_rn((float)n, inc);
           v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
         }
-        bus = __fadd_rn(bus, __fmul_rn(gain, v));  // dst += mul * src, rounded separately
+        bus = __fadd_rn(bus, __fmul_rn(en.gain, v));  // dst += mul * src, rounded separately
       }
     }
     tile[lane][cl] = bus;
@@ -859,7 +876,7 @@ struct bbx_engine {
   uint8_t* h_route = nullptr;
   uint8_t* d_route = nullptr;
   size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0,
-         roff_icur = 0, roff_iold = 0;
+         roff_icur = 0, roff_iold = 0, roff_entry = 0;
   bool route_dirty = true;
   // plans
   MacPlan plan_first, plan_steady;
@@ -1309,6 +1326,22 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
       flags[k] = (sw && p.xfade && p.pend_delay != p.delay) ? 1u : 0u;
     }
   }
+  // per-route entries in mixdown order (what k_pcm_out reads)
+  {
+    RouteEntry* en = (RouteEntry*)(e->h_route + e->roff_entry);
+    const uint32_t nroutes = ofirst[e->n_out_pcm < e->n_out ? e->n_out_pcm : e->n_out];
+    for (uint32_t r = 0; r < nroutes; r++) {
+      const uint32_t st = rstream[r];
+      en[r].stream = st;
+      en[r].gain = gain[st];
+      en[r].icur = icur[st];
+      en[r].iold = iold[st];
+      en[r].flags = flags[st];
+      en[r].pad = 0;
+      en[r].dcur = dcur[st];
+      en[r].dold = dold[st];
+    }
+  }
   BBX_CUDA_TRY(cudaMemcpyAsync(e->d_route, e->h_route, e->route_bytes, cudaMemcpyHostToDevice, e->stream));
   return mark_upload(e);
 }
@@ -1316,13 +1349,7 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
 RouteView route_view(const bbx_engine* e) {
   RouteView v;
   v.out_first = (const uint32_t*)(e->d_route + e->roff_first);
-  v.route_stream = (const uint32_t*)(e->d_route + e->roff_stream);
-  v.gain = (const float*)(e->d_route + e->roff_gain);
-  v.delay_cur = (const double*)(e->d_route + e->roff_dcur);
-  v.delay_old = (const double*)(e->d_route + e->roff_dold);
-  v.dflags = (const uint32_t*)(e->d_route + e->roff_flags);
-  v.idelay_cur = (const uint32_t*)(e->d_route + e->roff_icur);
-  v.idelay_old = (const uint32_t*)(e->d_route + e->roff_iold);
+  v.entry = (const RouteEntry*)(e->d_route + e->roff_entry);
   return v;
 }
 
@@ -1625,6 +1652,7 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     e->roff_flags = take(sizeof(uint32_t) * ns);
     e->roff_icur = take(sizeof(uint32_t) * ns);
     e->roff_iold = take(sizeof(uint32_t) * ns);
+    e->roff_entry = take(sizeof(RouteEntry) * ns);
     e->route_bytes = off;
     BBX_CUDA_TRY(cudaHostAlloc((void**)&e->h_route, off, cudaHostAllocDefault));
     memset(e->h_route, 0, off);
