@@ -20,6 +20,8 @@ between iterations.
   roofline            the dominant kernel of the timed region (k_fdl_mac_tb): FP32 FMA rate against the SIMT peak
   roofline_streaming  the streaming MAC (k_fdl_mac) timed in the same run: algorithmic HBM bytes against the
                       measured HBM peak -- the roofline BASELINE.json's north_star names
+  roofline_mimo       the tensor-core kernel (k_mimo_tc) on BASELINE.json's MIMO config (C5), same run: TF32 MMA
+                      rate against the measured tensor peak
 N > 1    weak scaling: every rank runs its own 128-channel shard (rank r = channels 128r .. 128r+127 of a
          128N-channel renderer); channels are independent, so there is no data-path collective.
 """
@@ -144,6 +146,56 @@ def cpu_convolver_rate(n_blocks, nthreads, want_seconds=None):
     return NCH * done * B / FS / el, el, done
 
 
+def mimo_leg(bbx, torch, device, steps=100):
+    """BASELINE.json configs[4] (C5): 64-in x 64-out matrix of 4096-tap IRs, B = 512, 64-block steps.  The per-bin
+    complex GEMM runs on the tensor cores (k_mimo_tc: tcgen05.mma kind::tf32, 3 MMAs per product for fp32 accuracy).
+    achieved = TF32 MMA flops issued per launch / the kernel's average launch time (CUDA events around every launch);
+    peak = the measured dense bf16 rate of MEASURED_PEAKS.json / 2 (TF32 runs at half the bf16 rate)."""
+    nin = nout = 64
+    Lm, Pm, Tm = 4096, 8, 64
+    eng = bbx.Convolver(B, Pm, nin, n_outputs=nout, mode=bbx.MODE_MIMO, max_blocks=Tm, device=device)
+    for o in range(nout):
+        for i in range(nin):
+            eng.SelectFilter(o * nin + i, eng.CreateFilter(make_ir(2000 + 64 * o + i, Lm)))
+    frames = Tm * B
+    x = (torch.rand((frames, nin), device="cuda") * 2 - 1).contiguous()
+    y = torch.empty((frames, nout), device="cuda", dtype=torch.float32)
+    for _ in range(5):
+        eng.ConvolveDev(x.data_ptr(), bbx.FMT_FLOAT, nin, y.data_ptr(), bbx.FMT_FLOAT, nout, frames)
+    eng.Sync()
+    eng.profile_mac(True)
+    eng.timer_start()
+    for _ in range(steps):
+        eng.ConvolveDev(x.data_ptr(), bbx.FMT_FLOAT, nin, y.data_ptr(), bbx.FMT_FLOAT, nout, frames)
+    ms = eng.timer_stop()
+    mac = eng.mac_time()
+    eng.profile_mac(False)
+    n_tc, status = eng.tensor_status()
+    eng.close()
+    lms = mac["ms"] / max(1, mac["launches"])
+    # per bin: M = 128 (64 outputs x re/im), K = 2 * nin * P = 1024, N = 64 block-steps, 3 TF32 MMAs per product
+    flops = 3 * 2 * 128 * (2 * nin * Pm) * Tm * B
+    peak_bf16, src = None, None
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            peak_bf16, src = float(json.load(open(path))["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 = half the bf16 rate)"
+        except Exception:
+            pass
+    if peak_bf16 is None:
+        peak_bf16, src = 2250.0, "nominal dense bf16 2.25 PF / 2 (TF32)"
+    peak = peak_bf16 / 2
+    ach = flops / (lms * 1e-3) / 1e12 if lms > 0 else 0.0
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 180.8e6,
+            "kernel": "k_mimo_tc<6>", "launch_ms": lms, "tf32_flops_per_launch": flops, "peak_source": src,
+            "workload": "C5: MIMO 64 in x 64 out, 4096-tap matrix, B=512, 64-block steps, f32 in/out",
+            "value": nout * steps * frames / FS / (ms * 1e-3), "unit_value": "output-channel-s/s", "ms_per_step": ms / steps,
+            "tensor_launches": n_tc, "status": status, "mac_share_of_step": mac["ms"] / ms if ms > 0 else None,
+            "useful_fp32_equivalent_TFLOPs": flops / 3 / (lms * 1e-3) / 1e12 if lms > 0 else 0.0,
+            "note": "traffic = dram__bytes_read + write of one launch (ncu --set full, profiles/); 134 MB of spectra are read "
+                    "once per 64 block-steps"}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -205,6 +257,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=T, help="blocks per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-mimo", action="store_true", help="skip the C5 MIMO tensor-core leg (roofline_mimo)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -390,6 +443,11 @@ def main():
                               "value_streaming": world * audio_s * ks / (ms_s * 1e-3), "steps": ks,
                               "mac_share_of_step": mac_s["ms"] / ms_s if ms_s > 0 else None}
 
+    # ---- the tensor-core kernel of the path (C5 MIMO, k_mimo_tc) in the same run: rank 0, N = 1 ----
+    roofline_mimo = None
+    if rank == 0 and world == 1 and not args.no_mimo:
+        roofline_mimo = mimo_leg(bbx, torch, local)
+
     # ---- CPU baseline on rank 0 at N = 1 (bounded sample of the same workload) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -410,7 +468,7 @@ def main():
                        "l2": "inputs larger than L2: 148 MB spectra + 181 MB FDL + partial sums per step vs 126 MB L2, no flush",
                        "parallelism": "channel-sharded x%d, no collective" % world},
             "x_realtime_per_channel": value / (NCH * world),
-            "roofline": roofline, "roofline_streaming": roofline_streaming, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_streaming": roofline_streaming, "roofline_mimo": roofline_mimo, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "channel-s/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "latency": latency,
