@@ -27,6 +27,25 @@ private:
   bbx_filter* f;
 };
 
+// Communicator of the input-sharded MIMO convolver (one rank per GPU; NCCL is loaded by libbbx at run time).
+// Rank 0 calls UniqueId() and ships the 128 bytes to the other ranks by whatever transport the application has.
+class ConvolverComm {
+public:
+  static void UniqueId(uint8_t id[128]) {
+    if (bbx_comm_unique_id(id) != BBX_OK) throw std::runtime_error(std::string("libbbx: ") + bbx_last_error());
+  }
+  ConvolverComm(int world, int rank, const uint8_t id[128], int device = 0) : c(0) {
+    if (bbx_comm_create(world, rank, id, device, &c) != BBX_OK) throw std::runtime_error(std::string("libbbx: ") + bbx_last_error());
+  }
+  ~ConvolverComm() { bbx_comm_destroy(c); }
+  bbx_comm* Handle() { return c; }
+
+private:
+  ConvolverComm(const ConvolverComm&);
+  ConvolverComm& operator=(const ConvolverComm&);
+  bbx_comm* c;
+};
+
 class Convolver {
 public:
   // per-channel convolver: channel c -> filter -> delay -> channel c
@@ -68,6 +87,8 @@ public:
   void Convolve(const T1* src, uint_t src_channels, T2* dst, uint_t dst_channels, uint_t nframes) {
     Convolve(src, SampleFormatOf(src), false, src_channels, dst, SampleFormatOf(dst), false, dst_channels, nframes);
   }
+  // input-sharded MIMO (bbx_config::mimo_shard_world > 1): attach the communicator before the first Convolve
+  void SetComm(ConvolverComm* comm) { Check(bbx_engine_set_comm(e, comm ? comm->Handle() : 0)); }
   bbx_engine* Handle() { return e; }
 
 private:
