@@ -417,3 +417,25 @@ def test_full_size_c5_mimo_property(bbx, orc):
     for o, row in noise_rows.items():
         want = sum(orc.direct(xi[:, i], row[i], n0=n0, count=256) for i in range(nin))
         assert_float_parity(y[n0:, o], want, "MIMO noise row %d" % o)
+
+
+@pytest.mark.parametrize("B,nch,L,T", [(64, 2000, 100, 8), (512, 600, 700, 4), (4096, 20, 5000, 8)])
+def test_persistent_fft_many_items(bbx, orc, B, nch, L, T):
+    """More (channel group, block) items than resident CTAs: every CTA of the persistent radix-8 FFT kernels
+    (k_rfft8 / k_irfft8) loops over several items with its prefetch and cached twiddles; ragged last channel group."""
+    P = -(-L // B)
+    g = GpuDriver(bbx, B, P, nch, max_blocks=T)
+    irs = [make_ir(900 + (c % 7), L) for c in range(7)]
+    fl = [g.filter(h) for h in irs]
+    for c in range(nch):
+        g.select(c, fl[c % 7])
+    rng = np.random.default_rng(77)
+    x = rng.uniform(-1, 1, (2 * T * B, nch)).astype(np.float32)
+    y = run_float(g, x, T * B)
+    g.close()
+    for c in (0, 1, nch // 2, nch - 2, nch - 1):
+        f = orc.filter(irs[c % 7], B)
+        obc = orc.blockconv(B, P)
+        obc.set_filter(f)
+        yo = np.concatenate([obc.convolve(np.ascontiguousarray(x[i * B:(i + 1) * B, c])) for i in range(2 * T)])
+        assert_float_parity(y[:, c], yo, "channel %d of %d" % (c, nch))

@@ -36,13 +36,15 @@ def tensor_ok(g, expect_launches=True):
     (256, 5, 3, 1000, [64, 48, 17]),     # K = 5 x 4 = 20 complex -> padded to 32; n_out < 64 (padded rows)
     (64, 3, 70, 200, [40]),              # two output groups (70 outputs), P2 = 4, K = 12 -> 16
     (128, 2, 2, 128 * 16, [64, 64]),     # 16 partitions per filter, tiny matrix
+    (256, 4, 4, 1024, [96, 80]),         # more than 64 blocks per call: two column tiles, the second one ragged
+    (128, 3, 2, 100, [32]),              # single-partition filters (P2 = 1): 16 inputs' worth of K per chunk, padded
 ])
 def test_mimo_tensor_vs_oracle(bbx, B, nin, nout, L, calls):
     P = -(-L // B)
     nblk = sum(calls)
     g = GpuDriver(bbx, B, P, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=max(calls))
     o = OracleDriver(B, P, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=max(calls))
-    fill_matrix((g, o), nin, nout, L, 2000, null={(0, 1), (nout - 1, nin - 1)}, lengths=[L, L - B, max(1, L // 3)])
+    fill_matrix((g, o), nin, nout, L, 2000, null={(0, 1), (nout - 1, nin - 1)}, lengths=[L, max(1, L - B), max(1, L // 3)])
     xi = interleave([make_noise(1000 + i, nblk * B) for i in range(nin)])
     sizes = [c * B for c in calls]
     yg, yo = run_float(g, xi, sizes), run_float(o, xi, sizes)
