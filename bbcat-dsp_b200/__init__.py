@@ -100,6 +100,15 @@ SYMBOLS = {
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
+    "bbx_biquad_calc_coeffs": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]),
+    "bbx_biquad_create": (C.c_int, [u32, C.POINTER(vp)]),
+    "bbx_biquad_destroy": (C.c_int, [vp]),
+    "bbx_biquad_set_coeffs": (C.c_int, [vp, C.POINTER(C.c_double), C.c_double]),
+    "bbx_biquad_calc": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "bbx_biquad_process": (C.c_int, [vp, vp, vp, u32, u32, u32, u32]),
+    "bbx_biquad_process_dev": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, vp]),
+    "bbx_biquad_get_state": (C.c_int, [vp, vp, vp, vp]),
+    "bbx_biquad_reset": (C.c_int, [vp]),
     "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
     "bbx_comm_available": (C.c_int, []),
     "bbx_comm_unique_id": (C.c_int, [C.POINTER(u8)]),
@@ -305,6 +314,54 @@ class MultilayerBuffer:
     def ReadBuffer(self, srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, overwrite=True):
         return lib().bbx_mlb_read_buffer(self.h, srcchannel, _p(dst), dstchannel, ndstchannels, nchannels & 0xFFFFFFFF,
                                          nframes, int(overwrite))
+
+
+# ---- next row: BiQuadCoeffs / BiQuad (src/BiQuad.h) -----------------------------------------
+BIQUAD_FLAT, BIQUAD_LPF6, BIQUAD_HPF6, BIQUAD_LPF12, BIQUAD_HPF12, BIQUAD_BPF, BIQUAD_NOTCH, BIQUAD_PEQ, BIQUAD_LSH, \
+    BIQUAD_HSH = range(10)
+
+
+def BiQuadCalcCoeffs(ftype, freq, fs, gain=0.0, bandwidth=1.0):
+    """BiQuadCoeffs(type, freq, fs, gain, bandwidth).current as [num0, num1, num2, den1, den2]."""
+    out = (C.c_double * 5)()
+    _check(lib().bbx_biquad_calc_coeffs(ftype, freq, fs, gain, bandwidth, out))
+    return np.array(out[:], dtype=np.float64)
+
+
+class BiQuadBank:
+    """One BiQuadCoeffs shared by `channels` BiQuad filters, processed like BiQuad::Process(filters, ...)."""
+
+    def __init__(self, channels):
+        h = vp()
+        _check(lib().bbx_biquad_create(channels, C.byref(h)))
+        self.h, self.channels = h, channels
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_biquad_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def SetCoeffs(self, c5, interp_samples=0.0):
+        arr = (C.c_double * 5)(*[float(v) for v in c5])
+        _check(lib().bbx_biquad_set_coeffs(self.h, arr, interp_samples))
+
+    def CalcCoeffs(self, ftype, freq, fs, gain=0.0, bandwidth=1.0, interp_time=0.0):
+        _check(lib().bbx_biquad_calc(self.h, ftype, freq, fs, gain, bandwidth, interp_time))
+
+    def Process(self, src, dst, nchannels, nsrcchannels, ndstchannels, nframes):
+        _check(lib().bbx_biquad_process(self.h, _p(src), _p(dst), nchannels, nsrcchannels, ndstchannels, nframes))
+
+    def GetState(self):
+        w = np.zeros(2 * max(1, self.channels), dtype=np.float64)
+        cur = np.zeros(5, dtype=np.float64)
+        md = np.zeros(2, dtype=np.float64)
+        _check(lib().bbx_biquad_get_state(self.h, _p(w), _p(cur), _p(md)))
+        return w[:2 * self.channels], cur, md
+
+    def Reset(self):
+        _check(lib().bbx_biquad_reset(self.h))
 
 
 # ---- a12-a14 ------------------------------------------------------------------------------

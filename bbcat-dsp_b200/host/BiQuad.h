@@ -1,0 +1,52 @@
+// BiQuadCoeffs / BiQuad surface (bbcat-dsp src/BiQuad.h:27-245): coefficient object with design (CalcCoeffs),
+// explicit coefficients (SetCoeffs) and ramping, shared by a bank of per-channel filters that run on the GPU.
+// Thin RAII wrapper over the bbx_biquad C ABI; filter type values equal BiQuadCoeffs::Filter_t.
+#pragma once
+
+#include <stdexcept>
+#include <string>
+
+#include "SoundFormatConversions.h"
+
+namespace bbcat {
+
+class BiQuadBank {
+public:
+  typedef enum { FLAT, LPF6, HPF6, LPF12, HPF12, BPF, NOTCH, PEQ, LSH, HSH } Filter_t;  // src/BiQuad.h:31-42
+  typedef struct {
+    double num0, num1, num2, den1, den2;
+  } COEFFS;
+
+  explicit BiQuadBank(uint_t channels) : b(0) { Check(bbx_biquad_create(channels, &b)); }
+  ~BiQuadBank() { bbx_biquad_destroy(b); }
+
+  // BiQuadCoeffs::SetCoeffs (interpolation time in SAMPLES) / CalcCoeffs (interpolation time in SECONDS)
+  void SetCoeffs(double num0, double num1 = 0.0, double num2 = 0.0, double den1 = 0.0, double den2 = 0.0, double interp_samples = 0.0) {
+    const double c[5] = {num0, num1, num2, den1, den2};
+    Check(bbx_biquad_set_coeffs(b, c, interp_samples));
+  }
+  void CalcCoeffs(Filter_t type, double freq, double fs, double gain = 0.0, double bandwidth = 1.0, double interp_time = 0.0) {
+    Check(bbx_biquad_calc(b, (int)type, freq, fs, gain, bandwidth, interp_time));
+  }
+  COEFFS GetCurrent() const {
+    double c[5];
+    Check(bbx_biquad_get_state(b, 0, c, 0));
+    COEFFS r = {c[0], c[1], c[2], c[3], c[4]};
+    return r;
+  }
+  // BiQuad::Process(filters, src, dst, nchannels, nsrcchannels, ndstchannels, nframes, coeffs); dst may equal src
+  void Process(const Sample_t* src, Sample_t* dst, uint_t nchannels, uint_t nsrcchannels, uint_t ndstchannels, uint_t nframes) {
+    Check(bbx_biquad_process(b, src, dst, nchannels, nsrcchannels, ndstchannels, nframes));
+  }
+  void Reset() { Check(bbx_biquad_reset(b)); }
+
+private:
+  static void Check(int rc) {
+    if (rc != BBX_OK) throw std::runtime_error(std::string("libbbx: ") + bbx_last_error());
+  }
+  BiQuadBank(const BiQuadBank&);
+  BiQuadBank& operator=(const BiQuadBank&);
+  bbx_biquad* b;
+};
+
+}  // namespace bbcat

@@ -259,6 +259,36 @@ uint32_t bbx_mlb_read_buffer(bbx_mlb* m, uint32_t srcchannel, float* dst, uint32
                              uint32_t nchannels, uint32_t nframes, int overwrite);
 
 /* ------------------------------------------------------------------------------------------
+ * next row  BiQuadCoeffs / BiQuad  src/BiQuad.h:27-245, src/BiQuad.cpp:11-497
+ *      One coefficient object shared by a bank of per-channel filters (what BiQuadFilterBank::Process runs per
+ *      filter): coefficient design (CalcCoeffs) and explicit coefficients (SetCoeffs) with the reference's ramp
+ *      (one Interpolate() step per frame), direct-form-II-transposed recurrence with double state, float samples,
+ *      interleaved [frame][channel], dst == src allowed.  Bit-exact against the reference build.
+ * ---------------------------------------------------------------------------------------- */
+/* BiQuadCoeffs::Filter_t, src/BiQuad.h:31-42 (same numeric values) */
+typedef enum {
+  BBX_BIQUAD_FLAT = 0, BBX_BIQUAD_LPF6 = 1, BBX_BIQUAD_HPF6 = 2, BBX_BIQUAD_LPF12 = 3, BBX_BIQUAD_HPF12 = 4,
+  BBX_BIQUAD_BPF = 5, BBX_BIQUAD_NOTCH = 6, BBX_BIQUAD_PEQ = 7, BBX_BIQUAD_LSH = 8, BBX_BIQUAD_HSH = 9
+} bbx_biquad_type;
+typedef struct bbx_biquad bbx_biquad;
+/* normalised {num0, num1, num2, den1, den2} of a filter description (host arithmetic, no GPU needed) */
+int bbx_biquad_calc_coeffs(int type, double freq, double fs, double gain, double bandwidth, double* out5);
+int bbx_biquad_create(uint32_t nchannels, bbx_biquad** out);
+int bbx_biquad_destroy(bbx_biquad* b);
+/* BiQuadCoeffs::SetCoeffs: interp_samples > 0 ramps to the new coefficients over that many SAMPLES, else jumps */
+int bbx_biquad_set_coeffs(bbx_biquad* b, const double* c5, double interp_samples);
+/* BiQuadCoeffs::CalcCoeffs: interp_time in SECONDS */
+int bbx_biquad_calc(bbx_biquad* b, int type, double freq, double fs, double gain, double bandwidth, double interp_time);
+/* BiQuad::Process(filters, src, dst, nchannels, nsrcchannels, ndstchannels, nframes, coeffs); host pointers */
+int bbx_biquad_process(bbx_biquad* b, const float* src, float* dst, uint32_t nchannels, uint32_t nsrcchannels,
+                       uint32_t ndstchannels, uint32_t nframes);
+int bbx_biquad_process_dev(bbx_biquad* b, const float* src, float* dst, uint32_t nchannels, uint32_t nsrcchannels,
+                           uint32_t ndstchannels, uint32_t nframes, void* stream);
+/* filter states w[nchannels][2], current coefficients, {mul, dec} of the ramp (any pointer may be NULL) */
+int bbx_biquad_get_state(const bbx_biquad* b, double* w, double* cur5, double* mul_dec);
+int bbx_biquad_reset(bbx_biquad* b); /* BiQuad::Reset on every filter */
+
+/* ------------------------------------------------------------------------------------------
  * measurement hooks (bench.py): CUDA-event timing on the engine stream, launch counting and
  * the dominant kernel's (FDL MAC) accumulated device time.
  * ---------------------------------------------------------------------------------------- */

@@ -93,6 +93,19 @@ unsigned orc_mlb_available_frames(const orc_mlb* m);
 unsigned orc_mlb_read_buffer(orc_mlb* m, unsigned srcchannel, float* dst, unsigned dstchannel, unsigned ndstchannels,
                              unsigned nchannels, unsigned nframes, int overwrite);
 
+/* ---- biquad.c : BiQuadCoeffs / BiQuad ("next" row) ---- */
+/* filter types: src/BiQuad.h:31-42 (FLAT 0, LPF6 1, HPF6 2, LPF12 3, HPF12 4, BPF 5, NOTCH 6, PEQ 7, LSH 8, HSH 9) */
+typedef struct orc_biquad orc_biquad;
+void orc_biquad_calc_coeffs(int type, double freq, double fs, double gain, double bandwidth, double* out5);
+orc_biquad* orc_biquad_create(unsigned nch);
+void orc_biquad_destroy(orc_biquad* b);
+void orc_biquad_set_coeffs(orc_biquad* b, const double* c5, double interp_samples);
+void orc_biquad_calc(orc_biquad* b, int type, double freq, double fs, double gain, double bandwidth, double interp_time);
+void orc_biquad_process(orc_biquad* b, const float* src, float* dst, unsigned nchannels, unsigned nsrc, unsigned ndst,
+                        unsigned nframes);
+void orc_biquad_get_state(const orc_biquad* b, double* w, double* cur5, double* mul_dec);
+void orc_biquad_reset(orc_biquad* b);
+
 /* ---- fft.c : own FFT (FFTW stand-in, unnormalised both directions) ---- */
 /* complex in-place FFT of n (power of two) interleaved float pairs; inverse != 0 conjugates the kernel */
 void orc_cfft(float* data, unsigned n, int inverse);

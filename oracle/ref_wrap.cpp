@@ -6,7 +6,7 @@
  * /root/reference/src and forwards calls.  Built by oracle/Makefile into
  * oracle/_ref/libbbcref.so together with the unmodified reference sources
  *   SoundFormatConversions.cpp, SoundFormatRawConversions.cpp, SoundMixing.cpp,
- *   FractionalSample.cpp, SoundDelayBuffer.cpp
+ *   FractionalSample.cpp, SoundDelayBuffer.cpp, BiQuad.cpp
  */
 #include "SoundFormatConversions.h"
 #include "SoundMixing.h"
@@ -14,6 +14,9 @@
 #include "FractionalSample.h"
 #include "SoundDelayBuffer.h"
 #include "MultilayerBuffer.h"
+#include "BiQuad.h"
+
+#include <vector>
 
 using namespace bbcat;
 
@@ -133,6 +136,67 @@ unsigned ref_mlb_read_buffer(void* h, unsigned srcchannel, float* dst, unsigned 
                              unsigned nchannels, unsigned nframes, int overwrite) {
   return ((MultilayerBuffer<float>*)h)->ReadBuffer(srcchannel, dst, dstchannel, ndstchannels, nchannels, nframes, true,
                                                    overwrite != 0);
+}
+
+
+/* ---- BiQuadCoeffs / BiQuad (src/BiQuad.h:27-245, src/BiQuad.cpp:11-497): one coefficient object shared by
+ *      nch filters, processed with BiQuad::Process(filters, ...) exactly like BiQuadFilterBank::Process does ---- */
+namespace {
+struct PeekCoeffs : public BiQuadCoeffs {  // read-only view of the protected interpolation state
+  double Mul() const { return mul; }
+  double Dec() const { return dec; }
+};
+struct PeekBiQuad : public BiQuad {
+  PeekBiQuad(const BiQuadCoeffs& c) : BiQuad(c) {}
+  const double* W() const { return w; }
+};
+struct RefBank {
+  BiQuadCoeffs coeffs;
+  std::vector<BiQuad> filters;
+  explicit RefBank(unsigned n) : coeffs(), filters(n, BiQuad(coeffs)) {}
+};
+}  // namespace
+
+void ref_biquad_calc_coeffs(int type, double freq, double fs, double gain, double bandwidth, double* out5) {
+  BiQuadCoeffs c((BiQuadCoeffs::Filter_t)type, freq, fs, gain, bandwidth, 0.0);
+  out5[0] = c.current.num0;
+  out5[1] = c.current.num1;
+  out5[2] = c.current.num2;
+  out5[3] = c.current.den1;
+  out5[4] = c.current.den2;
+}
+void* ref_biquad_create(unsigned nch) { return new RefBank(nch); }
+void ref_biquad_destroy(void* h) { delete (RefBank*)h; }
+void ref_biquad_set_coeffs(void* h, const double* c5, double interp_samples) {
+  ((RefBank*)h)->coeffs.SetCoeffs(c5[0], c5[1], c5[2], c5[3], c5[4], interp_samples);
+}
+void ref_biquad_calc(void* h, int type, double freq, double fs, double gain, double bandwidth, double interp_time) {
+  ((RefBank*)h)->coeffs.CalcCoeffs((BiQuadCoeffs::Filter_t)type, freq, fs, gain, bandwidth, interp_time);
+}
+void ref_biquad_process(void* h, const float* src, float* dst, unsigned nchannels, unsigned nsrc, unsigned ndst, unsigned nframes) {
+  RefBank* b = (RefBank*)h;
+  if (nchannels > b->filters.size()) nchannels = (unsigned)b->filters.size();
+  if (!nchannels) return;
+  BiQuad::Process(&b->filters[0], src, dst, nchannels, nsrc, ndst, nframes, b->coeffs);
+}
+void ref_biquad_get_state(void* h, double* w, double* cur5, double* mul_dec) {
+  RefBank* b = (RefBank*)h;
+  for (size_t j = 0; j < b->filters.size(); j++) {
+    const double* ww = static_cast<const PeekBiQuad&>(b->filters[j]).W();
+    w[2 * j] = ww[0];
+    w[2 * j + 1] = ww[1];
+  }
+  cur5[0] = b->coeffs.current.num0;
+  cur5[1] = b->coeffs.current.num1;
+  cur5[2] = b->coeffs.current.num2;
+  cur5[3] = b->coeffs.current.den1;
+  cur5[4] = b->coeffs.current.den2;
+  mul_dec[0] = static_cast<const PeekCoeffs&>(b->coeffs).Mul();
+  mul_dec[1] = static_cast<const PeekCoeffs&>(b->coeffs).Dec();
+}
+void ref_biquad_reset(void* h) {
+  RefBank* b = (RefBank*)h;
+  for (size_t j = 0; j < b->filters.size(); j++) b->filters[j].Reset();
 }
 
 }  // extern "C"

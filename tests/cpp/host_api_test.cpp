@@ -7,6 +7,7 @@
 
 #include <vector>
 
+#include "BiQuad.h"
 #include "Convolver.h"
 #include "FractionalSample.h"
 #include "SoundDelayBuffer.h"
@@ -75,6 +76,16 @@ int main() {
   CHECK(err < 5e-6);
   delete f0;
   delete f1;
+  // BiQuadBank: y[n] = x[n] + 0.5 x[n-1] - 0.25 y[n-1] on an impulse (exact in binary)
+  {
+    BiQuadBank bank(2);
+    bank.SetCoeffs(1.0, 0.5, 0.0, 0.25, 0.0);
+    float bx[8] = {1, 0, 0, 0, 0, 0, 0, 0}, by[8] = {9, 9, 9, 9, 9, 9, 9, 9};
+    bank.Process(bx, by, 1, 2, 2, 4);
+    CHECK(by[0] == 1.0f && by[2] == 0.25f && by[4] == -0.0625f && by[6] == 0.015625f && by[1] == 9.0f);
+    bank.CalcCoeffs(BiQuadBank::FLAT, 1000.0, 48000.0);
+    CHECK(bank.GetCurrent().num0 == 1.0 && bank.GetCurrent().den1 == 0.0);
+  }
   printf("PASS max_err=%g\n", err);
   return 0;
 }

@@ -77,6 +77,15 @@ class CpuLib:
         self._mlb_write = fn("mlb_write_layer", None, [vp, u32, vp, u32, u32, u32, u32, u32])
         self._mlb_avail = fn("mlb_available_frames", u32, [vp])
         self._mlb_read = fn("mlb_read_buffer", u32, [vp, u32, vp, u32, u32, u32, u32, C.c_int])
+        dbl = C.c_double
+        self._bq_coeffs = fn("biquad_calc_coeffs", None, [C.c_int, dbl, dbl, dbl, dbl, vp])
+        self._bq_create = fn("biquad_create", vp, [u32])
+        self._bq_destroy = fn("biquad_destroy", None, [vp])
+        self._bq_set = fn("biquad_set_coeffs", None, [vp, vp, dbl])
+        self._bq_calc = fn("biquad_calc", None, [vp, C.c_int, dbl, dbl, dbl, dbl, dbl])
+        self._bq_process = fn("biquad_process", None, [vp, vp, vp, u32, u32, u32, u32])
+        self._bq_state = fn("biquad_get_state", None, [vp, vp, vp, vp])
+        self._bq_reset = fn("biquad_reset", None, [vp])
 
     # ---- formats ----
     def bits_per_sample(self, fmt):
@@ -135,6 +144,44 @@ class CpuLib:
     # ---- MultilayerBuffer<float> ----
     def multilayer(self, channels, layers):
         return CpuMultilayer(self, channels, layers)
+
+    # ---- BiQuadCoeffs / BiQuad ----
+    def biquad_coeffs(self, ftype, freq, fs, gain=0.0, bandwidth=1.0):
+        out = np.zeros(5, dtype=np.float64)
+        self._bq_coeffs(ftype, freq, fs, gain, bandwidth, _ptr(out))
+        return out
+
+    def biquad(self, channels):
+        return CpuBiquad(self, channels)
+
+
+class CpuBiquad:
+    def __init__(self, lib, channels):
+        self.l, self.channels = lib, channels
+        self.h = lib._bq_create(channels)
+
+    def close(self):
+        if self.h:
+            self.l._bq_destroy(self.h)
+            self.h = None
+
+    def set_coeffs(self, c5, interp_samples=0.0):
+        self.l._bq_set(self.h, _ptr(np.ascontiguousarray(c5, dtype=np.float64)), interp_samples)
+
+    def calc(self, ftype, freq, fs, gain=0.0, bandwidth=1.0, interp_time=0.0):
+        self.l._bq_calc(self.h, ftype, freq, fs, gain, bandwidth, interp_time)
+
+    def process(self, src, dst, nchannels, nsrc, ndst, nframes):
+        self.l._bq_process(self.h, _ptr(src), _ptr(dst), nchannels, nsrc, ndst, nframes)
+
+    def state(self):
+        w = np.zeros(2 * max(1, self.channels), dtype=np.float64)
+        cur, md = np.zeros(5, dtype=np.float64), np.zeros(2, dtype=np.float64)
+        self.l._bq_state(self.h, _ptr(w), _ptr(cur), _ptr(md))
+        return w[:2 * self.channels], cur, md
+
+    def reset(self):
+        self.l._bq_reset(self.h)
 
 
 class CpuMultilayer:

@@ -46,6 +46,35 @@ class GpuLib:
     def multilayer(self, channels, layers):
         return GpuMultilayer(self.b, channels, layers)
 
+    def biquad_coeffs(self, ftype, freq, fs, gain=0.0, bandwidth=1.0):
+        return self.b.BiQuadCalcCoeffs(ftype, freq, fs, gain, bandwidth)
+
+    def biquad(self, channels):
+        return GpuBiquad(self.b, channels)
+
+
+class GpuBiquad:
+    def __init__(self, b, channels):
+        self.q = b.BiQuadBank(channels)
+
+    def close(self):
+        self.q.close()
+
+    def set_coeffs(self, c5, interp_samples=0.0):
+        self.q.SetCoeffs(c5, interp_samples)
+
+    def calc(self, ftype, freq, fs, gain=0.0, bandwidth=1.0, interp_time=0.0):
+        self.q.CalcCoeffs(ftype, freq, fs, gain, bandwidth, interp_time)
+
+    def process(self, src, dst, nchannels, nsrc, ndst, nframes):
+        self.q.Process(src, dst, nchannels, nsrc, ndst, nframes)
+
+    def state(self):
+        return self.q.GetState()
+
+    def reset(self):
+        self.q.Reset()
+
 
 class GpuMultilayer:
     def __init__(self, b, channels, layers):

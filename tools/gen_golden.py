@@ -210,6 +210,55 @@ def gen_conv():
     np.savez_compressed(os.path.join(OUT, "conv_truth.npz"), **d)
 
 
+# ---- BiQuadCoeffs / BiQuad (src/BiQuad.cpp), SURVEY 8f.4 ----
+BIQUAD_DESIGNS = [(t, f, fs, g, bw) for t in range(10)
+                  for (f, fs, g, bw) in ((1000.0, 48000.0, 6.0, 1.0), (120.5, 44100.0, -9.5, 0.7), (8000.0, 48000.0, 3.0, 2.5))]
+
+
+def biquad_script(lib, nch=5, nsrc=7, ndst=6, seed=4242):
+    """One scenario run on any implementation: jumps, ramps given in samples (SetCoeffs) and in seconds (CalcCoeffs),
+    a ramp that ends inside a call, a retarget in the middle of a ramp, partial channel counts, in-place processing,
+    Reset.  Returns every output block and the state after every call."""
+    rng = np.random.default_rng(seed)
+    bq = lib.biquad(nch)
+    outs = []
+
+    def run(nframes, nchannels=nch, s=nsrc, d=ndst, inplace=False):
+        x = rng.uniform(-1, 1, nframes * s).astype(np.float32)
+        if inplace:
+            y = x.copy()
+            bq.process(y, y, nchannels, s, s, nframes)
+        else:
+            y = np.full(nframes * d, 7.0, dtype=np.float32)
+            bq.process(x, y, nchannels, s, d, nframes)
+        w, cur, md = bq.state()
+        outs.extend([y, w.copy(), cur.copy(), md.copy()])
+
+    run(33)                                                    # default-constructed coeffs: flat
+    bq.calc(7, 1000.0, 48000.0, 6.0, 1.0, 0.0)                 # PEQ, immediate
+    run(100)
+    bq.calc(3, 3000.0, 48000.0, 0.0, 1.0, 0.004)               # LPF12, 4 ms = 192-sample ramp
+    run(64)
+    run(64, nchannels=3)                                       # two filters keep their state, ramp continues
+    run(200)                                                   # ramp ends inside this call
+    bq.set_coeffs(lib.biquad_coeffs(8, 250.0, 48000.0, -4.0, 1.0), 37.5)   # LSH, 37.5-sample ramp
+    run(20)
+    bq.calc(6, 5000.0, 48000.0, 0.0, 0.3, 0.001)               # retarget in the middle of the ramp
+    run(90, inplace=True)
+    bq.reset()
+    run(17, nchannels=99)                                      # clamped to the channels that exist
+    bq.close()
+    return outs
+
+
+def gen_biquad(ref):
+    d = {"designs": np.array(BIQUAD_DESIGNS, dtype=np.float64)}
+    d["coeffs"] = np.stack([ref.biquad_coeffs(int(t), f, fs, g, bw) for (t, f, fs, g, bw) in BIQUAD_DESIGNS])
+    for i, a in enumerate(biquad_script(ref)):
+        d["script_%03d" % i] = a
+    np.savez_compressed(os.path.join(OUT, "biquad.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = cl.reference()
@@ -219,6 +268,7 @@ def main():
     gen_mix(ref)
     gen_frac(ref)
     gen_delay(ref)
+    gen_biquad(ref)
     gen_conv()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
