@@ -919,7 +919,8 @@ struct bbx_engine {
   uint32_t* tc_fparts_h = nullptr;
   uint32_t* tc_fparts_d = nullptr;
   uint32_t* tc_view = nullptr;  // device: first[n_out] | count[n_out] | xjob[n_out]
-  int* tc_status = nullptr;
+  int* tc_status = nullptr;    // device view of tc_status_h
+  int* tc_status_h = nullptr;  // mapped pinned word the kernel sets when a barrier wait times out
   uint64_t tc_launches = 0;
 };
 
@@ -1388,8 +1389,9 @@ int tc_alloc(bbx_engine* e) {
   }
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_view, sizeof(uint32_t) * view.size()));
   BBX_CUDA_TRY(cudaMemcpy(e->tc_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
-  BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_status, sizeof(int)));
-  BBX_CUDA_TRY(cudaMemset(e->tc_status, 0, sizeof(int)));
+  BBX_CUDA_TRY(cudaHostAlloc((void**)&e->tc_status_h, sizeof(int), cudaHostAllocMapped));
+  *e->tc_status_h = 0;
+  BBX_CUDA_TRY(cudaHostGetDevicePointer((void**)&e->tc_status, e->tc_status_h, 0));
   BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax));
   BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax));
   BBX_CUDA_TRY(cudaFuncSetAttribute(k_mimo_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax));
@@ -1700,7 +1702,7 @@ int bbx_engine_destroy(bbx_engine* e) {
   cudaFree(e->tc_ftab_d);
   cudaFree(e->tc_fparts_d);
   cudaFree(e->tc_view);
-  cudaFree(e->tc_status);
+  if (e->tc_status_h) cudaFreeHost(e->tc_status_h);
   if (e->tc_ftab_h) cudaFreeHost(e->tc_ftab_h);
   if (e->tc_fparts_h) cudaFreeHost(e->tc_fparts_h);
   cudaFree(e->d_route);
@@ -2025,6 +2027,12 @@ int bbx_engine_sync(bbx_engine* e) {
   BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  if (e->tc_status_h && *(volatile int*)e->tc_status_h) {
+    // fail loudly: the output of that call is not valid
+    set_error("k_mimo_tc: a barrier wait timed out inside the tensor-core kernel (status %d); results are invalid",
+              *(volatile int*)e->tc_status_h);
+    return BBX_ERR_CUDA;
+  }
   return BBX_OK;
 }
 
@@ -2131,7 +2139,7 @@ int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status) {
   if (launches) *launches = e->tc_launches;
   if (status) {
     *status = 0;
-    if (e->tc_status) BBX_CUDA_TRY(cudaMemcpy(status, e->tc_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e->tc_status_h) *status = *(volatile int*)e->tc_status_h;
   }
   return BBX_OK;
 }

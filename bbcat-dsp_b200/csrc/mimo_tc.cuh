@@ -74,7 +74,7 @@ struct MimoTcArgs {
   const float4* hpack;
   const float2* xb;
   float2* ypart;     // [t][slot_stride][B], slot = output
-  int* status;       // set non-zero when a barrier wait times out (never hang the device)
+  int* status;       // mapped host memory: set non-zero when a barrier wait times out (never hang the device)
   uint32_t B, n_in, n_out, P2log, G /* float4 K groups = Kc/2 */, W, T, slot_stride;
   uint64_t xbin;     // float2 elements per bin of xb = (inputs padded to whole chunks) * W
   uint64_t xlo;      // float2 elements from the hi part of xb to the lo part (same layout)
@@ -170,6 +170,12 @@ __device__ __forceinline__ void commit(uint32_t bar) {
 __device__ __forceinline__ void split(float v, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
   lo = __uint_as_float(__float_as_uint(v - hi) + 0x1000u);
+}
+
+// a barrier wait gave up: tell the host (status lives in mapped pinned memory, read by bbx_engine_sync)
+__device__ __forceinline__ void report_timeout(int* status, int code) {
+  *reinterpret_cast<volatile int*>(status) = code;
+  __threadfence_system();
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
           }
         }
       }
-      if (!ok && lane == 0) atomicExch(a.status, 3);
+      if (!ok && lane == 0) report_timeout(a.status, 3);
     }
   } else if (warp == kTcWarpMma) {
     // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         }
       }
     }
-    if (!ok && lane == 0) atomicExch(a.status, 2);
+    if (!ok && lane == 0) report_timeout(a.status, 2);
   } else if (warp >= kTcWarpEpi && warp < kTcWarpEpi + 4) {
     // ================= epilogue (4 warps, one per TMEM lane quarter) =================
     // read out the accumulators of bin j: sum the four tiles, release them, pair (re, im) through the smem tile,
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");  // tile free for the next bin
     }
-    if (!ok && lane == 0) atomicExch(a.status, 4);
+    if (!ok && lane == 0) report_timeout(a.status, 4);
   } else if (warp < kTcGroups * kTcProducers / 32) {
     // ================= producers (2 groups of 8 warps): raw operands (smem) -> A tile (TMEM), B tile (smem) =====
     // A lives in tensor memory (row = lane, K along columns): warp w owns TMEM lanes 32 (w & 3) .. + 31 = rows m of
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         }
       }
     }
-    if (!ok && gtid == 0) atomicExch(a.status, 1);
+    if (!ok && gtid == 0) report_timeout(a.status, 1);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
