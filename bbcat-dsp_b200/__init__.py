@@ -110,6 +110,7 @@ SYMBOLS = {
     "bbx_biquad_get_state": (C.c_int, [vp, vp, vp, vp]),
     "bbx_biquad_reset": (C.c_int, [vp]),
     "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
+    "bbx_engine_tensor_trace": (C.c_int, [vp, vp, u32]),
     "bbx_comm_available": (C.c_int, []),
     "bbx_comm_unique_id": (C.c_int, [C.POINTER(u8)]),
     "bbx_comm_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(u8), C.c_int, C.POINTER(vp)]),
@@ -505,6 +506,15 @@ class Convolver:
         n, st = u64(0), C.c_int(0)
         _check(lib().bbx_engine_tensor_status(self.h, C.byref(n), C.byref(st)))
         return n.value, st.value
+
+    def tensor_trace(self, n_ctas, enable=None):
+        """enable=True/False switches the per-CTA role trace of k_mimo_tc; otherwise returns uint64[n_ctas][16]."""
+        if enable is not None:
+            _check(lib().bbx_engine_tensor_trace(self.h, None, n_ctas if enable else 0))
+            return None
+        out = np.zeros((n_ctas, 16), dtype=np.uint64)
+        _check(lib().bbx_engine_tensor_trace(self.h, _p(out), n_ctas))
+        return out
 
     def flush_l2(self, nbytes=256 << 20):
         _check(lib().bbx_engine_flush_l2(self.h, nbytes))

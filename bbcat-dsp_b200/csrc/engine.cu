@@ -910,8 +910,8 @@ struct bbx_engine {
   bool tc_on = false;          // buffers exist (MIMO mode, max_blocks >= tc_min_blocks, not disabled)
   bool tc_dirty = true;        // Hpack must be rebuilt from the current filter matrix
   uint32_t tc_min_blocks = 16; // calls with fewer blocks use the streaming SIMT MAC
-  uint32_t tc_P2 = 1, tc_P2log = 0, tc_G = 0, tc_nog = 0, tc_W = 0;
-  uint64_t tc_xbin = 0;
+  uint32_t tc_P2 = 1, tc_P2log = 0, tc_G = 0, tc_nog = 0;
+  uint64_t tc_xbin_max = 0;  // float2 elements per bin of tc_xb at N = 64
   float4* tc_hpack = nullptr;
   float2* tc_xb = nullptr;
   const float2** tc_ftab_h = nullptr;  // pinned staging [n_out][n_in]
@@ -921,6 +921,8 @@ struct bbx_engine {
   uint32_t* tc_view = nullptr;  // device: first[n_out] | count[n_out] | xjob[n_out]
   int* tc_status = nullptr;    // device view of tc_status_h
   int* tc_status_h = nullptr;  // mapped pinned word the kernel sets when a barrier wait times out
+  unsigned long long* tc_trace = nullptr;  // optional per-CTA role cycle counters (bbx_engine_tensor_trace)
+  uint32_t tc_trace_ctas = 0;
   uint64_t tc_launches = 0;
 };
 
@@ -1368,14 +1370,15 @@ int tc_alloc(bbx_engine* e) {
   const uint32_t Kc = ceil_div(e->n_in * P2, (uint32_t)kTcChunk) * kTcChunk;  // complex K, padded to whole chunks
   e->tc_G = Kc / 2;
   e->tc_nog = ceil_div(e->n_out, 64u);
-  // row length: history + columns, plus one element so the 16-byte TMA runs of the last column stay inside; even
-  e->tc_W = (P2 + ceil_div(e->Tmax, (uint32_t)kTcNmax) * kTcNmax + 1) & ~1u;
+  // pre-staged FDL runs: per bin [column tile][chunk][hi | lo][rows of the chunk][seg], sized for N = 64
+  {
+    const uint32_t ninp = lg < 4 ? (16u >> lg) : 1u, seg = lg < 4 ? ((kTcNmax + P2) & ~1u) : kTcNmax + 16;
+    e->tc_xbin_max = (uint64_t)ceil_div(e->Tmax, (uint32_t)kTcNmax) * (Kc / kTcChunk) * 2 * ninp * seg;
+  }
   const size_t hbytes = sizeof(float4) * (size_t)e->tc_nog * e->B * e->tc_G * 64;
-  e->tc_xbin = (uint64_t)(Kc >> lg) * e->tc_W;  // inputs padded (zero rows) to the padded K
-  const size_t xbytes = 2 * sizeof(float2) * (size_t)e->B * e->tc_xbin;  // hi part, then lo part
+  const size_t xbytes = sizeof(float2) * (size_t)e->B * e->tc_xbin_max;
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_hpack, hbytes));
   BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_xb, xbytes));
-  BBX_CUDA_TRY(cudaMemset(e->tc_xb, 0, xbytes));
   const size_t npaths = (size_t)e->n_out * e->n_in;
   BBX_CUDA_TRY(cudaHostAlloc((void**)&e->tc_ftab_h, sizeof(float2*) * npaths, cudaHostAllocDefault));
   BBX_CUDA_TRY(cudaHostAlloc((void**)&e->tc_fparts_h, sizeof(uint32_t) * npaths, cudaHostAllocDefault));
@@ -1430,8 +1433,12 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
     Nlog++;
   }
   const uint32_t ntiles = ceil_div(T, N);
-  k_mimo_pack_x<<<dim3(e->B / 32, ceil_div(e->tc_W, 32u), e->n_in), 256, 0, st>>>(e->fdl, e->tc_xb, e->B, e->R, e->head, e->tc_xbin,
-                                                                              (uint64_t)e->B * e->tc_xbin, e->tc_P2, T, e->tc_W);
+  const uint32_t nchunk = e->tc_G / (kTcChunk / 2);
+  const uint32_t ninp = e->tc_P2log < 4 ? (16u >> e->tc_P2log) : 1u;
+  const uint32_t seg = e->tc_P2log < 4 ? ((N + e->tc_P2) & ~1u) : N + 16;
+  const uint64_t xbin = (uint64_t)ntiles * nchunk * 2 * ninp * seg;
+  k_mimo_pack_x<<<dim3(e->B / 32, ntiles * nchunk * ninp, ceil_div(seg, 32u)), 256, 0, st>>>(e->fdl, e->tc_xb, e->B, e->R, e->head,
+                                                                                         e->n_in, e->tc_P2log, T, N, nchunk, xbin);
   BBX_CUDA_TRY(cudaGetLastError());
   e->launches++;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1454,16 +1461,13 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   a.n_out = e->n_out;
   a.P2log = e->tc_P2log;
   a.G = e->tc_G;
-  a.W = e->tc_W;
   a.T = T;
   a.slot_stride = e->max_slots;
-  a.xbin = e->tc_xbin;
-  a.xlo = (uint64_t)e->B * e->tc_xbin;
+  a.xbin = xbin;
+  a.trace = nullptr;
   if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
   // raw ring: 8 KB of H + hi and lo FDL runs per chunk (see mimo_tc.cuh); as many stages as fit, an even number
   {
-    const uint32_t ninp = e->tc_P2log < 4 ? (16u >> e->tc_P2log) : 1u;
-    const uint32_t seg = e->tc_P2log < 4 ? ((N + e->tc_P2) & ~1u) : N + 16;
     a.raw_stage_bytes = (8192 + 2 * ninp * seg * 8 + 127) & ~127u;
     uint32_t nst = (kTcSmemMax - kTcOffRaw) / a.raw_stage_bytes;
     nst = std::min(nst, (uint32_t)kTcRawStagesMax) & ~1u;
@@ -1471,6 +1475,7 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   }
   const uint32_t smem = kTcOffRaw + a.raw_stages * a.raw_stage_bytes;
   const dim3 grid(e->B / kTcBins, e->tc_nog, ntiles);
+  if (e->tc_trace && grid.x * grid.y * grid.z <= e->tc_trace_ctas) a.trace = e->tc_trace;
   if (Nlog == 4) k_mimo_tc<4><<<grid, kTcThreads, smem, st>>>(a);
   else if (Nlog == 5) k_mimo_tc<5><<<grid, kTcThreads, smem, st>>>(a);
   else k_mimo_tc<6><<<grid, kTcThreads, smem, st>>>(a);
@@ -1703,6 +1708,7 @@ int bbx_engine_destroy(bbx_engine* e) {
   cudaFree(e->tc_fparts_d);
   cudaFree(e->tc_view);
   if (e->tc_status_h) cudaFreeHost(e->tc_status_h);
+  cudaFree(e->tc_trace);
   if (e->tc_ftab_h) cudaFreeHost(e->tc_ftab_h);
   if (e->tc_fparts_h) cudaFreeHost(e->tc_fparts_h);
   cudaFree(e->d_route);
@@ -2141,6 +2147,26 @@ int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status) {
     *status = 0;
     if (e->tc_status_h) *status = *(volatile int*)e->tc_status_h;
   }
+  return BBX_OK;
+}
+
+int bbx_engine_tensor_trace(bbx_engine* e, uint64_t* out, uint32_t max_ctas) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (!out) {  // enable (max_ctas > 0) or disable
+    cudaFree(e->tc_trace);
+    e->tc_trace = nullptr;
+    e->tc_trace_ctas = 0;
+    if (max_ctas) {
+      BBX_CUDA_TRY(cudaMalloc((void**)&e->tc_trace, sizeof(unsigned long long) * 16 * (size_t)max_ctas));
+      BBX_CUDA_TRY(cudaMemset(e->tc_trace, 0, sizeof(unsigned long long) * 16 * (size_t)max_ctas));
+      e->tc_trace_ctas = max_ctas;
+    }
+    return BBX_OK;
+  }
+  BBX_REQUIRE(e->tc_trace && max_ctas <= e->tc_trace_ctas, "bbx_engine_tensor_trace: tracing is not enabled for that many CTAs");
+  BBX_CUDA_TRY(cudaMemcpy(out, e->tc_trace, sizeof(unsigned long long) * 16 * (size_t)max_ctas, cudaMemcpyDeviceToHost));
   return BBX_OK;
 }
 

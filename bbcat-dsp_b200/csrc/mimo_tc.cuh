@@ -15,16 +15,19 @@
 //   Hpack[og][k][g][64] float4   g indexes pairs of complex K elements j = 2g, 2g+1;  j = i*P2 + p',
 //                                 p' = P2-1-p (partition order reversed so a column of B is a contiguous
 //                                 run of the time axis), P2 = power of two >= P, K padded to 16 with zeros
-//   Xb[k][i][w] float2           w = t + p': block t - p of this call (negative = history) -> W = P2-1+Tcap;
-//                                 inputs padded with zero rows up to the padded K
+//   Xq[k][column tile][chunk][hi | lo][input row of the chunk][seg] float2
+//                                 the FDL runs of one chunk, already split into TF32 hi and lo parts and laid out
+//                                 exactly as the kernel stages them: ONE contiguous TMA copy per chunk.  Element wl of
+//                                 a row is block (tile start + p'0 + wl - (P2-1)) of this call (negative = history,
+//                                 beyond the call = 0); seg = N + P2 (P2 < 16: 16/P2 rows per chunk) or N + 16 (one row)
 // One CTA owns kTcBins adjacent bins (their 8-byte output writes fill one 32-byte sector in L2) and walks K in chunks
 // of 16 complex in three decoupled pipelines (mbarriers only, no block-wide barrier in the main loop):
 //   loader warp   TMA bulk copies (cp.async.bulk) of the chunk's raw H and FDL runs into a raw smem ring
-//   2 x 8 producer warps (alternating chunks)  raw H -> hi/lo split + sign/swap expansion -> A tile into TENSOR MEMORY (tcgen05.st); raw FDL
+//   4 x 4 producer warps (group g: chunks g mod 4)  raw H -> hi/lo split + sign/swap expansion -> A tile into TENSOR MEMORY (tcgen05.st); raw FDL
 //                 (already split by k_mimo_pack_x) -> B tile in shared memory (canonical no-swizzle K-major layout)
 //   4 epilogue warps  accumulators (TMEM) -> sum of the four tiles -> (re, im) pairs -> HBM
-//   MMA warp      one lane issues the 12 tcgen05.mma (A from TMEM, B from smem) of the chunk; tcgen05.commit
-//                 releases the stage
+//   2 MMA warps   one lane each issues tcgen05.mma (A from TMEM, B from smem): warp 20 the 4 hi*hi MMAs of the chunk,
+//                 warp 21 the 8 small-term MMAs (independent accumulator tiles); their tcgen05.commit's release the stage
 #pragma once
 
 #include <cuda_runtime.h>
@@ -32,14 +35,16 @@
 
 namespace bbx {
 
-static constexpr int kTcGroups = 2;        // producer groups: group g converts chunks it = g (mod 2), so the fences and
-                                          // barrier waits of one chunk overlap the arithmetic of the next
-static constexpr int kTcProducers = 256;  // threads per group (8 warps); warps 0..15 produce
+static constexpr int kTcGroups = 4;        // producer groups: group g converts chunks it = g (mod 4) into operand stage g, so
+                                          // the fences, store waits and barrier round trips of four chunks overlap
+static constexpr int kTcProducers = 128;  // threads per group (4 warps = the four TMEM lane quarters); warps 0..15 produce
 static constexpr int kTcWarpEpi = 16;     // warps 16..19: accumulator read-out (warp & 3 = TMEM lane quarter)
 static constexpr int kTcEpiThreads = 128;
-static constexpr int kTcWarpMma = 20;     // one elected lane issues the MMAs
-static constexpr int kTcWarpLoad = 21;    // one elected lane issues the TMA bulk copies
-static constexpr int kTcThreads = 704;
+static constexpr int kTcWarpMma = 20;     // warps 20, 21: one elected lane each issues the hi*hi MMAs / the small-term MMAs
+static constexpr int kTcMmaWarps = 2;     //   (an N = 64 MMA is shorter than one lane's issue overhead: two issue streams)
+static constexpr int kTcWarpLoad = 22;    // one elected lane issues the TMA bulk copies (a second loader warp changes nothing)
+static constexpr int kTcLoadWarps = 1;
+static constexpr int kTcThreads = 736;
 static constexpr int kTcBins = 4;      // adjacent bins per CTA
 static constexpr int kTcStages = 4;    // converted operand stages: A in TMEM, B in shared memory
 static constexpr int kTcRawStagesMax = 8; // raw operand stages (TMA bulk copies from HBM): as many as fit, even
@@ -75,10 +80,10 @@ struct MimoTcArgs {
   const float2* xb;
   float2* ypart;     // [t][slot_stride][B], slot = output
   int* status;       // mapped host memory: set non-zero when a barrier wait times out (never hang the device)
-  uint32_t B, n_in, n_out, P2log, G /* float4 K groups = Kc/2 */, W, T, slot_stride;
-  uint64_t xbin;     // float2 elements per bin of xb = (inputs padded to whole chunks) * W
-  uint64_t xlo;      // float2 elements from the hi part of xb to the lo part (same layout)
+  uint32_t B, n_in, n_out, P2log, G /* float4 K groups = Kc/2 */, T, slot_stride;
+  uint64_t xbin;     // float2 elements per bin of xb = column tiles * chunks * (2 * ninp * seg)
   uint32_t raw_stage_bytes, raw_stages;  // raw ring geometry (stages: even, <= kTcRawStagesMax)
+  unsigned long long* trace;             // optional [gridDim.x][16] cycle counters of the warp roles (NULL = off)
 };
 
 namespace tc {
@@ -178,6 +183,15 @@ __device__ __forceinline__ void report_timeout(int* status, int code) {
   __threadfence_system();
 }
 
+// timed wait for the optional role trace (cycles spent waiting are added to *acc)
+__device__ __forceinline__ bool mbar_wait_t(uint32_t bar, uint32_t parity, bool trace, unsigned long long& acc) {
+  if (!trace) return mbar_wait(bar, parity);
+  const long long t0 = clock64();
+  const bool r = mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+  return r;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -249,7 +263,11 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_
 }
 
 // the 12 MMAs of one chunk (4 k-steps of 8); FIRST = first chunk of a bin (accumulators start from zero)
-template <uint32_t N, bool FIRST>
+// the MMAs of one chunk (4 k-steps of 8) issued by one of the two issuer warps; FIRST = first chunk of a bin
+// (accumulators start from zero):
+//   PROD 0  hi*hi, one MMA per k-step, rotating over tiles 0..2 (k-step mod 3, rot0 = first k-step of the chunk mod 3)
+//   PROD 1  lo*hi and hi*lo, two MMAs per k-step into tile 3 (same issuing thread: program order)
+template <uint32_t N, int PROD, bool FIRST>
 __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tA, uint32_t blo, uint32_t rot0) {
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 @17, M >> 4 @24
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
@@ -257,14 +275,16 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tA, uint32_t
   for (int k8 = 0; k8 < kTcChunk / 4; k8++) {
     const uint32_t a_hi = tA + k8 * 8, a_lo = a_hi + 2 * kTcChunk;
     const uint32_t b_hi = blo + k8 * ((2 * N * 16) >> 4), b_lo = b_hi + (kTcBHalf >> 4);
-    uint32_t r = rot0 + k8;
-    r = r >= 3 ? r - 3 : r;
-    const uint32_t d_hh = tmem + r * kTcNmax;
-    if (FIRST && k8 == 0) mma_ts<false>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
-    else mma_ts<true>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
-    mma_ts<true>(tmem + 3 * kTcNmax, a_hi, b_lo, idesc);
-    if (FIRST && k8 < 3) mma_ts<false>(d_hh, a_hi, b_hi, idesc);
-    else mma_ts<true>(d_hh, a_hi, b_hi, idesc);
+    if (PROD == 0) {
+      uint32_t r = rot0 + k8;
+      r = r >= 3 ? r - 3 : r;
+      if (FIRST && k8 < 3) mma_ts<false>(tmem + r * kTcNmax, a_hi, b_hi, idesc);
+      else mma_ts<true>(tmem + r * kTcNmax, a_hi, b_hi, idesc);
+    } else {
+      if (FIRST && k8 == 0) mma_ts<false>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
+      else mma_ts<true>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
+      mma_ts<true>(tmem + 3 * kTcNmax, a_hi, b_lo, idesc);
+    }
   }
 }
 
@@ -295,9 +315,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
 #pragma unroll
     for (int s = 0; s < kTcStages; s++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "n"(kTcProducers));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_empty + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * s), "n"(kTcMmaWarps));
     }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_accf));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_accf), "n"(kTcMmaWarps));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_acce), "n"(kTcEpiThreads));
 #pragma unroll
     for (int d = 0; d < kTcRawStagesMax; d++) {
@@ -319,58 +339,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   // raw B segment of one chunk: ninp input rows of seg complex each (rounded to 16 bytes), once for hi, once for lo
   const uint32_t ninp = P2log < 4 ? (16u >> P2log) : 1u;
   const uint32_t seg = P2log < 4 ? ((N + P2) & ~1u) : N + 16;
-  const uint32_t bhalf = ninp * seg * 8;  // bytes of the hi (or lo) part
+  const uint32_t bhalf = ninp * seg * 8;  // bytes of the hi (or lo) part of a chunk's FDL runs
   bool ok = true;
+  const bool tr = a.trace != nullptr;
+  unsigned long long* trow = tr ? a.trace + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  unsigned long long tw0 = 0, tw1 = 0;  // cycles this role waited on its two barriers
+  const long long tstart = tr ? clock64() : 0;
 
-  if (warp == kTcWarpLoad) {
+  if (warp >= kTcWarpLoad) {
     // ================= loader: one lane issues the bulk copies (TMA) of the raw operands =================
     {
-      uint32_t d = 0, ph = 0, it = 0;
-      const uint32_t bytes = 8192 + 2 * bhalf;
-      for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
-        const char* asrc = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb + j) * a.G) * 64);
-        const float2* xrow = a.xb + (uint64_t)(kb + j) * a.xbin + t0;
-        for (uint32_t c = 0; c < nchunk; c++, it++) {
-          if (it >= RD) {
-            if (ok && !mbar_wait(bar_rawe + 8 * d, ph ^ 1)) ok = false;
-          }
-          if (elect_one()) {
-            const uint32_t dst = raw0 + d * RSB, bar = bar_rawf + 8 * d;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            bulk_g2s(dst, asrc + (uint64_t)c * 8192, 8192, bar);
-            // chunk c starts at complex K index 16 c = (input i0, reversed partition pp0)
-            const uint32_t i0 = P2log < 4 ? c * ninp : (c >> (P2log - 4)), pp0 = P2log < 4 ? 0u : ((c << 4) & P2m);
-            for (uint32_t il = 0; il < ninp; il++) {
-              const float2* src = xrow + (uint64_t)(i0 + il) * a.W + pp0;
-              bulk_g2s(dst + 8192 + il * seg * 8, src, seg * 8, bar);
-              bulk_g2s(dst + 8192 + bhalf + il * seg * 8, src + a.xlo, seg * 8, bar);
-            }
-          }
-          __syncwarp();
-          if (++d == RD) {
-            d = 0;
-            ph ^= 1;
-          }
+      // two bulk copies per chunk, both sources advance linearly: the packed H of the CTA's bins is one contiguous run
+      // of 8 KB chunks, the pre-staged FDL runs (k_mimo_pack_x) one run of 2 * bhalf bytes per chunk.  Loader warp l
+      // handles chunks it = l (mod 2).
+      const uint32_t lw = warp - kTcWarpLoad;
+      const uint32_t bbytes = 2 * bhalf, bytes = 8192 + bbytes, total = kTcBins * nchunk;
+      const char* asrc = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64) + (uint64_t)lw * 8192;
+      const char* xbase = reinterpret_cast<const char*>(a.xb + (uint64_t)kb * a.xbin) + (uint64_t)blockIdx.z * nchunk * bbytes;
+      const uint64_t xbin_bytes = a.xbin * 8;
+      uint32_t d = lw % RD, ph = 0, j = 0, c = lw;
+      for (uint32_t it = lw; it < total; it += kTcLoadWarps) {
+        while (c >= nchunk) {
+          c -= nchunk;
+          j++;
+        }
+        if (it >= RD) {
+          if (ok && !mbar_wait_t(bar_rawe + 8 * d, ph ^ 1, tr, tw0)) ok = false;
+        }
+        if (elect_one()) {
+          const uint32_t dst = raw0 + d * RSB, bar = bar_rawf + 8 * d;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          bulk_g2s(dst, asrc, 8192, bar);
+          bulk_g2s(dst + 8192, xbase + j * xbin_bytes + (uint64_t)c * bbytes, bbytes, bar);
+        }
+        __syncwarp();
+        asrc += kTcLoadWarps * 8192;
+        c += kTcLoadWarps;
+        d += kTcLoadWarps;
+        while (d >= RD) {
+          d -= RD;
+          ph ^= 1;
         }
       }
       if (!ok && lane == 0) report_timeout(a.status, 3);
+      if (tr && lane == 0 && lw == 0) {
+        trow[0] = (unsigned long long)(clock64() - tstart);  // loader: total, waiting for a free raw slot
+        trow[1] = tw0;
+      }
     }
-  } else if (warp == kTcWarpMma) {
+  } else if (warp >= kTcWarpMma && warp < kTcWarpMma + kTcMmaWarps) {
     // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
-    // accumulator tiles 0..2 take the hi*hi products by k-step mod 3, tile 3 the small lo*hi / hi*lo terms
+    // accumulator tiles 0..2: hi*hi products by k-step mod 3 (warp 20); tile 3: the small lo*hi / hi*lo terms (warp 21)
     const uint32_t blo0 = kDescLo<N> + (smem0 >> 4);  // low descriptor word of stage 0's B_hi tile
     uint32_t s = 0, ph = 0;
     for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
-      if (j >= 1 && ok && !mbar_wait(bar_acce, (j - 1) & 1)) ok = false;  // the previous bin has been read out
+      if (j >= 1 && ok && !mbar_wait_t(bar_acce, (j - 1) & 1, tr, tw1)) ok = false;  // the previous bin has been read out
       uint32_t rot0 = 0;
       for (uint32_t c = 0; c < nchunk; c++) {
-        if (ok && !mbar_wait(bar_full + 8 * s, ph)) ok = false;
+        if (ok && !mbar_wait_t(bar_full + 8 * s, ph, tr, tw0)) ok = false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t tA = tmem + kTcAccCols + s * kTcAStageCols;
           const uint32_t blo = blo0 + s * (kTcStageBytes >> 4);
-          if (c == 0) issue_chunk<N, true>(tmem, tA, blo, rot0);
-          else issue_chunk<N, false>(tmem, tA, blo, rot0);
+          if (warp == kTcWarpMma) {
+            if (c == 0) issue_chunk<N, 0, true>(tmem, tA, blo, rot0);
+            else issue_chunk<N, 0, false>(tmem, tA, blo, rot0);
+          } else {
+            if (c == 0) issue_chunk<N, 1, true>(tmem, tA, blo, rot0);
+            else issue_chunk<N, 1, false>(tmem, tA, blo, rot0);
+          }
           commit(bar_empty + 8 * s);
           if (c + 1 == nchunk) commit(bar_accf);
         }
@@ -383,6 +420,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       }
     }
     if (!ok && lane == 0) report_timeout(a.status, 2);
+    if (tr && lane == 0 && warp == kTcWarpMma) {
+      trow[2] = (unsigned long long)(clock64() - tstart);  // issuer: total, waiting for operands, waiting for the read-out
+      trow[3] = tw0;
+      trow[4] = tw1;
+    }
   } else if (warp >= kTcWarpEpi && warp < kTcWarpEpi + 4) {
     // ================= epilogue (4 warps, one per TMEM lane quarter) =================
     // read out the accumulators of bin j: sum the four tiles, release them, pair (re, im) through the smem tile,
@@ -390,7 +432,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     const uint32_t q = warp & 3, et = tid - kTcWarpEpi * 32;
     const uint32_t m = 32 * q + lane, cc = m >> 6, o = m & 63;
     for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
-      if (ok && !mbar_wait(bar_accf, j & 1)) ok = false;
+      if (ok && !mbar_wait_t(bar_accf, j & 1, tr, tw0)) ok = false;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (uint32_t cg = 0; cg < (N >> 4); cg++) {
@@ -425,19 +467,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");  // tile free for the next bin
     }
     if (!ok && lane == 0) report_timeout(a.status, 4);
+    if (tr && et == 0) {
+      trow[5] = (unsigned long long)(clock64() - tstart);  // epilogue: total, waiting for finished accumulators
+      trow[6] = tw0;
+    }
   } else if (warp < kTcGroups * kTcProducers / 32) {
-    // ================= producers (2 groups of 8 warps): raw operands (smem) -> A tile (TMEM), B tile (smem) =====
+    // ================= producers (4 groups of 4 warps): raw operands (smem) -> A tile (TMEM), B tile (smem) =====
+    // Group g converts chunks it = g (mod 4) into operand stage g: four chunks are in flight at different points of
+    // the chain (raw wait -> split -> TMEM / smem stores -> store wait + proxy fence -> hand-off).
     // A lives in tensor memory (row = lane, K along columns): warp w owns TMEM lanes 32 (w & 3) .. + 31 = rows m of
-    // the expanded matrix (m < 64: re of output m, m >= 64: im of output m - 64) and K columns 16 h .. 16 h + 15,
-    // h = bit 2 of the warp index
-    const uint32_t grp = warp >> 3, gtid = tid & (kTcProducers - 1);
-    const uint32_t q = warp & 3, half = (warp >> 2) & 1;
+    // the expanded matrix (m < 64: re of output m, m >= 64: im of output m - 64), all 32 K columns of the chunk in
+    // two halves of 16.
+    const uint32_t grp = warp >> 2, gtid = tid & (kTcProducers - 1);
+    const uint32_t q = warp & 3;
     const uint32_t m = 32 * q + lane, ao = m & 63;
     const bool im_row = (q >> 1) != 0;  // warp-uniform
-    const uint32_t srcA = (4 * half * 64 + ao) * 16;                   // raw [g][o] float4, g = 4 half .. 4 half + 3
-    const uint32_t dstA = ((32 * q) << 16) + kTcAccCols + 16 * half;  // + stage * kTcAStageCols (+ 32 for lo)
-    // B (pre-split by k_mimo_pack_x): items e = tid + 256 r -> (pair member, column t, K group); 16 N complex per chunk
-    constexpr int NBR = 16 * N / kTcProducers;  // 4, 2, 1
+    const uint32_t srcA = ao * 16;                                         // raw [g][o] float4
+    const uint32_t dstA = ((32 * q) << 16) + kTcAccCols + grp * kTcAStageCols;  // this group's stage (+ 32 for lo)
+    // B (pre-split by k_mimo_pack_x): items e = gtid + 128 r -> (pair member, column t, K group); 16 N complex per chunk
+    constexpr int NBR = 16 * N / kTcProducers;  // 8, 4, 2
     uint32_t offB[NBR], srcB[NBR];
 #pragma unroll
     for (int r = 0; r < NBR; r++) {
@@ -447,10 +495,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       // element (local K index jl, column t) of the raw segment: row jl / P2, position t + p'
       srcB[r] = 8192 + 8 * ((P2log < 4) ? (jl >> P2log) * seg + (jl & P2m) + t : jl + t);
     }
-
-    // this group's chunks: it = grp, grp + 2, ...; stage it mod NST, raw slot it mod RD, phases from the wrap counts
+    static_assert(kTcStages == kTcGroups, "one operand stage per producer group");
     const uint32_t total = kTcBins * nchunk;
-    uint32_t s = grp % kTcStages, ph = 0, d = grp % RD, phd = 0;
+    const uint32_t s = grp, sB = smem0 + s * kTcStageBytes;
+    uint32_t ph = 0, d = grp % RD, phd = 0;
     uint32_t cnext = grp;  // chunk index inside the bin, to find the bin of `it`
     uint32_t j = 0;
     for (uint32_t it = grp; it < total; it += kTcGroups) {
@@ -459,28 +507,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         j++;
       }
       cnext += kTcGroups;
-      {
-        // ---- raw operands of this chunk (landed by TMA) -> registers; release the raw slot at once ----
-        const uint32_t raw = raw0 + d * RSB;
-        if (ok && !mbar_wait(bar_rawf + 8 * d, phd)) ok = false;
+      const bool bin0 = (kb + j) == 0;  // packed bin 0 = (DC, Nyquist): two real products, no cross terms
+      const uint32_t raw = raw0 + d * RSB;
+      // ---- raw operands of this chunk have landed (TMA) ----
+      if (ok && !mbar_wait_t(bar_rawf + 8 * d, phd, tr, tw0)) ok = false;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        // ---- A: eight complex (a_i, b_i) of output ao -> 16 K columns of row m: re row (a, -b), im row (b, a) ----
+        // (converting both halves before the stage wait needs 64 live registers: it spills at the 80-register cap
+        // of a 768-thread CTA and measured slower)
         float4 qa[4];
 #pragma unroll
-        for (int g = 0; g < 4; g++) qa[g] = ld_shared4(raw + srcA + g * 1024);
-        float2 qh[NBR], ql[NBR];
-#pragma unroll
-        for (int r = 0; r < NBR; r++) {
-          qh[r] = ld_shared2(raw + srcB[r]);
-          ql[r] = ld_shared2(raw + srcB[r] + bhalf);
-        }
-        mbar_arrive(bar_rawe + 8 * d);
-        d += kTcGroups;
-        if (d >= RD) {
-          d -= RD;
-          phd ^= 1;
-        }
-        // ---- A: eight complex (a_i, b_i) of output ao -> 16 K columns of row m: re row (a, -b), im row (b, a) ----
+        for (int g = 0; g < 4; g++) qa[g] = ld_shared4(raw + srcA + (4 * half + g) * 1024);
         float hi[16], lo[16];
-        const bool bin0 = (kb + j) == 0;  // packed bin 0 = (DC, Nyquist): two real products, no cross terms
         if (!im_row) {
 #pragma unroll
           for (int g = 0; g < 4; g++) {
@@ -510,33 +549,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
             }
           }
         }
-        // ---- the MMAs that read this stage kTcStages chunks ago have completed ----
-        if (it >= (uint32_t)kTcStages) {
-          if (ok && !mbar_wait(bar_empty + 8 * s, ph ^ 1)) ok = false;
+        if (half == 0 && it >= (uint32_t)kTcStages) {
+          // ---- the MMAs that read this stage kTcStages chunks ago have completed ----
+          if (ok && !mbar_wait_t(bar_empty + 8 * s, ph ^ 1, tr, tw1)) ok = false;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        st_tmem16(tmem + dstA + s * kTcAStageCols, hi);
-        st_tmem16(tmem + dstA + s * kTcAStageCols + 2 * kTcChunk, lo);
-        // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo ----
-        const uint32_t sB = smem0 + s * kTcStageBytes;
-#pragma unroll
-        for (int r = 0; r < NBR; r++) {
-          st_shared2(sB + offB[r], qh[r].x, qh[r].y);
-          st_shared2(sB + kTcBHalf + offB[r], ql[r].x, ql[r].y);
-        }
-        // TMEM stores complete, smem writes visible to the tensor core (async proxy); hand the stage to the issuer
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bar_full + 8 * s);
-        s += kTcGroups;
-        if (s >= (uint32_t)kTcStages) {
-          s -= kTcStages;
-          ph ^= 1;
-        }
+        st_tmem16(tmem + dstA + 16 * half, hi);
+        st_tmem16(tmem + dstA + 16 * half + 2 * kTcChunk, lo);
       }
+      // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo (plain copies) ----
+#pragma unroll
+      for (int r = 0; r < NBR; r++) {
+        const float2 qh = ld_shared2(raw + srcB[r]), ql = ld_shared2(raw + srcB[r] + bhalf);
+        st_shared2(sB + offB[r], qh.x, qh.y);
+        st_shared2(sB + kTcBHalf + offB[r], ql.x, ql.y);
+      }
+      mbar_arrive(bar_rawe + 8 * d);  // raw slot free for the loader
+      d += kTcGroups;
+      while (d >= RD) {
+        d -= RD;
+        phd ^= 1;
+      }
+      // TMEM stores complete, smem writes visible to the tensor core (async proxy); hand the stage to the issuer
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + 8 * s);
+      ph ^= 1;
     }
     if (!ok && gtid == 0) report_timeout(a.status, 1);
+    if (tr && gtid == 0) {
+      trow[7 + 3 * grp] = (unsigned long long)(clock64() - tstart);  // producer group: total, raw wait, stage wait
+      trow[8 + 3 * grp] = tw0;
+      trow[9 + 3 * grp] = tw1;
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -545,39 +591,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTcTmemCols));
 }
 
-// Xb[k][i][w] = FDL[i][slot of block (w - (P2-1))][k] for w < P2-1+T, zero for the padding columns; written as
-// its TF32 hi part and (xlo elements further) its lo part, so the GEMM kernel only copies the B operand.
-// 32 x 32 tile transpose (k <-> w) through shared memory, one input per blockIdx.z.
-__global__ void __launch_bounds__(256) k_mimo_pack_x(const float2* __restrict__ fdl, float2* __restrict__ xb, uint32_t B,
-                                                     uint32_t R, uint32_t head, uint64_t xbin, uint64_t xlo, uint32_t P2,
-                                                     uint32_t T, uint32_t W) {
+// Xq (layout above) from the FDL ring: one (column tile, chunk, input row) segment per blockIdx.y, 32 bins x 32
+// positions per CTA through a shared-memory transpose (FDL rows are bin-contiguous, segments time-contiguous); the
+// TF32 hi / lo split happens here so that the GEMM kernel only copies its B operand.
+__global__ void __launch_bounds__(256) k_mimo_pack_x(const float2* __restrict__ fdl, float2* __restrict__ xq, uint32_t B,
+                                                     uint32_t R, uint32_t head, uint32_t n_in, uint32_t P2log, uint32_t T,
+                                                     uint32_t N, uint32_t nchunk, uint64_t xbin) {
   __shared__ float2 tile[32][33];
-  const uint32_t k0 = blockIdx.x * 32, w0 = blockIdx.y * 32, i = blockIdx.z;
+  const uint32_t P2 = 1u << P2log;
+  const uint32_t ninp = P2log < 4 ? (16u >> P2log) : 1u;
+  const uint32_t seg = P2log < 4 ? ((N + P2) & ~1u) : N + 16;
+  // segment -> (column tile tt, chunk c, row il of the chunk) -> input i, first reversed partition p'0
+  const uint32_t il = blockIdx.y % ninp, c = (blockIdx.y / ninp) % nchunk, tt = blockIdx.y / (ninp * nchunk);
+  const uint32_t i = P2log < 4 ? c * ninp + il : (c >> (P2log - 4));
+  const uint32_t pp0 = P2log < 4 ? 0u : ((c << 4) & (P2 - 1));
+  const uint32_t k0 = blockIdx.x * 32, w0 = blockIdx.z * 32;
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    const uint32_t wl = ty + 8 * r, w = w0 + wl;
+    const uint32_t wl = w0 + ty + 8 * r;
     float2 v = make_float2(0.f, 0.f);
-    if (w < P2 - 1 + T) {
-      long long blk = (long long)head + (long long)w - (long long)(P2 - 1);
-      long long sl = blk % (long long)R;
+    // block of this call (negative: history) met by column t = wl - p' at reversed partition p'
+    const long long blk = (long long)tt * N + pp0 + wl - (long long)(P2 - 1);
+    if (wl < seg && i < n_in && blk < (long long)T) {
+      long long sl = ((long long)head + blk) % (long long)R;
       if (sl < 0) sl += R;
       v = fdl[((uint64_t)i * R + (uint64_t)sl) * B + k0 + tx];
     }
-    tile[wl][tx] = v;
+    tile[ty + 8 * r][tx] = v;
   }
   __syncthreads();
+  const uint64_t chunk_elems = 2ull * ninp * seg;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    const uint32_t kl = ty + 8 * r, w = w0 + tx;
-    if (w < W) {
+    const uint32_t kl = ty + 8 * r, wl = w0 + tx;
+    if (wl < seg) {
       const float2 v = tile[tx][kl];
       float2 h, l;
       tc::split(v.x, h.x, l.x);
       tc::split(v.y, h.y, l.y);
-      const uint64_t at = (uint64_t)(k0 + kl) * xbin + (uint64_t)i * W + w;
-      xb[at] = h;
-      xb[at + xlo] = l;
+      const uint64_t at = (uint64_t)(k0 + kl) * xbin + ((uint64_t)tt * nchunk + c) * chunk_elems + (uint64_t)il * seg + wl;
+      xq[at] = h;
+      xq[at + (uint64_t)ninp * seg] = l;
     }
   }
 }

@@ -304,6 +304,11 @@ int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_
 /* tensor-core MIMO path: number of k_mimo_tc launches so far and the device status word (0 = ok; non-zero =
  * a barrier wait timed out inside the kernel, results invalid).  Synchronises the stream. */
 int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status);
+/* profiling hook of k_mimo_tc: out == NULL enables (max_ctas > 0) / disables the per-CTA role trace; otherwise copies
+ * 16 cycle counters per CTA of the last launch: [0,1] loader total / waiting for a raw slot, [2..4] MMA issuer total /
+ * waiting for operands / waiting for the read-out, [5,6] epilogue total / waiting for accumulators, [7+3g..9+3g]
+ * producer group g total / waiting for raw data / waiting for its operand stage */
+int bbx_engine_tensor_trace(bbx_engine* e, uint64_t* out, uint32_t max_ctas);
 /* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
 

@@ -153,3 +153,24 @@ def test_full_size_c5_mimo_tensor_property(bbx, orc):
         want = sum(orc.direct(xi[:, i], row[i], n0=n0, count=256) for i in range(nin))
         r = assert_float_parity(y[n0:, o], want, "MIMO noise row %d" % o)
         print("noise row", o, r)
+
+
+def test_mimo_tensor_longest_sum(bbx, orc):
+    """K = 1024 complex terms per output bin (kTcMaxK, the longest sum the tensor-core path accepts: 128 inputs x 8
+    partitions): accumulator truncation grows with K, the tolerance must still hold against float64 direct sums."""
+    B, L, nin, nout, T = 128, 1024, 128, 2, 32
+    g = GpuDriver(bbx, B, 8, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=T)
+    irs = {}
+    for o in range(nout):
+        for i in range(nin):
+            irs[(o, i)] = make_ir(8000 + 200 * o + i, L)
+            g.select(o * nin + i, g.filter(irs[(o, i)]))
+    xi = interleave([make_noise(8500 + i, 2 * T * B) for i in range(nin)])
+    y = run_float(g, xi, T * B)
+    assert tensor_ok(g) == 2
+    g.close()
+    n0 = 2 * T * B - 512
+    for o in range(nout):
+        want = sum(orc.direct(xi[:, i], irs[(o, i)], n0=n0, count=512) for i in range(nin))
+        r = assert_float_parity(y[n0:, o], want, "K = 1024, out %d" % o)
+        print("K=1024 out", o, r)

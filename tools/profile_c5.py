@@ -12,4 +12,12 @@ x = rng.uniform(-1, 1, (T * B, nin)).astype(np.float32)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     y = eng.Convolve(x, bbx.FMT_FLOAT, nin, bbx.FMT_FLOAT, nout, T * B)
 print(eng.tensor_status())
+if len(sys.argv) > 2 and sys.argv[2] == "trace":
+    eng.tensor_trace(128, enable=True)
+    y = eng.Convolve(x, bbx.FMT_FLOAT, nin, bbx.FMT_FLOAT, nout, T * B)
+    tr = eng.tensor_trace(128).astype(np.float64)
+    names = ["loader total", "loader wait raw slot", "mma total", "mma wait operands", "mma wait read-out", "epi total",
+             "epi wait acc"] + ["prod%d %s" % (g, w) for g in range(3) for w in ("total", "wait raw", "wait stage")]
+    for k, nme in enumerate(names):
+        print("%-22s mean %9.0f  min %9.0f  max %9.0f cycles" % (nme, tr[:, k].mean(), tr[:, k].min(), tr[:, k].max()))
 eng.close()
