@@ -82,6 +82,42 @@ __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
   }
 }
 
+// Same transpose with 128-frame tiles (B % 128 == 0): 16 independent loads per thread are in flight before the first
+// shared-memory store (the 32-frame kernel above is bound by the latency of its 4), a quarter of the CTAs.
+__global__ void __launch_bounds__(256) k_pcm_in128(PcmInArgs a) {
+  __shared__ float tile[128][33];
+  const uint32_t f0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool is_prev = f0 < a.B;  // B is a multiple of 128: a tile never straddles the boundary
+  const uint32_t bps = fmt_bytes(a.fmt);
+  if (!is_prev) {
+    // phase 1: lanes over channels (contiguous bytes within a frame)
+    float v[16];
+    const uint32_t c = c0 + lane;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t frame = f0 + warp + 8 * i - a.B;
+      v[i] = (c < a.n_inputs) ? load_as_f32(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps, a.fmt, a.be != 0, a.fast != 0) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) tile[warp + 8 * i][lane] = v[i];
+    __syncthreads();
+  }
+  // phase 2: lanes over frames (contiguous floats of one planar row); thread: channels warp + {0, 8, 16, 24}, 4 x 32 frames
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint32_t cl = warp + 8 * (i >> 2), c = c0 + cl, fl = (i & 3) * 32 + lane;
+    o[i] = 0.f;
+    if (c < a.n_inputs) o[i] = is_prev ? a.xin_prev[(uint64_t)c * a.xstride + a.prev_off + f0 + fl] : tile[fl][cl];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint32_t cl = warp + 8 * (i >> 2), c = c0 + cl, fl = (i & 3) * 32 + lane;
+    if (c < a.n_inputs) a.xin_cur[(uint64_t)c * a.xstride + f0 + fl] = o[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_rfft : windows of 2B floats -> packed spectra
 // ------------------------------------------------------------------------------------------
@@ -756,6 +792,85 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
     if (o >= a.n_outputs) continue;
     const uint32_t frame = f0 + fl;
     store_from_f32(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0, a.fast != 0);
+  }
+}
+
+// 128-frame tiles (B % 128 == 0).  Outputs fed by exactly one path with an integer delay and no delay crossfade in this
+// block (every output of the PER_CHANNEL and MIMO modes in the steady state) issue their four ring reads together; the
+// arithmetic is the same dst += mul * src, rounded separately.
+__global__ void __launch_bounds__(256) k_pcm_out128(PcmOutArgs a) {
+  __shared__ float tile[128][33];
+  __shared__ uint32_t s_first[33];
+  __shared__ RouteEntry s_rt[kPcmOutCache];
+  const uint32_t f0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t t = f0 / a.B;               // a tile lies inside one block (B % 128 == 0)
+  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
+  const float inc = 1.0f / (float)a.B;
+  const uint32_t no = min(32u, a.n_outputs - c0);
+  if (threadIdx.x <= no) s_first[threadIdx.x] = a.rv.out_first[c0 + threadIdx.x];
+  __syncthreads();
+  const uint32_t r0 = s_first[0], nr = s_first[no] - r0;
+  const bool cached = nr <= kPcmOutCache;
+  if (cached && threadIdx.x < nr) s_rt[threadIdx.x] = a.rv.entry[r0 + threadIdx.x];
+  __syncthreads();
+  // phase 1: lanes over frames; thread: outputs warp + {0, 8, 16, 24}, 4 x 32 frames each
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t cl = warp + 8 * q, o = c0 + cl;
+    float bus[4] = {0.f, 0.f, 0.f, 0.f};
+    if (o < a.n_outputs) {
+      const uint32_t rb = s_first[cl], re = s_first[cl + 1];
+      const uint32_t nb = f0 - t * a.B + lane;  // frame inside the block of the first of the four chunks
+      bool done = false;
+      if (re == rb + 1 && !a.fractional) {
+        const RouteEntry en = cached ? s_rt[rb - r0] : a.rv.entry[rb];
+        if (!(t == 0 && (en.flags & 1u))) {
+          done = true;
+          if (en.gain != 0.0f) {
+            const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = delayed_read(ring, a.Rd, w, nb + 32 * k, 0.0, en.icur, 0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) bus[k] = __fadd_rn(0.f, __fmul_rn(en.gain, v[k]));
+          }
+        }
+      }
+      if (!done) {
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+          const uint32_t n = nb + 32 * k;
+          float b = 0.f;
+          for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
+            const RouteEntry en = cached ? s_rt[r - r0] : a.rv.entry[r];
+            if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
+            const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
+            float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
+            if (t == 0 && (en.flags & 1u)) {
+              const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
+              const float g = __fmul_rn((float)n, inc);
+              v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
+            }
+            b = __fadd_rn(b, __fmul_rn(en.gain, v));  // dst += mul * src, rounded separately
+          }
+          bus[k] = b;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) tile[32 * k + lane][cl] = bus[k];
+  }
+  __syncthreads();
+  // phase 2: lanes over channels (contiguous bytes of one interleaved frame)
+  const uint32_t bps = fmt_bytes(a.fmt);
+  const uint32_t o = c0 + lane;
+  if (o < a.n_outputs) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t fl = warp + 8 * i;
+      store_from_f32(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0, a.fast != 0);
+    }
   }
 }
 
@@ -1921,8 +2036,9 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
       const uint32_t bps = fmt_bytes(infmt);
       a.fast = (!in_be && bps != 3 && ((uintptr_t)in % bps) == 0) ? 1 : 0;  // frame stride = in_channels * bps is aligned too
     }
-    dim3 grid((T + 1) * B / 32, ceil_div(e->n_in, 32));
-    k_pcm_in<<<grid, 256, 0, st>>>(a);
+    // wide tiles pay when the channel axis fills the lanes; few-channel engines keep the finer grid
+    if (B % 128 == 0 && e->n_in >= 16) k_pcm_in128<<<dim3((T + 1) * B / 128, ceil_div(e->n_in, 32)), 256, 0, st>>>(a);
+    else k_pcm_in<<<dim3((T + 1) * B / 32, ceil_div(e->n_in, 32)), 256, 0, st>>>(a);
     BBX_CUDA_TRY(cudaGetLastError());
     e->launches++;
   }
@@ -1970,8 +2086,11 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
       a.fast = (!out_be && bps != 3 && ((uintptr_t)out % bps) == 0) ? 1 : 0;
     }
     a.rv = route_view(e);
-    dim3 grid(T * B / 32, ceil_div(e->n_out_pcm, 32));
-    k_pcm_out<<<grid, 256, 0, st>>>(a);
+    // wide tiles for many outputs with integer delays (their ring reads batch); mixdowns of many paths into few
+    // outputs and fractional delays (14-tap double-precision reads) keep the finer grid
+    if (B % 128 == 0 && e->n_out_pcm >= 16 && !e->cfg.fractional_delay)
+      k_pcm_out128<<<dim3(T * B / 128, ceil_div(e->n_out_pcm, 32)), 256, 0, st>>>(a);
+    else k_pcm_out<<<dim3(T * B / 32, ceil_div(e->n_out_pcm, 32)), 256, 0, st>>>(a);
     BBX_CUDA_TRY(cudaGetLastError());
     e->launches++;
   }
