@@ -196,6 +196,26 @@ def mimo_leg(bbx, torch, device, steps=100):
                     "once per 64 block-steps"}
 
 
+def bind_near_gpu(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host memory is allocated
+    (first touch then places the staging buffers on that NUMA node).  Returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -271,6 +291,7 @@ def main():
     if bbx.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: libbbx has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None  # pinned staging on the GPU's own NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -466,7 +487,8 @@ def main():
                        "partitions": P, "blocks_per_step": nblk,
                        "mac": "time-batched (tile 16)" if args.tile in (0, 16) else ("streaming" if args.tile == 1 else "time-batched (tile %d)" % args.tile),
                        "l2": "inputs larger than L2: 148 MB spectra + 181 MB FDL + partial sums per step vs 126 MB L2, no flush",
-                       "parallelism": "channel-sharded x%d, no collective" % world},
+                       "parallelism": "channel-sharded x%d, no collective" % world,
+                       "host_binding": ("rank 0 bound to %d CPUs local to its GPU" % len(numa)) if numa else "none"},
             "x_realtime_per_channel": value / (NCH * world),
             "roofline": roofline, "roofline_streaming": roofline_streaming, "roofline_mimo": roofline_mimo, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "channel-s/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
