@@ -109,6 +109,11 @@ SYMBOLS = {
     "bbx_biquad_process_dev": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, vp]),
     "bbx_biquad_get_state": (C.c_int, [vp, vp, vp, vp]),
     "bbx_biquad_reset": (C.c_int, [vp]),
+    "bbx_allpass_create": (C.c_int, [u32, u32, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(vp)]),
+    "bbx_allpass_destroy": (C.c_int, [vp]),
+    "bbx_allpass_process": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, u32]),
+    "bbx_allpass_process_dev": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, u32, vp]),
+    "bbx_allpass_get_state": (u32, [vp, u32, vp, u32]),
     "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
     "bbx_engine_tensor_trace": (C.c_int, [vp, vp, u32]),
     "bbx_comm_available": (C.c_int, []),
@@ -363,6 +368,33 @@ class BiQuadBank:
 
     def Reset(self):
         _check(lib().bbx_biquad_reset(self.h))
+
+
+class AllPassChain:
+    """AllPassFilterChain<float> (src/AllPassFilter.h): Schroeder all-pass sections over interleaved channels."""
+
+    def __init__(self, channels, delays, coeffs):
+        n = len(delays)
+        d = (u32 * max(1, n))(*[int(v) for v in delays])
+        c = (C.c_float * max(1, n))(*[float(v) for v in coeffs])
+        h = vp()
+        _check(lib().bbx_allpass_create(channels, n, d, c, C.byref(h)))
+        self.h, self.channels, self.delays = h, channels, list(delays)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_allpass_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def Process(self, src, dst, srcchannel, nsrcchannels, dstchannel, ndstchannels, nframes):
+        _check(lib().bbx_allpass_process(self.h, _p(src), _p(dst), srcchannel, nsrcchannels, dstchannel, ndstchannels, nframes))
+
+    def GetState(self, f):
+        ring = np.zeros(self.channels * self.delays[f], dtype=np.float32)
+        pos = lib().bbx_allpass_get_state(self.h, f, _p(ring), ring.size)
+        return ring, pos
 
 
 # ---- a12-a14 ------------------------------------------------------------------------------

@@ -288,6 +288,19 @@ int bbx_biquad_process_dev(bbx_biquad* b, const float* src, float* dst, uint32_t
 int bbx_biquad_get_state(const bbx_biquad* b, double* w, double* cur5, double* mul_dec);
 int bbx_biquad_reset(bbx_biquad* b); /* BiQuad::Reset on every filter */
 
+/* AllPassFilterChain<float>  src/AllPassFilter.h:12-262 (ring semantics src/RingBuffer.h:17-121): nfilters Schroeder
+ * all-pass sections (delay[f] >= 1 frames, coefficient[f]) over nchannels interleaved channels, rings in HBM in the
+ * reference's layout; Process = AllPassFilterChain::Process (dst may equal src).  Bit-exact. */
+typedef struct bbx_allpass bbx_allpass;
+int bbx_allpass_create(uint32_t nchannels, uint32_t nfilters, const uint32_t* delays, const float* coeffs, bbx_allpass** out);
+int bbx_allpass_destroy(bbx_allpass* a);
+int bbx_allpass_process(bbx_allpass* a, const float* src, float* dst, uint32_t srcchannel, uint32_t nsrcchannels,
+                        uint32_t dstchannel, uint32_t ndstchannels, uint32_t nframes);
+int bbx_allpass_process_dev(bbx_allpass* a, const float* src, float* dst, uint32_t srcchannel, uint32_t nsrcchannels,
+                            uint32_t dstchannel, uint32_t ndstchannels, uint32_t nframes, void* stream);
+/* raw ring of section `filter` (nchannels * delay floats) into `ring`; returns RingBuffer::GetPosition() */
+uint32_t bbx_allpass_get_state(const bbx_allpass* a, uint32_t filter, float* ring, uint32_t maxitems);
+
 /* ------------------------------------------------------------------------------------------
  * measurement hooks (bench.py): CUDA-event timing on the engine stream, launch counting and
  * the dominant kernel's (FDL MAC) accumulated device time.

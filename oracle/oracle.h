@@ -106,6 +106,14 @@ void orc_biquad_process(orc_biquad* b, const float* src, float* dst, unsigned nc
 void orc_biquad_get_state(const orc_biquad* b, double* w, double* cur5, double* mul_dec);
 void orc_biquad_reset(orc_biquad* b);
 
+/* ---- allpass.c : AllPassFilterChain<float> ("next" row) ---- */
+typedef struct orc_allpass orc_allpass;
+orc_allpass* orc_allpass_create(unsigned nchannels, unsigned nfilters, const unsigned* delays, const float* coeffs);
+void orc_allpass_destroy(orc_allpass* a);
+void orc_allpass_process(orc_allpass* a, const float* src, float* dst, unsigned srcchannel, unsigned nsrc, unsigned dstchannel,
+                         unsigned ndst, unsigned nframes);
+unsigned orc_allpass_get_state(const orc_allpass* a, unsigned f, float* ring, unsigned maxitems);
+
 /* ---- fft.c : own FFT (FFTW stand-in, unnormalised both directions) ---- */
 /* complex in-place FFT of n (power of two) interleaved float pairs; inverse != 0 conjugates the kernel */
 void orc_cfft(float* data, unsigned n, int inverse);

@@ -15,6 +15,7 @@
 #include "SoundDelayBuffer.h"
 #include "MultilayerBuffer.h"
 #include "BiQuad.h"
+#include "AllPassFilter.h"
 
 #include <vector>
 
@@ -197,6 +198,39 @@ void ref_biquad_get_state(void* h, double* w, double* cur5, double* mul_dec) {
 void ref_biquad_reset(void* h) {
   RefBank* b = (RefBank*)h;
   for (size_t j = 0; j < b->filters.size(); j++) b->filters[j].Reset();
+}
+
+
+/* ---- AllPassFilterChain<float> (src/AllPassFilter.h:12-262, ring semantics src/RingBuffer.h:17-121) ---- */
+namespace {
+struct PeekAllPass : public AllPassFilter<float> {
+  uint_t Pos() const { return buffer.GetPosition(); }
+  const float* Buf() const { return buffer.GetBuffer(); }
+  uint_t Len() const { return buffer.GetLength(); }
+};
+struct PeekChain : public AllPassFilterChain<float> {
+  PeekChain(uint_t nch, uint_t nf, const uint_t* d, const float* c) : AllPassFilterChain<float>(nch, nf, d, c) {}
+  const PeekAllPass& F(size_t i) const { return static_cast<const PeekAllPass&>(filters[i]); }
+  size_t N() const { return filters.size(); }
+};
+}  // namespace
+
+void* ref_allpass_create(unsigned nchannels, unsigned nfilters, const unsigned* delays, const float* coeffs) {
+  return new PeekChain(nchannels, nfilters, delays, coeffs);
+}
+void ref_allpass_destroy(void* h) { delete (PeekChain*)h; }
+void ref_allpass_process(void* h, const float* src, float* dst, unsigned srcchannel, unsigned nsrc, unsigned dstchannel,
+                         unsigned ndst, unsigned nframes) {
+  ((PeekChain*)h)->Process(src, dst, srcchannel, nsrc, dstchannel, ndst, nframes);
+}
+/* ring contents of filter f (nchannels * delay floats, raw order) and its write position */
+unsigned ref_allpass_get_state(void* h, unsigned f, float* ring, unsigned maxitems) {
+  const PeekChain* c = (const PeekChain*)h;
+  if (f >= c->N()) return 0;
+  const PeekAllPass& a = c->F(f);
+  unsigned n = a.Len() < maxitems ? a.Len() : maxitems;
+  if (n) memcpy(ring, a.Buf(), n * sizeof(float));
+  return a.Pos();
 }
 
 }  // extern "C"

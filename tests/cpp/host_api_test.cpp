@@ -7,6 +7,7 @@
 
 #include <vector>
 
+#include "AllPassFilter.h"
 #include "BiQuad.h"
 #include "Convolver.h"
 #include "FractionalSample.h"
@@ -85,6 +86,15 @@ int main() {
     CHECK(by[0] == 1.0f && by[2] == 0.25f && by[4] == -0.0625f && by[6] == 0.015625f && by[1] == 9.0f);
     bank.CalcCoeffs(BiQuadBank::FLAT, 1000.0, 48000.0);
     CHECK(bank.GetCurrent().num0 == 1.0 && bank.GetCurrent().den1 == 0.0);
+  }
+  // AllPassFilterChain: one section, delay 2, c = 0.5, impulse -> 0.5, 0, 0.75, 0, -0.375
+  {
+    const uint_t d[1] = {2};
+    const float c[1] = {0.5f};
+    AllPassFilterChain chain(1, 1, d, c);
+    float ax[6] = {1, 0, 0, 0, 0, 0}, ay[6] = {0};
+    chain.Process(ax, ay, 0, 1, 0, 1, 6);
+    CHECK(ay[0] == 0.5f && ay[1] == 0.0f && ay[2] == 0.75f && ay[3] == 0.0f && ay[4] == -0.375f);
   }
   printf("PASS max_err=%g\n", err);
   return 0;

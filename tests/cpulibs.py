@@ -86,6 +86,10 @@ class CpuLib:
         self._bq_process = fn("biquad_process", None, [vp, vp, vp, u32, u32, u32, u32])
         self._bq_state = fn("biquad_get_state", None, [vp, vp, vp, vp])
         self._bq_reset = fn("biquad_reset", None, [vp])
+        self._ap_create = fn("allpass_create", vp, [u32, u32, vp, vp])
+        self._ap_destroy = fn("allpass_destroy", None, [vp])
+        self._ap_process = fn("allpass_process", None, [vp, vp, vp, u32, u32, u32, u32, u32])
+        self._ap_state = fn("allpass_get_state", u32, [vp, u32, vp, u32])
 
     # ---- formats ----
     def bits_per_sample(self, fmt):
@@ -153,6 +157,30 @@ class CpuLib:
 
     def biquad(self, channels):
         return CpuBiquad(self, channels)
+
+    def allpass(self, channels, delays, coeffs):
+        return CpuAllpass(self, channels, delays, coeffs)
+
+
+class CpuAllpass:
+    def __init__(self, lib, channels, delays, coeffs):
+        self.l, self.channels, self.delays = lib, channels, list(delays)
+        d = np.ascontiguousarray(delays, dtype=np.uint32)
+        c = np.ascontiguousarray(coeffs, dtype=np.float32)
+        self.h = lib._ap_create(channels, len(delays), _ptr(d), _ptr(c))
+
+    def close(self):
+        if self.h:
+            self.l._ap_destroy(self.h)
+            self.h = None
+
+    def process(self, src, dst, srcchannel, nsrc, dstchannel, ndst, nframes):
+        self.l._ap_process(self.h, _ptr(src), _ptr(dst), srcchannel, nsrc, dstchannel, ndst, nframes)
+
+    def state(self, f):
+        ring = np.zeros(self.channels * self.delays[f], dtype=np.float32)
+        pos = self.l._ap_state(self.h, f, _ptr(ring), ring.size)
+        return ring, pos
 
 
 class CpuBiquad:

@@ -52,6 +52,23 @@ class GpuLib:
     def biquad(self, channels):
         return GpuBiquad(self.b, channels)
 
+    def allpass(self, channels, delays, coeffs):
+        return GpuAllpass(self.b, channels, delays, coeffs)
+
+
+class GpuAllpass:
+    def __init__(self, b, channels, delays, coeffs):
+        self.a = b.AllPassChain(channels, delays, coeffs)
+
+    def close(self):
+        self.a.close()
+
+    def process(self, src, dst, srcchannel, nsrc, dstchannel, ndst, nframes):
+        self.a.Process(src, dst, srcchannel, nsrc, dstchannel, ndst, nframes)
+
+    def state(self, f):
+        return self.a.GetState(f)
+
 
 class GpuBiquad:
     def __init__(self, b, channels):

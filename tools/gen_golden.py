@@ -259,6 +259,45 @@ def gen_biquad(ref):
     np.savez_compressed(os.path.join(OUT, "biquad.npz"), **d)
 
 
+# ---- AllPassFilterChain<float> (src/AllPassFilter.h), SURVEY 8f.4 ----
+def allpass_script(lib, nch=5, delays=(7, 1, 23, 4), coeffs=(0.5, -0.7, 0.3, 0.9), nsrc=8, ndst=6, seed=777, offs=((1, 1), (2, 3))):
+    """Chain processed in several calls (ring wrap inside a call, positions carried over), a channel offset, a geometry
+    that fits only some of the channels (the others are skipped with Advance), in-place.  Returns outputs and states."""
+    rng = np.random.default_rng(seed)
+    ap = lib.allpass(nch, delays, coeffs)
+    outs = []
+
+    def run(nframes, sc=0, dc=0, s=nsrc, d=ndst, inplace=False):
+        x = rng.uniform(-1, 1, nframes * s).astype(np.float32)
+        if inplace:
+            y = x.copy()
+            ap.process(y, y, sc, s, sc, s, nframes)
+        else:
+            y = np.full(nframes * d, 3.0, dtype=np.float32)
+            ap.process(x, y, sc, s, dc, d, nframes)
+        outs.append(y)
+        for f in range(len(delays)):
+            ring, pos = ap.state(f)
+            outs.extend([ring.copy(), np.array([pos], dtype=np.uint32)])
+
+    run(40)
+    run(3, sc=offs[0][0], dc=offs[0][1])    # default geometry: 5 channels fit from offset 1
+    run(50, sc=offs[1][0], dc=offs[1][1])   # default geometry: only 3 channels fit the destination, two are skipped
+    run(31, inplace=True)
+    ap.close()
+    return outs
+
+
+def gen_allpass(ref):
+    d = {}
+    for i, a in enumerate(allpass_script(ref)):
+        d["script_%03d" % i] = a
+    # single channel (the reference's unclamped branch): offsets must stay inside the frames
+    for i, a in enumerate(allpass_script(ref, nch=1, delays=(5,), coeffs=(0.6,), nsrc=3, ndst=2, seed=778, offs=((1, 1), (2, 0)))):
+        d["mono_%03d" % i] = a
+    np.savez_compressed(os.path.join(OUT, "allpass.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = cl.reference()
@@ -269,6 +308,7 @@ def main():
     gen_frac(ref)
     gen_delay(ref)
     gen_biquad(ref)
+    gen_allpass(ref)
     gen_conv()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
