@@ -116,6 +116,7 @@ SYMBOLS = {
     "bbx_allpass_get_state": (u32, [vp, u32, vp, u32]),
     "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
     "bbx_engine_tensor_trace": (C.c_int, [vp, vp, u32]),
+    "bbx_probe_fp32_tflops": (C.c_int, [C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bbx_comm_available": (C.c_int, []),
     "bbx_comm_unique_id": (C.c_int, [C.POINTER(u8)]),
     "bbx_comm_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(u8), C.c_int, C.POINTER(vp)]),
@@ -550,6 +551,13 @@ class Convolver:
 
     def flush_l2(self, nbytes=256 << 20):
         _check(lib().bbx_engine_flush_l2(self.h, nbytes))
+
+
+def probe_fp32_tflops(device=0, seconds=0.5):
+    """(burst, sustained) TFLOP/s of a pure packed-FMA kernel on this GPU (FP32 roofline denominator)."""
+    b, s_ = C.c_float(0), C.c_float(0)
+    _check(lib().bbx_probe_fp32_tflops(device, seconds, C.byref(b), C.byref(s_)))
+    return b.value, s_.value
 
 
 def comm_unique_id():

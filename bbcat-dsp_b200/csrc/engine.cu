@@ -874,6 +874,29 @@ __global__ void __launch_bounds__(256) k_pcm_out128(PcmOutArgs a) {
   }
 }
 
+// FP32 roofline probe (measurement hook): nothing but packed FMAs on 16 float2 accumulators per thread, the operand
+// pattern of k_fdl_mac_tb's inner loop.  Its rate is the FP32 ceiling this GPU reaches under its power / clock limits
+// (the nominal 148 x 128 x 2 x 1965 MHz is not reachable: bench.py reports both).
+__global__ void __launch_bounds__(256) k_fp32_probe(float2* out, int iters, float2 h0, float2 x0) {
+  float2 acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+  float2 h = h0, x = x0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) cmac_x2(acc[i], h, x);
+    h.x += 1e-7f;
+    x.y -= 1e-7f;
+  }
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    s.x += acc[i].x;
+    s.y += acc[i].y;
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void k_flush(float4* p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_float4(1.f, 2.f, 3.f, 4.f);
@@ -2266,6 +2289,48 @@ int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status) {
     *status = 0;
     if (e->tc_status_h) *status = *(volatile int*)e->tc_status_h;
   }
+  return BBX_OK;
+}
+
+int bbx_probe_fp32_tflops(int device, float seconds, float* burst, float* sustained) {
+  BBX_REQUIRE(burst || sustained, "bbx_probe_fp32_tflops: null outputs");
+  int rc = require_device();
+  if (rc) return rc;
+  BBX_CUDA_TRY(cudaSetDevice(device));
+  const int grid = kNumSMs * 4, iters = 4096;
+  const double flops = 8.0 * 16 * (double)iters * grid * 256;  // 16 complex MACs = 64 FMA = 128 flop per thread and iteration
+  float2* out = nullptr;
+  BBX_CUDA_TRY(cudaMalloc((void**)&out, sizeof(float2) * (size_t)grid * 256));
+  cudaEvent_t e0, e1;
+  BBX_CUDA_TRY(cudaEventCreate(&e0));
+  BBX_CUDA_TRY(cudaEventCreate(&e1));
+  const float2 h = make_float2(1.0001f, 0.0001f), x = make_float2(0.9999f, 0.0002f);
+  k_fp32_probe<<<grid, 256>>>(out, 64, h, x);  // warm-up
+  BBX_CUDA_TRY(cudaDeviceSynchronize());
+  float best = 0.f;
+  for (int r = 0; r < 5; r++) {  // burst: best of five isolated launches
+    BBX_CUDA_TRY(cudaEventRecord(e0));
+    k_fp32_probe<<<grid, 256>>>(out, iters, h, x);
+    BBX_CUDA_TRY(cudaEventRecord(e1));
+    BBX_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    BBX_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms > 0.f) best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+  }
+  if (burst) *burst = best;
+  if (sustained) {  // back-to-back launches for `seconds`: the rate under the power cap
+    const int n = std::max(1, (int)(seconds * 1e3f / 1.3f));
+    BBX_CUDA_TRY(cudaEventRecord(e0));
+    for (int r = 0; r < n; r++) k_fp32_probe<<<grid, 256>>>(out, iters, h, x);
+    BBX_CUDA_TRY(cudaEventRecord(e1));
+    BBX_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    BBX_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *sustained = ms > 0.f ? (float)(flops * n / (ms * 1e-3) / 1e12) : 0.f;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
   return BBX_OK;
 }
 

@@ -322,6 +322,9 @@ int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status);
  * waiting for operands / waiting for the read-out, [5,6] epilogue total / waiting for accumulators, [7+3g..9+3g]
  * producer group g total / waiting for raw data / waiting for its operand stage */
 int bbx_engine_tensor_trace(bbx_engine* e, uint64_t* out, uint32_t max_ctas);
+/* FP32 roofline probe: the rate (TFLOP/s) a pure packed-FMA kernel with the MAC's operand pattern reaches on this GPU:
+ * best of five isolated launches (burst) and averaged over `seconds` of back-to-back launches (sustained, power cap) */
+int bbx_probe_fp32_tflops(int device, float seconds, float* burst, float* sustained);
 /* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
 
