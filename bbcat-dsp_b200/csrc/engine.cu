@@ -1008,6 +1008,10 @@ struct bbx_engine {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   cudaEvent_t ev_join_in = nullptr, ev_join_out = nullptr;
   uint64_t host_calls = 0;
+  // short host calls: the PCM kernels read / write the caller's pinned (device-mapped) buffers directly over PCIe
+  // instead of going through the copy engines and the staging buffers; 0 disables
+  size_t direct_io_max_bytes = 1u << 20;
+  uint64_t direct_calls = 0;
   float4* flush_buf = nullptr;
   size_t flush_bytes = 0;
   // route tables (device blob + pinned staging)
@@ -2125,6 +2129,18 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   return BBX_OK;
 }
 
+// Device-side address of a pinned host buffer (cudaHostAlloc / cudaHostRegister under unified addressing), or false.
+static bool mapped_device_ptr(const void* host, void** dev) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+  *dev = at.devicePointer;
+  return true;
+}
+
 int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
                       int out_be, uint32_t out_channels, uint32_t nframes) {
   BBX_REQUIRE(e && in && out, "bbx_process: null argument");
@@ -2133,6 +2149,17 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   size_t in_bytes = (size_t)nframes * in_channels * fmt_bytes(infmt);
   size_t out_bytes = (size_t)nframes * out_channels * fmt_bytes(outfmt);
   size_t need = std::max(in_bytes, out_bytes);
+  if (need <= e->direct_io_max_bytes) {
+    // latency path (real-time callers: one or a few blocks per call).  When both buffers are pinned host memory that
+    // the device can address, k_pcm_in reads the input and k_pcm_out writes the output straight over PCIe: no
+    // copy-engine operations, no cross-stream events, five kernels back to back on the engine stream.  Channels
+    // beyond n_outputs are simply not written.  Pageable buffers take the staged path below.
+    void *din = nullptr, *dout = nullptr;
+    if (mapped_device_ptr(in, &din) && mapped_device_ptr(out, &dout)) {
+      e->direct_calls++;
+      return bbx_process_dev(e, din, infmt, in_be, in_channels, dout, outfmt, out_be, out_channels, nframes);
+    }
+  }
   if (!e->d_in[0] || e->d_io_bytes < need) {
     BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
     BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -2254,6 +2281,13 @@ int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_
   apply_tuning(e, ctas_per_sm, l2_keep_16ths, time_tile);
   return BBX_OK;
 }
+
+int bbx_engine_set_direct_io(bbx_engine* e, size_t max_bytes) {
+  BBX_REQUIRE(e != nullptr, "bbx_engine_set_direct_io: null engine");
+  e->direct_io_max_bytes = max_bytes;
+  return BBX_OK;
+}
+uint64_t bbx_engine_direct_calls(const bbx_engine* e) { return e ? e->direct_calls : 0; }
 
 int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c) {
   BBX_REQUIRE(e != nullptr, "null engine");

@@ -119,8 +119,10 @@ def test_mac_variants_bit_identical(bbx, kw):
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
-def test_async_host_pipeline_matches_sync(bbx):
-    """bbx_process_async with double-buffered pinned I/O == the synchronous call, bit for bit."""
+@pytest.mark.parametrize("direct", [True, False])
+def test_async_host_pipeline_matches_sync(bbx, direct):
+    """bbx_process_async with pinned I/O == the synchronous call, bit for bit: short calls through the direct path
+    (kernels read / write the pinned buffers over PCIe) and through the staged copy-engine pipeline."""
     B, L, nch, nblk, T = 256, 3000, 4, 24, 4
     irs = [make_ir(700 + c, L) for c in range(nch)]
     xi = interleave([make_noise(710 + c, nblk * B) for c in range(nch)])
@@ -133,12 +135,15 @@ def test_async_host_pipeline_matches_sync(bbx):
     for c in range(nch):
         g.select(c, g.filter(irs[c]))
     nbytes = T * B * nch * 4
+    if not direct:
+        g.eng.set_direct_io(0)
     hin = [bbx.PinnedBuffer(nbytes) for _ in range(nblk // T)]
     hout = [bbx.PinnedBuffer(nbytes) for _ in range(nblk // T)]
     for i in range(nblk // T):
         hin[i].array[:] = xi[i * T * B:(i + 1) * T * B].reshape(-1).view(np.uint8)
         g.eng.ConvolveHostPtrAsync(hin[i].ptr, cl.FMT_FLOAT, nch, hout[i].ptr, cl.FMT_FLOAT, nch, T * B)
     g.eng.Sync()
+    assert g.eng.direct_calls() == (nblk // T if direct else 0)
     got = np.concatenate([h.array.view(np.float32).reshape(T * B, nch).copy() for h in hout])
     g.close()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
@@ -310,6 +315,45 @@ def test_formats_in_out_and_extra_channels(bbx, orc):
             lsb = {cl.FMT_16: 2.0 ** -15, cl.FMT_24: 2.0 ** -23}.get(fmt, 0.0)
             r = compare_float(fa, fb)
             assert r["max_abs"] <= lsb + 1e-5 * r["peak"], (fmt, be, r)
+
+
+@pytest.mark.parametrize("fmt", [cl.FMT_16, cl.FMT_24, cl.FMT_FLOAT])
+def test_direct_io_formats_and_extra_channels(bbx, orc, fmt):
+    """The direct path (pinned buffers, T = 1 calls: the PCM kernels address host memory) gives the same bytes as the staged
+    path, leaves the channels beyond n_outputs untouched, and pageable buffers fall back to staging."""
+    B, L, nch, nblk = 128, 300, 2, 6
+    irs = [make_ir(190 + c, L) * 0.5 for c in range(nch)]
+    x = (interleave([make_noise(195 + c, nblk * B) for c in range(3)]) * 0.9).astype(np.float32)
+    bps = cl.FMT_BYTES[fmt]
+    pcm = np.zeros(x.size * bps, dtype=np.uint8)
+    orc.transfer(x.view(np.uint8).reshape(-1), cl.FMT_FLOAT, 0, 0, 3, pcm, fmt, 0, 0, 3, 3, nblk * B)
+    res = {}
+    for mode in ("direct", "staged", "pageable"):
+        g = GpuDriver(bbx, B, 3, nch, max_blocks=1)
+        for c in range(nch):
+            g.select(c, g.filter(irs[c]))
+        if mode == "staged":
+            g.eng.set_direct_io(0)
+        nin, nout = B * 3 * bps, B * 4 * bps
+        if mode == "pageable":
+            hin, hout = np.zeros(nin, dtype=np.uint8), np.zeros(nout, dtype=np.uint8)
+            pin, pout = hin, hout
+            ain, aout = hin.ctypes.data, hout.ctypes.data
+        else:
+            pin, pout = bbx.PinnedBuffer(nin), bbx.PinnedBuffer(nout)
+            hin, hout = pin.array, pout.array
+            ain, aout = pin.ptr, pout.ptr
+        got = []
+        for b in range(nblk):
+            hin[:] = pcm[b * nin:(b + 1) * nin]
+            hout[:] = 0x3C
+            g.eng.ConvolveHostPtr(ain, fmt, 3, aout, fmt, 4, B)
+            got.append(hout.copy())
+        assert g.eng.direct_calls() == (nblk if mode == "direct" else 0)
+        g.close()
+        res[mode] = np.concatenate(got).reshape(nblk * B, 4, bps)
+    assert (res["direct"][:, 2:] == 0x3C).all()
+    assert np.array_equal(res["direct"], res["staged"]) and np.array_equal(res["direct"], res["pageable"])
 
 
 def test_engine_argument_errors(bbx):
