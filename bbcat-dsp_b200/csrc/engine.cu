@@ -959,10 +959,24 @@ struct JobTerm {
   uint32_t input;
 };
 
+// Ring of pinned upload buffers for one device table.  Every upload is a copy on the engine stream followed by an event;
+// re-using a slot waits only for the copy that last read it (kDepth uploads ago), so the host can prepare the plans and
+// routes of the next calls while the device still works on the previous ones (dynamic IR switching: one upload set per
+// switch).
+struct Staging {
+  static constexpr int kDepth = 4;
+  uint8_t* h[kDepth] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kDepth] = {nullptr, nullptr, nullptr, nullptr};
+  bool pending[kDepth] = {false, false, false, false};
+  int cur = 0;
+  size_t bytes = 0;
+};
+
 // device-resident MAC plan + host mirror
 struct MacPlan {
-  // host staging (pinned) and device blob, same layout
-  uint8_t* h_blob = nullptr;
+  // host staging (pinned ring) and device blob, same layout
+  Staging stg;
+  uint8_t* h_blob = nullptr;  // the slot being filled by build_plan
   uint8_t* d_blob = nullptr;
   size_t blob_bytes = 0;
   // offsets inside the blob
@@ -1015,7 +1029,8 @@ struct bbx_engine {
   float4* flush_buf = nullptr;
   size_t flush_bytes = 0;
   // route tables (device blob + pinned staging)
-  uint8_t* h_route = nullptr;
+  Staging route_stg;
+  uint8_t* h_route = nullptr;  // the slot being filled by upload_routes
   uint8_t* d_route = nullptr;
   size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0,
          roff_icur = 0, roff_iold = 0, roff_entry = 0;
@@ -1129,6 +1144,9 @@ PlanView shard_plan_view(const bbx_engine* e) {
 
 template <int M>
 void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaStream_t st) {
+  const float2* ypart = e->ypart;
+  const float* nyq_part = e->nyq_part;
+  const uint32_t wpos = e->wpos;
   constexpr int FPB = FftCfg<M>::FPB;
   constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1158,17 +1176,16 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaSt
     }
     const uint32_t nitems = ceil_div(e->n_streams, FPB) * T;
     k_irfft8<M><<<std::min(nitems, per_sm_grid), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
-        e->ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams, tc ? nullptr : e->nyq_part,
+        ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, wpos, e->n_streams, tc ? nullptr : nyq_part,
         (uint64_t)e->max_slots * M, (uint64_t)M, 0u, T);
     return;
   }
   k_irfft<M><<<dim3(ceil_div(e->n_streams, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
-      e->ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, e->wpos, e->n_streams,
-      tc ? nullptr : e->nyq_part, (uint64_t)e->max_slots * M, (uint64_t)M, 0u);
+      ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, wpos, e->n_streams,
+      tc ? nullptr : nyq_part, (uint64_t)e->max_slots * M, (uint64_t)M, 0u);
 }
 
-int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc = false) {
-  cudaStream_t st = e->stream;
+int launch_irfft(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaStream_t st) {
   switch (e->B) {
     case 64: launch_irfft_t<64>(e, T, n_first, tc, st); break;
     case 128: launch_irfft_t<128>(e, T, n_first, tc, st); break;
@@ -1230,6 +1247,12 @@ void launch_mac_tb(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, c
   else launch_mac_tb_t<TT, 64>(e, pl, t0, nt, st);
 }
 
+// the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters and enough block-steps
+bool mac_uses_time_batching(const bbx_engine* e, const MacPlan& pl, uint32_t nt) {
+  const uint32_t tb = e->mac_time_tile;  // 0: streaming only
+  return tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb;
+}
+
 int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
   if (pl.n_ctas == 0 || nt == 0) return BBX_OK;
   cudaStream_t st = e->stream;
@@ -1246,7 +1269,7 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
   const uint32_t halfB = e->B / 2;
   // the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters
   const uint32_t tb = e->mac_time_tile;  // 0: streaming only
-  const bool use_tb = tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb;
+  const bool use_tb = mac_uses_time_batching(e, pl, nt);
   if (use_tb) {
     // Nyquist sums of column 0 (the streaming kernel accumulates them inline): a few hundred latency-bound warps,
     // forked onto the side stream so they run underneath the MAC instead of after it
@@ -1294,7 +1317,41 @@ int mark_upload(bbx_engine* e) {
   return BBX_OK;
 }
 
-// Build a MAC plan from a job list into plan.h_blob (pinned) and enqueue its upload.
+int staging_alloc(Staging& s, size_t bytes) {
+  s.bytes = bytes;
+  for (int i = 0; i < Staging::kDepth; i++) {
+    BBX_CUDA_TRY(cudaHostAlloc((void**)&s.h[i], bytes, cudaHostAllocDefault));
+    memset(s.h[i], 0, bytes);
+    BBX_CUDA_TRY(cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming));
+  }
+  return BBX_OK;
+}
+void staging_free(Staging& s) {
+  for (int i = 0; i < Staging::kDepth; i++) {
+    if (s.h[i]) cudaFreeHost(s.h[i]);
+    if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    s.h[i] = nullptr;
+    s.ev[i] = nullptr;
+  }
+}
+// next slot to fill; blocks only while the copy that last read this slot is still queued
+int staging_acquire(Staging& s, uint8_t** out) {
+  if (s.pending[s.cur]) {
+    BBX_CUDA_TRY(cudaEventSynchronize(s.ev[s.cur]));
+    s.pending[s.cur] = false;
+  }
+  *out = s.h[s.cur];
+  return BBX_OK;
+}
+int staging_commit(Staging& s, void* dst, cudaStream_t st) {
+  BBX_CUDA_TRY(cudaMemcpyAsync(dst, s.h[s.cur], s.bytes, cudaMemcpyHostToDevice, st));
+  BBX_CUDA_TRY(cudaEventRecord(s.ev[s.cur], st));
+  s.pending[s.cur] = true;
+  s.cur = (s.cur + 1) % Staging::kDepth;
+  return BBX_OK;
+}
+
+// Build a MAC plan from a job list into a pinned staging slot and enqueue its upload.
 int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm>>& jobs, const std::vector<uint32_t>& xjob) {
   uint32_t total = 0, nterms = 0;
   for (auto& j : jobs)
@@ -1305,7 +1362,7 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
       }
   pl.n_terms = nterms;
   {
-    int wrc = wait_uploads(e);
+    int wrc = staging_acquire(pl.stg, &pl.h_blob);
     if (wrc) return wrc;
   }
   MacSeg* segs = (MacSeg*)(pl.h_blob + pl.off_segs);
@@ -1381,8 +1438,7 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
     pl.n_slots = nslot;
   }
   pl.valid = true;
-  BBX_CUDA_TRY(cudaMemcpyAsync(pl.d_blob, pl.h_blob, pl.blob_bytes, cudaMemcpyHostToDevice, e->stream));
-  return mark_upload(e);
+  return staging_commit(pl.stg, pl.d_blob, e->stream);
 }
 
 int alloc_plan(bbx_engine* e, MacPlan& pl) {
@@ -1398,8 +1454,10 @@ int alloc_plan(bbx_engine* e, MacPlan& pl) {
   pl.off_count = take(sizeof(uint32_t) * e->max_jobs);
   pl.off_xjob = take(sizeof(uint32_t) * std::max(1u, e->n_streams));
   pl.blob_bytes = off;
-  BBX_CUDA_TRY(cudaHostAlloc((void**)&pl.h_blob, off, cudaHostAllocDefault));
-  memset(pl.h_blob, 0, off);
+  {
+    int src = staging_alloc(pl.stg, off);
+    if (src) return src;
+  }
   BBX_CUDA_TRY(cudaMalloc((void**)&pl.d_blob, off));
   BBX_CUDA_TRY(cudaMemset(pl.d_blob, 0, off));
   return BBX_OK;
@@ -1429,7 +1487,7 @@ void make_jobs(const bbx_engine* e, bool use_pending, std::vector<std::vector<Jo
 
 int upload_routes(bbx_engine* e, bool first_block_transition) {
   {
-    int wrc = wait_uploads(e);
+    int wrc = staging_acquire(e->route_stg, &e->h_route);
     if (wrc) return wrc;
   }
   uint32_t* ofirst = (uint32_t*)(e->h_route + e->roff_first);
@@ -1487,8 +1545,7 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
       en[r].dold = dold[st];
     }
   }
-  BBX_CUDA_TRY(cudaMemcpyAsync(e->d_route, e->h_route, e->route_bytes, cudaMemcpyHostToDevice, e->stream));
-  return mark_upload(e);
+  return staging_commit(e->route_stg, e->d_route, e->stream);
 }
 
 RouteView route_view(const bbx_engine* e) {
@@ -1803,8 +1860,10 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     e->roff_iold = take(sizeof(uint32_t) * ns);
     e->roff_entry = take(sizeof(RouteEntry) * ns);
     e->route_bytes = off;
-    BBX_CUDA_TRY(cudaHostAlloc((void**)&e->h_route, off, cudaHostAllocDefault));
-    memset(e->h_route, 0, off);
+    {
+      int src = staging_alloc(e->route_stg, off);
+      if (src) return src;
+    }
     BBX_CUDA_TRY(cudaMalloc((void**)&e->d_route, off));
   }
   BBX_CUDA_TRY(cudaDeviceSynchronize());
@@ -1854,10 +1913,10 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->tc_ftab_h) cudaFreeHost(e->tc_ftab_h);
   if (e->tc_fparts_h) cudaFreeHost(e->tc_fparts_h);
   cudaFree(e->d_route);
-  cudaFreeHost(e->h_route);
+  staging_free(e->route_stg);
   for (MacPlan* pl : {&e->plan_first, &e->plan_steady}) {
     cudaFree(pl->d_blob);
-    cudaFreeHost(pl->h_blob);
+    staging_free(pl->stg);
   }
   for (cudaEvent_t ev : e->mac_events) cudaEventDestroy(ev);
   if (e->ev_start) cudaEventDestroy(e->ev_start);
@@ -2092,11 +2151,12 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
       return rc;
   }
   // ---- 4. inverse transforms, crossfade, delay ring ----
-  if ((rc = launch_irfft(e, T, n_first, use_tc))) return rc;
+  if ((rc = launch_irfft(e, T, n_first, use_tc, st))) return rc;
   e->launches++;
   // ---- 5. delay read, mixdown, output format ----
   {
     PcmOutArgs a;
+    const uint32_t obps = fmt_bytes(outfmt);
     a.pcm = (uint8_t*)out;
     a.fmt = outfmt;
     a.be = out_be;
@@ -2108,10 +2168,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     a.Rd = e->Rd;
     a.wpos0 = e->wpos;
     a.fractional = e->cfg.fractional_delay;
-    {
-      const uint32_t bps = fmt_bytes(outfmt);
-      a.fast = (!out_be && bps != 3 && ((uintptr_t)out % bps) == 0) ? 1 : 0;
-    }
+    a.fast = (!out_be && obps != 3 && ((uintptr_t)out % obps) == 0) ? 1 : 0;
     a.rv = route_view(e);
     // wide tiles for many outputs with integer delays (their ring reads batch); mixdowns of many paths into few
     // outputs and fractional delays (14-tap double-precision reads) keep the finer grid
@@ -2146,19 +2203,25 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   BBX_REQUIRE(e && in && out, "bbx_process: null argument");
   BBX_REQUIRE(infmt > FMT_UNKNOWN && infmt < FMT_COUNT && outfmt > FMT_UNKNOWN && outfmt < FMT_COUNT, "bbx_process: bad format");
   BBX_CUDA_TRY(cudaSetDevice(e->device));
-  size_t in_bytes = (size_t)nframes * in_channels * fmt_bytes(infmt);
-  size_t out_bytes = (size_t)nframes * out_channels * fmt_bytes(outfmt);
+  const uint32_t ibps = fmt_bytes(infmt), obps = fmt_bytes(outfmt);
+  size_t in_bytes = (size_t)nframes * in_channels * ibps;
+  size_t out_bytes = (size_t)nframes * out_channels * obps;
   size_t need = std::max(in_bytes, out_bytes);
-  if (need <= e->direct_io_max_bytes) {
-    // latency path (real-time callers: one or a few blocks per call).  When both buffers are pinned host memory that
-    // the device can address, k_pcm_in reads the input and k_pcm_out writes the output straight over PCIe: no
-    // copy-engine operations, no cross-stream events, five kernels back to back on the engine stream.  Channels
-    // beyond n_outputs are simply not written.  Pageable buffers take the staged path below.
-    void *din = nullptr, *dout = nullptr;
-    if (mapped_device_ptr(in, &din) && mapped_device_ptr(out, &dout)) {
-      e->direct_calls++;
-      return bbx_process_dev(e, din, infmt, in_be, in_channels, dout, outfmt, out_be, out_channels, nframes);
-    }
+  // Latency path (real-time callers: one or a few blocks per call): a short buffer in pinned host memory that the
+  // device can address is read by k_pcm_in / written by k_pcm_out straight over PCIe -- no copy-engine operation and no
+  // cross-stream hand-off on that side.  Decided per side, and only where the kernel's accesses suit the bus: typed
+  // little-endian samples (no 3-byte formats) and at least 128 contiguous bytes of used channels per frame (a warp
+  // covers 32 channels of one frame); narrow or byte-wise layouts would turn into many small PCIe transactions and
+  // stay on the staged path, like pageable buffers.
+  void *din = nullptr, *dout = nullptr;
+  const bool typed_in = !in_be && ibps != 3 && ((uintptr_t)in % ibps) == 0;
+  const bool typed_out = !out_be && obps != 3 && ((uintptr_t)out % obps) == 0;
+  const bool direct_in = in_bytes <= e->direct_io_max_bytes && typed_in && (size_t)e->n_in * ibps >= 128 && mapped_device_ptr(in, &din);
+  const bool direct_out =
+      out_bytes <= e->direct_io_max_bytes && typed_out && (size_t)e->n_out_pcm * obps >= 128 && mapped_device_ptr(out, &dout);
+  if (direct_in && direct_out) {
+    e->direct_calls++;
+    return bbx_process_dev(e, din, infmt, in_be, in_channels, dout, outfmt, out_be, out_channels, nframes);
   }
   if (!e->d_in[0] || e->d_io_bytes < need) {
     BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
@@ -2175,25 +2238,36 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   }
   const int k = (int)(e->host_calls & 1);
   e->host_calls++;
+  if (direct_in || direct_out) e->direct_calls++;
   // H2D on the input-copy stream, once the kernels of call n-2 have finished reading this staging buffer
-  BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
-  BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
-  if (out_channels > e->n_out_pcm) {
+  bool fed = false;
+  if (!direct_in) {
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
+    BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
+    fed = true;
+  }
+  if (!direct_out && out_channels > e->n_out_pcm) {
     // channels beyond n_outputs keep the caller's bytes: seed the output staging with them
     BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_d2h[k], 0));
     BBX_CUDA_TRY(cudaMemcpyAsync(e->d_out[k], out, out_bytes, cudaMemcpyHostToDevice, e->s_in));
+    fed = true;
   }
-  BBX_CUDA_TRY(cudaEventRecord(e->ev_h2d[k], e->s_in));
+  if (fed) {
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_h2d[k], e->s_in));
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[k], 0));
+  }
   // kernels on the engine stream
-  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[k], 0));
-  BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_d2h[k], 0));
-  int rc = bbx_process_dev(e, e->d_in[k], infmt, in_be, in_channels, e->d_out[k], outfmt, out_be, out_channels, nframes);
+  if (!direct_out) BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_d2h[k], 0));
+  int rc = bbx_process_dev(e, direct_in ? din : e->d_in[k], infmt, in_be, in_channels, direct_out ? dout : e->d_out[k], outfmt, out_be,
+                           out_channels, nframes);
   if (rc) return rc;
   BBX_CUDA_TRY(cudaEventRecord(e->ev_comp[k], e->stream));
-  // D2H on the output-copy stream
-  BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_comp[k], 0));
-  BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out[k], out_bytes, cudaMemcpyDeviceToHost, e->s_out));
-  BBX_CUDA_TRY(cudaEventRecord(e->ev_d2h[k], e->s_out));
+  if (!direct_out) {
+    // D2H on the output-copy stream
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_comp[k], 0));
+    BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out[k], out_bytes, cudaMemcpyDeviceToHost, e->s_out));
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_d2h[k], e->s_out));
+  }
   return BBX_OK;
 }
 

@@ -314,10 +314,12 @@ int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint
                         uint64_t* algorithmic_bytes);
 /* change the tuning knobs of bbx_config at run time (0 = leave as is); takes effect at the next call */
 int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile);
-/* latency path of bbx_process / bbx_process_async: calls whose PCM buffers are both at most max_bytes long and both
- * pinned host memory the device can address (bbx_host_alloc, cudaHostAlloc, cudaHostRegister) skip the copy engines
- * -- the PCM kernels read and write the caller's buffers directly over PCIe.  Default 1 MiB; 0 disables (every host
- * call is staged).  _direct_calls counts the calls that took this path. */
+/* latency path of bbx_process / bbx_process_async, decided for the input and the output side separately: a PCM buffer of
+ * at most max_bytes in pinned host memory the device can address (bbx_host_alloc, cudaHostAlloc, cudaHostRegister) is
+ * read / written by the PCM kernels directly over PCIe instead of going through a copy engine and the staging buffer.
+ * Only layouts that suit the bus qualify: typed little-endian samples (not 24-bit) and at least 128 bytes of used
+ * channels per frame.  Default 1 MiB; 0 disables (every host call is staged).  _direct_calls counts the calls in which
+ * at least one side took this path. */
 int bbx_engine_set_direct_io(bbx_engine* e, size_t max_bytes);
 uint64_t bbx_engine_direct_calls(const bbx_engine* e);
 /* tensor-core MIMO path: number of k_mimo_tc launches so far and the device status word (0 = ok; non-zero =

@@ -123,7 +123,7 @@ def test_mac_variants_bit_identical(bbx, kw):
 def test_async_host_pipeline_matches_sync(bbx, direct):
     """bbx_process_async with pinned I/O == the synchronous call, bit for bit: short calls through the direct path
     (kernels read / write the pinned buffers over PCIe) and through the staged copy-engine pipeline."""
-    B, L, nch, nblk, T = 256, 3000, 4, 24, 4
+    B, L, nch, nblk, T = 256, 3000, 32, 24, 4   # 32 float channels = 128 B per frame: wide enough for the direct path
     irs = [make_ir(700 + c, L) for c in range(nch)]
     xi = interleave([make_noise(710 + c, nblk * B) for c in range(nch)])
     g = GpuDriver(bbx, B, 12, nch, max_blocks=T)
@@ -317,42 +317,54 @@ def test_formats_in_out_and_extra_channels(bbx, orc):
             assert r["max_abs"] <= lsb + 1e-5 * r["peak"], (fmt, be, r)
 
 
-@pytest.mark.parametrize("fmt", [cl.FMT_16, cl.FMT_24, cl.FMT_FLOAT])
-def test_direct_io_formats_and_extra_channels(bbx, orc, fmt):
-    """The direct path (pinned buffers, T = 1 calls: the PCM kernels address host memory) gives the same bytes as the staged
-    path, leaves the channels beyond n_outputs untouched, and pageable buffers fall back to staging."""
-    B, L, nch, nblk = 128, 300, 2, 6
-    irs = [make_ir(190 + c, L) * 0.5 for c in range(nch)]
-    x = (interleave([make_noise(195 + c, nblk * B) for c in range(3)]) * 0.9).astype(np.float32)
+@pytest.mark.parametrize("fmt,nch,routed,expect_direct", [
+    (cl.FMT_FLOAT, 32, False, True),    # 128 B of used channels per frame on both sides: both direct
+    (cl.FMT_16, 64, False, True),
+    (cl.FMT_16, 32, False, False),      # 64 B per frame: too narrow for the bus
+    (cl.FMT_24, 48, False, False),      # 3-byte samples are byte-wise accesses: staged
+    (cl.FMT_FLOAT, 32, True, True),     # wide input direct, 2-channel mixdown output staged
+])
+def test_direct_io_formats_and_extra_channels(bbx, orc, fmt, nch, routed, expect_direct):
+    """The latency path (pinned buffers: the PCM kernels address host memory over PCIe, decided per side) gives the
+    same bytes as the staged path and as pageable buffers, and leaves the channels beyond n_outputs untouched."""
+    B, L, nblk = 128, 300, 5
+    nout = 2 if routed else nch
+    irs = [make_ir(190 + c, L) * 0.25 for c in range(nch)]
+    x = (interleave([make_noise(195 + c, nblk * B) for c in range(nch + 1)]) * 0.9).astype(np.float32)  # one extra in-channel
     bps = cl.FMT_BYTES[fmt]
     pcm = np.zeros(x.size * bps, dtype=np.uint8)
-    orc.transfer(x.view(np.uint8).reshape(-1), cl.FMT_FLOAT, 0, 0, 3, pcm, fmt, 0, 0, 3, 3, nblk * B)
+    orc.transfer(x.view(np.uint8).reshape(-1), cl.FMT_FLOAT, 0, 0, nch + 1, pcm, fmt, 0, 0, nch + 1, nch + 1, nblk * B)
     res = {}
     for mode in ("direct", "staged", "pageable"):
-        g = GpuDriver(bbx, B, 3, nch, max_blocks=1)
+        if routed:
+            g = GpuDriver(bbx, B, 3, nch, n_outputs=2, n_paths=nch, mode=cl.MODE_ROUTED, max_blocks=1, max_delay=20)
+            for c in range(nch):
+                g.route(c, c, c % 2, 0.5)
+        else:
+            g = GpuDriver(bbx, B, 3, nch, max_blocks=1, max_delay=20)
         for c in range(nch):
-            g.select(c, g.filter(irs[c]))
+            g.select(c, g.filter(irs[c]), delay=float(c % 7))
         if mode == "staged":
             g.eng.set_direct_io(0)
-        nin, nout = B * 3 * bps, B * 4 * bps
+        nin, nob = B * (nch + 1) * bps, B * (nout + 2) * bps  # two extra out-channels
         if mode == "pageable":
-            hin, hout = np.zeros(nin, dtype=np.uint8), np.zeros(nout, dtype=np.uint8)
-            pin, pout = hin, hout
+            hin, hout = np.zeros(nin, dtype=np.uint8), np.zeros(nob, dtype=np.uint8)
             ain, aout = hin.ctypes.data, hout.ctypes.data
         else:
-            pin, pout = bbx.PinnedBuffer(nin), bbx.PinnedBuffer(nout)
+            pin, pout = bbx.PinnedBuffer(nin), bbx.PinnedBuffer(nob)
             hin, hout = pin.array, pout.array
             ain, aout = pin.ptr, pout.ptr
         got = []
         for b in range(nblk):
             hin[:] = pcm[b * nin:(b + 1) * nin]
             hout[:] = 0x3C
-            g.eng.ConvolveHostPtr(ain, fmt, 3, aout, fmt, 4, B)
+            g.eng.ConvolveHostPtr(ain, fmt, nch + 1, aout, fmt, nout + 2, B)
             got.append(hout.copy())
-        assert g.eng.direct_calls() == (nblk if mode == "direct" else 0)
+        assert g.eng.direct_calls() == (nblk if (mode == "direct" and expect_direct) else 0)
         g.close()
-        res[mode] = np.concatenate(got).reshape(nblk * B, 4, bps)
-    assert (res["direct"][:, 2:] == 0x3C).all()
+        res[mode] = np.concatenate(got).reshape(nblk * B, nout + 2, bps)
+    assert (res["direct"][:, nout:] == 0x3C).all()
+    assert res["direct"][:, :nout].any()
     assert np.array_equal(res["direct"], res["staged"]) and np.array_equal(res["direct"], res["pageable"])
 
 
