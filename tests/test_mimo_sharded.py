@@ -39,16 +39,16 @@ def _paths():
             sys.path.insert(0, p)
 
 
-def _full_oracle():
+def _full_oracle(nin=NIN, nout=NOUT):
     _paths()
     import cpulibs as cl
     from convkit import OracleDriver, interleave, make_ir, make_noise, run_float
     P = -(-L // B)
-    o = OracleDriver(B, P, NIN, n_outputs=NOUT, mode=cl.MODE_MIMO, max_blocks=T)
-    for oo in range(NOUT):
-        for i in range(NIN):
-            o.select(oo * NIN + i, o.filter(make_ir(7000 + 64 * oo + i, L)))
-    x = interleave([make_noise(7100 + i, NBLK * B) for i in range(NIN)])
+    o = OracleDriver(B, P, nin, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=T)
+    for oo in range(nout):
+        for i in range(nin):
+            o.select(oo * nin + i, o.filter(make_ir(7000 + 64 * oo + i, L)))
+    x = interleave([make_noise(7100 + i, NBLK * B) for i in range(nin)])
     return x, run_float(o, x, T * B)
 
 
@@ -99,16 +99,16 @@ def test_input_sharded_mimo_host_logic_gloo_world2():
 # ------------------------------------------------------------------------------------------------
 # GPU: the product path
 # ------------------------------------------------------------------------------------------------
-def _gpu_run(bbx, rank, world, comm, tensor_off):
-    """one rank of the sharded engine; returns [frames][NOUT / world]"""
+def _gpu_run(bbx, rank, world, comm, tensor_off, nin=NIN, nout=NOUT):
+    """one rank of the sharded engine; returns [frames][nout / world]"""
     import cpulibs as cl
     from convkit import GpuDriver, interleave, make_ir, make_noise, run_float
     P = -(-L // B)
-    i0, ni = bbx.shard_range(NIN, rank, world)
-    g = GpuDriver(bbx, B, P, ni, n_outputs=NOUT, mode=cl.MODE_MIMO, max_blocks=T, mimo_tensor=tensor_off,
+    i0, ni = bbx.shard_range(nin, rank, world)
+    g = GpuDriver(bbx, B, P, ni, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=T, mimo_tensor=tensor_off,
                   mimo_shard_world=world, mimo_shard_rank=rank, device=rank if world > 1 else 0)
     g.eng.SetComm(comm)
-    for oo in range(NOUT):
+    for oo in range(nout):
         for i in range(ni):
             g.select(oo * ni + i, g.filter(make_ir(7000 + 64 * oo + i0 + i, L)))
     x = interleave([make_noise(7100 + i0 + i, NBLK * B) for i in range(ni)])
@@ -133,7 +133,7 @@ def test_sharded_path_one_rank_vs_oracle(bbx, tensor_off):
         assert_float_parity(y[:, oo], y_full[:, oo], "1-rank sharded path out %d" % oo)
 
 
-def _gpu_worker(rank, world, port, ret):
+def _gpu_worker(rank, world, port, ret, nin=NIN, nout=NOUT):
     _paths()
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -142,7 +142,7 @@ def _gpu_worker(rank, world, port, ret):
     uid = [bbx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     comm = bbx.Comm(world, rank, uid[0], device=rank)
-    y, st = _gpu_run(bbx, rank, world, comm, 0)
+    y, st = _gpu_run(bbx, rank, world, comm, 0, nin, nout)
     comm.close()
     ret[rank] = (y, st)
     dist.barrier()
@@ -162,3 +162,21 @@ def test_input_sharded_mimo_two_gpus_vs_oracle(bbx):
     assert ret[0][1][1] == 0 and ret[1][1][1] == 0 and ret[0][1][0] > 0
     for oo in range(NOUT):
         assert_float_parity(y[:, oo], y_full[:, oo], "2-GPU sharded MIMO out %d" % oo)
+
+
+@pytest.mark.gpu
+def test_input_sharded_mimo_all_gpus_vs_oracle(bbx):
+    """The same on every GPU of the box (4 or 8 ranks: 16 inputs and 8 outputs of the matrix sharded over them)."""
+    from parity import assert_float_parity
+    world = 8 if bbx.device_count() >= 8 else 4
+    if bbx.device_count() < world:
+        pytest.skip("needs four or eight GPUs (gpurun --gpus 4 / 8)")
+    nin, nout = 16, 8
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), ret, nin, nout), nprocs=world, join=True)
+    _, y_full = _full_oracle(nin, nout)
+    y = np.concatenate([ret[r][0] for r in range(world)], axis=1)
+    assert all(ret[r][1][1] == 0 for r in range(world)) and ret[0][1][0] > 0
+    for oo in range(nout):
+        assert_float_parity(y[:, oo], y_full[:, oo], "%d-GPU sharded MIMO out %d" % (world, oo))
