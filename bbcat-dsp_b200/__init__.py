@@ -72,6 +72,11 @@ SYMBOLS = {
     "bbx_delay_read_sample": (C.c_float, [vp, u32, u32]),
     "bbx_delay_get_buffer_dev": (vp, [vp]),
     "bbx_delay_copy_buffer": (u32, [vp, vp, u32]),
+    "bbx_ring_create": (C.c_int, [C.POINTER(vp)]),
+    "bbx_ring_get_read_position": (u32, [vp]),
+    "bbx_ring_get_read_frames_available": (u32, [vp]),
+    "bbx_ring_get_write_frames_available": (u32, [vp]),
+    "bbx_ring_increment_read_position": (C.c_int, [vp, u32]),
     "bbx_mlb_create": (C.c_int, [u32, u32, C.POINTER(vp)]),
     "bbx_mlb_destroy": (C.c_int, [vp]),
     "bbx_mlb_get_channels": (u32, [vp]),
@@ -116,6 +121,13 @@ SYMBOLS = {
     "bbx_allpass_process": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, u32]),
     "bbx_allpass_process_dev": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, u32, vp]),
     "bbx_allpass_get_state": (u32, [vp, u32, vp, u32]),
+    "bbx_cascade_create": (C.c_int, [u32, u32, C.c_int, C.c_int, C.POINTER(vp)]),
+    "bbx_cascade_destroy": (C.c_int, [vp]),
+    "bbx_cascade_set_coefficients": (C.c_int, [vp, u32, vp, u32]),
+    "bbx_cascade_reset": (C.c_int, [vp]),
+    "bbx_cascade_process": (C.c_int, [vp, vp, vp, u32, C.c_int]),
+    "bbx_cascade_process_dev": (C.c_int, [vp, vp, C.c_longlong, C.c_longlong, vp, C.c_longlong, C.c_longlong, u32, vp]),
+    "bbx_cascade_get_state": (u32, [vp, u32, vp, vp, vp, vp, vp]),
     "bbx_engine_tensor_status": (C.c_int, [vp, C.POINTER(u64), C.POINTER(C.c_int)]),
     "bbx_engine_tensor_trace": (C.c_int, [vp, vp, u32]),
     "bbx_probe_fp32_tflops": (C.c_int, [C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -293,6 +305,27 @@ class SoundDelayBuffer:
         return out
 
 
+class SoundRingBuffer(SoundDelayBuffer):
+    """SoundRingBuffer (src/SoundDelayBuffer.h:105-181): the delay buffer with a read position limiting reads and writes."""
+
+    def __init__(self):
+        h = vp()
+        _check(lib().bbx_ring_create(C.byref(h)))
+        self.h = h
+
+    def GetReadPosition(self):
+        return lib().bbx_ring_get_read_position(self.h)
+
+    def GetReadFramesAvailable(self):
+        return lib().bbx_ring_get_read_frames_available(self.h)
+
+    def GetWriteFramesAvailable(self):
+        return lib().bbx_ring_get_write_frames_available(self.h)
+
+    def IncrementReadPosition(self, nframes=1):
+        _check(lib().bbx_ring_increment_read_position(self.h, nframes))
+
+
 # ---- next row: MultilayerBuffer (src/MultilayerBuffer.h) -------------------------------------
 class MultilayerBuffer:
     def __init__(self, channels, layers):
@@ -398,6 +431,39 @@ class AllPassChain:
         ring = np.zeros(self.channels * self.delays[f], dtype=np.float32)
         pos = lib().bbx_allpass_get_state(self.h, f, _p(ring), ring.size)
         return ring, pos
+
+
+class BiQuadCascadeBank:
+    """BiQuadCascade (src/BiQuad.h:373-792), one independent cascade of up to 12 float biquads per channel."""
+
+    def __init__(self, channels, numfilters, vectorise=True, unroll=True):
+        h = vp()
+        _check(lib().bbx_cascade_create(channels, numfilters, int(vectorise), int(unroll), C.byref(h)))
+        self.h, self.channels, self.numfilters = h, channels, numfilters
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_cascade_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def SetCoefficients(self, coeffs, channel=None):
+        """(g, b1[0], b2[0], a1[0], a2[0], b1[1], ...): 4 * numfilters + 1 floats; channel None = every cascade."""
+        c = np.ascontiguousarray(coeffs, dtype=np.float32)
+        _check(lib().bbx_cascade_set_coefficients(self.h, 0xFFFFFFFF if channel is None else channel, _p(c), c.size))
+
+    def Reset(self):
+        _check(lib().bbx_cascade_reset(self.h))
+
+    def ProcessCascade(self, src, dst, nframes, interleaved=True):
+        _check(lib().bbx_cascade_process(self.h, _p(src), _p(dst), nframes, int(interleaved)))
+
+    def GetState(self, channel):
+        a = [np.zeros(12, dtype=np.float32) for _ in range(4)]
+        last = np.zeros(1, dtype=np.float32)
+        info = lib().bbx_cascade_get_state(self.h, channel, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(last))
+        return a[0], a[1], a[2], a[3], last, info
 
 
 # ---- a12-a14 ------------------------------------------------------------------------------

@@ -496,7 +496,17 @@ struct bbx_delay {
   int format = FMT_F32;
   uint32_t channels = 0, bytesperframe = 0, buflen = 0, writepos = 0;
   int device = 0;
+  // SoundRingBuffer (src/SoundDelayBuffer.h:105-181, src/SoundDelayBuffer.cpp:195-304): the same buffer with a read
+  // position that limits writes, reads and both increments; the entry points branch where the reference dispatches
+  // virtually
+  bool ring = false;
+  uint32_t readpos = 0;
 };
+
+static uint32_t ring_read_available(const bbx_delay* d) { return d->buflen ? (d->writepos + d->buflen - d->readpos) % d->buflen : 0; }
+static uint32_t ring_write_available(const bbx_delay* d) {
+  return d->buflen ? (d->readpos + d->buflen - d->writepos - 1) % d->buflen : 0;  // one frame stays free (.h:123)
+}
 
 int bbx_delay_create(bbx_delay** out) {
   BBX_REQUIRE(out != nullptr, "bbx_delay_create: null out pointer");
@@ -505,6 +515,22 @@ int bbx_delay_create(bbx_delay** out) {
   bbx_delay* d = new bbx_delay();
   BBX_CUDA_TRY(cudaGetDevice(&d->device));
   *out = d;
+  return BBX_OK;
+}
+
+int bbx_ring_create(bbx_delay** out) {
+  int rc = bbx_delay_create(out);
+  if (rc) return rc;
+  (*out)->ring = true;
+  return BBX_OK;
+}
+uint32_t bbx_ring_get_read_position(const bbx_delay* d) { return d ? d->readpos : 0; }
+uint32_t bbx_ring_get_read_frames_available(const bbx_delay* d) { return d ? ring_read_available(d) : 0; }
+uint32_t bbx_ring_get_write_frames_available(const bbx_delay* d) { return d ? ring_write_available(d) : 0; }
+int bbx_ring_increment_read_position(bbx_delay* d, uint32_t nframes) {
+  // src/SoundDelayBuffer.h:175
+  BBX_REQUIRE(d != nullptr && d->ring, "bbx_ring_increment_read_position: not a ring buffer handle");
+  if (d->buflen) d->readpos = (d->readpos + std::min(nframes, ring_read_available(d))) % d->buflen;
   return BBX_OK;
 }
 
@@ -549,6 +575,7 @@ int bbx_delay_set_size(bbx_delay* d, uint32_t chans, uint32_t length, int format
   d->format = format;
   d->writepos %= d->buflen;
   d->bytesperframe = chans * bps;
+  if (d->ring) d->readpos %= d->buflen;  // src/SoundDelayBuffer.cpp:214-218
   return BBX_OK;
 }
 
@@ -562,6 +589,10 @@ uint32_t bbx_delay_write_samples(bbx_delay* d, const void* vsrc, int srcformat, 
                                  uint32_t nframes) {
   // src/SoundDelayBuffer.cpp:77-116; does not move the write position
   if (!d || !d->buf || !vsrc || !valid_fmt(srcformat) || nframes == 0) return 0;
+  if (d->ring) {  // SoundRingBuffer::WriteSamples (src/SoundDelayBuffer.cpp:234-254): limited by the space up to the read position
+    nframes = std::min(nframes, ring_write_available(d));
+    if (nframes == 0) return 0;
+  }
   uint32_t srclen = fmt_bytes(srcformat), pos = d->writepos, frames = 0;
   channel = std::min(channel, d->channels - 1);
   nchannels = std::min(nchannels, d->channels - channel);
@@ -589,6 +620,7 @@ uint32_t bbx_delay_write_samples(bbx_delay* d, const void* vsrc, int srcformat, 
 
 int bbx_delay_increment_write_position(bbx_delay* d, uint32_t nframes) {
   BBX_REQUIRE(d != nullptr, "bbx_delay_increment_write_position: null handle");
+  if (d->ring) nframes = std::min(nframes, ring_write_available(d));  // src/SoundDelayBuffer.h:148
   if (d->buflen) d->writepos = (d->writepos + nframes) % d->buflen;
   return BBX_OK;
 }
@@ -597,6 +629,12 @@ uint32_t bbx_delay_read_samples(bbx_delay* d, void* vdst, int dstformat, uint32_
                                 uint32_t nchannels, uint32_t nframes) {
   // src/SoundDelayBuffer.cpp:134-170
   if (!d || !d->buf || !vdst || !valid_fmt(dstformat)) return 0;
+  if (d->ring) {
+    // SoundRingBuffer::ReadSamples (src/SoundDelayBuffer.cpp:274-303): delay limited to (read - write) mod length, the frame
+    // count to (write + delay - read) mod length; the base class then reads relative to the WRITE position
+    delay = std::min(delay, (d->readpos + d->buflen - d->writepos) % d->buflen);
+    nframes = std::min(nframes, (d->writepos + d->buflen + delay - d->readpos) % d->buflen);
+  }
   uint32_t dstlen = fmt_bytes(dstformat), frames = 0;
   uint32_t pos = (d->writepos + d->buflen - delay) % d->buflen;
   channel = std::min(channel, d->channels - 1);

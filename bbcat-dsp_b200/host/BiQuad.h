@@ -49,4 +49,35 @@ private:
   bbx_biquad* b;
 };
 
+// BiQuadCascade surface (src/BiQuad.h:373-792) for a bank of independent per-channel cascades on the GPU: numfilters (1..12)
+// float biquads per channel, plain or "vectorised" (pipelined) Tick, coefficient vector (g, b1[0], b2[0], a1[0], a2[0], ...).
+// The reference object filters one mono stream (ProcessCascade(input, dest, blocksize)); the bank runs `channels` of
+// them in one call, interleaved or planar.
+class BiQuadCascadeBank {
+public:
+  BiQuadCascadeBank(uint_t channels, uint_t numfilters, bool vectorise = true, bool unroll = true) : c(0), nch(channels) {
+    Check(bbx_cascade_create(channels, numfilters, vectorise, unroll, &c));
+  }
+  ~BiQuadCascadeBank() { bbx_cascade_destroy(c); }
+  // BiQuadCascade::SetCoefficients(const std::vector<float>&): false (and no change) on a wrong length, like the reference
+  bool SetCoefficients(const float* coefficients, uint_t n) { return bbx_cascade_set_coefficients(c, ~0u, coefficients, n) == BBX_OK; }
+  bool SetCoefficients(uint_t channel, const float* coefficients, uint_t n) {
+    return bbx_cascade_set_coefficients(c, channel, coefficients, n) == BBX_OK;
+  }
+  void Reset() { Check(bbx_cascade_reset(c)); }
+  // ProcessCascade on every channel: [blocksize][channels] when interleaved, else [channels][blocksize]
+  void ProcessCascade(const float* input, float* dest, uint_t blocksize, bool interleaved = true) {
+    Check(bbx_cascade_process(c, input, dest, blocksize, interleaved));
+  }
+
+private:
+  static void Check(int rc) {
+    if (rc != BBX_OK) throw std::runtime_error(std::string("libbbx: ") + bbx_last_error());
+  }
+  BiQuadCascadeBank(const BiQuadCascadeBank&);
+  BiQuadCascadeBank& operator=(const BiQuadCascadeBank&);
+  bbx_cascade* c;
+  uint_t nch;
+};
+
 }  // namespace bbcat

@@ -40,11 +40,24 @@ public:
   virtual Sample_t ReadSample(uint_t channel, uint_t delay) const { return bbx_delay_read_sample(h, channel, delay); }
 
 protected:
+  struct RingTag {};
+  explicit SoundDelayBuffer(RingTag) : h(0) { bbx_ring_create(&h); }
   bbx_delay* h;
 
 private:
   SoundDelayBuffer(const SoundDelayBuffer&);
   SoundDelayBuffer& operator=(const SoundDelayBuffer&);
+};
+
+// SoundRingBuffer (src/SoundDelayBuffer.h:105-181): the overrides of SetSize / WriteSamples / IncrementWritePosition /
+// ReadSamples live behind the same C entry points (a handle made by bbx_ring_create applies the read-position limits)
+class SoundRingBuffer : public SoundDelayBuffer {
+public:
+  SoundRingBuffer() : SoundDelayBuffer(RingTag()) {}
+  virtual uint_t GetReadPosition() const { return bbx_ring_get_read_position(h); }
+  virtual uint_t GetReadFramesAvailable() const { return bbx_ring_get_read_frames_available(h); }
+  virtual uint_t GetWriteFramesAvailable() const { return bbx_ring_get_write_frames_available(h); }
+  virtual void IncrementReadPosition(uint_t nframes = 1) { bbx_ring_increment_read_position(h, nframes); }
 };
 
 }  // namespace bbcat

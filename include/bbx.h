@@ -149,6 +149,15 @@ float bbx_delay_read_sample(bbx_delay* d, uint32_t channel, uint32_t delay);
 const void* bbx_delay_get_buffer_dev(const bbx_delay* d);
 /* copy the raw ring to host memory; returns bytes copied (0 on error) */
 uint32_t bbx_delay_copy_buffer(const bbx_delay* d, void* dst, uint32_t maxbytes);
+/* SoundRingBuffer  src/SoundDelayBuffer.h:105-181, src/SoundDelayBuffer.cpp:195-304: a SoundDelayBuffer with a read
+ * position.  Create with bbx_ring_create and use the bbx_delay_* entry points above: like the reference's virtual
+ * overrides they then limit SetSize / WriteSamples / IncrementWritePosition / ReadSamples by the read position (one
+ * frame always stays free; reads stay relative to the WRITE position, as in the reference). */
+int bbx_ring_create(bbx_delay** out);
+uint32_t bbx_ring_get_read_position(const bbx_delay* d);
+uint32_t bbx_ring_get_read_frames_available(const bbx_delay* d);
+uint32_t bbx_ring_get_write_frames_available(const bbx_delay* d);
+int bbx_ring_increment_read_position(bbx_delay* d, uint32_t nframes);
 
 /* ------------------------------------------------------------------------------------------
  * a12-a14  BlockConvolver / Convolver / FFT  (absent from the tree: README:38-51, 68-69;
@@ -287,6 +296,29 @@ int bbx_biquad_process_dev(bbx_biquad* b, const float* src, float* dst, uint32_t
 /* filter states w[nchannels][2], current coefficients, {mul, dec} of the ramp (any pointer may be NULL) */
 int bbx_biquad_get_state(const bbx_biquad* b, double* w, double* cur5, double* mul_dec);
 int bbx_biquad_reset(bbx_biquad* b); /* BiQuad::Reset on every filter */
+
+/* BiQuadCascade  src/BiQuad.h:373-792: a bank of nchannels independent cascades of numfilters (1..12) biquads in float,
+ * both forms of Tick -- the plain cascade and the "vectorised" pipeline of the SSE3 build (numfilters a multiple of four,
+ * else switched off like the reference; it delays the signal by numfilters - 1 samples).  unroll is accepted for signature
+ * parity (same arithmetic).  The output gain g of the coefficient vector is stored and never applied, as in the reference.
+ * More than 12 filters is an error here (the reference logs and leaves an unusable object).  Bit-exact. */
+typedef struct bbx_cascade bbx_cascade;
+int bbx_cascade_create(uint32_t nchannels, uint32_t numfilters, int vectorise, int unroll, bbx_cascade** out);
+int bbx_cascade_destroy(bbx_cascade* c);
+/* BiQuadCascade::SetCoefficients(const std::vector<float>&): (g, b1[0], b2[0], a1[0], a2[0], b1[1], ...), n = 4 * numfilters + 1,
+ * resets the registers; channel 0xFFFFFFFF = every cascade of the bank */
+int bbx_cascade_set_coefficients(bbx_cascade* c, uint32_t channel, const float* coeffs, uint32_t n);
+int bbx_cascade_reset(bbx_cascade* c); /* BiQuadCascade::Reset on every channel */
+/* ProcessCascade on every channel; host buffers [nframes][nchannels] (interleaved != 0) or [nchannels][nframes] */
+int bbx_cascade_process(bbx_cascade* c, const float* src, float* dst, uint32_t nframes, int interleaved);
+/* device pointers; channel j reads src[j * src_channel_stride + i * src_frame_stride] (strides in samples) */
+int bbx_cascade_process_dev(bbx_cascade* c, const float* src, long long src_channel_stride, long long src_frame_stride,
+                            float* dst, long long dst_channel_stride, long long dst_frame_stride, uint32_t nframes,
+                            void* stream);
+/* registers x, y, w0, w1 (12 floats each) and lastoutput of one channel (any pointer may be NULL);
+ * returns numfilters | vectorise << 8 */
+uint32_t bbx_cascade_get_state(const bbx_cascade* c, uint32_t channel, float* x12, float* y12, float* w0_12, float* w1_12,
+                               float* lastoutput);
 
 /* AllPassFilterChain<float>  src/AllPassFilter.h:12-262 (ring semantics src/RingBuffer.h:17-121): nfilters Schroeder
  * all-pass sections (delay[f] >= 1 frames, coefficient[f]) over nchannels interleaved channels, rings in HBM in the

@@ -14,6 +14,10 @@ struct orc_delay {
   uint8_t* buf;
   int format;
   unsigned channels, bytesperframe, buflen, writepos;
+  /* SoundRingBuffer (SoundDelayBuffer.h:105-181, .cpp:195-304): the same buffer with a read position that limits
+   * writes, reads and both increments; the entry points below branch where the reference dispatches virtually */
+  int is_ring;
+  unsigned readpos;
 };
 
 static unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
@@ -23,6 +27,27 @@ orc_delay* orc_delay_create(void) {
   orc_delay* d = (orc_delay*)calloc(1, sizeof(*d));
   d->format = ORC_FMT_FLOAT;
   return d;
+}
+
+orc_delay* orc_ring_create(void) {
+  orc_delay* d = orc_delay_create();
+  d->is_ring = 1;
+  return d;
+}
+
+unsigned orc_ring_get_read_position(const orc_delay* d) { return d->readpos; }
+/* SoundDelayBuffer.h:122-123 (the write side keeps one frame free so that the positions never coincide after a write) */
+unsigned orc_ring_get_read_frames_available(const orc_delay* d) {
+  return d->buflen ? (d->writepos + d->buflen - d->readpos) % d->buflen : 0;
+}
+unsigned orc_ring_get_write_frames_available(const orc_delay* d) {
+  return d->buflen ? (d->readpos + d->buflen - d->writepos - 1) % d->buflen : 0;
+}
+/* SoundDelayBuffer.h:175 */
+void orc_ring_increment_read_position(orc_delay* d, unsigned nframes) {
+  if (!d->buflen) return;
+  nframes = nframes < orc_ring_get_read_frames_available(d) ? nframes : orc_ring_get_read_frames_available(d);
+  d->readpos = (d->readpos + nframes) % d->buflen;
 }
 
 void orc_delay_destroy(orc_delay* d) {
@@ -54,6 +79,7 @@ void orc_delay_set_size(orc_delay* d, unsigned chans, unsigned length, int fmt) 
   d->format = fmt;
   d->writepos %= d->buflen;
   d->bytesperframe = chans * bps;
+  if (d->is_ring) d->readpos %= d->buflen; /* .cpp:214-218 (a no-op on the unchanged-geometry early return above) */
 }
 
 unsigned orc_delay_get_channels(const orc_delay* d) { return d->channels; }
@@ -65,6 +91,7 @@ unsigned orc_delay_write_samples(orc_delay* d, const void* vsrc, int srcformat, 
                                  unsigned nframes) {
   unsigned frames = 0;
   if (!d->buf) return 0;
+  if (d->is_ring) nframes = umin(nframes, orc_ring_get_write_frames_available(d)); /* .cpp:234-254 */
   const uint8_t* src = (const uint8_t*)vsrc;
   unsigned srclen = orc_get_bytes_per_sample(srcformat), pos = d->writepos;
   channel = umin(channel, d->channels - 1);
@@ -82,6 +109,7 @@ unsigned orc_delay_write_samples(orc_delay* d, const void* vsrc, int srcformat, 
 }
 
 void orc_delay_increment_write_position(orc_delay* d, unsigned nframes) {
+  if (d->is_ring && d->buflen) nframes = umin(nframes, orc_ring_get_write_frames_available(d)); /* .h:148 */
   if (d->buflen) d->writepos = (d->writepos + nframes) % d->buflen;
 }
 
@@ -89,6 +117,12 @@ unsigned orc_delay_read_samples(orc_delay* d, void* vdst, int dstformat, unsigne
                                 unsigned nchannels, unsigned nframes) {
   unsigned frames = 0;
   if (!d->buf) return 0;
+  if (d->is_ring) {
+    /* .cpp:274-303: the delay is limited to (read - write) mod length, the frame count to (write + delay - read) mod
+     * length, then the base class reads relative to the WRITE position */
+    delay = umin(delay, (d->readpos + d->buflen - d->writepos) % d->buflen);
+    nframes = umin(nframes, (d->writepos + d->buflen + delay - d->readpos) % d->buflen);
+  }
   uint8_t* dst = (uint8_t*)vdst;
   unsigned dstlen = orc_get_bytes_per_sample(dstformat);
   unsigned pos = (d->writepos + d->buflen - delay) % d->buflen;

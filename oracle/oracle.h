@@ -82,6 +82,13 @@ void orc_delay_increment_write_position(orc_delay* d, unsigned nframes);
 unsigned orc_delay_read_samples(orc_delay* d, void* dst, int dstformat, unsigned delay, unsigned channel,
                                 unsigned nchannels, unsigned nframes);
 unsigned orc_delay_copy_buffer(const orc_delay* d, void* dst, unsigned maxbytes);
+/* SoundRingBuffer (SoundDelayBuffer.h:105-181, .cpp:195-304): created with orc_ring_create, used through the
+ * orc_delay_* entry points (which apply the ring's limits, like the reference's virtual methods) plus: */
+orc_delay* orc_ring_create(void);
+unsigned orc_ring_get_read_position(const orc_delay* d);
+unsigned orc_ring_get_read_frames_available(const orc_delay* d);
+unsigned orc_ring_get_write_frames_available(const orc_delay* d);
+void orc_ring_increment_read_position(orc_delay* d, unsigned nframes);
 
 /* ---- multilayer.c : MultilayerBuffer.h ("next" row) ---- */
 typedef struct orc_mlb orc_mlb;
@@ -113,6 +120,20 @@ void orc_allpass_destroy(orc_allpass* a);
 void orc_allpass_process(orc_allpass* a, const float* src, float* dst, unsigned srcchannel, unsigned nsrc, unsigned dstchannel,
                          unsigned ndst, unsigned nframes);
 unsigned orc_allpass_get_state(const orc_allpass* a, unsigned f, float* ring, unsigned maxitems);
+
+/* ---- cascade.c : BiQuadCascade, one per channel ("next" row) ---- */
+typedef struct orc_cascade orc_cascade;
+orc_cascade* orc_cascade_create(unsigned nchannels, unsigned numfilters, int vectorise, int unroll);
+void orc_cascade_destroy(orc_cascade* b);
+/* channel == ~0u: every channel; n must be 4 * numfilters + 1; returns 1 on success */
+int orc_cascade_set_coefficients(orc_cascade* b, unsigned channel, const float* coeffs, unsigned n);
+void orc_cascade_reset(orc_cascade* b);
+/* channel j reads src[j * src_cs + i * src_fs], writes dst[j * dst_cs + i * dst_fs] */
+void orc_cascade_process(orc_cascade* b, const float* src, long src_cs, long src_fs, float* dst, long dst_cs, long dst_fs,
+                         unsigned nframes);
+/* registers of one channel (12 floats each); returns numfilters | vectorise << 8 */
+unsigned orc_cascade_get_state(const orc_cascade* b, unsigned channel, float* x12, float* y12, float* w0_12, float* w1_12,
+                               float* last);
 
 /* ---- fft.c : own FFT (FFTW stand-in, unnormalised both directions) ---- */
 /* complex in-place FFT of n (power of two) interleaved float pairs; inverse != 0 conjugates the kernel */

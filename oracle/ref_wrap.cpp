@@ -88,6 +88,12 @@ void ref_fractional_samples_f64(const double* buffer, unsigned channel, unsigned
 
 /* ---- SoundDelayBuffer ---- */
 void* ref_delay_create(void) { return new SoundDelayBuffer(); }
+/* SoundRingBuffer through the same entry points (its overrides are virtual) plus the read-position methods */
+void* ref_ring_create(void) { return static_cast<SoundDelayBuffer*>(new SoundRingBuffer()); }
+unsigned ref_ring_get_read_position(void* h) { return static_cast<SoundRingBuffer*>((SoundDelayBuffer*)h)->GetReadPosition(); }
+unsigned ref_ring_get_read_frames_available(void* h) { return static_cast<SoundRingBuffer*>((SoundDelayBuffer*)h)->GetReadFramesAvailable(); }
+unsigned ref_ring_get_write_frames_available(void* h) { return static_cast<SoundRingBuffer*>((SoundDelayBuffer*)h)->GetWriteFramesAvailable(); }
+void ref_ring_increment_read_position(void* h, unsigned nframes) { static_cast<SoundRingBuffer*>((SoundDelayBuffer*)h)->IncrementReadPosition(nframes); }
 void ref_delay_destroy(void* h) { delete (SoundDelayBuffer*)h; }
 void ref_delay_set_size(void* h, unsigned chans, unsigned length, int fmt) {
   ((SoundDelayBuffer*)h)->SetSize(chans, length, (SampleFormat_t)fmt);
@@ -232,5 +238,70 @@ unsigned ref_allpass_get_state(void* h, unsigned f, float* ring, unsigned maxite
   if (n) memcpy(ring, a.Buf(), n * sizeof(float));
   return a.Pos();
 }
+
+/* ---- BiQuadCascade (src/BiQuad.h:373-792): one cascade object per channel of a bank ---- */
+namespace {
+struct PeekCascade : public BiQuadCascade {
+  PeekCascade(uint_t n, bool vec, bool unr) : BiQuadCascade(n, vec, unr) {}
+  uint_t N() const { return numfilters; }
+  bool Vec() const { return vectorise; }
+  void State(float* x12, float* y12, float* w0_12, float* w1_12, float* last) const {
+    memcpy(x12, x, sizeof(x));
+    memcpy(y12, y, sizeof(y));
+    memcpy(w0_12, w0, sizeof(w0));
+    memcpy(w1_12, w1, sizeof(w1));
+    *last = lastoutput;
+  }
+};
+struct RefCascadeBank {
+  std::vector<PeekCascade*> c;
+};
+}  // namespace
+
+void* ref_cascade_create(unsigned nchannels, unsigned numfilters, int vectorise, int unroll) {
+  RefCascadeBank* b = new RefCascadeBank();
+  for (unsigned j = 0; j < nchannels; j++) {
+    PeekCascade* pc = new PeekCascade(numfilters, vectorise != 0, unroll != 0);
+    pc->Reset();  /* the reference's constructor leaves the registers uninitialised */
+    b->c.push_back(pc);
+  }
+  return b;
+}
+void ref_cascade_destroy(void* h) {
+  RefCascadeBank* b = (RefCascadeBank*)h;
+  for (size_t j = 0; j < b->c.size(); j++) delete b->c[j];
+  delete b;
+}
+/* channel == ~0u: every channel; returns 1 when the reference accepted the vector */
+int ref_cascade_set_coefficients(void* h, unsigned channel, const float* coeffs, unsigned n) {
+  RefCascadeBank* b = (RefCascadeBank*)h;
+  std::vector<float> v(coeffs, coeffs + n);
+  int ok = 1;
+  for (size_t j = 0; j < b->c.size(); j++)
+    if (channel == ~0u || channel == j) ok &= b->c[j]->SetCoefficients(v) ? 1 : 0;
+  return ok;
+}
+void ref_cascade_reset(void* h) {
+  RefCascadeBank* b = (RefCascadeBank*)h;
+  for (size_t j = 0; j < b->c.size(); j++) b->c[j]->Reset();
+}
+/* channel j reads src[j * src_cs + i * src_fs] and writes dst[j * dst_cs + i * dst_fs] through ProcessCascade */
+void ref_cascade_process(void* h, const float* src, long src_cs, long src_fs, float* dst, long dst_cs, long dst_fs, unsigned nframes) {
+  RefCascadeBank* b = (RefCascadeBank*)h;
+  std::vector<float> in(nframes), out(nframes);
+  for (size_t j = 0; j < b->c.size(); j++) {
+    for (unsigned i = 0; i < nframes; i++) in[i] = src[(long)j * src_cs + (long)i * src_fs];
+    if (nframes) b->c[j]->ProcessCascade(&in[0], &out[0], nframes);
+    for (unsigned i = 0; i < nframes; i++) dst[(long)j * dst_cs + (long)i * dst_fs] = out[i];
+  }
+}
+/* returns numfilters | vectorise << 8 */
+unsigned ref_cascade_get_state(void* h, unsigned channel, float* x12, float* y12, float* w0_12, float* w1_12, float* last) {
+  RefCascadeBank* b = (RefCascadeBank*)h;
+  if (channel >= b->c.size()) return 0;
+  b->c[channel]->State(x12, y12, w0_12, w1_12, last);
+  return b->c[channel]->N() | ((unsigned)b->c[channel]->Vec() << 8);
+}
+
 
 }  // extern "C"

@@ -87,6 +87,28 @@ int main() {
     bank.CalcCoeffs(BiQuadBank::FLAT, 1000.0, 48000.0);
     CHECK(bank.GetCurrent().num0 == 1.0 && bank.GetCurrent().den1 == 0.0);
   }
+  // SoundRingBuffer: one frame always stays free; writes are limited by the read position
+  {
+    SoundRingBuffer ring;
+    ring.SetSize(1, 8, SampleFormat_Float);
+    float rx[10] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
+    CHECK(ring.GetWriteFramesAvailable() == 7 && ring.WriteSamples(rx, 0, 1, 10) == 7);
+    ring.IncrementWritePosition(10);
+    CHECK(ring.GetWritePosition() == 7 && ring.GetReadFramesAvailable() == 7 && ring.GetWriteFramesAvailable() == 0);
+    ring.IncrementReadPosition(3);
+    float ry[8] = {0};
+    CHECK(ring.ReadSamples(ry, 2, 0, 1, 8) == 2 && ry[0] == 6.0f && ry[1] == 7.0f);
+  }
+  // BiQuadCascadeBank: one section per channel, b1 = 1 -> y[n] = x[n] + x[n-1]; a wrong-length vector is refused
+  {
+    BiQuadCascadeBank casc(2, 1, false);
+    const float cf[5] = {7.0f, 1.0f, 0.0f, 0.0f, 0.0f};
+    CHECK(casc.SetCoefficients(cf, 5));
+    CHECK(!casc.SetCoefficients(cf, 4));
+    float cx[8] = {1, 10, 2, 20, 3, 30, 4, 40}, cy[8] = {0};
+    casc.ProcessCascade(cx, cy, 4);
+    CHECK(cy[0] == 1.0f && cy[1] == 10.0f && cy[2] == 3.0f && cy[3] == 30.0f && cy[6] == 7.0f && cy[7] == 70.0f);
+  }
   // AllPassFilterChain: one section, delay 2, c = 0.5, impulse -> 0.5, 0, 0.75, 0, -0.375
   {
     const uint_t d[1] = {2};

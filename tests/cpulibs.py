@@ -72,6 +72,11 @@ class CpuLib:
         self._dl_inc = fn("delay_increment_write_position", None, [vp, u32])
         self._dl_read = fn("delay_read_samples", u32, [vp, vp, C.c_int, u32, u32, u32, u32])
         self._dl_copy = fn("delay_copy_buffer", u32, [vp, vp, u32])
+        self._rg_create = fn("ring_create", vp, [])
+        self._rg_rpos = fn("ring_get_read_position", u32, [vp])
+        self._rg_ravail = fn("ring_get_read_frames_available", u32, [vp])
+        self._rg_wavail = fn("ring_get_write_frames_available", u32, [vp])
+        self._rg_rinc = fn("ring_increment_read_position", None, [vp, u32])
         self._mlb_create = fn("mlb_create", vp, [u32, u32])
         self._mlb_destroy = fn("mlb_destroy", None, [vp])
         self._mlb_write = fn("mlb_write_layer", None, [vp, u32, vp, u32, u32, u32, u32, u32])
@@ -90,6 +95,13 @@ class CpuLib:
         self._ap_destroy = fn("allpass_destroy", None, [vp])
         self._ap_process = fn("allpass_process", None, [vp, vp, vp, u32, u32, u32, u32, u32])
         self._ap_state = fn("allpass_get_state", u32, [vp, u32, vp, u32])
+        lng = C.c_long
+        self._cs_create = fn("cascade_create", vp, [u32, u32, C.c_int, C.c_int])
+        self._cs_destroy = fn("cascade_destroy", None, [vp])
+        self._cs_set = fn("cascade_set_coefficients", C.c_int, [vp, u32, vp, u32])
+        self._cs_reset = fn("cascade_reset", None, [vp])
+        self._cs_process = fn("cascade_process", None, [vp, vp, lng, lng, vp, lng, lng, u32])
+        self._cs_state = fn("cascade_get_state", u32, [vp, u32, vp, vp, vp, vp, vp])
 
     # ---- formats ----
     def bits_per_sample(self, fmt):
@@ -142,8 +154,8 @@ class CpuLib:
         return out
 
     # ---- delay buffer ----
-    def delay(self):
-        return CpuDelay(self)
+    def delay(self, ring=False):
+        return CpuDelay(self, ring)
 
     # ---- MultilayerBuffer<float> ----
     def multilayer(self, channels, layers):
@@ -160,6 +172,39 @@ class CpuLib:
 
     def allpass(self, channels, delays, coeffs):
         return CpuAllpass(self, channels, delays, coeffs)
+
+    def cascade(self, channels, numfilters, vectorise=True, unroll=True):
+        return CpuCascade(self, channels, numfilters, vectorise, unroll)
+
+
+class CpuCascade:
+    """BiQuadCascade bank (one reference object / C restatement per channel)."""
+
+    def __init__(self, lib, channels, numfilters, vectorise, unroll):
+        self.l, self.channels = lib, channels
+        self.h = lib._cs_create(channels, numfilters, int(vectorise), int(unroll))
+
+    def close(self):
+        if self.h:
+            self.l._cs_destroy(self.h)
+            self.h = None
+
+    def set_coefficients(self, coeffs, channel=None):
+        c = np.ascontiguousarray(coeffs, dtype=np.float32)
+        return bool(self.l._cs_set(self.h, 0xFFFFFFFF if channel is None else channel, _ptr(c), c.size))
+
+    def reset(self):
+        self.l._cs_reset(self.h)
+
+    def process(self, src, dst, nframes, interleaved=True):
+        cs, fs = (1, self.channels) if interleaved else (nframes, 1)
+        self.l._cs_process(self.h, _ptr(src), cs, fs, _ptr(dst), cs, fs, nframes)
+
+    def state(self, channel):
+        a = [np.zeros(12, dtype=np.float32) for _ in range(4)]
+        last = np.zeros(1, dtype=np.float32)
+        info = self.l._cs_state(self.h, channel, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(last))
+        return a[0], a[1], a[2], a[3], last, info
 
 
 class CpuAllpass:
@@ -234,9 +279,16 @@ class CpuMultilayer:
 
 
 class CpuDelay:
-    def __init__(self, lib):
+    def __init__(self, lib, ring=False):
         self.l = lib
-        self.h = lib._dl_create()
+        self.h = lib._rg_create() if ring else lib._dl_create()
+
+    read_position = property(lambda s: s.l._rg_rpos(s.h))
+    read_available = property(lambda s: s.l._rg_ravail(s.h))
+    write_available = property(lambda s: s.l._rg_wavail(s.h))
+
+    def increment_read(self, nframes):
+        self.l._rg_rinc(self.h, nframes)
 
     def close(self):
         if self.h:

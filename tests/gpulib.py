@@ -40,8 +40,8 @@ class GpuLib:
     def frac(self, buffer, channel, channels, length, pos):
         return self.b.FractionalSample(buffer, channel, channels, length, np.asarray(pos, dtype=np.float64))
 
-    def delay(self):
-        return GpuDelay(self.b)
+    def delay(self, ring=False):
+        return GpuDelay(self.b, ring)
 
     def multilayer(self, channels, layers):
         return GpuMultilayer(self.b, channels, layers)
@@ -54,6 +54,33 @@ class GpuLib:
 
     def allpass(self, channels, delays, coeffs):
         return GpuAllpass(self.b, channels, delays, coeffs)
+
+    def cascade(self, channels, numfilters, vectorise=True, unroll=True):
+        return GpuCascade(self.b, channels, numfilters, vectorise, unroll)
+
+
+class GpuCascade:
+    def __init__(self, b, channels, numfilters, vectorise, unroll):
+        self.c = b.BiQuadCascadeBank(channels, numfilters, vectorise, unroll)
+
+    def close(self):
+        self.c.close()
+
+    def set_coefficients(self, coeffs, channel=None):
+        try:
+            self.c.SetCoefficients(coeffs, channel)
+            return True
+        except Exception:
+            return False
+
+    def reset(self):
+        self.c.Reset()
+
+    def process(self, src, dst, nframes, interleaved=True):
+        self.c.ProcessCascade(src, dst, nframes, interleaved)
+
+    def state(self, channel):
+        return self.c.GetState(channel)
 
 
 class GpuAllpass:
@@ -111,8 +138,15 @@ class GpuMultilayer:
 
 
 class GpuDelay:
-    def __init__(self, b):
-        self.d = b.SoundDelayBuffer()
+    def __init__(self, b, ring=False):
+        self.d = b.SoundRingBuffer() if ring else b.SoundDelayBuffer()
+
+    read_position = property(lambda s: s.d.GetReadPosition())
+    read_available = property(lambda s: s.d.GetReadFramesAvailable())
+    write_available = property(lambda s: s.d.GetWriteFramesAvailable())
+
+    def increment_read(self, nframes):
+        self.d.IncrementReadPosition(nframes)
 
     def close(self):
         self.d.close()

@@ -152,6 +152,45 @@ def delay_script(seed, n_ops=60):
     return ops
 
 
+def run_ring_script(lib, seed, chans=3, length=37, fmt=cl.FMT_FLOAT, n_ops=120):
+    """Random op sequence against SoundRingBuffer: writes / reads limited by the read position, both increments, a
+    resize; every op records its return value and the three position getters."""
+    rng = np.random.default_rng(seed)
+    d = lib.delay(ring=True)
+    d.set_size(chans, length, fmt)
+    trace = []
+
+    def pos():
+        trace.append(np.array([d.write_position, d.read_position, d.read_available, d.write_available], dtype=np.float64))
+
+    pos()
+    for k in range(n_ops):
+        kind = rng.choice(["write", "winc", "read", "rinc", "write", "winc", "read"])
+        if kind == "write":
+            sfmt, ch, nch, nfr = int(rng.integers(1, 5)), int(rng.integers(0, 4)), int(rng.integers(1, 4)), int(rng.integers(1, 50))
+            if sfmt >= cl.FMT_FLOAT:
+                src = (rng.standard_normal(nfr * chans) * 0.5).astype("<f4" if sfmt == cl.FMT_FLOAT else "<f8").view(np.uint8)
+            else:
+                src = rng.integers(0, 256, nfr * chans * cl.FMT_BYTES[sfmt], dtype=np.uint8)
+            trace.append(np.array([d.write(src.copy(), sfmt, ch, nch, nfr)], dtype=np.float64))
+        elif kind == "winc":
+            d.increment(int(rng.integers(0, 25)))
+        elif kind == "rinc":
+            d.increment_read(int(rng.integers(0, 25)))
+        else:
+            dfmt, delay, ch, nch, nfr = int(rng.integers(1, 6)), int(rng.integers(0, 60)), int(rng.integers(0, 4)), int(rng.integers(1, 4)), int(rng.integers(1, 50))
+            dst = np.full(nfr * chans * cl.FMT_BYTES[dfmt], 0x5A, dtype=np.uint8)
+            got = d.read(dst, dfmt, delay, ch, nch, nfr)
+            trace.append(np.concatenate([[got], dst.astype(np.float64)]))
+        pos()
+        if k == n_ops // 2:
+            d.set_size(chans, length + 11, fmt)  # grow: contents kept, positions stay valid
+            pos()
+    trace.append(d.raw().astype(np.float64))
+    d.close()
+    return np.concatenate(trace)
+
+
 def run_delay_script(lib, seed, chans=3, length=37, fmt=cl.FMT_FLOAT):
     rng = np.random.default_rng(seed + 1000)
     d = lib.delay()
@@ -187,6 +226,14 @@ def gen_delay(ref):
         for fmt in (cl.FMT_FLOAT, cl.FMT_16, cl.FMT_DOUBLE):
             d["trace_seed%d_fmt%d" % (seed, fmt)] = run_delay_script(ref, seed, fmt=fmt)
     np.savez_compressed(os.path.join(OUT, "delay.npz"), **d)
+
+
+def gen_ring(ref):
+    d = {}
+    for seed in (21, 22, 23):
+        for fmt in (cl.FMT_FLOAT, cl.FMT_16):
+            d["trace_seed%d_fmt%d" % (seed, fmt)] = run_ring_script(ref, seed, fmt=fmt)
+    np.savez_compressed(os.path.join(OUT, "ring.npz"), **d)
 
 
 def conv_case(seed, L, B, nblk, nch=1):
@@ -298,6 +345,67 @@ def gen_allpass(ref):
     np.savez_compressed(os.path.join(OUT, "allpass.npz"), **d)
 
 
+# ---- BiQuadCascade (src/BiQuad.h:373-792), SURVEY 8f.4 ----
+def cascade_coeffs(rng, nf):
+    """stable sections: poles inside the unit circle (|a2| < 1, |a1| < 1 + a2), arbitrary zeros; g is never applied"""
+    v = [0.5]
+    for _ in range(nf):
+        a2 = rng.uniform(-0.6, 0.9)
+        a1 = rng.uniform(-1, 1) * (1 + a2) * 0.95
+        v += [rng.uniform(-1.5, 1.5), rng.uniform(-1, 1), a1, a2]
+    return np.array(v, dtype=np.float32)
+
+
+def cascade_script(lib, nch=5, nf=8, vectorise=True, seed=4242):
+    """A bank processed in several calls (registers carried over): shared coefficients, one channel re-programmed (which
+    resets only that channel), planar and interleaved layouts, Reset.  Returns outputs and register states."""
+    rng = np.random.default_rng(seed)
+    cs = lib.cascade(nch, nf, vectorise, True)
+    outs = []
+
+    def snap():
+        for j in (0, nch - 1):
+            x, y, w0, w1, last, info = cs.state(j)
+            outs.extend([x[:nf].copy(), y[:nf].copy(), w0[:nf].copy(), w1[:nf].copy(), last.copy(), np.array([info], dtype=np.uint32)])
+
+    def run(nframes, interleaved=True):
+        x = rng.uniform(-1, 1, nframes * nch).astype(np.float32)
+        y = np.full(nframes * nch, 3.0, dtype=np.float32)
+        cs.process(x, y, nframes, interleaved)
+        outs.append(y)
+        snap()
+
+    run(9)                                             # default pass-through (delayed by nf - 1 samples when vectorised)
+    assert cs.set_coefficients(cascade_coeffs(rng, nf))
+    assert not cs.set_coefficients(np.zeros(4 * nf, dtype=np.float32))   # wrong length: rejected, nothing changes
+    run(50)
+    run(7, interleaved=False)
+    assert cs.set_coefficients(cascade_coeffs(rng, nf), channel=nch - 1)  # resets the registers of that channel only
+    run(33)
+    cs.reset()
+    run(1)
+    run(18)
+    cs.close()
+    return outs
+
+
+def gen_cascade(ref):
+    d = {}
+    for name, kw in CASCADE_CASES.items():
+        for i, a in enumerate(cascade_script(ref, **kw)):
+            d["%s_%03d" % (name, i)] = a
+    np.savez_compressed(os.path.join(OUT, "cascade.npz"), **d)
+
+
+CASCADE_CASES = {
+    "vec8": dict(nch=5, nf=8, vectorise=True, seed=4242),
+    "vec12": dict(nch=3, nf=12, vectorise=True, seed=4243),
+    "plain5": dict(nch=4, nf=5, vectorise=False, seed=4244),
+    "novec6": dict(nch=2, nf=6, vectorise=True, seed=4245),   # 6 % 4 != 0: the reference switches vectorise off
+    "one": dict(nch=1, nf=1, vectorise=False, seed=4246),
+}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = cl.reference()
@@ -307,8 +415,10 @@ def main():
     gen_mix(ref)
     gen_frac(ref)
     gen_delay(ref)
+    gen_ring(ref)
     gen_biquad(ref)
     gen_allpass(ref)
+    gen_cascade(ref)
     gen_conv()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
