@@ -106,6 +106,7 @@ SYMBOLS = {
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
     "bbx_engine_set_direct_io": (C.c_int, [vp, C.c_size_t]),
+    "bbx_engine_set_mixdown_kernel": (C.c_int, [vp, C.c_int]),
     "bbx_engine_direct_calls": (u64, [vp]),
     "bbx_biquad_calc_coeffs": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "bbx_biquad_create": (C.c_int, [u32, C.POINTER(vp)]),
@@ -596,6 +597,10 @@ class Convolver:
     def set_tuning(self, ctas_per_sm=0, l2_keep_16ths=0, time_tile=0):
         """0 = leave as is; time_tile=1 forces the streaming MAC, l2_keep_16ths > 16 switches the hints off."""
         _check(lib().bbx_engine_set_tuning(self.h, ctas_per_sm, l2_keep_16ths, time_tile))
+
+    def set_mixdown_kernel(self, per_output):
+        """True keeps many-path mixdowns on the per-output kernel instead of k_pcm_out_mix (identical bytes)."""
+        _check(lib().bbx_engine_set_mixdown_kernel(self.h, int(bool(per_output))))
 
     def set_direct_io(self, max_bytes):
         """Largest PCM buffer (bytes) for which host calls with pinned buffers bypass the copy engines; 0 disables."""

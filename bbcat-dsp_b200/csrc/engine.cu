@@ -795,6 +795,70 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
   }
 }
 
+// Mixdown of many paths into few outputs (the binaural renderer: 64 sources x 2 ears -> 2 outputs).  The kernel above
+// walks the routes of an output one after the other inside one thread: 64 dependent table + ring reads per sample, and
+// only n_outputs of its 32 channel slots do anything.  Here every thread of the CTA takes (route, frame) items: the
+// delayed reads, the delay crossfade and the products gain * v of ALL routes of a 32-frame tile are formed in parallel
+// into shared memory, then one thread per (output, frame) adds the products in ascending route order -- the same
+// dst += mul * src with separately rounded product and sum (src/SoundMixing.h:76-79), zero gains skipped, so the bytes are
+// those of k_pcm_out (tests: routed engines run both kernels' shapes against the oracle and each other).
+static constexpr uint32_t kMixMaxRoutes = 256;
+
+__global__ void __launch_bounds__(256) k_pcm_out_mix(PcmOutArgs a) {
+  __shared__ float prod[kMixMaxRoutes][32];
+  __shared__ RouteEntry s_rt[kMixMaxRoutes];
+  __shared__ uint32_t s_first[33];
+  const uint32_t f0 = blockIdx.x * 32;
+  const uint32_t t = f0 / a.B;  // a tile lies inside one block (B % 32 == 0)
+  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
+  const float inc = 1.0f / (float)a.B;
+  const uint32_t no = a.n_outputs;  // <= 32 (host)
+  if (threadIdx.x <= no) s_first[threadIdx.x] = a.rv.out_first[threadIdx.x];
+  __syncthreads();
+  const uint32_t r0 = s_first[0], nr = s_first[no] - r0;  // <= kMixMaxRoutes (host)
+  for (uint32_t r = threadIdx.x; r < nr; r += 256) s_rt[r] = a.rv.entry[r0 + r];
+  __syncthreads();
+  const uint32_t nb0 = f0 - t * a.B;  // frame of the tile's first sample inside its block
+  // stage 1: items (route, frame), four per thread and pass so that their ring reads are in flight together
+  for (uint32_t base = threadIdx.x; base < nr * 32; base += 4 * 256) {
+    float p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t idx = base + 256 * k;
+      p[k] = 0.f;
+      if (idx < nr * 32) {
+        const uint32_t r = idx >> 5, n = nb0 + (idx & 31);
+        const RouteEntry en = s_rt[r];
+        if (en.gain != 0.0f) {
+          const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
+          float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
+          if (t == 0 && (en.flags & 1u)) {
+            const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
+            const float g = __fmul_rn((float)n, inc);
+            v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
+          }
+          p[k] = __fmul_rn(en.gain, v);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t idx = base + 256 * k;
+      if (idx < nr * 32) prod[idx >> 5][idx & 31] = p[k];
+    }
+  }
+  __syncthreads();
+  // stage 2: one thread per (output, frame): the ordered sum, then the sample in the output format
+  const uint32_t bps = fmt_bytes(a.fmt);
+  for (uint32_t item = threadIdx.x; item < no * 32; item += 256) {
+    const uint32_t o = item >> 5, fl = item & 31;
+    float bus = 0.f;
+    for (uint32_t r = s_first[o] - r0; r < s_first[o + 1] - r0; r++)
+      if (s_rt[r].gain != 0.0f) bus = __fadd_rn(bus, prod[r][fl]);  // a zero gain is a no-op, not "+ 0"
+    store_from_f32(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, bus, a.fmt, a.be != 0, a.fast != 0);
+  }
+}
+
 // 128-frame tiles (B % 128 == 0).  Outputs fed by exactly one path with an integer delay and no delay crossfade in this
 // block (every output of the PER_CHANNEL and MIMO modes in the steady state) issue their four ring reads together; the
 // arithmetic is the same dst += mul * src, rounded separately.
@@ -1030,6 +1094,8 @@ struct bbx_engine {
   size_t flush_bytes = 0;
   // route tables (device blob + pinned staging)
   Staging route_stg;
+  uint32_t n_routes_pcm = 0;  // routes feeding the PCM outputs (set by upload_routes)
+  bool pcm_out_mix = true;  // bbx_engine_set_mixdown_kernel: false keeps mixdowns on the per-output kernel
   uint8_t* h_route = nullptr;  // the slot being filled by upload_routes
   uint8_t* d_route = nullptr;
   size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0,
@@ -1533,6 +1599,7 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
   {
     RouteEntry* en = (RouteEntry*)(e->h_route + e->roff_entry);
     const uint32_t nroutes = ofirst[e->n_out_pcm < e->n_out ? e->n_out_pcm : e->n_out];
+    e->n_routes_pcm = nroutes;
     for (uint32_t r = 0; r < nroutes; r++) {
       const uint32_t st = rstream[r];
       en[r].stream = st;
@@ -2172,7 +2239,11 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     a.rv = route_view(e);
     // wide tiles for many outputs with integer delays (their ring reads batch); mixdowns of many paths into few
     // outputs and fractional delays (14-tap double-precision reads) keep the finer grid
-    if (B % 128 == 0 && e->n_out_pcm >= 16 && !e->cfg.fractional_delay)
+    // mixdowns (at least four paths per output on average, few outputs): the (route, frame)-parallel kernel
+    const bool mix = e->n_out_pcm <= 32 && e->n_routes_pcm <= kMixMaxRoutes && e->n_routes_pcm >= 4 * e->n_out_pcm &&
+                     e->pcm_out_mix;
+    if (mix) k_pcm_out_mix<<<dim3(T * B / 32), 256, 0, st>>>(a);
+    else if (B % 128 == 0 && e->n_out_pcm >= 16 && !e->cfg.fractional_delay)
       k_pcm_out128<<<dim3(T * B / 128, ceil_div(e->n_out_pcm, 32)), 256, 0, st>>>(a);
     else k_pcm_out<<<dim3(T * B / 32, ceil_div(e->n_out_pcm, 32)), 256, 0, st>>>(a);
     BBX_CUDA_TRY(cudaGetLastError());
@@ -2353,6 +2424,12 @@ int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_
   BBX_REQUIRE(e != nullptr, "null engine");
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   apply_tuning(e, ctas_per_sm, l2_keep_16ths, time_tile);
+  return BBX_OK;
+}
+
+int bbx_engine_set_mixdown_kernel(bbx_engine* e, int per_output) {
+  BBX_REQUIRE(e != nullptr, "bbx_engine_set_mixdown_kernel: null engine");
+  e->pcm_out_mix = per_output == 0;
   return BBX_OK;
 }
 

@@ -259,6 +259,34 @@ def test_routed_binaural_vs_oracle(bbx):
         assert_float_parity(yg[:, ear], yo[:, ear], "ear %d" % ear)
 
 
+@pytest.mark.parametrize("fractional,fmt", [(False, cl.FMT_FLOAT), (True, cl.FMT_FLOAT), (False, cl.FMT_24)])
+def test_mixdown_kernels_bit_identical(bbx, fractional, fmt):
+    """k_pcm_out_mix (route-parallel products, ordered sums) against the per-output kernel: same bytes for a many-path
+    mixdown with zero gains, per-path delays, a delay crossfade on a switching call, ragged call sizes and three outputs."""
+    B, L, nsrc, nout, nblk = 128, 200, 40, 3, 14
+    xi = interleave([make_noise(1500 + s, nblk * B) for s in range(nsrc)])
+    outs = []
+    for per_output in (False, True):
+        g = GpuDriver(bbx, B, 2, nsrc, n_outputs=nout, n_paths=2 * nsrc, mode=cl.MODE_ROUTED, max_blocks=4, max_delay=90,
+                      fractional_delay=fractional)
+        g.eng.set_mixdown_kernel(per_output)
+        fl = [g.filter(make_ir(1600 + p, L)) for p in range(2 * nsrc)]
+        for p in range(2 * nsrc):
+            g.route(p, p % nsrc, (p * 7) % nout, 0.0 if p % 9 == 4 else 0.05 + 0.01 * (p % 5))
+            g.select(p, fl[p], delay=(p % 13) * 6.25 if fractional else float((p * 5) % 80))
+        got, pos = [], 0
+        for k, nb in enumerate([4, 1, 3, 2, 4]):
+            if k == 2:
+                for p in (0, 5, 41):
+                    g.select(p, fl[(p + 1) % (2 * nsrc)], delay=33.5 if fractional else 17.0, crossfade=True)
+            y = g.process(xi[pos * B:(pos + nb) * B], cl.FMT_FLOAT, nsrc, fmt, nout + 1, nb * B)
+            got.append(np.array(y, copy=True))
+            pos += nb
+        outs.append(np.concatenate(got))
+        g.close()
+    assert outs[0].any() and np.array_equal(outs[0], outs[1])
+
+
 def test_mimo_vs_oracle(bbx):
     """C5 shape at reduced size: 8 x 8 matrix of 4096-tap IRs, B = 512, frequency-domain mixdown."""
     B, L, nin, nout, nblk = 512, 4096, 8, 8, 12
