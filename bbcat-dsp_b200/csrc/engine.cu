@@ -53,12 +53,13 @@ struct PcmInArgs {
   int fast;               // little-endian, base and frame stride aligned to the sample size: typed loads
 };
 
+template <int FMT, int ACC>
 __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
   __shared__ float tile[32][33];
   const uint32_t f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool is_prev = f0 < a.B;  // B is a multiple of 32: a tile never straddles the boundary
-  const uint32_t bps = fmt_bytes(a.fmt);
+  constexpr uint32_t bps = FmtBytes<FMT>::value;
   if (!is_prev) {
     // phase 1: lanes over channels (contiguous bytes within a frame)
 #pragma unroll
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
       uint32_t fl = warp + 8 * i, c = c0 + lane;
       uint32_t frame = f0 + fl - a.B;
       float v = 0.f;
-      if (c < a.n_inputs) v = load_as_f32(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps, a.fmt, a.be != 0, a.fast != 0);
+      if (c < a.n_inputs) v = load_as_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps);
       tile[fl][lane] = v;
     }
     __syncthreads();
@@ -84,12 +85,13 @@ __global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
 
 // Same transpose with 128-frame tiles (B % 128 == 0): 16 independent loads per thread are in flight before the first
 // shared-memory store (the 32-frame kernel above is bound by the latency of its 4), a quarter of the CTAs.
+template <int FMT, int ACC>
 __global__ void __launch_bounds__(256) k_pcm_in128(PcmInArgs a) {
   __shared__ float tile[128][33];
   const uint32_t f0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool is_prev = f0 < a.B;  // B is a multiple of 128: a tile never straddles the boundary
-  const uint32_t bps = fmt_bytes(a.fmt);
+  constexpr uint32_t bps = FmtBytes<FMT>::value;
   if (!is_prev) {
     // phase 1: lanes over channels (contiguous bytes within a frame)
     float v[16];
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) k_pcm_in128(PcmInArgs a) {
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const uint32_t frame = f0 + warp + 8 * i - a.B;
-      v[i] = (c < a.n_inputs) ? load_as_f32(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps, a.fmt, a.be != 0, a.fast != 0) : 0.f;
+      v[i] = (c < a.n_inputs) ? load_as_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) tile[warp + 8 * i][lane] = v[i];
@@ -742,6 +744,7 @@ __device__ __forceinline__ float delayed_read(const float* __restrict__ ring, ui
 
 static constexpr uint32_t kPcmOutCache = 64;  // routes of one 32-output tile kept in shared memory
 
+template <int FMT, int ACC>
 __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
   __shared__ float tile[32][33];
   __shared__ uint32_t s_first[33];
@@ -785,13 +788,13 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
   }
   __syncthreads();
   // phase 2: lanes over channels (contiguous bytes of one interleaved frame)
-  const uint32_t bps = fmt_bytes(a.fmt);
+  constexpr uint32_t bps = FmtBytes<FMT>::value;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const uint32_t fl = warp + 8 * i, o = c0 + lane;
     if (o >= a.n_outputs) continue;
     const uint32_t frame = f0 + fl;
-    store_from_f32(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0, a.fast != 0);
+    store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane]);
   }
 }
 
@@ -804,6 +807,7 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
 // those of k_pcm_out (tests: routed engines run both kernels' shapes against the oracle and each other).
 static constexpr uint32_t kMixMaxRoutes = 256;
 
+template <int FMT, int ACC>
 __global__ void __launch_bounds__(256) k_pcm_out_mix(PcmOutArgs a) {
   __shared__ float prod[kMixMaxRoutes][32];
   __shared__ RouteEntry s_rt[kMixMaxRoutes];
@@ -849,19 +853,20 @@ __global__ void __launch_bounds__(256) k_pcm_out_mix(PcmOutArgs a) {
   }
   __syncthreads();
   // stage 2: one thread per (output, frame): the ordered sum, then the sample in the output format
-  const uint32_t bps = fmt_bytes(a.fmt);
+  constexpr uint32_t bps = FmtBytes<FMT>::value;
   for (uint32_t item = threadIdx.x; item < no * 32; item += 256) {
     const uint32_t o = item >> 5, fl = item & 31;
     float bus = 0.f;
     for (uint32_t r = s_first[o] - r0; r < s_first[o + 1] - r0; r++)
       if (s_rt[r].gain != 0.0f) bus = __fadd_rn(bus, prod[r][fl]);  // a zero gain is a no-op, not "+ 0"
-    store_from_f32(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, bus, a.fmt, a.be != 0, a.fast != 0);
+    store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, bus);
   }
 }
 
 // 128-frame tiles (B % 128 == 0).  Outputs fed by exactly one path with an integer delay and no delay crossfade in this
 // block (every output of the PER_CHANNEL and MIMO modes in the steady state) issue their four ring reads together; the
 // arithmetic is the same dst += mul * src, rounded separately.
+template <int FMT, int ACC>
 __global__ void __launch_bounds__(256) k_pcm_out128(PcmOutArgs a) {
   __shared__ float tile[128][33];
   __shared__ uint32_t s_first[33];
@@ -927,13 +932,13 @@ __global__ void __launch_bounds__(256) k_pcm_out128(PcmOutArgs a) {
   }
   __syncthreads();
   // phase 2: lanes over channels (contiguous bytes of one interleaved frame)
-  const uint32_t bps = fmt_bytes(a.fmt);
+  constexpr uint32_t bps = FmtBytes<FMT>::value;
   const uint32_t o = c0 + lane;
   if (o < a.n_outputs) {
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const uint32_t fl = warp + 8 * i;
-      store_from_f32(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, tile[fl][lane], a.fmt, a.be != 0, a.fast != 0);
+      store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, tile[fl][lane]);
     }
   }
 }
@@ -2071,6 +2076,24 @@ int bbx_set_filter(bbx_engine* e, uint32_t path, const bbx_filter* filter, int c
   return BBX_OK;
 }
 
+// launch KERNEL<FMT, ACC> for a runtime (format, big-endian, typed-access) triple; ACC as in formats.cuh
+#define BBX_PCM_LAUNCH_ACC(KERNEL, FMT, be, fast, GRID, STREAM, ARGS)            \
+  do {                                                                            \
+    if ((fast) && FMT != FMT_24) KERNEL<FMT, 2><<<GRID, 256, 0, STREAM>>>(ARGS);  \
+    else if (be) KERNEL<FMT, 1><<<GRID, 256, 0, STREAM>>>(ARGS);                  \
+    else KERNEL<FMT, 0><<<GRID, 256, 0, STREAM>>>(ARGS);                          \
+  } while (0)
+#define BBX_PCM_LAUNCH(KERNEL, fmt, be, fast, GRID, STREAM, ARGS)                          \
+  do {                                                                                      \
+    switch (fmt) {                                                                          \
+      case FMT_16: BBX_PCM_LAUNCH_ACC(KERNEL, FMT_16, be, fast, GRID, STREAM, ARGS); break;   \
+      case FMT_24: BBX_PCM_LAUNCH_ACC(KERNEL, FMT_24, be, fast, GRID, STREAM, ARGS); break;   \
+      case FMT_32: BBX_PCM_LAUNCH_ACC(KERNEL, FMT_32, be, fast, GRID, STREAM, ARGS); break;   \
+      case FMT_F32: BBX_PCM_LAUNCH_ACC(KERNEL, FMT_F32, be, fast, GRID, STREAM, ARGS); break; \
+      default: BBX_PCM_LAUNCH_ACC(KERNEL, FMT_F64, be, fast, GRID, STREAM, ARGS); break;      \
+    }                                                                                       \
+  } while (0)
+
 int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
                     int out_be, uint32_t out_channels, uint32_t nframes) {
   BBX_REQUIRE(e && in && out, "bbx_process: null argument");
@@ -2190,8 +2213,9 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
       a.fast = (!in_be && bps != 3 && ((uintptr_t)in % bps) == 0) ? 1 : 0;  // frame stride = in_channels * bps is aligned too
     }
     // wide tiles pay when the channel axis fills the lanes; few-channel engines keep the finer grid
-    if (B % 128 == 0 && e->n_in >= 16) k_pcm_in128<<<dim3((T + 1) * B / 128, ceil_div(e->n_in, 32)), 256, 0, st>>>(a);
-    else k_pcm_in<<<dim3((T + 1) * B / 32, ceil_div(e->n_in, 32)), 256, 0, st>>>(a);
+    if (B % 128 == 0 && e->n_in >= 16)
+      BBX_PCM_LAUNCH(k_pcm_in128, infmt, in_be, a.fast, dim3((T + 1) * B / 128, ceil_div(e->n_in, 32)), st, a);
+    else BBX_PCM_LAUNCH(k_pcm_in, infmt, in_be, a.fast, dim3((T + 1) * B / 32, ceil_div(e->n_in, 32)), st, a);
     BBX_CUDA_TRY(cudaGetLastError());
     e->launches++;
   }
@@ -2242,10 +2266,10 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     // mixdowns (at least four paths per output on average, few outputs): the (route, frame)-parallel kernel
     const bool mix = e->n_out_pcm <= 32 && e->n_routes_pcm <= kMixMaxRoutes && e->n_routes_pcm >= 4 * e->n_out_pcm &&
                      e->pcm_out_mix;
-    if (mix) k_pcm_out_mix<<<dim3(T * B / 32), 256, 0, st>>>(a);
+    if (mix) BBX_PCM_LAUNCH(k_pcm_out_mix, outfmt, out_be, a.fast, dim3(T * B / 32), st, a);
     else if (B % 128 == 0 && e->n_out_pcm >= 16 && !e->cfg.fractional_delay)
-      k_pcm_out128<<<dim3(T * B / 128, ceil_div(e->n_out_pcm, 32)), 256, 0, st>>>(a);
-    else k_pcm_out<<<dim3(T * B / 32, ceil_div(e->n_out_pcm, 32)), 256, 0, st>>>(a);
+      BBX_PCM_LAUNCH(k_pcm_out128, outfmt, out_be, a.fast, dim3(T * B / 128, ceil_div(e->n_out_pcm, 32)), st, a);
+    else BBX_PCM_LAUNCH(k_pcm_out, outfmt, out_be, a.fast, dim3(T * B / 32, ceil_div(e->n_out_pcm, 32)), st, a);
     BBX_CUDA_TRY(cudaGetLastError());
     e->launches++;
   }
