@@ -105,6 +105,8 @@ SYMBOLS = {
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
+    "bbx_engine_peer_export": (C.c_int, [vp, vp]),
+    "bbx_engine_peer_attach": (C.c_int, [vp, vp]),
     "bbx_engine_set_direct_io": (C.c_int, [vp, C.c_size_t]),
     "bbx_engine_set_mixdown_kernel": (C.c_int, [vp, C.c_int]),
     "bbx_engine_direct_calls": (u64, [vp]),
@@ -597,6 +599,18 @@ class Convolver:
     def set_tuning(self, ctas_per_sm=0, l2_keep_16ths=0, time_tile=0):
         """0 = leave as is; time_tile=1 forces the streaming MAC, l2_keep_16ths > 16 switches the hints off."""
         _check(lib().bbx_engine_set_tuning(self.h, ctas_per_sm, l2_keep_16ths, time_tile))
+
+    def PeerExport(self):
+        """64-byte CUDA IPC handle of this rank's receive buffer (input-sharded MIMO engine, peer-memory mixdown)."""
+        h = (C.c_uint8 * 64)()
+        _check(lib().bbx_engine_peer_export(self.h, h))
+        return bytes(h)
+
+    def PeerAttach(self, handles):
+        """handles: the PeerExport() results of all ranks, in rank order."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(lib().bbx_engine_peer_attach(self.h, buf))
 
     def set_mixdown_kernel(self, per_output):
         """True keeps many-path mixdowns on the per-output kernel instead of k_pcm_out_mix (identical bytes)."""

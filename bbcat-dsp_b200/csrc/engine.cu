@@ -995,6 +995,71 @@ __global__ void __launch_bounds__(256) k_gather_spectra(const float2* __restrict
   }
 }
 
+// ---- peer-memory mixdown: the reduce of the input-sharded MIMO engine without a collective library ----------------------
+// Every rank adds its partial slots like k_gather_spectra, but stores the spectrum of output o straight into the memory of
+// the rank that owns o (NVLink peer stores into a buffer opened with cudaIpcOpenMemHandle), at slot (o_local, source rank).
+// The owner's inverse-transform kernel then adds the `world` slots of an output in rank order -- the same fixed-order slot
+// sum it already runs over the MAC's partial sums, so the result does not depend on a collective's reduction schedule.
+// Completion: the last CTA of a launch publishes the call's epoch in every peer's flag array after a system-scope fence;
+// k_peer_wait (one warp, in stream order before the inverse transforms) spins until all sources have published it.  The
+// receive buffer is double-buffered by epoch parity: a source can only be two calls ahead after it has seen this rank's
+// flag of the call in between, which this rank publishes after its own inverse transforms of the older call (stream order).
+struct PeerTable {
+  float2* data[16];     // receive buffers of the ranks (own rank: the local buffer)
+  uint32_t* flags[16];  // their flag arrays, [2][world]
+};
+
+__global__ void __launch_bounds__(256) k_gather_spectra_peer(const float2* __restrict__ ypart, const float* __restrict__ nyq_part,
+                                                             uint32_t slot_stride, PlanView pv, PeerTable pt, uint32_t world,
+                                                             uint32_t rank, uint32_t nloc, uint32_t B, uint32_t T, uint64_t half,
+                                                             uint32_t parity, uint32_t epoch, uint32_t* __restrict__ done) {
+  const uint32_t o = blockIdx.x, t = blockIdx.y;
+  const uint32_t first = pv.job_slot_first[o], count = pv.job_slot_count[o];
+  const float2* yt = ypart + (uint64_t)t * slot_stride * B;
+  const uint32_t r = o / nloc, ol = o - r * nloc;
+  float2* dst = pt.data[r] + (uint64_t)parity * half + (((uint64_t)ol * world + rank) * T + t) * B;
+  for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) {
+    float2 a = make_float2(0.f, 0.f);
+    for (uint32_t sl = 0; sl < count; sl++) {
+      const float2 v = yt[(uint64_t)(first + sl) * B + k];
+      a.x += v.x;
+      a.y += v.y;
+    }
+    if (k == 0 && nyq_part) {
+      float n = 0.f;
+      for (uint32_t sl = 0; sl < count; sl++) n += nyq_part[(uint64_t)t * slot_stride + first + sl];
+      a = make_float2(a.x + n, n);
+    }
+    dst[k] = a;
+  }
+  __threadfence_system();  // this thread's peer stores are performed before the CTA counts itself done
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t total = gridDim.x * gridDim.y;
+    if (atomicAdd(done, 1u) == total - 1) {
+      *done = 0;  // ready for the next launch (stream-ordered)
+      __threadfence_system();
+      for (uint32_t q = 0; q < world; q++) *((volatile uint32_t*)pt.flags[q] + parity * world + rank) = epoch;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) k_peer_wait(const uint32_t* flags, uint32_t world, uint32_t parity, uint32_t epoch,
+                                                  int* status) {
+  if (threadIdx.x < world) {
+    const volatile uint32_t* f = flags + parity * world + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(*f - epoch) < 0) {
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a source never arrived; bbx_engine_sync reports it
+        *status = 1 + (int)threadIdx.x;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
 // comm.cu
 int comm_reduce_scatter_f32(bbx_comm* c, const float* send, float* recv, size_t recvcount, cudaStream_t st);
 int comm_world(const bbx_comm* c);
@@ -1131,6 +1196,18 @@ struct bbx_engine {
   uint32_t sh_world = 1, sh_rank = 0, sh_o0 = 0, sh_nloc = 0;  // local outputs [sh_o0, sh_o0 + sh_nloc)
   uint32_t n_out_pcm = 0;                                      // channels written by bbx_process (= sh_nloc when sharded)
   bbx_comm* comm = nullptr;
+  // peer-memory mixdown (bbx_engine_peer_export / _attach): receive buffer [2][sh_nloc][world][Tmax][B] + flags [2][world]
+  bool px_on = false;
+  uint8_t* px_mem = nullptr;       // one allocation: data, then the flags
+  size_t px_half = 0;              // float2 elements of one parity half
+  size_t px_flag_off = 0;          // byte offset of the flags
+  void* px_peer[16] = {nullptr};   // opened peer allocations (own rank: nullptr)
+  PeerTable px_table;
+  uint32_t px_epoch = 0;
+  uint32_t* px_done = nullptr;     // last-CTA counter of k_gather_spectra_peer
+  uint32_t* px_view = nullptr;     // device: first[n_out] | count[n_out] | xjob[n_out] for the world slots per local output
+  int* px_status_h = nullptr;      // mapped pinned word: k_peer_wait timed out
+  int* px_status = nullptr;
   float2* sh_send = nullptr;  // [n_out][T][B]
   float2* sh_recv = nullptr;  // [sh_nloc][T][B]
   uint32_t* sh_view = nullptr;  // device: first[n_out] | count[n_out] | xjob[n_out], first[o] = o - sh_o0
@@ -1205,6 +1282,14 @@ PlanView tc_plan_view(const bbx_engine* e) {
   return v;
 }
 
+PlanView peer_plan_view(const bbx_engine* e) {
+  PlanView v;
+  v.job_slot_first = e->px_view;
+  v.job_slot_count = e->px_view + e->n_out;
+  v.xjob = e->px_view + 2 * (size_t)e->n_out;
+  return v;
+}
+
 PlanView shard_plan_view(const bbx_engine* e) {
   PlanView v;
   v.job_slot_first = e->sh_view;
@@ -1222,18 +1307,20 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaSt
   constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e->sh_world > 1 || e->comm) {
-    // reduced spectra of the local outputs, [local output][t][M]
-    const PlanView v = shard_plan_view(e);
+    // reduced spectra of the local outputs, [local output][t][M]; peer mode: [local output][source rank][t][M], the
+    // kernel adds the `world` slots of an output in rank order
+    const PlanView v = e->px_on ? peer_plan_view(e) : shard_plan_view(e);
+    const float2* spectra = e->px_on ? (const float2*)e->px_mem + (uint64_t)(e->px_epoch & 1u) * e->px_half : e->sh_recv;
     if constexpr (FftCfg<M>::R == 8) {
       if (smem > 48 * 1024) cudaFuncSetAttribute(k_irfft8<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       const uint32_t nitems = ceil_div(e->sh_nloc, FPB) * T;
       k_irfft8<M><<<std::min(nitems, (uint32_t)kNumSMs * 2), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
-          e->sh_recv, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
+          spectra, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
           e->sh_o0, T);
       return;
     }
     k_irfft<M><<<dim3(ceil_div(e->sh_nloc, FPB), T), dim3(FftCfg<M>::NT, FPB), smem, st>>>(
-        e->sh_recv, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
+        spectra, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
         e->sh_o0);
     return;
   }
@@ -1972,6 +2059,12 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   cudaFree(e->flush_buf);
+  for (void* pp : e->px_peer)
+    if (pp) cudaIpcCloseMemHandle(pp);
+  cudaFree(e->px_mem);
+  cudaFree(e->px_done);
+  cudaFree(e->px_view);
+  if (e->px_status_h) cudaFreeHost(e->px_status_h);
   cudaFree(e->sh_send);
   cudaFree(e->sh_recv);
   cudaFree(e->sh_view);
@@ -2103,7 +2196,8 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   const uint32_t B = e->B, T = nframes / B;
   BBX_REQUIRE(T <= e->Tmax, "bbx_process: %u blocks exceed max_blocks %u", T, e->Tmax);
   BBX_REQUIRE(in_channels >= e->n_in && out_channels >= e->n_out_pcm, "bbx_process: too few channels in the PCM buffers");
-  BBX_REQUIRE(e->sh_world <= 1 || e->comm, "bbx_process: the input-sharded MIMO engine needs bbx_engine_set_comm()");
+  BBX_REQUIRE(e->sh_world <= 1 || e->comm || e->px_on,
+              "bbx_process: the input-sharded MIMO engine needs bbx_engine_set_comm() or bbx_engine_peer_attach()");
   BBX_CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
   int rc;
@@ -2235,11 +2329,23 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   // ---- 3b. input-sharded MIMO: sum the partial spectra over the ranks, keep the local outputs ----
   if (e->sh_world > 1 || e->comm) {
     const PlanView pv = use_tc ? tc_plan_view(e) : e->plan_steady.view();
-    k_gather_spectra<<<dim3(e->n_out, T), 256, 0, st>>>(e->ypart, use_tc ? nullptr : e->nyq_part, e->max_slots, pv, e->sh_send, B, T);
-    BBX_CUDA_TRY(cudaGetLastError());
-    e->launches++;
-    if ((rc = comm_reduce_scatter_f32(e->comm, (const float*)e->sh_send, (float*)e->sh_recv, (size_t)e->sh_nloc * T * B * 2, st)))
-      return rc;
+    if (e->px_on) {
+      e->px_epoch++;
+      const uint32_t parity = e->px_epoch & 1u;
+      k_gather_spectra_peer<<<dim3(e->n_out, T), 256, 0, st>>>(e->ypart, use_tc ? nullptr : e->nyq_part, e->max_slots, pv,
+                                                               e->px_table, e->sh_world, e->sh_rank, e->sh_nloc, B, T, e->px_half,
+                                                               parity, e->px_epoch, e->px_done);
+      BBX_CUDA_TRY(cudaGetLastError());
+      k_peer_wait<<<1, 32, 0, st>>>((const uint32_t*)(e->px_mem + e->px_flag_off), e->sh_world, parity, e->px_epoch, e->px_status);
+      BBX_CUDA_TRY(cudaGetLastError());
+      e->launches += 2;
+    } else {
+      k_gather_spectra<<<dim3(e->n_out, T), 256, 0, st>>>(e->ypart, use_tc ? nullptr : e->nyq_part, e->max_slots, pv, e->sh_send, B, T);
+      BBX_CUDA_TRY(cudaGetLastError());
+      e->launches++;
+      if ((rc = comm_reduce_scatter_f32(e->comm, (const float*)e->sh_send, (float*)e->sh_recv, (size_t)e->sh_nloc * T * B * 2, st)))
+        return rc;
+    }
   }
   // ---- 4. inverse transforms, crossfade, delay ring ----
   if ((rc = launch_irfft(e, T, n_first, use_tc, st))) return rc;
@@ -2371,6 +2477,11 @@ int bbx_engine_sync(bbx_engine* e) {
   BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  if (e->px_status_h && *(volatile int*)e->px_status_h) {
+    set_error("peer mixdown: rank %d never published its partial spectra (timed out); results are invalid",
+              *(volatile int*)e->px_status_h - 1);
+    return BBX_ERR_CUDA;
+  }
   if (e->tc_status_h && *(volatile int*)e->tc_status_h) {
     // fail loudly: the output of that call is not valid
     set_error("k_mimo_tc: a barrier wait timed out inside the tensor-core kernel (status %d); results are invalid",
@@ -2486,6 +2597,62 @@ int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c) {
     BBX_CUDA_TRY(cudaMemcpy(e->sh_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
   }
   e->comm = c;
+  return BBX_OK;
+}
+
+int bbx_engine_peer_export(bbx_engine* e, uint8_t* handle64) {
+  BBX_REQUIRE(e && handle64, "bbx_engine_peer_export: null argument");
+  BBX_REQUIRE(e->mode == BBX_MODE_MIMO && e->sh_world > 1 && e->sh_world <= 16,
+              "bbx_engine_peer_export: only the input-sharded MIMO engine (2..16 ranks) exchanges spectra");
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  if (!e->px_mem) {
+    e->px_half = (size_t)e->sh_nloc * e->sh_world * e->Tmax * e->B;
+    e->px_flag_off = (2 * e->px_half * sizeof(float2) + 255) & ~(size_t)255;
+    const size_t bytes = e->px_flag_off + 2 * sizeof(uint32_t) * e->sh_world;
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->px_mem, bytes));
+    BBX_CUDA_TRY(cudaMemset(e->px_mem, 0, bytes));
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->px_done, sizeof(uint32_t)));
+    BBX_CUDA_TRY(cudaMemset(e->px_done, 0, sizeof(uint32_t)));
+    std::vector<uint32_t> view(3 * (size_t)e->n_out);
+    for (uint32_t o = 0; o < e->n_out; o++) {
+      const bool mine = o >= e->sh_o0 && o < e->sh_o0 + e->sh_nloc;
+      view[o] = mine ? (o - e->sh_o0) * e->sh_world : 0u;
+      view[e->n_out + o] = e->sh_world;
+      view[2 * (size_t)e->n_out + o] = kNoJob;
+    }
+    BBX_CUDA_TRY(cudaMalloc((void**)&e->px_view, sizeof(uint32_t) * view.size()));
+    BBX_CUDA_TRY(cudaMemcpy(e->px_view, view.data(), sizeof(uint32_t) * view.size(), cudaMemcpyHostToDevice));
+    BBX_CUDA_TRY(cudaHostAlloc((void**)&e->px_status_h, sizeof(int), cudaHostAllocMapped));
+    *e->px_status_h = 0;
+    BBX_CUDA_TRY(cudaHostGetDevicePointer((void**)&e->px_status, e->px_status_h, 0));
+    BBX_CUDA_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  BBX_CUDA_TRY(cudaIpcGetMemHandle(&h, e->px_mem));
+  static_assert(sizeof(h) == BBX_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  memcpy(handle64, &h, sizeof(h));
+  return BBX_OK;
+}
+
+int bbx_engine_peer_attach(bbx_engine* e, const uint8_t* handles) {
+  BBX_REQUIRE(e && handles, "bbx_engine_peer_attach: null argument");
+  BBX_REQUIRE(e->px_mem != nullptr, "bbx_engine_peer_attach: call bbx_engine_peer_export first");
+  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for (uint32_t r = 0; r < e->sh_world; r++) {
+    uint8_t* base = e->px_mem;
+    if (r != e->sh_rank) {
+      if (!e->px_peer[r]) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * BBX_PEER_HANDLE_BYTES, sizeof(h));
+        BBX_CUDA_TRY(cudaIpcOpenMemHandle(&e->px_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+      }
+      base = (uint8_t*)e->px_peer[r];
+    }
+    e->px_table.data[r] = (float2*)base;
+    e->px_table.flags[r] = (uint32_t*)(base + e->px_flag_off);
+  }
+  e->px_on = true;
   return BBX_OK;
 }
 

@@ -244,6 +244,17 @@ int bbx_comm_create(int world, int rank, const uint8_t* id128, int device, bbx_c
 int bbx_comm_destroy(bbx_comm* c);
 /* attach the communicator (world and rank must match bbx_config::mimo_shard_*); the engine does not own it */
 int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c);
+/* Peer-memory mixdown: the same reduce without a collective library, for one process per GPU on an NVLink / NVSwitch box.
+ * Every rank stores the partial spectrum of output o straight into the memory of the rank that owns o (peer stores into a
+ * buffer shared through CUDA IPC) and the owner's inverse-transform kernel adds the `world` partials of an output in rank
+ * order, so the sums do not depend on a collective's schedule; completion travels as epoch flags next to the data.
+ * Set-up: every rank calls _peer_export, the application gathers the world handles in rank order (the same out-of-band
+ * channel that carries the NCCL id) and every rank calls _peer_attach with all of them.  After that bbx_process* uses the
+ * peer path instead of a communicator.  Crossfaded switches stay rejected; a rank that never arrives is reported by
+ * bbx_engine_sync after a time-out. */
+#define BBX_PEER_HANDLE_BYTES 64
+int bbx_engine_peer_export(bbx_engine* e, uint8_t* handle64);
+int bbx_engine_peer_attach(bbx_engine* e, const uint8_t* handles /* [world][BBX_PEER_HANDLE_BYTES] */);
 
 /* Single-channel convenience = BlockConvolver::Convolve (README:38-39): path 0 of a
  * PER_CHANNEL engine, one float block in, one float block out (host pointers). */

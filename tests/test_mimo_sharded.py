@@ -99,21 +99,29 @@ def test_input_sharded_mimo_host_logic_gloo_world2():
 # ------------------------------------------------------------------------------------------------
 # GPU: the product path
 # ------------------------------------------------------------------------------------------------
-def _gpu_run(bbx, rank, world, comm, tensor_off, nin=NIN, nout=NOUT):
-    """one rank of the sharded engine; returns [frames][nout / world]"""
+def _gpu_run(bbx, rank, world, comm, tensor_off, nin=NIN, nout=NOUT, peer=False):
+    """one rank of the sharded engine; returns [frames][nout / world].  peer: the partial spectra travel as peer-memory
+    stores (CUDA IPC buffers, handles gathered over the gloo group) instead of an NCCL reduce-scatter."""
     import cpulibs as cl
     from convkit import GpuDriver, interleave, make_ir, make_noise, run_float
     P = -(-L // B)
     i0, ni = bbx.shard_range(nin, rank, world)
     g = GpuDriver(bbx, B, P, ni, n_outputs=nout, mode=cl.MODE_MIMO, max_blocks=T, mimo_tensor=tensor_off,
                   mimo_shard_world=world, mimo_shard_rank=rank, device=rank if world > 1 else 0)
-    g.eng.SetComm(comm)
+    if peer:
+        handles = [None] * world
+        dist.all_gather_object(handles, g.eng.PeerExport())
+        g.eng.PeerAttach(handles)
+    else:
+        g.eng.SetComm(comm)
     for oo in range(nout):
         for i in range(ni):
             g.select(oo * ni + i, g.filter(make_ir(7000 + 64 * oo + i0 + i, L)))
     x = interleave([make_noise(7100 + i0 + i, NBLK * B) for i in range(ni)])
     y = run_float(g, x, [T * B, 3 * B, (T - 3) * B])  # tensor-core call, SIMT call, SIMT/TC call
     st = g.eng.tensor_status()
+    if peer:
+        dist.barrier()  # nobody frees a receive buffer that the others still have mapped
     g.close()
     return y, st
 
@@ -133,17 +141,25 @@ def test_sharded_path_one_rank_vs_oracle(bbx, tensor_off):
         assert_float_parity(y[:, oo], y_full[:, oo], "1-rank sharded path out %d" % oo)
 
 
-def _gpu_worker(rank, world, port, ret, nin=NIN, nout=NOUT):
+def _gpu_worker(rank, world, port, ret, nin=NIN, nout=NOUT, peer=False):
     _paths()
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bbcat_dsp_b200 as bbx
-    uid = [bbx.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    comm = bbx.Comm(world, rank, uid[0], device=rank)
-    y, st = _gpu_run(bbx, rank, world, comm, 0, nin, nout)
-    comm.close()
+    import torch
+    torch.cuda.set_device(rank)
+    if peer:
+        y, st = _gpu_run(bbx, rank, world, None, 0, nin, nout, peer=True)
+        dist.barrier()  # every rank has finished reading the others' stores before anybody runs again
+        y2, _ = _gpu_run(bbx, rank, world, None, 0, nin, nout, peer=True)
+        assert np.array_equal(y.view(np.uint32), y2.view(np.uint32)), "peer mixdown is not bit-reproducible"
+    else:
+        uid = [bbx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = bbx.Comm(world, rank, uid[0], device=rank)
+        y, st = _gpu_run(bbx, rank, world, comm, 0, nin, nout)
+        comm.close()
     ret[rank] = (y, st)
     dist.barrier()
     dist.destroy_process_group()
@@ -180,3 +196,37 @@ def test_input_sharded_mimo_all_gpus_vs_oracle(bbx):
     assert all(ret[r][1][1] == 0 for r in range(world)) and ret[0][1][0] > 0
     for oo in range(nout):
         assert_float_parity(y[:, oo], y_full[:, oo], "%d-GPU sharded MIMO out %d" % (world, oo))
+
+
+@pytest.mark.gpu
+def test_peer_mixdown_two_gpus_vs_oracle(bbx):
+    """Input-sharded MIMO with the peer-memory mixdown (NVLink stores into CUDA IPC buffers + epoch flags, no NCCL):
+    two processes on two GPUs against the oracle, and bit-reproducible from run to run (fixed rank-order sums)."""
+    from parity import assert_float_parity
+    if bbx.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gpu_worker, args=(2, _free_port(), ret, NIN, NOUT, True), nprocs=2, join=True)
+    _, y_full = _full_oracle()
+    y = np.concatenate([ret[0][0], ret[1][0]], axis=1)
+    assert ret[0][1][1] == 0 and ret[1][1][1] == 0 and ret[0][1][0] > 0
+    for oo in range(NOUT):
+        assert_float_parity(y[:, oo], y_full[:, oo], "2-GPU peer mixdown out %d" % oo)
+
+
+@pytest.mark.gpu
+def test_peer_mixdown_all_gpus_vs_oracle(bbx):
+    from parity import assert_float_parity
+    world = 8 if bbx.device_count() >= 8 else 4
+    if bbx.device_count() < world:
+        pytest.skip("needs four or eight GPUs (gpurun --gpus 4 / 8)")
+    nin, nout = 16, 8
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), ret, nin, nout, True), nprocs=world, join=True)
+    _, y_full = _full_oracle(nin, nout)
+    y = np.concatenate([ret[r][0] for r in range(world)], axis=1)
+    assert all(ret[r][1][1] == 0 for r in range(world)) and ret[0][1][0] > 0
+    for oo in range(nout):
+        assert_float_parity(y[:, oo], y_full[:, oo], "%d-GPU peer mixdown out %d" % (world, oo))

@@ -140,7 +140,7 @@ def c5(steps):
     return r
 
 
-def c5_sharded(steps):
+def c5_sharded(steps, peer=False):
     """C5 input-sharded over the ranks of a torchrun launch (one process per GPU): rank g holds 64 / world inputs and
     all 64 outputs; per call one ncclReduceScatter of the partial output spectra (16.8 MB at T = 64); rank g converts
     64 / world outputs.  Device time = max over ranks between barriers; prints on rank 0.
@@ -163,7 +163,12 @@ def c5_sharded(steps):
     i0, ni = bbx.shard_range(nin, rank, world)
     eng = bbx.Convolver(B, 8, ni, n_outputs=nout, mode=bbx.MODE_MIMO, max_blocks=T, mimo_shard_world=world,
                         mimo_shard_rank=rank, device=local)
-    eng.SetComm(comm)
+    if peer and world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.PeerExport())
+        eng.PeerAttach(handles)
+    else:
+        eng.SetComm(comm)
     for o in range(nout):
         for i in range(ni):
             eng.SelectFilter(o * ni + i, eng.CreateFilter(make_ir(2000 + 64 * o + i0 + i, L)))
@@ -185,9 +190,12 @@ def c5_sharded(steps):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    r = {"config": "C5 MIMO 64 x 64, 4096 taps, B=512, f32, input-sharded over %d GPU(s), ncclReduceScatter of %d MB per "
-                   "step" % (world, nout * T * B * 8 >> 20), "channels": nout, "n_gpus": world,
+    r = {"config": "C5 MIMO 64 x 64, 4096 taps, B=512, f32, input-sharded over %d GPU(s), %s of %d MB per "
+                   "step" % (world, "peer-memory mixdown (NVLink stores + epoch flags)" if peer and world > 1 else "ncclReduceScatter",
+                             nout * T * B * 8 >> 20), "channels": nout, "n_gpus": world,
          "channel_s_per_s": nout * steps * frames / FS / (ms * 1e-3), "ms_per_step": ms / steps, "blocks_per_step": T}
+    if world > 1:
+        dist.barrier()  # peer mode: nobody frees a receive buffer the others still have mapped
     eng.close()
     comm.close()
     if world > 1:
@@ -201,7 +209,7 @@ def main():
     ap.add_argument("--configs", default="C1,C2,C4,C5")
     ap.add_argument("--steps", type=int, default=200)
     args = ap.parse_args()
-    fns = {"C1": c1, "C2": c2, "C4": c4, "C5": c5, "C5S": c5_sharded}
+    fns = {"C1": c1, "C2": c2, "C4": c4, "C5": c5, "C5S": c5_sharded, "C5P": lambda steps: c5_sharded(steps, peer=True)}
     for name in args.configs.split(","):
         r = fns[name](args.steps)
         if r is not None:
