@@ -89,6 +89,10 @@ public:
   }
   // input-sharded MIMO (bbx_config::mimo_shard_world > 1): attach the communicator before the first Convolve
   void SetComm(ConvolverComm* comm) { Check(bbx_engine_set_comm(e, comm ? comm->Handle() : 0)); }
+  // peer-memory mixdown of the input-sharded MIMO engine (instead of SetComm): export this rank's 64-byte handle, gather
+  // all ranks' handles in rank order, attach them
+  void PeerExport(uint8_t* handle64) { Check(bbx_engine_peer_export(e, handle64)); }
+  void PeerAttach(const uint8_t* handles) { Check(bbx_engine_peer_attach(e, handles)); }
   bbx_engine* Handle() { return e; }
 
 private:
