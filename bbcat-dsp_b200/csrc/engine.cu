@@ -2,7 +2,8 @@
 //
 // The reference's BlockConvolver.{h,cpp}, Convolver.{h,cpp}, FFT*.cpp and simd_utils (README:38-51,
 // 68-69) are absent from the mounted tree; behaviour follows SURVEY.md 8.A.  Data flow of one
-// bbx_process call over T blocks of B frames (all kernels on the engine stream):
+// bbx_process call over T blocks of B frames (all kernels on the engine stream; the kernels live in kernels_pcm.cuh,
+// kernels_fft.cuh, kernels_mac.cuh and mimo_tc.cuh, this file is the host side: plans, routes, launches, the C ABI):
 //
 //   k_pcm_in   interleaved PCM (any SampleFormat_t, LE/BE) -> planar fp32 xin[input][(T+1)B]
 //              (block 0 of the row is the previous call's last block = the overlap-save history)
@@ -25,1042 +26,19 @@
 #include <vector>
 
 #include "common.cuh"
-#include "fft.cuh"
-#include "formats.cuh"
-#include "fracsample.cuh"
+#include "kernels_common.cuh"
+#include "kernels_fft.cuh"
+#include "kernels_mac.cuh"
+#include "kernels_pcm.cuh"
 #include "mimo_tc.cuh"
 
 namespace bbx {
-
-static constexpr uint32_t kNoJob = 0xFFFFFFFFu;
-static constexpr uint32_t kSameJob = 0xFFFFFFFEu;  // crossfade a stream with itself (delay-only switch)
-static constexpr int kNumSMs = 148;
-__host__ __device__ __forceinline__ uint32_t ceil_div_dev(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
-
-// ------------------------------------------------------------------------------------------
-// k_pcm_in
-// ------------------------------------------------------------------------------------------
-struct PcmInArgs {
-  const uint8_t* pcm;
-  int fmt;
-  int be;
-  uint32_t in_channels, n_inputs;
-  uint32_t B, T;
-  float* xin_cur;         // [n_inputs][xstride]
-  const float* xin_prev;  // previous call's buffer
-  uint32_t xstride;
-  uint32_t prev_off;      // offset of the previous call's last block inside xin_prev rows
-  int fast;               // little-endian, base and frame stride aligned to the sample size: typed loads
-};
-
-template <int FMT, int ACC>
-__global__ void __launch_bounds__(256) k_pcm_in(PcmInArgs a) {
-  __shared__ float tile[32][33];
-  const uint32_t f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool is_prev = f0 < a.B;  // B is a multiple of 32: a tile never straddles the boundary
-  constexpr uint32_t bps = FmtBytes<FMT>::value;
-  if (!is_prev) {
-    // phase 1: lanes over channels (contiguous bytes within a frame)
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint32_t fl = warp + 8 * i, c = c0 + lane;
-      uint32_t frame = f0 + fl - a.B;
-      float v = 0.f;
-      if (c < a.n_inputs) v = load_as_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps);
-      tile[fl][lane] = v;
-    }
-    __syncthreads();
-  }
-  // phase 2: lanes over frames (contiguous floats of one planar row)
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    uint32_t cl = warp + 8 * i, c = c0 + cl;
-    if (c >= a.n_inputs) continue;
-    uint32_t f = f0 + lane;
-    float v = is_prev ? a.xin_prev[(uint64_t)c * a.xstride + a.prev_off + f] : tile[lane][cl];
-    a.xin_cur[(uint64_t)c * a.xstride + f] = v;
-  }
-}
-
-// Same transpose with 128-frame tiles (B % 128 == 0): 16 independent loads per thread are in flight before the first
-// shared-memory store (the 32-frame kernel above is bound by the latency of its 4), a quarter of the CTAs.
-template <int FMT, int ACC>
-__global__ void __launch_bounds__(256) k_pcm_in128(PcmInArgs a) {
-  __shared__ float tile[128][33];
-  const uint32_t f0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool is_prev = f0 < a.B;  // B is a multiple of 128: a tile never straddles the boundary
-  constexpr uint32_t bps = FmtBytes<FMT>::value;
-  if (!is_prev) {
-    // phase 1: lanes over channels (contiguous bytes within a frame)
-    float v[16];
-    const uint32_t c = c0 + lane;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const uint32_t frame = f0 + warp + 8 * i - a.B;
-      v[i] = (c < a.n_inputs) ? load_as_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.in_channels + c) * bps) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 16; i++) tile[warp + 8 * i][lane] = v[i];
-    __syncthreads();
-  }
-  // phase 2: lanes over frames (contiguous floats of one planar row); thread: channels warp + {0, 8, 16, 24}, 4 x 32 frames
-  float o[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const uint32_t cl = warp + 8 * (i >> 2), c = c0 + cl, fl = (i & 3) * 32 + lane;
-    o[i] = 0.f;
-    if (c < a.n_inputs) o[i] = is_prev ? a.xin_prev[(uint64_t)c * a.xstride + a.prev_off + f0 + fl] : tile[fl][cl];
-  }
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const uint32_t cl = warp + 8 * (i >> 2), c = c0 + cl, fl = (i & 3) * 32 + lane;
-    if (c < a.n_inputs) a.xin_cur[(uint64_t)c * a.xstride + f0 + fl] = o[i];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_rfft : windows of 2B floats -> packed spectra
-// ------------------------------------------------------------------------------------------
-template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
-k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, float2* __restrict__ dst, uint64_t dst_ch_stride,
-       uint32_t R, uint32_t slot0, const float2* __restrict__ tw, float scale, uint32_t nch) {
-  constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
-  __shared__ float2 smem[FPB][MP];
-  float2* s = smem[threadIdx.y];
-  const int tid = threadIdx.x;
-  const uint32_t chq = blockIdx.x * FPB + threadIdx.y, t = blockIdx.y;
-  const bool active = chq < nch;
-  const uint32_t ch = active ? chq : nch - 1;  // idle transforms of the last CTA recompute a valid one, stores masked
-  const float2* win = reinterpret_cast<const float2*>(src + ch * ch_stride + (uint64_t)t * win_stride);
-#pragma unroll
-  for (int h = 0; h < RAD; h++) s[PAD(tid + h * NT)] = win[tid + h * NT];
-  __syncthreads();
-  cfft_smem<M, false>(s, tw, tid);
-  const uint32_t slot = (slot0 + t) % R;
-  rfft_split_store<M>(s, tw, dst + ch * dst_ch_stride + (uint64_t)slot * M, scale, tid, active);
-}
-
-// Radix-8 sizes: persistent CTAs loop over (channel group, block) items with their twiddles in registers, the next
-// item's window prefetched into registers, the first pass straight from those registers, and (for M = 512) one named
-// barrier per transform instead of the block barrier.
-template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
-k_rfft8(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, float2* __restrict__ dst, uint64_t dst_ch_stride,
-        uint32_t R, uint32_t slot0, const float2* __restrict__ tw, float scale, uint32_t nch, uint32_t T) {
-  constexpr int NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
-  __shared__ float2 smem[FPB][MP];
-  float2* s = smem[threadIdx.y];
-  const int tid = threadIdx.x;
-  Tw8<M> tw8;
-  load_tw8<M>(tw8, tw, tid);
-  const uint32_t nchg = ceil_div_dev(nch, (uint32_t)FPB), nitems = nchg * T;
-  auto window = [&](uint32_t item, uint32_t& ch, uint32_t& t, bool& active) {
-    t = item / nchg;
-    const uint32_t chq = (item - t * nchg) * FPB + threadIdx.y;
-    active = chq < nch;
-    ch = active ? chq : nch - 1;  // idle transforms of a last group recompute a valid one, stores masked
-    return reinterpret_cast<const float2*>(src + ch * ch_stride + (uint64_t)t * win_stride);
-  };
-  uint32_t item = blockIdx.x, ch = 0, t = 0;
-  bool active = false;
-  float2 vn[8];
-  if (item < nitems) {
-    const float2* win = window(item, ch, t, active);
-#pragma unroll
-    for (int r = 0; r < 8; r++) vn[r] = win[tid + r * NT];
-  }
-  for (; item < nitems; item += gridDim.x) {
-    float2 v[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = vn[r];
-    const uint32_t ch_c = ch, t_c = t;
-    const bool active_c = active;
-    if (item + gridDim.x < nitems) {
-      const float2* win = window(item + gridDim.x, ch, t, active);
-#pragma unroll
-      for (int r = 0; r < 8; r++) vn[r] = win[tid + r * NT];
-    }
-    fft_bar<M>();  // the previous item's split stage is done with the workspace
-    pass8_first<M, false>(v, s, tid);
-    passes8_rest<M, false>(s, tw8, tid);
-    const uint32_t slot = (slot0 + t_c) % R;
-    rfft_split_store8<M>(s, tw8, dst + ch_c * dst_ch_stride + (uint64_t)slot * M, scale, tid, active_c);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_fdl_mac : the hot kernel
-// ------------------------------------------------------------------------------------------
-struct MacSeg {
-  const float4* H;    // filter spectra, row 0 (row stride = B/2 float4)
-  uint32_t fdl_ch;    // input channel whose FDL this term reads
-  uint32_t p0, np;    // partition range of this segment
-  uint32_t slot;      // partial-sum slot the run is written to
-  uint32_t flags;     // bit0: reset accumulator before, bit1: write accumulator after
-  uint32_t pad;
-};
-static_assert(sizeof(MacSeg) == 32, "MacSeg layout");
-
-__device__ __forceinline__ float4 ld_stream(const float4* p) {
-  // read-once data: bypass L1 allocation
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float4 ld_policy(const float4* p, uint64_t pol) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ float2 ld_stream2(const float2* p) {
-  float2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-}
-
-// One complex multiply-accumulate acc += h * x: four FMAs in a fixed order (every MAC kernel uses exactly this
-// sequence per output, so their results are bit-identical):
-//   re = fma(hr, xr, re); re = fma(-hi, xi, re); im = fma(hi, xr, im); im = fma(hr, xi, im)
-//
-// Bin 0 of a packed row holds (DC, Nyquist), two REAL spectra.  The MAC kernels do not special-case it: column 0
-// runs the generic complex MAC, whose real part is G = sum DCh DCx - sum Nqh Nqx, and the Nyquist sum
-// N = sum Nqh Nqx is accumulated separately (one extra FMA per row in the streaming kernel, k_nyq_mac next to the
-// time-batched kernel; same order, same fma).  k_irfft restores bin 0 = (G + N, N).  This keeps selects and
-// register-pair shuffles out of the hot loops (profiles/: ALU pipe 45 % -> see DESIGN.md).
-__device__ __forceinline__ void cmac(float& re, float& im, float hr, float hi, float xr, float xi) {
-  re = fmaf(hr, xr, re);
-  re = fmaf(-hi, xi, re);
-  im = fmaf(hi, xr, im);
-  im = fmaf(hr, xi, im);
-}
-
-// The same complex MAC as two packed FP32x2 FMAs (Blackwell FFMA2: one instruction, two lanes):
-//   (re, im) += (hr, hi) * xr ;  (re, im) += (-hi, hr) * xi
-// ptxas folds the scalar broadcast and the swapped / negated pair into FFMA2 operand modifiers, so no extra
-// registers or moves are needed.  Each lane is an IEEE fma: bit-identical to cmac().
-__device__ __forceinline__ void cmac_x2(float2& acc, float2 h, float2 x) {
-  acc = __ffma2_rn(h, make_float2(x.x, x.x), acc);
-  acc = __ffma2_rn(make_float2(-h.y, h.x), make_float2(x.y, x.y), acc);
-}
-
-// ---- streaming form: one launch covers nt block-steps, every step re-streams H and the FDL ----
-template <int U, int THREADS, int OCC, bool POLICY>
-__global__ void __launch_bounds__(THREADS, OCC)
-k_fdl_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float4* __restrict__ fdl,
-          float4* __restrict__ ypart, float* __restrict__ nyq_part, uint32_t halfB, uint32_t R, uint32_t head0,
-          uint32_t t0, uint32_t slot_stride, float l2_keep, int policy_x) {
-  const uint32_t t = t0 + blockIdx.z;
-  const uint32_t head = (head0 + t) % R;
-  const uint32_t col = blockIdx.y * THREADS + threadIdx.x;
-  const uint32_t sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
-  uint64_t pol = 0;
-  if (POLICY) {
-    // keep a fixed fraction of the lines resident in L2 across block-steps (the same H / FDL addresses are
-    // re-read every step), stream the rest with evict-first so they do not displace the resident set
-    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(l2_keep));
-  }
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float nacc = 0.f;  // Nyquist sum of the row's first slot; only column 0's copy is meaningful
-  for (uint32_t si = sb; si < se; si++) {
-    const MacSeg sg = segs[si];
-    if (sg.flags & 1u) {
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      nacc = 0.f;
-    }
-    const float4* hp = sg.H + (uint64_t)sg.p0 * halfB + col;
-    const float4* xbase = fdl + (uint64_t)sg.fdl_ch * R * halfB + col;
-    int slot = (int)head - (int)sg.p0;  // p0 < R
-    if (slot < 0) slot += (int)R;
-    // U rows per iteration, all 2U loads issued before the first FMA; rows past the end of a short segment are
-    // predicated off and contribute h = x = 0 (acc += 0 exactly), so short filters keep their loads in flight
-    for (uint32_t p = 0; p < sg.np; p += U) {
-      float4 h[U], x[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        int s = slot - u;
-        s += (s >> 31) & (int)R;  // ring wrap, once per row
-        h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p + u < sg.np) {
-          if (POLICY) {
-            h[u] = ld_policy(hp + (uint64_t)u * halfB, pol);
-            x[u] = policy_x ? ld_policy(xbase + (uint64_t)s * halfB, pol) : __ldg(xbase + (uint64_t)s * halfB);
-          } else {
-            h[u] = ld_stream(hp + (uint64_t)u * halfB);
-            x[u] = __ldg(xbase + (uint64_t)s * halfB);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        cmac(acc.x, acc.y, h[u].x, h[u].y, x[u].x, x[u].y);
-        cmac(acc.z, acc.w, h[u].z, h[u].w, x[u].z, x[u].w);
-        nacc = fmaf(h[u].y, x[u].y, nacc);
-      }
-      hp += (uint64_t)U * halfB;
-      slot -= U;
-      if (slot < 0) slot += (int)R;
-    }
-    if (sg.flags & 2u) {
-      ypart[((uint64_t)blockIdx.z * slot_stride + sg.slot) * halfB + col] = acc;
-      if (col == 0) nyq_part[(uint64_t)blockIdx.z * slot_stride + sg.slot] = nacc;
-    }
-  }
-}
-
-// ---- time-batched form: one CTA produces TT consecutive block-steps of its row range at once ----
-// Y_t[k] = sum_p H[p][k] X[s_t - p][k] for t = t_base .. t_base+TT-1 is a length-P FIR along the block axis:
-// H[p] is loaded once and applied to TT outputs, and the TT FDL rows it meets slide by one row per
-// partition, so the rows live in a register window rotated by static indexing (the p loop is unrolled TT
-// times).  Per partition a thread loads one complex of H and one of the FDL and issues 4*TT FMAs
-// (8 FMA per byte at TT = 32): the MAC becomes FP32-bound instead of HBM-bound.  Same plan, same per-output
-// FMA order as k_fdl_mac, hence bit-identical results.
-__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* gptr) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// Operands are staged through shared memory with cp.async: every thread copies the H and FDL values of its own
-// column NST-1 partitions ahead and reads them back itself (no block barrier), and cp.async.wait_group gives
-// the "at most N groups pending" wait that register-target loads cannot express (their scoreboards only count to
-// zero, which collapses a deep software pipeline to a depth of one; see profiles/r01 notes in DESIGN.md).
-template <int TT, int THREADS, int NST>
-__global__ void __launch_bounds__(THREADS, (TT <= 16) ? 2 : 1)
-k_fdl_mac_tb(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float2* __restrict__ fdl,
-             float2* __restrict__ ypart, uint32_t B, uint32_t R, uint32_t head0, uint32_t t0, uint32_t nt,
-             uint32_t ncoltiles, uint32_t slot_stride) {
-  static_assert(TT % NST == 0, "stage count must divide the tile so that stage indices are static");
-  __shared__ float2 stage[NST][2][THREADS];
-  // blockIdx.x enumerates (column tile, t tile) so the CTAs that share H / FDL rows run in the same wave
-  const uint32_t coltile = blockIdx.x % ncoltiles, ttile = blockIdx.x / ncoltiles;
-  const uint32_t tbase = ttile * TT;                  // first block-step of this tile, relative to t0
-  const uint32_t s0 = (head0 + t0 + tbase) % R;       // its FDL slot
-  const uint32_t col = coltile * THREADS + threadIdx.x;
-  const uint32_t sb = cta_seg_begin[blockIdx.y], se = cta_seg_begin[blockIdx.y + 1];
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&stage[0][0][threadIdx.x]);
-  constexpr uint32_t kStageBytes = 2 * THREADS * sizeof(float2);
-  constexpr uint32_t kXOff = THREADS * sizeof(float2);
-  const uint32_t row_bytes = B * (uint32_t)sizeof(float2);
-  float2 acc[TT];
-#pragma unroll
-  for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
-  for (uint32_t si = sb; si < se; si++) {
-    const MacSeg sg = segs[si];
-    if (sg.flags & 1u) {
-#pragma unroll
-      for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
-    }
-    // byte pointers: one 32x32+64 multiply-add per address
-    const char* hp = reinterpret_cast<const char*>(reinterpret_cast<const float2*>(sg.H) + (uint64_t)sg.p0 * B + col);
-    const char* xb = reinterpret_cast<const char*>(fdl + (uint64_t)sg.fdl_ch * R * B + col);
-    // FDL row met by output i at segment step q: base + i - q (mod R), base = s0 - p0
-    uint32_t base = s0 + R - (sg.p0 % R);
-    if (base >= R) base -= R;
-    uint32_t prow = base;  // FDL row of the next step to be staged
-    // stage the first NST-1 steps (one commit group per step, empty past the end so the count stays uniform)
-#pragma unroll
-    for (int j = 0; j < NST - 1; j++) {
-      if ((uint32_t)j < sg.np) {
-        cp_async8(sbase + j * kStageBytes, hp + (uint64_t)j * row_bytes);
-        cp_async8(sbase + j * kStageBytes + kXOff, xb + (uint64_t)prow * row_bytes);
-        prow = prow ? prow - 1 : R - 1;
-      }
-      cp_async_commit();
-    }
-    float2 W[TT];  // W[e mod TT] = row base + e, e = i - q
-#pragma unroll
-    for (int e = 1; e < TT; e++) {
-      uint32_t r = base + e;
-      if (r >= R) r -= R;
-      W[e] = __ldg(reinterpret_cast<const float2*>(xb + (uint64_t)r * row_bytes));
-    }
-    W[0] = make_float2(0.f, 0.f);
-    uint32_t qb = 0;
-    // fast path: whole groups of TT steps whose look-ahead stays inside the segment, no per-step checks
-    for (; qb + TT + NST - 1 <= sg.np; qb += TT) {
-#pragma unroll
-      for (int u = 0; u < TT; u++) {
-        const uint32_t qn = qb + u + NST - 1;
-        const int sn = (u + NST - 1) % NST;
-        cp_async8(sbase + sn * kStageBytes, hp + (uint64_t)qn * row_bytes);
-        cp_async8(sbase + sn * kStageBytes + kXOff, xb + (uint64_t)prow * row_bytes);
-        prow = prow ? prow - 1 : R - 1;
-        cp_async_commit();
-        cp_async_wait<NST - 1>();  // step qb + u has landed
-        const float2 h = stage[u % NST][0][threadIdx.x];
-        W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
-#pragma unroll
-        for (int i = 0; i < TT; i++) cmac_x2(acc[i], h, W[(i - u + TT) % TT]);
-      }
-    }
-    // tail: same steps with bound checks
-    for (; qb < sg.np; qb += TT) {
-#pragma unroll
-      for (int u = 0; u < TT; u++) {
-        const uint32_t q = qb + u;
-        if (q < sg.np) {
-          const uint32_t qn = q + NST - 1;
-          const int sn = (u + NST - 1) % NST;
-          if (qn < sg.np) {
-            cp_async8(sbase + sn * kStageBytes, hp + (uint64_t)qn * row_bytes);
-            cp_async8(sbase + sn * kStageBytes + kXOff, xb + (uint64_t)prow * row_bytes);
-            prow = prow ? prow - 1 : R - 1;
-          }
-          cp_async_commit();
-          cp_async_wait<NST - 1>();
-          const float2 h = stage[u % NST][0][threadIdx.x];
-          W[(TT - u) % TT] = stage[u % NST][1][threadIdx.x];
-#pragma unroll
-          for (int i = 0; i < TT; i++) cmac_x2(acc[i], h, W[(i - u + TT) % TT]);
-        }
-      }
-    }
-    cp_async_wait<0>();
-    if (sg.flags & 2u) {
-#pragma unroll
-      for (int i = 0; i < TT; i++)
-        if (tbase + i < nt) ypart[((uint64_t)(tbase + i) * slot_stride + sg.slot) * B + col] = acc[i];
-    }
-  }
-}
-
-// Nyquist sums next to the time-batched MAC: N[t][run] = sum over the run's rows of Nqh[p] * Nqx[s_t - p] (the
-// imaginary parts of column 0), p ascending, one fma per row -- the same sequence the streaming kernel runs inline.
-// One warp per (row range, tile of 32 block-steps), lane = block-step.
-__global__ void __launch_bounds__(32)
-k_nyq_mac(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, const float2* __restrict__ fdl,
-          float* __restrict__ nyq_part, uint32_t B, uint32_t R, uint32_t head0, uint32_t t0, uint32_t nt, uint32_t slot_stride) {
-  const uint32_t tq = blockIdx.y * 32 + threadIdx.x;
-  const bool active = tq < nt;
-  const uint32_t t = active ? tq : nt - 1;
-  const uint32_t s_t = (head0 + t0 + t) % R;
-  const uint32_t sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
-  float acc = 0.f;
-  for (uint32_t si = sb; si < se; si++) {
-    const MacSeg sg = segs[si];
-    if (sg.flags & 1u) acc = 0.f;
-    const float2* hcol = reinterpret_cast<const float2*>(sg.H) + (uint64_t)sg.p0 * B;
-    const float2* xb = fdl + (uint64_t)sg.fdl_ch * R * B;
-    uint32_t row = s_t + R - (sg.p0 % R);
-    if (row >= R) row -= R;
-#pragma unroll 16
-    for (uint32_t p = 0; p < sg.np; p++) {
-      const float h = __ldg(&hcol[(uint64_t)p * B]).y;
-      const float x = __ldg(&xb[(uint64_t)row * B]).y;
-      acc = fmaf(h, x, acc);
-      row = row ? row - 1 : R - 1;
-    }
-    if ((sg.flags & 2u) && active) nyq_part[(uint64_t)t * slot_stride + sg.slot] = acc;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_irfft : partial sums -> time domain -> crossfade -> delay ring
-// ------------------------------------------------------------------------------------------
-struct PlanView {
-  const uint32_t* job_slot_first;
-  const uint32_t* job_slot_count;
-  const uint32_t* xjob;  // per stream: extra job to crossfade into, kNoJob, or kSameJob
-};
-
-template <int M>
-__device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t, const float* __restrict__ nyq_t, uint64_t s_stride,
-                                             uint32_t first, uint32_t count, float2* __restrict__ x,
-                                             float2* __restrict__ s, const float2* __restrict__ tw, int tid,
-                                             float (&o)[FftCfg<M>::R]) {
-  constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT;
-#pragma unroll
-  for (int h = 0; h < RAD; h++) {
-    const int k = tid + h * NT;
-    float2 a = make_float2(0.f, 0.f);
-    // fixed slot order (deterministic sums); four loads in flight per step
-    for (uint32_t sl = 0; sl < count; sl += 4) {
-      float2 v[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        v[q] = (sl + q < count) ? ypart_t[(uint64_t)(first + sl + q) * s_stride + k] : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (sl + q < count) {
-          a.x += v[q].x;
-          a.y += v[q].y;
-        }
-    }
-    if (k == 0 && nyq_t) {
-      // bin 0: the MAC kernels left G = DC - N in the real part; add the Nyquist sum back (same slot order)
-      // (nyq_t == NULL: the tensor-core MIMO path writes bin 0 = (DC, Nyquist) directly)
-      float n = 0.f;
-      for (uint32_t sl = 0; sl < count; sl++) n += nyq_t[first + sl];
-      a = make_float2(a.x + n, n);
-    }
-    x[k] = a;
-  }
-  __syncthreads();
-  irfft_unsplit<M>(x, tw, s, tid);
-  __syncthreads();
-  cfft_smem<M, true>(s, tw, tid);
-  // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(tid + h NT) + {0,1}, h < R/2
-#pragma unroll
-  for (int h = 0; h < RAD / 2; h++) {
-    float2 z = s[PAD(M / 2 + tid + h * NT)];
-    o[2 * h] = z.x;
-    o[2 * h + 1] = z.y;
-  }
-  __syncthreads();
-}
-
-template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
-k_irfft(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
-        const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
-        const float* __restrict__ nyq_part, uint64_t t_stride, uint64_t s_stride, uint32_t stream0) {
-  // spectrum of (block t, slot s) at ypart + t * t_stride + s * s_stride (the MAC kernels: t_stride = slot_stride * M,
-  // s_stride = M; after the sharded reduce-scatter: [slot][t][M]); streams stream0 .. stream0 + n_streams - 1
-  constexpr int RAD = FftCfg<M>::R, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
-  extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
-  float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
-  float2* s = x + M;
-  const int tid = threadIdx.x;
-  const uint32_t sq = blockIdx.x * FPB + threadIdx.y, t = blockIdx.y;
-  const bool active = sq < n_streams;
-  const uint32_t stream = stream0 + (active ? sq : n_streams - 1);
-  const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
-  const PlanView pv = first ? first_blk : steady;
-  const float2* ypart_t = ypart + (uint64_t)t * t_stride;
-  const float* nyq_t = nyq_part ? nyq_part + (uint64_t)t * slot_stride : nullptr;
-  float o[RAD];
-  job_to_block<M>(ypart_t, nyq_t, s_stride, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw, tid, o);
-  // the crossfade decision must be uniform across the CTA (block-wide barriers inside job_to_block):
-  // every transform of the CTA runs the second pass when any of them needs it
-  const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
-  const int any_x = __syncthreads_or(xj != kNoJob && xj != kSameJob);
-  float o2[RAD];
-  if (any_x) {
-    const bool mine = (xj != kNoJob && xj != kSameJob);
-    job_to_block<M>(ypart_t, nyq_t, s_stride, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw, tid, o2);
-  }
-  if (xj != kNoJob) {
-    if (xj == kSameJob) {
-#pragma unroll
-      for (int i = 0; i < RAD; i++) o2[i] = o[i];
-    }
-    // out = (1-g) o_f + g o_f', g_n = n/B  (MixSamples + Interpolator ramp, sampled before the step)
-    const float inc = 1.0f / (float)M;
-#pragma unroll
-    for (int h = 0; h < RAD / 2; h++)
-#pragma unroll
-      for (int c = 0; c < 2; c++) {
-        const uint32_t n = 2 * (tid + h * NT) + c;
-        const float g = __fmul_rn((float)n, inc);
-        const float a = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
-        const float b = __fmul_rn(g, o2[2 * h + c]);
-        o[2 * h + c] = __fadd_rn(a, b);
-      }
-  }
-  if (!active) return;
-  float* ring = ybuf + (uint64_t)stream * Rd;
-  const uint32_t w = (wpos0 + t * (uint32_t)M) % Rd;
-#pragma unroll
-  for (int h = 0; h < RAD / 2; h++)
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const uint32_t n = 2 * (tid + h * NT) + c;
-      uint32_t idx = w + n;
-      if (idx >= Rd) idx -= Rd;
-      ring[idx] = o[2 * h + c];
-    }
-}
-
-// Radix-8 sizes: same contract as job_to_block, with cached twiddles, all of a slot's partial loads in flight at once,
-// the inverse split and the first pass in registers, per-transform barriers.
-template <int M>
-__device__ __forceinline__ void job_to_block8(const float2* __restrict__ ypart_t, const float* __restrict__ nyq_t, uint64_t s_stride,
-                                              uint32_t first, uint32_t count, float2* __restrict__ x, float2* __restrict__ s,
-                                              const Tw8<M>& tw8, int tid, float (&o)[8]) {
-  constexpr int NT = M / 8;
-  float2 a[8];
-#pragma unroll
-  for (int h = 0; h < 8; h++) a[h] = make_float2(0.f, 0.f);
-  for (uint32_t sl = 0; sl < count; sl++) {  // fixed slot order (deterministic sums)
-    const float2* row = ypart_t + (uint64_t)(first + sl) * s_stride;
-    float2 v[8];
-#pragma unroll
-    for (int h = 0; h < 8; h++) v[h] = row[tid + h * NT];
-#pragma unroll
-    for (int h = 0; h < 8; h++) {
-      a[h].x += v[h].x;
-      a[h].y += v[h].y;
-    }
-  }
-  if (tid == 0 && nyq_t) {
-    // bin 0: the MAC kernels left G = DC - N in the real part; add the Nyquist sum back (same slot order)
-    float n = 0.f;
-    for (uint32_t sl = 0; sl < count; sl++) n += nyq_t[first + sl];
-    a[0] = make_float2(a[0].x + n, n);
-  }
-#pragma unroll
-  for (int h = 0; h < 8; h++) x[tid + h * NT] = a[h];
-  fft_bar<M>();  // x complete; also: every thread of the transform is past its reads of s from the previous job
-  float2 v[8];
-  irfft_unsplit8<M>(x, tw8, v, tid);
-  pass8_first<M, true>(v, s, tid);
-  passes8_rest<M, true>(s, tw8, tid);
-  // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(tid + h NT) + {0,1}, h < 4
-#pragma unroll
-  for (int h = 0; h < 4; h++) {
-    float2 z = s[PAD(M / 2 + tid + h * NT)];
-    o[2 * h] = z.x;
-    o[2 * h + 1] = z.y;
-  }
-}
-
-template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
-k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
-         const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
-         const float* __restrict__ nyq_part, uint64_t t_stride, uint64_t s_stride, uint32_t stream0, uint32_t T) {
-  constexpr int RAD = 8, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
-  extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
-  float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
-  float2* s = x + M;
-  const int tid = threadIdx.x;
-  Tw8<M> tw8;
-  load_tw8<M>(tw8, tw, tid);
-  const uint32_t nsg = ceil_div_dev(n_streams, (uint32_t)FPB), nitems = nsg * T;
-  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const uint32_t t = item / nsg, sq = (item - t * nsg) * FPB + threadIdx.y;
-    const bool active = sq < n_streams;
-    const uint32_t stream = stream0 + (active ? sq : n_streams - 1);
-    const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
-    const PlanView pv = first ? first_blk : steady;
-    const float2* ypart_t = ypart + (uint64_t)t * t_stride;
-    const float* nyq_t = nyq_part ? nyq_part + (uint64_t)t * slot_stride : nullptr;
-    float o[RAD];
-    job_to_block8<M>(ypart_t, nyq_t, s_stride, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw8, tid, o);
-    const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
-    // the barriers inside job_to_block8 span one transform (M = 512) or the CTA: the decision to run the second
-    // pass is made CTA-uniform so that both cases are safe
-    const int any_x = __syncthreads_or(xj != kNoJob && xj != kSameJob);
-    float o2[RAD];
-    if (any_x) {
-      const bool mine = (xj != kNoJob && xj != kSameJob);
-      job_to_block8<M>(ypart_t, nyq_t, s_stride, mine ? pv.job_slot_first[xj] : 0u, mine ? pv.job_slot_count[xj] : 0u, x, s, tw8,
-                       tid, o2);
-    }
-    if (xj != kNoJob) {
-      if (xj == kSameJob) {
-#pragma unroll
-        for (int i = 0; i < RAD; i++) o2[i] = o[i];
-      }
-      // out = (1-g) o_f + g o_f', g_n = n/B  (MixSamples + Interpolator ramp, sampled before the step)
-      const float inc = 1.0f / (float)M;
-#pragma unroll
-      for (int h = 0; h < RAD / 2; h++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const uint32_t n = 2 * (tid + h * NT) + c;
-          const float g = __fmul_rn((float)n, inc);
-          const float a = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
-          const float b = __fmul_rn(g, o2[2 * h + c]);
-          o[2 * h + c] = __fadd_rn(a, b);
-        }
-    }
-    if (active) {
-      float* ring = ybuf + (uint64_t)stream * Rd;
-      const uint32_t w = (wpos0 + t * (uint32_t)M) % Rd;
-#pragma unroll
-      for (int h = 0; h < RAD / 2; h++) {
-        const uint32_t n = 2 * (tid + h * NT);
-        uint32_t idx = w + n;  // w and n are even, Rd is a multiple of the block size: the pair never straddles the wrap
-        if (idx >= Rd) idx -= Rd;
-        if ((Rd & 1u) == 0 && (w & 1u) == 0) {
-          *reinterpret_cast<float2*>(ring + idx) = make_float2(o[2 * h], o[2 * h + 1]);
-        } else {
-          ring[idx] = o[2 * h];
-          uint32_t i1 = idx + 1;
-          if (i1 >= Rd) i1 -= Rd;
-          ring[i1] = o[2 * h + 1];
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_pcm_out : delay read + mixdown + format conversion
-// ------------------------------------------------------------------------------------------
-// one routed path in mixdown order (ascending stream per output == MixSamples call order), everything k_pcm_out
-// needs about it in one place
-struct RouteEntry {
-  uint32_t stream;  // delay ring of the path
-  float gain;
-  uint32_t icur, iold;  // (uint32)delay mod Rd for the integer-delay mode: in force after / before this call's first block boundary
-  uint32_t flags;       // bit0: crossfade old->cur over the first block
-  uint32_t pad;
-  double dcur, dold;    // the same delays in samples (fractional mode)
-};
-static_assert(sizeof(RouteEntry) == 40, "RouteEntry layout");
-
-struct RouteView {
-  const uint32_t* out_first;  // [n_outputs+1] CSR over outputs
-  const RouteEntry* entry;    // per route
-};
-
-struct PcmOutArgs {
-  uint8_t* pcm;
-  int fmt;
-  int be;
-  uint32_t out_channels, n_outputs;
-  uint32_t B, T;
-  const float* ybuf;
-  uint32_t Rd, wpos0;
-  int fractional;
-  int fast;  // typed stores (see PcmInArgs::fast)
-  RouteView rv;
-};
-
-__device__ __forceinline__ float delayed_read(const float* __restrict__ ring, uint32_t Rd, uint32_t w, uint32_t n, double d,
-                                              uint32_t di, int fractional) {
-  if (fractional) {
-    // FractionalSample(ring, 0, 1, Rd, fmod((w + n + Rd) - d, Rd))   (src/FractionalSample.cpp:312-341)
-    const double pos = fmod((double)(w + n + Rd) - d, (double)Rd);
-    return __double2float_rn(fractional_sample_dev<float>(ring, 0, 1, Rd, pos));
-  }
-  // ring[(w + n - d) mod R] with d = (uint)delay mod R precomputed on the host   (src/SoundDelayBuffer.cpp:141)
-  uint32_t idx = w + n + Rd - di;  // w < Rd, n < B <= Rd, di < Rd  ->  idx < 3 Rd
-  if (idx >= Rd) idx -= Rd;
-  if (idx >= Rd) idx -= Rd;
-  return ring[idx];
-}
-
-static constexpr uint32_t kPcmOutCache = 64;  // routes of one 32-output tile kept in shared memory
-
-template <int FMT, int ACC>
-__global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
-  __shared__ float tile[32][33];
-  __shared__ uint32_t s_first[33];
-  __shared__ RouteEntry s_rt[kPcmOutCache];
-  const uint32_t f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t t = f0 / a.B;               // a tile lies inside one block (B % 32 == 0)
-  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
-  const float inc = 1.0f / (float)a.B;
-  // the tile's slice of the route tables -> shared memory (two dependent loads per CTA instead of a chain of table
-  // lookups per sample); tiles with more than kPcmOutCache routes read the entries from global memory
-  const uint32_t no = min(32u, a.n_outputs - c0);
-  if (threadIdx.x <= no) s_first[threadIdx.x] = a.rv.out_first[c0 + threadIdx.x];
-  __syncthreads();
-  const uint32_t r0 = s_first[0], nr = s_first[no] - r0;
-  const bool cached = nr <= kPcmOutCache;
-  if (cached && threadIdx.x < nr) s_rt[threadIdx.x] = a.rv.entry[r0 + threadIdx.x];
-  __syncthreads();
-  // phase 1: lanes over frames (ring reads are contiguous), one output channel per warp pass
-#pragma unroll 1
-  for (int i = 0; i < 4; i++) {
-    const uint32_t cl = warp + 8 * i, o = c0 + cl;
-    float bus = 0.f;
-    if (o < a.n_outputs) {
-      const uint32_t n = f0 + lane - t * a.B;  // frame inside the block
-      const uint32_t rb = s_first[cl], re = s_first[cl + 1];
-      for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
-        const RouteEntry en = cached ? s_rt[r - r0] : a.rv.entry[r];
-        if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
-        const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
-        float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
-        if (t == 0 && (en.flags & 1u)) {
-          const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
-          const float g = __fmul_rn((float)n, inc);
-          v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
-        }
-        bus = __fadd_rn(bus, __fmul_rn(en.gain, v));  // dst += mul * src, rounded separately
-      }
-    }
-    tile[lane][cl] = bus;
-  }
-  __syncthreads();
-  // phase 2: lanes over channels (contiguous bytes of one interleaved frame)
-  constexpr uint32_t bps = FmtBytes<FMT>::value;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const uint32_t fl = warp + 8 * i, o = c0 + lane;
-    if (o >= a.n_outputs) continue;
-    const uint32_t frame = f0 + fl;
-    store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, tile[fl][lane]);
-  }
-}
-
-// Mixdown of many paths into few outputs (the binaural renderer: 64 sources x 2 ears -> 2 outputs).  The kernel above
-// walks the routes of an output one after the other inside one thread: 64 dependent table + ring reads per sample, and
-// only n_outputs of its 32 channel slots do anything.  Here every thread of the CTA takes (route, frame) items: the
-// delayed reads, the delay crossfade and the products gain * v of ALL routes of a 32-frame tile are formed in parallel
-// into shared memory, then one thread per (output, frame) adds the products in ascending route order -- the same
-// dst += mul * src with separately rounded product and sum (src/SoundMixing.h:76-79), zero gains skipped, so the bytes are
-// those of k_pcm_out (tests: routed engines run both kernels' shapes against the oracle and each other).
-static constexpr uint32_t kMixMaxRoutes = 256;
-
-template <int FMT, int ACC>
-__global__ void __launch_bounds__(256) k_pcm_out_mix(PcmOutArgs a) {
-  __shared__ float prod[kMixMaxRoutes][32];
-  __shared__ RouteEntry s_rt[kMixMaxRoutes];
-  __shared__ uint32_t s_first[33];
-  const uint32_t f0 = blockIdx.x * 32;
-  const uint32_t t = f0 / a.B;  // a tile lies inside one block (B % 32 == 0)
-  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
-  const float inc = 1.0f / (float)a.B;
-  const uint32_t no = a.n_outputs;  // <= 32 (host)
-  if (threadIdx.x <= no) s_first[threadIdx.x] = a.rv.out_first[threadIdx.x];
-  __syncthreads();
-  const uint32_t r0 = s_first[0], nr = s_first[no] - r0;  // <= kMixMaxRoutes (host)
-  for (uint32_t r = threadIdx.x; r < nr; r += 256) s_rt[r] = a.rv.entry[r0 + r];
-  __syncthreads();
-  const uint32_t nb0 = f0 - t * a.B;  // frame of the tile's first sample inside its block
-  // stage 1: items (route, frame), four per thread and pass so that their ring reads are in flight together
-  for (uint32_t base = threadIdx.x; base < nr * 32; base += 4 * 256) {
-    float p[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t idx = base + 256 * k;
-      p[k] = 0.f;
-      if (idx < nr * 32) {
-        const uint32_t r = idx >> 5, n = nb0 + (idx & 31);
-        const RouteEntry en = s_rt[r];
-        if (en.gain != 0.0f) {
-          const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
-          float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
-          if (t == 0 && (en.flags & 1u)) {
-            const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
-            const float g = __fmul_rn((float)n, inc);
-            v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
-          }
-          p[k] = __fmul_rn(en.gain, v);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t idx = base + 256 * k;
-      if (idx < nr * 32) prod[idx >> 5][idx & 31] = p[k];
-    }
-  }
-  __syncthreads();
-  // stage 2: one thread per (output, frame): the ordered sum, then the sample in the output format
-  constexpr uint32_t bps = FmtBytes<FMT>::value;
-  for (uint32_t item = threadIdx.x; item < no * 32; item += 256) {
-    const uint32_t o = item >> 5, fl = item & 31;
-    float bus = 0.f;
-    for (uint32_t r = s_first[o] - r0; r < s_first[o + 1] - r0; r++)
-      if (s_rt[r].gain != 0.0f) bus = __fadd_rn(bus, prod[r][fl]);  // a zero gain is a no-op, not "+ 0"
-    store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, bus);
-  }
-}
-
-// 128-frame tiles (B % 128 == 0).  Outputs fed by exactly one path with an integer delay and no delay crossfade in this
-// block (every output of the PER_CHANNEL and MIMO modes in the steady state) issue their four ring reads together; the
-// arithmetic is the same dst += mul * src, rounded separately.
-template <int FMT, int ACC>
-__global__ void __launch_bounds__(256) k_pcm_out128(PcmOutArgs a) {
-  __shared__ float tile[128][33];
-  __shared__ uint32_t s_first[33];
-  __shared__ RouteEntry s_rt[kPcmOutCache];
-  const uint32_t f0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t t = f0 / a.B;               // a tile lies inside one block (B % 128 == 0)
-  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
-  const float inc = 1.0f / (float)a.B;
-  const uint32_t no = min(32u, a.n_outputs - c0);
-  if (threadIdx.x <= no) s_first[threadIdx.x] = a.rv.out_first[c0 + threadIdx.x];
-  __syncthreads();
-  const uint32_t r0 = s_first[0], nr = s_first[no] - r0;
-  const bool cached = nr <= kPcmOutCache;
-  if (cached && threadIdx.x < nr) s_rt[threadIdx.x] = a.rv.entry[r0 + threadIdx.x];
-  __syncthreads();
-  // phase 1: lanes over frames; thread: outputs warp + {0, 8, 16, 24}, 4 x 32 frames each
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const uint32_t cl = warp + 8 * q, o = c0 + cl;
-    float bus[4] = {0.f, 0.f, 0.f, 0.f};
-    if (o < a.n_outputs) {
-      const uint32_t rb = s_first[cl], re = s_first[cl + 1];
-      const uint32_t nb = f0 - t * a.B + lane;  // frame inside the block of the first of the four chunks
-      bool done = false;
-      if (re == rb + 1 && !a.fractional) {
-        const RouteEntry en = cached ? s_rt[rb - r0] : a.rv.entry[rb];
-        if (!(t == 0 && (en.flags & 1u))) {
-          done = true;
-          if (en.gain != 0.0f) {
-            const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = delayed_read(ring, a.Rd, w, nb + 32 * k, 0.0, en.icur, 0);
-#pragma unroll
-            for (int k = 0; k < 4; k++) bus[k] = __fadd_rn(0.f, __fmul_rn(en.gain, v[k]));
-          }
-        }
-      }
-      if (!done) {
-#pragma unroll 1
-        for (int k = 0; k < 4; k++) {
-          const uint32_t n = nb + 32 * k;
-          float b = 0.f;
-          for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
-            const RouteEntry en = cached ? s_rt[r - r0] : a.rv.entry[r];
-            if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
-            const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
-            float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
-            if (t == 0 && (en.flags & 1u)) {
-              const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
-              const float g = __fmul_rn((float)n, inc);
-              v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
-            }
-            b = __fadd_rn(b, __fmul_rn(en.gain, v));  // dst += mul * src, rounded separately
-          }
-          bus[k] = b;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) tile[32 * k + lane][cl] = bus[k];
-  }
-  __syncthreads();
-  // phase 2: lanes over channels (contiguous bytes of one interleaved frame)
-  constexpr uint32_t bps = FmtBytes<FMT>::value;
-  const uint32_t o = c0 + lane;
-  if (o < a.n_outputs) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const uint32_t fl = warp + 8 * i;
-      store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)(f0 + fl) * a.out_channels + o) * bps, tile[fl][lane]);
-    }
-  }
-}
-
-// FP32 roofline probe (measurement hook): nothing but packed FMAs on 16 float2 accumulators per thread, the operand
-// pattern of k_fdl_mac_tb's inner loop.  Its rate is the FP32 ceiling this GPU reaches under its power / clock limits
-// (the nominal 148 x 128 x 2 x 1965 MHz is not reachable: bench.py reports both).
-__global__ void __launch_bounds__(256) k_fp32_probe(float2* out, int iters, float2 h0, float2 x0) {
-  float2 acc[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
-  float2 h = h0, x = x0;
-  for (int it = 0; it < iters; it++) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) cmac_x2(acc[i], h, x);
-    h.x += 1e-7f;
-    x.y -= 1e-7f;
-  }
-  float2 s = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    s.x += acc[i].x;
-    s.y += acc[i].y;
-  }
-  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
 
 __global__ void k_flush(float4* p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_float4(1.f, 2.f, 3.f, 4.f);
 }
 
-// Input-sharded MIMO: this rank's partial output spectra, job by job (slots summed in fixed order, bin 0 restored to
-// (DC, Nyquist)), into the reduce-scatter send buffer [output][t][B] -- one contiguous chunk per destination rank.
-__global__ void __launch_bounds__(256) k_gather_spectra(const float2* __restrict__ ypart, const float* __restrict__ nyq_part,
-                                                        uint32_t slot_stride, PlanView pv, float2* __restrict__ send, uint32_t B,
-                                                        uint32_t T) {
-  const uint32_t o = blockIdx.x, t = blockIdx.y;
-  const uint32_t first = pv.job_slot_first[o], count = pv.job_slot_count[o];
-  const float2* yt = ypart + (uint64_t)t * slot_stride * B;
-  for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) {
-    float2 a = make_float2(0.f, 0.f);
-    for (uint32_t sl = 0; sl < count; sl++) {
-      const float2 v = yt[(uint64_t)(first + sl) * B + k];
-      a.x += v.x;
-      a.y += v.y;
-    }
-    if (k == 0 && nyq_part) {
-      float n = 0.f;
-      for (uint32_t sl = 0; sl < count; sl++) n += nyq_part[(uint64_t)t * slot_stride + first + sl];
-      a = make_float2(a.x + n, n);
-    }
-    send[((uint64_t)o * T + t) * B + k] = a;
-  }
-}
-
-// ---- peer-memory mixdown: the reduce of the input-sharded MIMO engine without a collective library ----------------------
-// Every rank adds its partial slots like k_gather_spectra, but stores the spectrum of output o straight into the memory of
-// the rank that owns o (NVLink peer stores into a buffer opened with cudaIpcOpenMemHandle), at slot (o_local, source rank).
-// The owner's inverse-transform kernel then adds the `world` slots of an output in rank order -- the same fixed-order slot
-// sum it already runs over the MAC's partial sums, so the result does not depend on a collective's reduction schedule.
-// Completion: the last CTA of a launch publishes the call's epoch in every peer's flag array after a system-scope fence;
-// k_peer_wait (one warp, in stream order before the inverse transforms) spins until all sources have published it.  The
-// receive buffer is double-buffered by epoch parity: a source can only be two calls ahead after it has seen this rank's
-// flag of the call in between, which this rank publishes after its own inverse transforms of the older call (stream order).
-struct PeerTable {
-  float2* data[16];     // receive buffers of the ranks (own rank: the local buffer)
-  uint32_t* flags[16];  // their flag arrays, [2][world]
-};
-
-__global__ void __launch_bounds__(256) k_gather_spectra_peer(const float2* __restrict__ ypart, const float* __restrict__ nyq_part,
-                                                             uint32_t slot_stride, PlanView pv, PeerTable pt, uint32_t world,
-                                                             uint32_t rank, uint32_t nloc, uint32_t B, uint32_t T, uint64_t half,
-                                                             uint32_t parity, uint32_t epoch, uint32_t* __restrict__ done) {
-  const uint32_t o = blockIdx.x, t = blockIdx.y;
-  const uint32_t first = pv.job_slot_first[o], count = pv.job_slot_count[o];
-  const float2* yt = ypart + (uint64_t)t * slot_stride * B;
-  const uint32_t r = o / nloc, ol = o - r * nloc;
-  float2* dst = pt.data[r] + (uint64_t)parity * half + (((uint64_t)ol * world + rank) * T + t) * B;
-  for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) {
-    float2 a = make_float2(0.f, 0.f);
-    for (uint32_t sl = 0; sl < count; sl++) {
-      const float2 v = yt[(uint64_t)(first + sl) * B + k];
-      a.x += v.x;
-      a.y += v.y;
-    }
-    if (k == 0 && nyq_part) {
-      float n = 0.f;
-      for (uint32_t sl = 0; sl < count; sl++) n += nyq_part[(uint64_t)t * slot_stride + first + sl];
-      a = make_float2(a.x + n, n);
-    }
-    dst[k] = a;
-  }
-  __threadfence_system();  // this thread's peer stores are performed before the CTA counts itself done
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t total = gridDim.x * gridDim.y;
-    if (atomicAdd(done, 1u) == total - 1) {
-      *done = 0;  // ready for the next launch (stream-ordered)
-      __threadfence_system();
-      for (uint32_t q = 0; q < world; q++) *((volatile uint32_t*)pt.flags[q] + parity * world + rank) = epoch;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(32) k_peer_wait(const uint32_t* flags, uint32_t world, uint32_t parity, uint32_t epoch,
-                                                  int* status) {
-  if (threadIdx.x < world) {
-    const volatile uint32_t* f = flags + parity * world + threadIdx.x;
-    const long long t0 = clock64();
-    while ((int32_t)(*f - epoch) < 0) {
-      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a source never arrived; bbx_engine_sync reports it
-        *status = 1 + (int)threadIdx.x;
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
-  __threadfence_system();
-}
-
-// comm.cu
 int comm_reduce_scatter_f32(bbx_comm* c, const float* send, float* recv, size_t recvcount, cudaStream_t st);
 int comm_world(const bbx_comm* c);
 int comm_rank(const bbx_comm* c);
@@ -1551,7 +529,6 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
     for (uint32_t j = 0; j < jobs.size(); j++) {
       jfirst[j] = nslot;
       uint32_t before = nslot;
-      bool job_has_run = false;
       for (auto& tm : jobs[j]) {
         if (!tm.f) continue;
         uint32_t p = 0;
@@ -1581,14 +558,12 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
             sg.flags = 1u | 2u;
             sg.slot = nslot++;
             run_job = (int)j;
-            job_has_run = true;
           }
           nseg++;
           p += np;
           row += np;
         }
       }
-      (void)job_has_run;
       jcount[j] = nslot - before;
     }
     for (uint32_t c = cur_cta + 1; c <= G; c++) cta[c] = nseg;
@@ -2205,10 +1180,9 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   e->last_outfmt = outfmt;
 
   // ---- latch pending switches: they apply at this call's first block boundary ----
-  bool any_pending = false, any_xfade = false;
+  bool any_xfade = false;
   for (auto& p : e->paths)
     if (p.has_pending) {
-      any_pending = true;
       if (p.xfade) any_xfade = true;
       else {  // hard switch: filter and delay jump now
         if (p.cur != p.pend) e->steady_dirty = true;
@@ -2275,10 +1249,10 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     if ((rc = upload_routes(e, false))) return rc;
     e->route_dirty = false;
   }
-  (void)any_pending;
   if (e->steady_dirty || !e->plan_steady.valid) {
     make_jobs(e, false, jobs);
-    if ((rc = build_plan(e, e->plan_steady, jobs, std::vector<uint32_t>()))) return rc;
+    rc = build_plan(e, e->plan_steady, jobs, std::vector<uint32_t>());
+    if (rc) return rc;
     e->steady_dirty = false;
     e->tc_dirty = true;
   }
