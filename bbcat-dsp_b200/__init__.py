@@ -91,6 +91,7 @@ SYMBOLS = {
     "bbx_filter_create": (C.c_int, [vp, vp, u32, C.POINTER(vp)]),
     "bbx_filter_destroy": (C.c_int, [vp]),
     "bbx_filter_partitions": (u32, [vp]),
+    "bbx_filter_read_spectra": (C.c_int, [vp, vp, C.c_size_t]),
     "bbx_set_route": (C.c_int, [vp, u32, u32, u32, C.c_float]),
     "bbx_set_filter": (C.c_int, [vp, u32, vp, C.c_int, C.c_double]),
     "bbx_process": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
@@ -480,6 +481,12 @@ class Filter:
         self.h = h
         self.engine = engine
         self.partitions = lib().bbx_filter_partitions(h)
+
+    def Spectra(self):
+        """complex64 [partitions][B]: R2C_2B of each zero-padded partition / 2B, bin 0 = (DC, Nyquist)."""
+        out = np.zeros((self.partitions, self.engine.block_size, 2), dtype=np.float32)
+        _check(lib().bbx_filter_read_spectra(self.h, _p(out), out.size))
+        return out.view(np.complex64)[..., 0]
 
     def close(self):
         if getattr(self, "h", None) and getattr(self.engine, "h", None):

@@ -1103,6 +1103,15 @@ int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filte
   return BBX_OK;
 }
 
+int bbx_filter_read_spectra(const bbx_filter* f, float* out, size_t max_floats) {
+  BBX_REQUIRE(f && out, "bbx_filter_read_spectra: null argument");
+  const size_t n = (size_t)f->P * f->engine->B * 2;
+  BBX_REQUIRE(max_floats >= n, "bbx_filter_read_spectra: %zu floats needed, %zu given", n, max_floats);
+  BBX_CUDA_TRY(cudaSetDevice(f->engine->device));
+  BBX_CUDA_TRY(cudaMemcpy(out, f->H, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return BBX_OK;
+}
+
 int bbx_filter_destroy(bbx_filter* f) {
   if (!f) return BBX_OK;
   cudaSetDevice(f->engine->device);

@@ -211,6 +211,9 @@ void* bbx_engine_get_stream(const bbx_engine* e);
 int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filter** out);
 int bbx_filter_destroy(bbx_filter* f);
 uint32_t bbx_filter_partitions(const bbx_filter* f);
+/* the filter object's spectra as the MAC kernels read them: [partitions][B] interleaved complex fp32, partition p =
+ * R2C_2B([h[pB .. pB+B-1], 0^B]) / 2B with bin 0 holding (DC, Nyquist) (both real); for inspection and the FFT unit tests */
+int bbx_filter_read_spectra(const bbx_filter* f, float* out, size_t max_floats);
 
 /* ROUTED mode: connect path -> (input, output, gain).  Takes effect at the next bbx_process. */
 int bbx_set_route(bbx_engine* e, uint32_t path, uint32_t input, uint32_t output, float gain);

@@ -523,3 +523,36 @@ def test_persistent_fft_many_items(bbx, orc, B, nch, L, T):
         obc.set_filter(f)
         yo = np.concatenate([obc.convolve(np.ascontiguousarray(x[i * B:(i + 1) * B, c])) for i in range(2 * T)])
         assert_float_parity(y[:, c], yo, "channel %d of %d" % (c, nch))
+
+
+@pytest.mark.parametrize("B", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_forward_fft_vs_float64_fft(bbx, B):
+    """The forward transform kernels alone (a14: FFT): the filter object's spectra against numpy's float64 FFT of every
+    zero-padded partition -- H[p] = R2C_2B([h[pB .. pB+B-1], 0^B]) / 2B, bin 0 packed as (DC, Nyquist) -- for every
+    block size (radix-8 and radix-4 paths), a ragged last partition and a KAT (unit impulse -> flat spectrum 1/2B)."""
+    rng = np.random.default_rng(4000 + B)
+    L = 5 * B - 37
+    h = rng.standard_normal(L).astype(np.float32)
+    eng = bbx.Convolver(B, 6, 1)
+    f = eng.CreateFilter(h)
+    got = f.Spectra()
+    P = -(-L // B)
+    assert got.shape == (P, B)
+    hp = np.zeros(P * B, dtype=np.float64)
+    hp[:L] = h
+    worst = 0.0
+    for p in range(P):
+        w = np.zeros(2 * B, dtype=np.float64)
+        w[:B] = hp[p * B:(p + 1) * B]
+        ref = np.fft.rfft(w) / (2 * B)
+        want = ref[:B].copy()
+        want[0] = ref[0].real + 1j * ref[B].real
+        scale = np.abs(ref).max()
+        worst = max(worst, np.abs(got[p].astype(np.complex128) - want).max() / scale)
+    assert worst <= 2e-6, worst  # fp32 FFT of 2B points: a few ulp per pass, log2(2B) passes
+    imp = np.zeros(B, dtype=np.float32)
+    imp[0] = 1.0
+    s = eng.CreateFilter(imp).Spectra()
+    assert np.array_equal(s.real, np.full((1, B), 1.0 / (2 * B), dtype=np.float32))
+    assert np.array_equal(s.imag[0, 1:], np.zeros(B - 1, dtype=np.float32)) and s.imag[0, 0] == np.float32(1.0 / (2 * B))
+    eng.close()
