@@ -287,9 +287,15 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if bbx.device_count() < 1:
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ndev = bbx.device_count()
+    if ndev < 1:
         raise SystemExit("bench.py needs a CUDA device: libbbx has no CPU fallback")
+    # Rank -> GPU.  With more visible GPUs than ranks the ranks are spread evenly over the box (N = 2 on an 8-GPU box: GPUs 0
+    # and 4): the path has no GPU-to-GPU traffic, and the host-to-device copies of the e2e leg then share fewer PCIe switch
+    # uplinks (profiles/r01_pcie_diag_n8.txt: two GPUs copying both ways get 26 GB/s each on GPUs 0,1 and 34 / 42 on 0,4).
+    stride = ndev // world if (world > 1 and ndev >= world) else 1
+    local = (local_rank * stride) % ndev
     torch.cuda.set_device(local)
     numa = bind_near_gpu(local) if world > 1 else None  # pinned staging on the GPU's own NUMA node
     dist = None
@@ -504,6 +510,7 @@ def main():
                        "mac": "time-batched (tile 16)" if args.tile in (0, 16) else ("streaming" if args.tile == 1 else "time-batched (tile %d)" % args.tile),
                        "l2": "inputs larger than L2: 148 MB spectra + 181 MB FDL + partial sums per step vs 126 MB L2, no flush",
                        "parallelism": "channel-sharded x%d, no collective" % world,
+                       "devices": "rank r on GPU %d*r of %d visible" % (stride, ndev),
                        "host_binding": ("rank 0 bound to %d CPUs local to its GPU" % len(numa)) if numa else "none"},
             "x_realtime_per_channel": value / (NCH * world),
             "roofline": roofline, "roofline_streaming": roofline_streaming, "roofline_mimo": roofline_mimo, "cpu_baseline": cpu,
