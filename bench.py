@@ -146,6 +146,55 @@ def cpu_convolver_rate(n_blocks, nthreads, want_seconds=None):
     return NCH * done * B / FS / el, el, done
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def reference_function_rates():
+    """the in-tree reference functions of the path timed single-threaded on this host -- the reference's
+    own code when oracle/_ref was built, else the C restatement.  Sanity anchors next to the convolver baseline."""
+    import cpulibs
+    lib, kind = cpulibs.reference(), "reference"
+    if lib is None:
+        lib, kind = cpulibs.oracle(), "port"
+    nch, nfr = 32, 48000
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, nch * nfr).astype(np.float32)
+    s24 = np.zeros(nch * nfr * 3, dtype=np.uint8)
+    back = np.zeros(nch * nfr, dtype=np.float32)
+
+    def rate(fn, samples):
+        fn()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 0.4:
+            fn()
+            n += 1
+        return samples * n / (time.perf_counter() - t0) / 1e6
+
+    out = {"kind": kind, "threads": 1, "unit": "Msample/s"}
+    out["transfer_f32_to_s24_32ch"] = rate(lambda: lib.transfer(x.view(np.uint8), cpulibs.FMT_FLOAT, 0, 0, nch, s24, cpulibs.FMT_24, 0, 0,
+                                                                nch, nch, nfr), nch * nfr)
+    out["transfer_s24_to_f32_32ch"] = rate(lambda: lib.transfer(s24, cpulibs.FMT_24, 0, 0, nch, back.view(np.uint8), cpulibs.FMT_FLOAT, 0,
+                                                                0, nch, nch, nfr), nch * nfr)
+    bus = np.zeros(2 * nfr, dtype=np.float32)
+    mono = x[:nfr].copy()
+
+    def mix32():
+        for p in range(32):
+            lib.mix(mono, 0, 1, bus, p & 1, 2, 1, nfr, 0.5)
+    out["mix_32_mono_paths_to_stereo"] = rate(mix32, 32 * nfr)
+    ring = x[:4096].copy()
+    pos = rng.uniform(16, 4000, 20000)
+    out["fractional_sample_f32"] = rate(lambda: lib.frac(ring, 0, 1, 4096, pos), pos.size)
+    return out
+
+
 def mimo_leg(bbx, torch, device, steps=100):
     """BASELINE.json configs[4] (C5): 64-in x 64-out matrix of 4096-tap IRs, B = 512, 64-block steps.  The per-bin
     complex GEMM runs on the tensor cores (k_mimo_tc: tcgen05.mma kind::tf32, 3 MMAs per product for fp32 accuracy).
@@ -256,7 +305,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "channels": NCH, "block": B, "partitions": P, "blocks_per_step": blocks_per_step,
                    "note": "CPU port of the absent BlockConvolver/Convolver (own FFT, FFTW unavailable)"},
-        "cpu_baseline": {"value": value, "unit": "channel-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "channel-s/s", "cores": cores, "kind": "port", "nproc": os.cpu_count(),
+                         "cpu_model": cpu_model(), "sample": sample},
         "e2e": {"value": value, "unit": "channel-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -396,12 +446,12 @@ def main():
     # ---- per-block latency, streaming T = 1 through the host API ----
     latency = None
     if not args.no_latency and rank == 0:
-        def block_latency(nlat=600):
+        def block_latency(nlat=1000, warm=100):  # 1000+ steps after 100 warm-up
             lat = []
-            for i in range(nlat + 50):
+            for i in range(nlat + warm):
                 t0 = time.perf_counter()
                 eng.ConvolveHostPtr(hin.ptr, bbx.FMT_FLOAT, NCH, hout.ptr, bbx.FMT_FLOAT, NCH, B)
-                if i >= 50:
+                if i >= warm:
                     lat.append(time.perf_counter() - t0)
             lat = np.array(lat) * 1e6
             return float(np.percentile(lat, 50)), float(np.percentile(lat, 99)), nlat
@@ -496,7 +546,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         rate, secs, blocks = cpu_convolver_rate(64, cores, want_seconds=12.0)
-        cpu = {"value": rate, "unit": "channel-s/s", "cores": cores, "kind": "port",
+        cpu = {"value": rate, "unit": "channel-s/s", "cores": cores, "kind": "port", "nproc": os.cpu_count(), "cpu_model": cpu_model(),
+               "reference_functions": reference_function_rates(),
                "sample": "%d block-steps x %d channels of the C3 workload in %.1f s (oracle UPOLS, OpenMP over channels, own FFT)" % (
                    blocks, NCH, secs)}
 
