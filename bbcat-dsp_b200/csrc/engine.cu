@@ -1356,6 +1356,8 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     const bool mix = e->n_out_pcm <= 32 && e->n_routes_pcm <= kMixMaxRoutes && e->n_routes_pcm >= 4 * e->n_out_pcm &&
                      e->pcm_out_mix;
     if (mix) BBX_PCM_LAUNCH(k_pcm_out_mix, outfmt, out_be, a.fast, dim3(T * B / 32), st, a);
+    else if (e->cfg.fractional_delay && e->pcm_out_mix)  // one sample per thread (the same switch keeps it on the tile kernel)
+      BBX_PCM_LAUNCH(k_pcm_out_frac, outfmt, out_be, a.fast, dim3(T * B / 8, ceil_div(e->n_out_pcm, 32)), st, a);
     else if (B % 128 == 0 && e->n_out_pcm >= 16 && !e->cfg.fractional_delay)
       BBX_PCM_LAUNCH(k_pcm_out128, outfmt, out_be, a.fast, dim3(T * B / 128, ceil_div(e->n_out_pcm, 32)), st, a);
     else BBX_PCM_LAUNCH(k_pcm_out, outfmt, out_be, a.fast, dim3(T * B / 32, ceil_div(e->n_out_pcm, 32)), st, a);

@@ -194,6 +194,38 @@ __global__ void __launch_bounds__(256) k_pcm_out(PcmOutArgs a) {
   }
 }
 
+// Fractional-delay engines (14-tap polyphase reads in double, C4): one sample per thread.  The tile kernel above gives a
+// thread four samples one after the other, each a chain of table -> ring -> 14 dependent double adds; with 16 CTAs for
+// a 512-frame block the chains, not the arithmetic, set the kernel time (ncu: 13 % issue, long-scoreboard bound).  Here a
+// warp is one frame and a lane one output channel, so the 32 stores of a warp are one contiguous piece of the interleaved
+// frame (no shared-memory transpose) and four times as many threads are in flight.  Same per-sample arithmetic and route
+// order as k_pcm_out.
+template <int FMT, int ACC>
+__global__ void __launch_bounds__(256) k_pcm_out_frac(PcmOutArgs a) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t frame = blockIdx.x * 8 + warp, o = blockIdx.y * 32 + lane;
+  if (o >= a.n_outputs) return;
+  const uint32_t t = frame / a.B, n = frame - t * a.B;
+  const uint32_t w = (a.wpos0 + t * a.B) % a.Rd;
+  const float inc = 1.0f / (float)a.B;
+  const uint32_t rb = a.rv.out_first[o], re = a.rv.out_first[o + 1];
+  float bus = 0.f;
+  for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
+    const RouteEntry en = a.rv.entry[r];
+    if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
+    const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
+    float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
+    if (t == 0 && (en.flags & 1u)) {
+      const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
+      const float g = __fmul_rn((float)n, inc);
+      v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
+    }
+    bus = __fadd_rn(bus, __fmul_rn(en.gain, v));  // dst += mul * src, rounded separately
+  }
+  constexpr uint32_t bps = FmtBytes<FMT>::value;
+  store_from_f32_t<FMT, ACC>(a.pcm + ((uint64_t)frame * a.out_channels + o) * bps, bus);
+}
+
 // Mixdown of many paths into few outputs (the binaural renderer: 64 sources x 2 ears -> 2 outputs).  The kernel above
 // walks the routes of an output one after the other inside one thread: 64 dependent table + ring reads per sample, and
 // only n_outputs of its 32 channel slots do anything.  Here every thread of the CTA takes (route, frame) items: the

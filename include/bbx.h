@@ -362,7 +362,8 @@ int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint
 int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile);
 /* mixdowns of many paths into few outputs (>= 4 paths per output, <= 32 outputs, <= 256 routes) run k_pcm_out_mix, which
  * forms the delayed, gained path samples of a tile in parallel and adds them in route order; per_output != 0 keeps them
- * on the per-output kernel (tuning / A-B: the bytes are identical) */
+ * on the per-output kernel (tuning / A-B: the bytes are identical); the same switch keeps fractional-delay engines on
+ * the tile kernel instead of the one-sample-per-thread kernel k_pcm_out_frac */
 int bbx_engine_set_mixdown_kernel(bbx_engine* e, int per_output);
 /* latency path of bbx_process / bbx_process_async, decided for the input and the output side separately: a PCM buffer of
  * at most max_bytes in pinned host memory the device can address (bbx_host_alloc, cudaHostAlloc, cudaHostRegister) is

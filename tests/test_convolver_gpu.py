@@ -287,6 +287,35 @@ def test_mixdown_kernels_bit_identical(bbx, fractional, fmt):
     assert outs[0].any() and np.array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("fmt", [cl.FMT_FLOAT, cl.FMT_24, cl.FMT_16])
+def test_fractional_output_kernels_bit_identical(bbx, fmt):
+    """k_pcm_out_frac (one sample per thread, a warp per frame) against the tile kernel: same bytes for per-channel
+    fractional delays, a crossfaded delay + filter switch, a hard switch, 35 channels (a ragged channel tile) and an
+    unused PCM channel."""
+    B, L, nch, nblk = 64, 150, 35, 12
+    xi = interleave([make_noise(1700 + c, nblk * B) for c in range(nch)]) * 0.5
+    outs = []
+    for tile_kernel in (False, True):
+        g = GpuDriver(bbx, B, 3, nch, max_blocks=5, max_delay=70, fractional_delay=True)
+        g.eng.set_mixdown_kernel(tile_kernel)
+        fl = [g.filter(make_ir(1800 + c, L)) for c in range(nch + 2)]
+        for c in range(nch):
+            g.select(c, fl[c], delay=(c % 9) * 7.3)
+        got, pos = [], 0
+        for k, nb in enumerate([5, 1, 3, 3]):
+            if k == 1:
+                g.select(2, fl[nch], delay=55.125, crossfade=True)
+                g.select(30, fl[30], delay=0.5, crossfade=True)
+            if k == 3:
+                g.select(7, fl[nch + 1], delay=12.75, crossfade=False)
+            y = g.process(xi[pos * B:(pos + nb) * B], cl.FMT_FLOAT, nch, fmt, nch + 1, nb * B)
+            got.append(np.array(y, copy=True))
+            pos += nb
+        outs.append(np.concatenate(got))
+        g.close()
+    assert outs[0].any() and np.array_equal(outs[0], outs[1])
+
+
 def test_mimo_vs_oracle(bbx):
     """C5 shape at reduced size: 8 x 8 matrix of 4096-tap IRs, B = 512, frequency-domain mixdown."""
     B, L, nin, nout, nblk = 512, 4096, 8, 8, 12
