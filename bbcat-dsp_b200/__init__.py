@@ -94,6 +94,7 @@ SYMBOLS = {
     "bbx_filter_read_spectra": (C.c_int, [vp, vp, C.c_size_t]),
     "bbx_set_route": (C.c_int, [vp, u32, u32, u32, C.c_float]),
     "bbx_set_filter": (C.c_int, [vp, u32, vp, C.c_int, C.c_double]),
+    "bbx_set_filters": (C.c_int, [vp, u32, vp, vp, vp, vp]),
     "bbx_process": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
     "bbx_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
     "bbx_process_async": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32]),
@@ -554,6 +555,15 @@ class Convolver:
 
     def SelectFilter(self, path, flt, delay=0.0, crossfade=False):
         _check(lib().bbx_set_filter(self.h, path, flt.h if flt is not None else None, int(crossfade), delay))
+
+    def SelectFilters(self, paths, filters, delays=None, crossfade=None):
+        """SelectFilter for many paths in one call (all validated before any is latched)."""
+        n = len(paths)
+        pa = (u32 * n)(*[int(p) for p in paths])
+        fa = (vp * n)(*[(f.h if f is not None else None) for f in filters])
+        xa = (C.c_int * n)(*[int(bool(x)) for x in crossfade]) if crossfade is not None else None
+        da = (C.c_double * n)(*[float(d) for d in delays]) if delays is not None else None
+        _check(lib().bbx_set_filters(self.h, n, pa, fa, xa, da))
 
     def Convolve(self, inp, infmt, in_channels, outfmt, out_channels, nframes, in_be=False, out_be=False, out=None):
         """Host buffers.  inp: interleaved PCM bytes/typed array; returns the output byte buffer."""

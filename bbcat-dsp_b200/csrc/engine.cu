@@ -1153,6 +1153,29 @@ int bbx_set_filter(bbx_engine* e, uint32_t path, const bbx_filter* filter, int c
   return BBX_OK;
 }
 
+int bbx_set_filters(bbx_engine* e, uint32_t n, const uint32_t* paths, const bbx_filter* const* filters, const int* crossfade,
+                    const double* delays) {
+  BBX_REQUIRE(e != nullptr && (n == 0 || (paths && filters)), "bbx_set_filters: null argument");
+  // validate everything first: either all n switches are latched or none
+  for (uint32_t k = 0; k < n; k++) {
+    const double d = delays ? delays[k] : 0.0;
+    BBX_REQUIRE(paths[k] < e->n_paths, "bbx_set_filters: path %u out of range", paths[k]);
+    BBX_REQUIRE(!filters[k] || filters[k]->engine == e, "bbx_set_filters: filter %u belongs to another engine", k);
+    BBX_REQUIRE(d >= 0.0 && d <= (double)e->cfg.max_delay, "bbx_set_filters: delay %g outside [0, max_delay=%u]", d, e->cfg.max_delay);
+    BBX_REQUIRE(e->mode != BBX_MODE_MIMO || d == 0.0, "bbx_set_filters: MIMO mode has no per-path delay");
+    BBX_REQUIRE(!(e->sh_world > 1 || e->comm) || !(crossfade && crossfade[k]),
+                "bbx_set_filters: the input-sharded MIMO engine switches filters without crossfade");
+  }
+  for (uint32_t k = 0; k < n; k++) {
+    PathState& p = e->paths[paths[k]];
+    p.pend = filters[k];
+    p.pend_delay = delays ? delays[k] : 0.0;
+    p.xfade = crossfade && crossfade[k] != 0;
+    p.has_pending = true;
+  }
+  return BBX_OK;
+}
+
 // launch KERNEL<FMT, ACC> for a runtime (format, big-endian, typed-access) triple; ACC as in formats.cuh
 #define BBX_PCM_LAUNCH_ACC(KERNEL, FMT, be, fast, GRID, STREAM, ARGS)            \
   do {                                                                            \

@@ -6,6 +6,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "SoundFormatConversions.h"
 
@@ -77,6 +78,13 @@ public:
   // latched; applied at the next block boundary (= first block of the next Convolve call)
   void SelectFilter(uint_t path, const ConvolverFilter* filter, double delay = 0.0, bool crossfade = false) {
     Check(bbx_set_filter(e, path, filter ? filter->f : 0, crossfade ? 1 : 0, delay));
+  }
+  // the same for n paths in one call (all validated before any is latched); delays / crossfade may be NULL (= 0)
+  void SelectFilters(uint_t n, const uint_t* paths, const ConvolverFilter* const* filters, const double* delays = 0,
+                     const int* crossfade = 0) {
+    std::vector<const bbx_filter*> fv(n);
+    for (uint_t k = 0; k < n; k++) fv[k] = filters[k] ? filters[k]->f : 0;
+    Check(bbx_set_filters(e, n, paths, n ? &fv[0] : 0, crossfade, delays));
   }
   // nframes must be a multiple of the block size
   void Convolve(const void* src, SampleFormat_t srctype, bool src_be, uint_t src_channels, void* dst, SampleFormat_t dsttype,

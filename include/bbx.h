@@ -221,6 +221,10 @@ int bbx_set_route(bbx_engine* e, uint32_t path, uint32_t input, uint32_t output,
  * next bbx_process call); filter and delay switch together; crossfade != 0 blends old and new
  * over that one block with g_n = n/B.  filter == NULL silences the path. */
 int bbx_set_filter(bbx_engine* e, uint32_t path, const bbx_filter* filter, int crossfade, double delay_samples);
+/* the same for n paths in one call (a renderer that re-selects every channel's IR at once: C4); all n requests are validated
+ * before any is latched; crossfade and delays may be NULL (= 0) */
+int bbx_set_filters(bbx_engine* e, uint32_t n, const uint32_t* paths, const bbx_filter* const* filters, const int* crossfade,
+                    const double* delays);
 
 /* Process nframes (a multiple of B, at most max_blocks*B) of interleaved PCM.
  * in: [nframes][in_channels] in `infmt`, channels 0..n_inputs-1 are used.

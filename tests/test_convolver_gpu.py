@@ -316,6 +316,33 @@ def test_fractional_output_kernels_bit_identical(bbx, fmt):
     assert outs[0].any() and np.array_equal(outs[0], outs[1])
 
 
+def test_select_filters_batch(bbx):
+    """bbx_set_filters == a loop of bbx_set_filter (same bytes), and a bad entry latches nothing."""
+    B, L, nch, nblk = 64, 150, 5, 6
+    xi = interleave([make_noise(1900 + c, nblk * B) for c in range(nch)])
+    outs = []
+    for batch in (False, True):
+        g = GpuDriver(bbx, B, 3, nch, max_blocks=3, max_delay=20)
+        fl = [g.filter(make_ir(1950 + c, L)) for c in range(2 * nch)]
+        if batch:
+            g.eng.SelectFilters(range(nch), fl[:nch], delays=[float(c) for c in range(nch)])
+        else:
+            for c in range(nch):
+                g.select(c, fl[c], delay=float(c))
+        a = run_float(g, xi[:3 * B], 3 * B)
+        if batch:
+            with pytest.raises(bbx.BbxError):   # path 99 does not exist: nothing of this request may be latched
+                g.eng.SelectFilters([0, 99], [fl[nch], fl[nch + 1]], delays=[1.0, 1.0], crossfade=[True, True])
+            g.eng.SelectFilters([1, 3], [fl[nch + 1], fl[nch + 3]], delays=[7.0, 0.0], crossfade=[True, False])
+        else:
+            g.select(1, fl[nch + 1], delay=7.0, crossfade=True)
+            g.select(3, fl[nch + 3], delay=0.0, crossfade=False)
+        b = run_float(g, xi[3 * B:], 3 * B)
+        outs.append(np.concatenate([a, b]))
+        g.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
 def test_mimo_vs_oracle(bbx):
     """C5 shape at reduced size: 8 x 8 matrix of 4096-tap IRs, B = 512, frequency-domain mixdown."""
     B, L, nin, nout, nblk = 512, 4096, 8, 8, 12

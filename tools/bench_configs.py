@@ -108,8 +108,8 @@ def c4(steps):
     def before(i):
         m = state["m"]
         state["m"] += 1
-        for c in range(nch):
-            eng.SelectFilter(c, bank[c][(m + c) % nbank], delay=16 + 37.3 * ((m * 7 + c) % 11) / 11, crossfade=m > 0)
+        eng.SelectFilters(range(nch), [bank[c][(m + c) % nbank] for c in range(nch)],
+                          delays=[16 + 37.3 * ((m * 7 + c) % 11) / 11 for c in range(nch)], crossfade=[m > 0] * nch)
         # switch every 100 ms: block index ceil(m * 4800 / 512)
         cd = lambda a: -(-a // 512)
         return cd((m + 1) * 4800) - cd(m * 4800)
