@@ -847,6 +847,9 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   bbx_engine* e = new bbx_engine();
   e->cfg = *cfg;
   e->device = cfg->device;
+  // everything below returns through BBX_REQUIRE / BBX_CUDA_TRY: run it as one unit so that a failure half way releases
+  // what was allocated so far (bbx_engine_destroy accepts a partially built engine)
+  rc = [&]() -> int {
   BBX_CUDA_TRY(cudaSetDevice(e->device));
   e->B = cfg->block_size;
   e->Pmax = std::max(1u, cfg->max_partitions);
@@ -1001,6 +1004,14 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     BBX_CUDA_TRY(cudaMalloc((void**)&e->d_route, off));
   }
   BBX_CUDA_TRY(cudaDeviceSynchronize());
+  return BBX_OK;
+  }();
+  if (rc) {
+    const std::string msg = get_error();  // the clean-up below must not replace the message of the failure
+    bbx_engine_destroy(e);
+    set_error("%s", msg.c_str());
+    return rc;
+  }
   *out = e;
   return BBX_OK;
 }
@@ -1081,23 +1092,29 @@ int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filte
   std::vector<float> pad((size_t)P * N, 0.0f);
   for (uint32_t i = 0; i < length; i++) pad[(size_t)(i / B) * N + (i % B)] = ir[i];
   float* d_pad = nullptr;
-  BBX_CUDA_TRY(cudaMalloc((void**)&d_pad, sizeof(float) * pad.size()));
   bbx_filter* f = new bbx_filter();
   f->engine = e;
   f->P = P;
   f->H = nullptr;
-  BBX_CUDA_TRY(cudaMalloc((void**)&f->H, sizeof(float2) * (size_t)P * B));
-  BBX_CUDA_TRY(cudaMemcpyAsync(d_pad, pad.data(), sizeof(float) * pad.size(), cudaMemcpyHostToDevice, e->stream));
-  // H = R2C(window) / N : the only normalisation of the whole path, exact (power of two)
-  int rc = launch_rfft(B, d_pad, 0, N, f->H, 0, P, 0, e->tw, 1.0f / (float)N, 1, P, e->stream);
-  e->launches++;
-  cudaError_t se = cudaStreamSynchronize(e->stream);
+  int rc = [&]() -> int {
+    BBX_CUDA_TRY(cudaMalloc((void**)&d_pad, sizeof(float) * pad.size()));
+    BBX_CUDA_TRY(cudaMalloc((void**)&f->H, sizeof(float2) * (size_t)P * B));
+    BBX_CUDA_TRY(cudaMemcpyAsync(d_pad, pad.data(), sizeof(float) * pad.size(), cudaMemcpyHostToDevice, e->stream));
+    // H = R2C(window) / N : the only normalisation of the whole path, exact (power of two)
+    int lrc = launch_rfft(B, d_pad, 0, N, f->H, 0, P, 0, e->tw, 1.0f / (float)N, 1, P, e->stream);
+    e->launches++;
+    cudaError_t se = cudaStreamSynchronize(e->stream);
+    if (!lrc && se != cudaSuccess) {
+      set_error("filter transform failed: %s", cudaGetErrorString(se));
+      lrc = BBX_ERR_CUDA;
+    }
+    return lrc;
+  }();
   cudaFree(d_pad);
-  if (rc || se != cudaSuccess) {
-    if (!rc) set_error("filter transform failed: %s", cudaGetErrorString(se));
+  if (rc) {
     cudaFree(f->H);
     delete f;
-    return rc ? rc : BBX_ERR_CUDA;
+    return rc;
   }
   *out = f;
   return BBX_OK;
