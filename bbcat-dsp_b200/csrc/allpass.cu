@@ -67,6 +67,7 @@ int bbx_allpass_create(uint32_t nchannels, uint32_t nfilters, const uint32_t* de
   int rc = require_device();
   if (rc) return rc;
   bbx_allpass* a = new bbx_allpass();
+  CreateGuard<bbx_allpass> guard(a, bbx_allpass_destroy);
   a->nch = nchannels;
   a->nf = nfilters;
   a->delay.assign(delays, delays + nfilters);
@@ -79,7 +80,7 @@ int bbx_allpass_create(uint32_t nchannels, uint32_t nfilters, const uint32_t* de
     BBX_CUDA_TRY(cudaMemset(a->ring[f], 0, bytes));
   }
   BBX_CUDA_TRY(cudaMalloc((void**)&a->d_sec, sizeof(AllpassSection) * (nfilters ? nfilters : 1)));
-  *out = a;
+  *out = guard.release();
   return BBX_OK;
 }
 

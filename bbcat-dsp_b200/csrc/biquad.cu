@@ -146,6 +146,7 @@ int bbx_biquad_create(uint32_t nchannels, bbx_biquad** out) {
   int rc = require_device();
   if (rc) return rc;
   bbx_biquad* b = new bbx_biquad();
+  CreateGuard<bbx_biquad> guard(b, bbx_biquad_destroy);
   b->nch = nchannels;
   BBX_CUDA_TRY(cudaGetDevice(&b->device));
   memset(&b->c, 0, sizeof(b->c));
@@ -153,7 +154,7 @@ int bbx_biquad_create(uint32_t nchannels, bbx_biquad** out) {
   b->c.dec = 1.0;
   BBX_CUDA_TRY(cudaMalloc((void**)&b->w, sizeof(double) * 2 * (size_t)(nchannels ? nchannels : 1)));
   BBX_CUDA_TRY(cudaMemset(b->w, 0, sizeof(double) * 2 * (size_t)(nchannels ? nchannels : 1)));
-  *out = b;
+  *out = guard.release();
   return BBX_OK;
 }
 

@@ -103,6 +103,7 @@ int bbx_cascade_create(uint32_t nchannels, uint32_t numfilters, int vectorise, i
   int rc = require_device();
   if (rc) return rc;
   bbx_cascade* c = new bbx_cascade();
+  CreateGuard<bbx_cascade> guard(c, bbx_cascade_destroy);
   c->nch = nchannels;
   c->nf = numfilters;
   c->vectorise = vectorise && (numfilters % 4) == 0;  // src/BiQuad.h:405-409
@@ -112,7 +113,7 @@ int bbx_cascade_create(uint32_t nchannels, uint32_t numfilters, int vectorise, i
   memset(h.data(), 0, sizeof(CascadeRegs) * nchannels);
   for (auto& r : h) r.g = 1.0f;
   BBX_CUDA_TRY(cudaMemcpy(c->d_regs, h.data(), sizeof(CascadeRegs) * nchannels, cudaMemcpyHostToDevice));
-  *out = c;
+  *out = guard.release();
   return BBX_OK;
 }
 

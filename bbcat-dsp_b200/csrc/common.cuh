@@ -45,6 +45,25 @@ struct DeviceScratch {
 };
 DeviceScratch& scratch(int which);  // which = 0..3, thread-local
 
+// owner of a half-built object inside a *_create function: BBX_CUDA_TRY / BBX_REQUIRE return early, and the destructor then
+// releases what was allocated so far through the object's own destroy entry point (which accepts partial objects)
+template <typename T>
+struct CreateGuard {
+  T* p;
+  int (*destroy)(T*);
+  CreateGuard(T* obj, int (*d)(T*)) : p(obj), destroy(d) {}
+  ~CreateGuard() {
+    if (p) destroy(p);
+  }
+  T* release() {
+    T* q = p;
+    p = nullptr;
+    return q;
+  }
+  CreateGuard(const CreateGuard&) = delete;
+  CreateGuard& operator=(const CreateGuard&) = delete;
+};
+
 // make sure a CUDA device is usable; sets the error and returns BBX_ERR_CUDA otherwise
 int require_device();
 
