@@ -490,11 +490,19 @@ class Filter:
         return out.view(np.complex64)[..., 0]
 
     def close(self):
+        """Release the spectra.  A filter that a path still has selected is refused by the library (BbxError); it
+        is released together with its engine at the latest."""
         if getattr(self, "h", None) and getattr(self.engine, "h", None):
-            lib().bbx_filter_destroy(self.h)
+            _check(lib().bbx_filter_destroy(self.h))
+            if self in self.engine._filters:
+                self.engine._filters.remove(self)
         self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Convolver:
@@ -537,10 +545,10 @@ class Convolver:
 
     def close(self):
         if getattr(self, "h", None):
+            lib().bbx_engine_destroy(self.h)  # releases every filter the engine still owns
             for f in self._filters:
-                f.close()
+                f.h = None
             self._filters = []
-            lib().bbx_engine_destroy(self.h)
             self.h = None
 
     __del__ = close

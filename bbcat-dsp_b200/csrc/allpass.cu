@@ -20,16 +20,27 @@ struct AllpassSection {
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(128) k_allpass(const AllpassSection* __restrict__ sec, uint32_t nfilters, const float* src,
-                                                 float* dst, uint32_t nch, uint32_t n, uint32_t srcchannel, uint32_t nsrc,
-                                                 uint32_t dstchannel, uint32_t ndst, uint32_t nframes) {
+// up to kAllpassBatch sections travel by value in the launch parameters: the _dev entry point stays asynchronous (no
+// staging copy, no stream synchronisation); longer chains are run as consecutive launches
+constexpr uint32_t kAllpassBatch = 16;
+struct AllpassBatch {
+  AllpassSection sec[kAllpassBatch];
+};
+
+// n_first channels run the first section of the chain (it reads src), n_rest channels the following ones (in place on dst):
+// the reference's chain switches to the dst geometry after its first filter and every filter recomputes its own channel
+// count (src/AllPassFilter.h:108-111, 238-255), so a src narrower than dst leaves channels that only the later sections touch
+__global__ void __launch_bounds__(128) k_allpass(const AllpassBatch b, uint32_t nfilters, uint32_t first_is_head, const float* src,
+                                                 float* dst, uint32_t nch, uint32_t n_first, uint32_t n_rest, uint32_t srcchannel,
+                                                 uint32_t nsrc, uint32_t dstchannel, uint32_t ndst, uint32_t nframes) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const float* in = src + srcchannel + j;
-  uint32_t in_stride = nsrc;
   float* out = dst + dstchannel + j;
   for (uint32_t f = 0; f < nfilters; f++) {
-    const AllpassSection s = sec[f];
+    const bool head = first_is_head && f == 0;
+    if (j >= (head ? n_first : n_rest)) continue;
+    const float* in = head ? src + srcchannel + j : out;
+    const uint32_t in_stride = head ? nsrc : ndst;
+    const AllpassSection s = b.sec[f];
     float* ring = s.ring + j;
     uint32_t slot = s.slot;
     const float c = s.coeff;
@@ -41,8 +52,6 @@ __global__ void __launch_bounds__(128) k_allpass(const AllpassSection* __restric
       out[(size_t)i * ndst] = y;
       if (++slot >= s.delay) slot = 0;
     }
-    in = out;  // the following sections run in place on dst
-    in_stride = ndst;
   }
 }
 
@@ -55,7 +64,7 @@ struct bbx_allpass {
   std::vector<uint32_t> delay, pos;  // pos in ring items, like RingBuffer::GetPosition()
   std::vector<float> coeff;
   std::vector<float*> ring;
-  AllpassSection* d_sec = nullptr;
+  int device = 0;
 };
 
 extern "C" {
@@ -70,6 +79,7 @@ int bbx_allpass_create(uint32_t nchannels, uint32_t nfilters, const uint32_t* de
   CreateGuard<bbx_allpass> guard(a, bbx_allpass_destroy);
   a->nch = nchannels;
   a->nf = nfilters;
+  BBX_CUDA_TRY(cudaGetDevice(&a->device));
   a->delay.assign(delays, delays + nfilters);
   a->coeff.assign(coeffs, coeffs + nfilters);
   a->pos.assign(nfilters, 0);
@@ -79,15 +89,14 @@ int bbx_allpass_create(uint32_t nchannels, uint32_t nfilters, const uint32_t* de
     BBX_CUDA_TRY(cudaMalloc((void**)&a->ring[f], bytes));
     BBX_CUDA_TRY(cudaMemset(a->ring[f], 0, bytes));
   }
-  BBX_CUDA_TRY(cudaMalloc((void**)&a->d_sec, sizeof(AllpassSection) * (nfilters ? nfilters : 1)));
   *out = guard.release();
   return BBX_OK;
 }
 
 int bbx_allpass_destroy(bbx_allpass* a) {
   if (!a) return BBX_OK;
+  DeviceGuard dg(a->device);
   for (float* r : a->ring) cudaFree(r);
-  cudaFree(a->d_sec);
   delete a;
   return BBX_OK;
 }
@@ -97,28 +106,35 @@ int bbx_allpass_process_dev(bbx_allpass* a, const float* src, float* dst, uint32
   BBX_REQUIRE(a != nullptr, "bbx_allpass_process: null argument");
   if (!a->nf || !nframes) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_allpass_process: null buffer");
-  // channels that fit both geometries (src/AllPassFilter.h:108-111); the single-channel branch does not clamp
-  uint32_t n = a->nch;
+  // channels that fit the geometries (src/AllPassFilter.h:108-111); the single-channel branch does not clamp.  The first
+  // section sees (src, dst), the following ones (dst, dst): the chain re-points src at dst after its first filter
+  uint32_t n_first = a->nch, n_rest = a->nch;
   if (a->nch != 1) {
-    n = std::min(n, nsrcchannels >= srcchannel ? nsrcchannels - srcchannel : 0u);
-    n = std::min(n, ndstchannels >= dstchannel ? ndstchannels - dstchannel : 0u);
+    const uint32_t fit_src = nsrcchannels >= srcchannel ? nsrcchannels - srcchannel : 0u;
+    const uint32_t fit_dst = ndstchannels >= dstchannel ? ndstchannels - dstchannel : 0u;
+    n_first = std::min(a->nch, std::min(fit_src, fit_dst));
+    n_rest = std::min(a->nch, fit_dst);
   } else {
     BBX_REQUIRE(srcchannel < nsrcchannels && dstchannel < ndstchannels, "bbx_allpass_process: channel outside the buffers");
   }
+  BBX_REQUIRE(!(src == dst && (srcchannel != dstchannel || nsrcchannels != ndstchannels)),
+              "bbx_allpass_process: in-place use needs equal source and destination channels (src/AllPassFilter.h:87)");
+  DeviceGuard dg(a->device);
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<AllpassSection> sec(a->nf);
-  for (uint32_t f = 0; f < a->nf; f++) {
-    sec[f].ring = a->ring[f];
-    sec[f].delay = a->delay[f];
-    sec[f].slot = a->pos[f] / a->nch;
-    sec[f].coeff = a->coeff[f];
-    sec[f].pad = 0;
-  }
-  if (n) {
-    BBX_CUDA_TRY(cudaMemcpyAsync(a->d_sec, sec.data(), sizeof(AllpassSection) * a->nf, cudaMemcpyHostToDevice, st));
-    BBX_CUDA_TRY(cudaStreamSynchronize(st));  // sec is a stack vector
-    k_allpass<<<ceil_div(n, 128u), 128, 0, st>>>(a->d_sec, a->nf, src, dst, a->nch, n, srcchannel, nsrcchannels, dstchannel,
-                                                ndstchannels, nframes);
+  const uint32_t n = std::max(n_first, n_rest);
+  for (uint32_t f0 = 0; f0 < a->nf && n; f0 += kAllpassBatch) {
+    AllpassBatch b;
+    const uint32_t nb = std::min(kAllpassBatch, a->nf - f0);
+    for (uint32_t k = 0; k < nb; k++) {
+      const uint32_t f = f0 + k;
+      b.sec[k].ring = a->ring[f];
+      b.sec[k].delay = a->delay[f];
+      b.sec[k].slot = a->pos[f] / a->nch;
+      b.sec[k].coeff = a->coeff[f];
+      b.sec[k].pad = 0;
+    }
+    k_allpass<<<ceil_div(n, 128u), 128, 0, st>>>(b, nb, f0 == 0 ? 1u : 0u, src, dst, a->nch, n_first, n_rest, srcchannel,
+                                                nsrcchannels, dstchannel, ndstchannels, nframes);
     BBX_CUDA_TRY(cudaGetLastError());
   }
   // every section's ring position advances nchannels items per frame, processed or skipped (Advance)
@@ -135,6 +151,7 @@ int bbx_allpass_process(bbx_allpass* a, const float* src, float* dst, uint32_t s
   if (!a->nf || !nframes || !nsrcchannels || !ndstchannels) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_allpass_process: null buffer");
   const size_t sb = sizeof(float) * (size_t)nframes * nsrcchannels, db = sizeof(float) * (size_t)nframes * ndstchannels;
+  DeviceGuard dg(a->device);
   DeviceScratch& s0 = scratch(0);
   DeviceScratch& s1 = scratch(1);
   int rc;
@@ -154,6 +171,7 @@ uint32_t bbx_allpass_get_state(const bbx_allpass* a, uint32_t filter, float* rin
   if (!a || filter >= a->nf) return 0;
   uint32_t n = std::min(a->nch * a->delay[filter], maxitems);
   if (n && ring) {
+    DeviceGuard dg(a->device);
     cudaStreamSynchronize(cudaStreamPerThread);
     cudaMemcpy(ring, a->ring[filter], sizeof(float) * n, cudaMemcpyDeviceToHost);
   }

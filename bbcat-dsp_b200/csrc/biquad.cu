@@ -160,6 +160,7 @@ int bbx_biquad_create(uint32_t nchannels, bbx_biquad** out) {
 
 int bbx_biquad_destroy(bbx_biquad* b) {
   if (!b) return BBX_OK;
+  DeviceGuard dg(b->device);
   cudaFree(b->w);
   delete b;
   return BBX_OK;
@@ -185,6 +186,7 @@ int bbx_biquad_process_dev(bbx_biquad* b, const float* src, float* dst, uint32_t
   nchannels = std::min(std::min(nchannels, nsrcchannels), std::min(ndstchannels, b->nch));
   if (!nchannels || !nframes) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_biquad_process: null buffer");
+  DeviceGuard dg(b->device);
   k_biquad<<<ceil_div(nchannels, 128u), 128, 0, (cudaStream_t)stream>>>(src, dst, b->w, b->c, nchannels, nsrcchannels,
                                                                         ndstchannels, nframes);
   BBX_CUDA_TRY(cudaGetLastError());
@@ -199,6 +201,7 @@ int bbx_biquad_process(bbx_biquad* b, const float* src, float* dst, uint32_t nch
   if (!nframes || !nsrcchannels || !ndstchannels) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_biquad_process: null buffer");
   const size_t sb = sizeof(float) * (size_t)nframes * nsrcchannels, db = sizeof(float) * (size_t)nframes * ndstchannels;
+  DeviceGuard dg(b->device);
   DeviceScratch& s0 = scratch(0);
   DeviceScratch& s1 = scratch(1);
   int rc;
@@ -216,6 +219,7 @@ int bbx_biquad_process(bbx_biquad* b, const float* src, float* dst, uint32_t nch
 
 int bbx_biquad_get_state(const bbx_biquad* b, double* w, double* cur5, double* mul_dec) {
   BBX_REQUIRE(b != nullptr, "bbx_biquad_get_state: null argument");
+  DeviceGuard dg(b->device);
   if (w && b->nch) {
     BBX_CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));
     BBX_CUDA_TRY(cudaMemcpy(w, b->w, sizeof(double) * 2 * (size_t)b->nch, cudaMemcpyDeviceToHost));
@@ -230,6 +234,7 @@ int bbx_biquad_get_state(const bbx_biquad* b, double* w, double* cur5, double* m
 
 int bbx_biquad_reset(bbx_biquad* b) {
   BBX_REQUIRE(b != nullptr, "bbx_biquad_reset: null argument");
+  DeviceGuard dg(b->device);
   BBX_CUDA_TRY(cudaMemset(b->w, 0, sizeof(double) * 2 * (size_t)(b->nch ? b->nch : 1)));
   return BBX_OK;
 }

@@ -89,6 +89,7 @@ using namespace bbx;
 struct bbx_cascade {
   uint32_t nch = 0, nf = 0;
   bool vectorise = false;
+  int device = 0;
   CascadeRegs* d_regs = nullptr;
 };
 
@@ -106,6 +107,7 @@ int bbx_cascade_create(uint32_t nchannels, uint32_t numfilters, int vectorise, i
   CreateGuard<bbx_cascade> guard(c, bbx_cascade_destroy);
   c->nch = nchannels;
   c->nf = numfilters;
+  BBX_CUDA_TRY(cudaGetDevice(&c->device));
   c->vectorise = vectorise && (numfilters % 4) == 0;  // src/BiQuad.h:405-409
   BBX_CUDA_TRY(cudaMalloc((void**)&c->d_regs, sizeof(CascadeRegs) * nchannels));
   // pass-through default: zero coefficients, g = 1 (src/BiQuad.h:410-415); registers start from Reset()
@@ -119,6 +121,7 @@ int bbx_cascade_create(uint32_t nchannels, uint32_t numfilters, int vectorise, i
 
 int bbx_cascade_destroy(bbx_cascade* c) {
   if (!c) return BBX_OK;
+  DeviceGuard dg(c->device);
   cudaFree(c->d_regs);
   delete c;
   return BBX_OK;
@@ -129,6 +132,7 @@ int bbx_cascade_set_coefficients(bbx_cascade* c, uint32_t channel, const float* 
   // "coefficients vector must be 4*numfilters + 1 long" (src/BiQuad.h:533-537)
   BBX_REQUIRE(n == 4 * c->nf + 1, "bbx_cascade_set_coefficients: %u coefficients, expected 4 * %u + 1", n, c->nf);
   BBX_REQUIRE(channel == 0xFFFFFFFFu || channel < c->nch, "bbx_cascade_set_coefficients: channel %u outside the bank", channel);
+  DeviceGuard dg(c->device);
   CascadeRegs r;
   memset(&r, 0, sizeof(r));  // SetCoefficients ends with Reset()
   const float* p = coeffs;
@@ -160,6 +164,7 @@ int bbx_cascade_set_coefficients(bbx_cascade* c, uint32_t channel, const float* 
 
 int bbx_cascade_reset(bbx_cascade* c) {
   BBX_REQUIRE(c != nullptr, "bbx_cascade_reset: null argument");
+  DeviceGuard dg(c->device);
   BBX_CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));
   // x, y, w0, w1, lastoutput are contiguous in CascadeRegs
   const size_t off = offsetof(CascadeRegs, x), len = offsetof(CascadeRegs, g) - off;
@@ -173,6 +178,7 @@ int bbx_cascade_process_dev(bbx_cascade* c, const float* src, long long src_chan
   BBX_REQUIRE(c != nullptr, "bbx_cascade_process: null argument");
   if (!nframes) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_cascade_process: null buffer");
+  DeviceGuard dg(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   const uint32_t grid = ceil_div(c->nch, 64u);
   if (c->vectorise)
@@ -190,6 +196,7 @@ int bbx_cascade_process(bbx_cascade* c, const float* src, float* dst, uint32_t n
   if (!nframes) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_cascade_process: null buffer");
   const size_t bytes = sizeof(float) * (size_t)nframes * c->nch;
+  DeviceGuard dg(c->device);
   DeviceScratch& s0 = scratch(0);
   DeviceScratch& s1 = scratch(1);
   int rc;
@@ -207,6 +214,7 @@ uint32_t bbx_cascade_get_state(const bbx_cascade* c, uint32_t channel, float* x1
                                float* lastoutput) {
   if (!c || channel >= c->nch) return 0;
   CascadeRegs r;
+  DeviceGuard dg(c->device);
   cudaStreamSynchronize(cudaStreamPerThread);
   if (cudaMemcpy(&r, c->d_regs + channel, sizeof(r), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   if (x12) memcpy(x12, r.x, sizeof(r.x));

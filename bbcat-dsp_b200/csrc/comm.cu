@@ -106,7 +106,7 @@ int bbx_comm_create(int world, int rank, const uint8_t* id128, int device, bbx_c
   }
   int rc = require_device();
   if (rc) return rc;
-  BBX_CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard dg(device);
   NcclUniqueId id;
   memcpy(id.internal, id128, 128);
   bbx_comm* c = new bbx_comm();
@@ -127,7 +127,7 @@ int bbx_comm_destroy(bbx_comm* c) {
   if (!c) return BBX_OK;
   NcclApi* api = nccl_api();
   if (api && c->nccl) {
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     api->CommDestroy(c->nccl);
   }
   delete c;

@@ -43,7 +43,7 @@ struct DeviceScratch {
   int ensure(size_t bytes);
   ~DeviceScratch();
 };
-DeviceScratch& scratch(int which);  // which = 0..3, thread-local
+DeviceScratch& scratch(int which);  // which = 0..3, thread-local, one set per device (the current device's)
 
 // owner of a half-built object inside a *_create function: BBX_CUDA_TRY / BBX_REQUIRE return early, and the destructor then
 // releases what was allocated so far through the object's own destroy entry point (which accepts partial objects)
@@ -66,5 +66,20 @@ struct CreateGuard {
 
 // make sure a CUDA device is usable; sets the error and returns BBX_ERR_CUDA otherwise
 int require_device();
+
+// Every handle-based entry point runs with the device its object was created on and gives the caller's current device back
+// on return (a single process may hold engines and delay / filter-bank objects on several GPUs).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 }  // namespace bbx

@@ -23,6 +23,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -154,6 +156,7 @@ struct bbx_engine {
   uint32_t max_segs = 0, max_slots = 0, max_ctas = 0, max_jobs = 0;
   bool steady_dirty = true;
   // state
+  std::vector<bbx_filter*> filters;  // every live filter of this engine (they die with it at the latest)
   std::vector<PathState> paths;
   uint32_t head = 0, wpos = 0, parity = 0, tprev = 1;
   // measurement
@@ -210,6 +213,12 @@ struct bbx_engine {
 };
 
 namespace {
+
+// Live filter handles of the process.  An engine releases the filters it still owns when it is destroyed; a filter
+// handle destroyed after its engine (C++ destruction order, Python garbage collection) is then simply unknown here
+// instead of a dangling pointer.
+std::mutex g_filter_mu;
+std::unordered_set<const bbx_filter*> g_live_filters;
 
 // persistent grid of the radix-8 kernels: enough CTAs to fill the machine, never more than there are items
 template <typename K>
@@ -849,8 +858,13 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   e->device = cfg->device;
   // everything below returns through BBX_REQUIRE / BBX_CUDA_TRY: run it as one unit so that a failure half way releases
   // what was allocated so far (bbx_engine_destroy accepts a partially built engine)
+  DeviceGuard dg(e->device);  // the caller's current device comes back on return
   rc = [&]() -> int {
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  {
+    int cur = -1;
+    BBX_CUDA_TRY(cudaGetDevice(&cur));
+    BBX_REQUIRE(cur == e->device, "bbx_engine_create: device %d cannot be selected", e->device);
+  }
   e->B = cfg->block_size;
   e->Pmax = std::max(1u, cfg->max_partitions);
   e->n_in = cfg->n_inputs;
@@ -1018,7 +1032,7 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
 
 int bbx_engine_destroy(bbx_engine* e) {
   if (!e) return BBX_OK;
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
@@ -1074,6 +1088,15 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->ev_stop) cudaEventDestroy(e->ev_stop);
   if (e->ev_upload) cudaEventDestroy(e->ev_upload);
   if (e->stream) cudaStreamDestroy(e->stream);
+  // filters that were never destroyed die with their engine (their handles are invalid from here on)
+  {
+    std::lock_guard<std::mutex> lk(g_filter_mu);
+    for (bbx_filter* f : e->filters) {
+      g_live_filters.erase(f);
+      cudaFree(f->H);
+      delete f;
+    }
+  }
   delete e;
   return BBX_OK;
 }
@@ -1087,7 +1110,7 @@ int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filte
   const uint32_t B = e->B, N = 2 * B;
   uint32_t P = std::max(1u, ceil_div(length, B));
   BBX_REQUIRE(P <= e->Pmax, "impulse response of %u taps needs %u partitions, engine max_partitions is %u", length, P, e->Pmax);
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard dg(e->device);
   // zero-padded windows [h[pB .. pB+B-1], 0^B]
   std::vector<float> pad((size_t)P * N, 0.0f);
   for (uint32_t i = 0; i < length; i++) pad[(size_t)(i / B) * N + (i % B)] = ir[i];
@@ -1116,6 +1139,11 @@ int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filte
     delete f;
     return rc;
   }
+  e->filters.push_back(f);
+  {
+    std::lock_guard<std::mutex> lk(g_filter_mu);
+    g_live_filters.insert(f);
+  }
   *out = f;
   return BBX_OK;
 }
@@ -1124,15 +1152,36 @@ int bbx_filter_read_spectra(const bbx_filter* f, float* out, size_t max_floats) 
   BBX_REQUIRE(f && out, "bbx_filter_read_spectra: null argument");
   const size_t n = (size_t)f->P * f->engine->B * 2;
   BBX_REQUIRE(max_floats >= n, "bbx_filter_read_spectra: %zu floats needed, %zu given", n, max_floats);
-  BBX_CUDA_TRY(cudaSetDevice(f->engine->device));
+  DeviceGuard dg(f->engine->device);
   BBX_CUDA_TRY(cudaMemcpy(out, f->H, sizeof(float) * n, cudaMemcpyDeviceToHost));
   return BBX_OK;
 }
 
 int bbx_filter_destroy(bbx_filter* f) {
   if (!f) return BBX_OK;
-  cudaSetDevice(f->engine->device);
-  cudaStreamSynchronize(f->engine->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_filter_mu);
+    if (!g_live_filters.count(f)) return BBX_OK;  // already released together with its engine
+  }
+  bbx_engine* e = f->engine;
+  // The MAC plans and the tensor-core operand pack hold raw device pointers into the spectra of every selected filter:
+  // a filter that a path still uses (current or latched) cannot go.  Select another filter (or NULL) first and run one
+  // bbx_process call so that the switch has been applied, or destroy the engine, which releases all its filters.
+  for (size_t k = 0; k < e->paths.size(); k++) {
+    const PathState& p = e->paths[k];
+    if (p.cur == f || (p.has_pending && p.pend == f)) {
+      set_error("bbx_filter_destroy: the filter is still selected on path %zu (%s); select another filter and process a block first",
+                k, p.cur == f ? "current" : "latched");
+      return BBX_ERR_STATE;
+    }
+  }
+  DeviceGuard dg(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->filters.erase(std::remove(e->filters.begin(), e->filters.end(), f), e->filters.end());
+  {
+    std::lock_guard<std::mutex> lk(g_filter_mu);
+    g_live_filters.erase(f);
+  }
   cudaFree(f->H);
   delete f;
   return BBX_OK;
@@ -1211,20 +1260,27 @@ int bbx_set_filters(bbx_engine* e, uint32_t n, const uint32_t* paths, const bbx_
     }                                                                                       \
   } while (0)
 
-int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
-                    int out_be, uint32_t out_channels, uint32_t nframes) {
+// argument and geometry checks shared by every form of bbx_process: they run before anything is staged, copied or latched
+static int validate_call(const bbx_engine* e, const void* in, int infmt, uint32_t in_channels, const void* out, int outfmt,
+                         uint32_t out_channels, uint32_t nframes) {
   BBX_REQUIRE(e && in && out, "bbx_process: null argument");
   BBX_REQUIRE(infmt > FMT_UNKNOWN && infmt < FMT_COUNT && outfmt > FMT_UNKNOWN && outfmt < FMT_COUNT, "bbx_process: bad format");
   BBX_REQUIRE(nframes > 0 && nframes % e->B == 0, "bbx_process: nframes %u is not a positive multiple of the block size %u",
               nframes, e->B);
-  const uint32_t B = e->B, T = nframes / B;
-  BBX_REQUIRE(T <= e->Tmax, "bbx_process: %u blocks exceed max_blocks %u", T, e->Tmax);
+  BBX_REQUIRE(nframes / e->B <= e->Tmax, "bbx_process: %u blocks exceed max_blocks %u", nframes / e->B, e->Tmax);
   BBX_REQUIRE(in_channels >= e->n_in && out_channels >= e->n_out_pcm, "bbx_process: too few channels in the PCM buffers");
   BBX_REQUIRE(e->sh_world <= 1 || e->comm || e->px_on,
               "bbx_process: the input-sharded MIMO engine needs bbx_engine_set_comm() or bbx_engine_peer_attach()");
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  return BBX_OK;
+}
+
+int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
+                    int out_be, uint32_t out_channels, uint32_t nframes) {
+  int rc = validate_call(e, in, infmt, in_channels, out, outfmt, out_channels, nframes);
+  if (rc) return rc;
+  const uint32_t B = e->B, T = nframes / B;
+  DeviceGuard dg(e->device);
   cudaStream_t st = e->stream;
-  int rc;
   e->last_infmt = infmt;
   e->last_outfmt = outfmt;
 
@@ -1426,9 +1482,11 @@ static bool mapped_device_ptr(const void* host, void** dev) {
 
 int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt,
                       int out_be, uint32_t out_channels, uint32_t nframes) {
-  BBX_REQUIRE(e && in && out, "bbx_process: null argument");
-  BBX_REQUIRE(infmt > FMT_UNKNOWN && infmt < FMT_COUNT && outfmt > FMT_UNKNOWN && outfmt < FMT_COUNT, "bbx_process: bad format");
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  {
+    const int vrc = validate_call(e, in, infmt, in_channels, out, outfmt, out_channels, nframes);
+    if (vrc) return vrc;  // nothing staged, no copy queued
+  }
+  DeviceGuard dg(e->device);
   const uint32_t ibps = fmt_bytes(infmt), obps = fmt_bytes(outfmt);
   size_t in_bytes = (size_t)nframes * in_channels * ibps;
   size_t out_bytes = (size_t)nframes * out_channels * obps;
@@ -1499,6 +1557,7 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
 
 int bbx_engine_sync(bbx_engine* e) {
   BBX_REQUIRE(e != nullptr, "bbx_engine_sync: null engine");
+  DeviceGuard dg(e->device);
   BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
@@ -1606,7 +1665,7 @@ int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c) {
   BBX_REQUIRE(!c || ((uint32_t)comm_world(c) == e->sh_world && (uint32_t)comm_rank(c) == e->sh_rank),
               "bbx_engine_set_comm: communicator (rank %d of %d) does not match the engine (rank %u of %u)", comm_rank(c),
               comm_world(c), e->sh_rank, e->sh_world);
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard dg(e->device);
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   if (c && !e->sh_send) {
     // world == 1 with a communicator: the sharded code path on one GPU (tests)
@@ -1629,7 +1688,7 @@ int bbx_engine_peer_export(bbx_engine* e, uint8_t* handle64) {
   BBX_REQUIRE(e && handle64, "bbx_engine_peer_export: null argument");
   BBX_REQUIRE(e->mode == BBX_MODE_MIMO && e->sh_world > 1 && e->sh_world <= 16,
               "bbx_engine_peer_export: only the input-sharded MIMO engine (2..16 ranks) exchanges spectra");
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard dg(e->device);
   if (!e->px_mem) {
     e->px_half = (size_t)e->sh_nloc * e->sh_world * e->Tmax * e->B;
     e->px_flag_off = (2 * e->px_half * sizeof(float2) + 255) & ~(size_t)255;
@@ -1662,7 +1721,7 @@ int bbx_engine_peer_export(bbx_engine* e, uint8_t* handle64) {
 int bbx_engine_peer_attach(bbx_engine* e, const uint8_t* handles) {
   BBX_REQUIRE(e && handles, "bbx_engine_peer_attach: null argument");
   BBX_REQUIRE(e->px_mem != nullptr, "bbx_engine_peer_attach: call bbx_engine_peer_export first");
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard dg(e->device);
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   for (uint32_t r = 0; r < e->sh_world; r++) {
     uint8_t* base = e->px_mem;
@@ -1683,7 +1742,7 @@ int bbx_engine_peer_attach(bbx_engine* e, const uint8_t* handles) {
 
 int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status) {
   BBX_REQUIRE(e != nullptr, "null engine");
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard dg(e->device);
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   if (launches) *launches = e->tc_launches;
   if (status) {
@@ -1737,7 +1796,7 @@ int bbx_probe_fp32_tflops(int device, float seconds, float* burst, float* sustai
 
 int bbx_engine_tensor_trace(bbx_engine* e, uint64_t* out, uint32_t max_ctas) {
   BBX_REQUIRE(e != nullptr, "null engine");
-  BBX_CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard dg(e->device);
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
   if (!out) {  // enable (max_ctas > 0) or disable
     cudaFree(e->tc_trace);
@@ -1758,6 +1817,7 @@ int bbx_engine_tensor_trace(bbx_engine* e, uint64_t* out, uint32_t max_ctas) {
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes) {
   BBX_REQUIRE(e != nullptr, "null engine");
   bytes = (bytes + 15) & ~(size_t)15;
+  DeviceGuard dg(e->device);
   if (e->flush_bytes < bytes) {
     cudaStreamSynchronize(e->stream);
     cudaFree(e->flush_buf);

@@ -17,6 +17,7 @@ struct bbx_mlb {
   size_t capacity = 0;   // floats allocated
   std::vector<uint32_t> positions;
   uint32_t channels = 0, minposition = 0, maxposition = 0;
+  int device = 0;
 };
 
 namespace {
@@ -76,6 +77,7 @@ int bbx_mlb_create(uint32_t channels, uint32_t layers, bbx_mlb** out) {
   int rc = require_device();
   if (rc) return rc;
   bbx_mlb* m = new bbx_mlb();
+  if (cudaGetDevice(&m->device) != cudaSuccess) m->device = 0;
   m->channels = channels;
   m->positions.assign(layers, 0u);
   *out = m;
@@ -84,6 +86,7 @@ int bbx_mlb_create(uint32_t channels, uint32_t layers, bbx_mlb** out) {
 
 int bbx_mlb_destroy(bbx_mlb* m) {
   if (!m) return BBX_OK;
+  DeviceGuard dg(m->device);
   cudaFree(m->buf);
   delete m;
   return BBX_OK;
@@ -97,6 +100,7 @@ int bbx_mlb_write_layer(bbx_mlb* m, uint32_t layer, const float* src, uint32_t s
                         uint32_t dstchannel, uint32_t nchannels, uint32_t nframes) {
   BBX_REQUIRE(m && src, "bbx_mlb_write_layer: null argument");
   if (layer >= m->positions.size()) return BBX_OK;  // silent, like the reference (.h:187)
+  DeviceGuard dg(m->device);
   cudaStream_t st = cudaStreamPerThread;
   int rc = reserve_space(m, layer, nframes, st);
   if (rc) return rc;
@@ -119,6 +123,7 @@ uint32_t bbx_mlb_read_buffer(bbx_mlb* m, uint32_t srcchannel, float* dst, uint32
   if (!m || !dst) return 0;
   nframes = std::min(nframes, m->minposition);
   if (!nframes) return 0;
+  DeviceGuard dg(m->device);
   cudaStream_t st = cudaStreamPerThread;
   if (ndstchannels && m->channels) {
     DeviceScratch& s = scratch(1);

@@ -62,8 +62,11 @@ DeviceScratch::~DeviceScratch() {
   if (ptr) cudaFree(ptr);
 }
 DeviceScratch& scratch(int which) {
-  static thread_local DeviceScratch s[4];
-  return s[which & 3];
+  // one set per device: objects on different GPUs used from one thread do not evict each other's scratch
+  static thread_local DeviceScratch s[16][4];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return s[dev & 15][which & 3];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -513,7 +516,12 @@ int bbx_delay_create(bbx_delay** out) {
   int rc = require_device();
   if (rc) return rc;
   bbx_delay* d = new bbx_delay();
-  BBX_CUDA_TRY(cudaGetDevice(&d->device));
+  cudaError_t ce = cudaGetDevice(&d->device);
+  if (ce != cudaSuccess) {
+    delete d;
+    set_error("cudaGetDevice failed: %s", cudaGetErrorString(ce));
+    return BBX_ERR_CUDA;
+  }
   *out = d;
   return BBX_OK;
 }
@@ -536,6 +544,7 @@ int bbx_ring_increment_read_position(bbx_delay* d, uint32_t nframes) {
 
 int bbx_delay_destroy(bbx_delay* d) {
   if (!d) return BBX_OK;
+  DeviceGuard dg(d->device);
   if (d->buf) cudaFree(d->buf);
   delete d;
   return BBX_OK;
@@ -548,10 +557,18 @@ int bbx_delay_set_size(bbx_delay* d, uint32_t chans, uint32_t length, int format
   chans = std::max(chans, 1u);
   length = std::max(length, 1u);
   if (chans == d->channels && length == d->buflen && format == d->format) return BBX_OK;
+  DeviceGuard dg(d->device);
   uint32_t bps = fmt_bytes(format);
   uint8_t* nb = nullptr;
   size_t bytes = (size_t)chans * length * bps;
   BBX_CUDA_TRY(cudaMalloc((void**)&nb, bytes));
+  // every failure below releases the new buffer; the object keeps its old ring
+  struct Drop {
+    uint8_t*& p;
+    ~Drop() {
+      if (p) cudaFree(p);
+    }
+  } drop{nb};
   cudaStream_t st = cudaStreamPerThread;
   BBX_CUDA_TRY(cudaMemsetAsync(nb, 0, bytes, st));
   if (d->buf) {
@@ -570,6 +587,7 @@ int bbx_delay_set_size(bbx_delay* d, uint32_t chans, uint32_t length, int format
   }
   BBX_CUDA_TRY(cudaStreamSynchronize(st));
   d->buf = nb;
+  nb = nullptr;  // owned by the object now
   d->channels = chans;
   d->buflen = length;
   d->format = format;
@@ -597,6 +615,7 @@ uint32_t bbx_delay_write_samples(bbx_delay* d, const void* vsrc, int srcformat, 
   channel = std::min(channel, d->channels - 1);
   nchannels = std::min(nchannels, d->channels - channel);
   if (nchannels == 0) return 0;
+  DeviceGuard dg(d->device);
   DeviceScratch& ds = scratch(0);
   size_t bytes = (size_t)nchannels * srclen * nframes;
   if (ds.ensure(bytes)) return 0;
@@ -641,6 +660,7 @@ uint32_t bbx_delay_read_samples(bbx_delay* d, void* vdst, int dstformat, uint32_
   nchannels = std::min(nchannels, d->channels - channel);
   nframes = std::min(nframes, delay);  // cannot read past the write position
   if (nchannels == 0 || nframes == 0) return 0;
+  DeviceGuard dg(d->device);
   DeviceScratch& dd = scratch(1);
   size_t bytes = (size_t)nchannels * dstlen * nframes;
   if (dd.ensure(bytes)) return 0;
@@ -669,6 +689,7 @@ float bbx_delay_read_sample(bbx_delay* d, uint32_t channel, uint32_t delay) {
   float res = 0.0f;
   if (!d || !d->buf || channel >= d->channels) return res;
   uint32_t pos = (d->writepos + d->buflen - delay) % d->buflen;
+  DeviceGuard dg(d->device);
   DeviceScratch& dd = scratch(1);
   if (dd.ensure(sizeof(float))) return res;
   cudaStream_t st = cudaStreamPerThread;
@@ -684,6 +705,7 @@ uint32_t bbx_delay_copy_buffer(const bbx_delay* d, void* dst, uint32_t maxbytes)
   if (!d || !d->buf || !dst) return 0;
   uint32_t bytes = d->bytesperframe * d->buflen;
   if (bytes > maxbytes) return 0;
+  DeviceGuard dg(d->device);
   if (cudaMemcpy(dst, d->buf, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return bytes;
 }

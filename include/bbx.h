@@ -207,7 +207,11 @@ uint32_t bbx_engine_get_ring_length(const bbx_engine* e);
 void* bbx_engine_get_stream(const bbx_engine* e);
 
 /* Filter object: H[p] = R2C_2B([h[pB .. pB+B-1], 0^B]), built on the device once, immutable,
- * shareable between paths of the engine that created it. */
+ * shareable between paths of the engine that created it.
+ * Ownership: the engine keeps a registry of its filters.  bbx_filter_destroy refuses (BBX_ERR_STATE) while a path still
+ * has the filter selected or latched -- the MAC plans hold device pointers into its spectra; select another filter (or
+ * NULL) and process one call first.  bbx_engine_destroy releases every filter the engine still owns; destroying such a
+ * handle afterwards is a harmless no-op. */
 int bbx_filter_create(bbx_engine* e, const float* ir, uint32_t length, bbx_filter** out);
 int bbx_filter_destroy(bbx_filter* f);
 uint32_t bbx_filter_partitions(const bbx_filter* f);

@@ -612,3 +612,90 @@ def test_forward_fft_vs_float64_fft(bbx, B):
     assert np.array_equal(s.real, np.full((1, B), 1.0 / (2 * B), dtype=np.float32))
     assert np.array_equal(s.imag[0, 1:], np.zeros(B - 1, dtype=np.float32)) and s.imag[0, 0] == np.float32(1.0 / (2 * B))
     eng.close()
+
+
+def test_filter_destroy_refused_while_selected(bbx):
+    """Ownership rule of include/bbx.h: a filter that a path still has selected (current or latched) cannot be destroyed --
+    the MAC plans hold device pointers into its spectra; once another filter has taken over it can, and whatever is left
+    dies with the engine (destroying such a handle later is a no-op)."""
+    B = 128
+    eng = bbx.Convolver(B, 4, 2, max_blocks=2)
+    f0, f1, f2 = (eng.CreateFilter(make_ir(300 + k, 3 * B)) for k in range(3))
+    x = interleave([make_noise(310 + c, 2 * B) for c in range(2)])
+    eng.SelectFilter(0, f0)
+    eng.SelectFilter(1, f1)
+    with pytest.raises(bbx.BbxError, match="latched"):
+        f0.close()  # latched, not yet applied
+    y0 = eng.Convolve(x, bbx.FMT_FLOAT, 2, bbx.FMT_FLOAT, 2, 2 * B).view(np.float32).copy()
+    with pytest.raises(bbx.BbxError, match="current"):
+        f0.close()
+    eng.SelectFilter(0, f2)
+    eng.Convolve(x, bbx.FMT_FLOAT, 2, bbx.FMT_FLOAT, 2, 2 * B)
+    f0.close()  # path 0 runs f2 now: f0 can go
+    assert f0.h is None
+    y1 = eng.Convolve(x, bbx.FMT_FLOAT, 2, bbx.FMT_FLOAT, 2, 2 * B).view(np.float32)
+    assert np.isfinite(y1).all() and np.abs(y0).max() > 0
+    h1 = f1.h
+    eng.close()  # releases f1 and f2
+    assert f1.h is None and f2.h is None
+    assert bbx.lib().bbx_filter_destroy(h1) == 0  # a stale handle of a dead engine is ignored, not dereferenced
+
+
+def test_rejected_call_consumes_nothing(bbx, orc):
+    """bbx_process_async validates the geometry before it stages, copies or latches anything: a rejected call leaves the
+    stream of results unchanged."""
+    B, nch = 128, 3
+    g, o = both(bbx, B, 4, nch, max_blocks=2)
+    for c in range(nch):
+        h = make_ir(400 + c, 2 * B + 5)
+        g.select(c, g.filter(h))
+        o.select(c, o.filter(h))
+    xs = interleave([make_noise(410 + c, 6 * B) for c in range(nch)])
+    yg = [g.process(xs[:2 * B], cl.FMT_FLOAT, nch, cl.FMT_FLOAT, nch, 2 * B).view(np.float32).reshape(-1, nch)]
+    flat = xs.reshape(-1)
+    for nframes, in_ch in ((B + 1, nch), (3 * B, nch), (2 * B, nch - 1)):  # not whole blocks / more than max_blocks / too few channels
+        with pytest.raises(bbx.BbxError):
+            g.eng.Convolve(flat[:nframes * in_ch], bbx.FMT_FLOAT, in_ch, bbx.FMT_FLOAT, nch, nframes)
+    yg.append(g.process(xs[2 * B:4 * B], cl.FMT_FLOAT, nch, cl.FMT_FLOAT, nch, 2 * B).view(np.float32).reshape(-1, nch))
+    yg.append(g.process(xs[4 * B:], cl.FMT_FLOAT, nch, cl.FMT_FLOAT, nch, 2 * B).view(np.float32).reshape(-1, nch))
+    yo = run_float(o, xs, 2 * B)
+    g.close()
+    yg = np.concatenate(yg)
+    for c in range(nch):
+        assert_float_parity(yg[:, c], yo[:, c], "after rejected calls, ch %d" % c)
+
+
+def test_objects_keep_their_device(bbx, gpu):
+    """Handle-based entry points run on the device their object was created on and give the caller's device back: an
+    engine on GPU 1 next to a delay buffer and a biquad bank created on GPU 0, used alternately from one thread."""
+    if bbx.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch
+    torch.cuda.set_device(0)
+    d = bbx.SoundDelayBuffer()
+    d.SetSize(2, 64, bbx.FMT_FLOAT)
+    bq = bbx.BiQuadBank(2)
+    bq.CalcCoeffs(bbx.BIQUAD_LPF12, 1000.0, 48000.0)
+    B = 128
+    eng = bbx.Convolver(B, 2, 2, max_blocks=1, device=1)
+    h = make_ir(500, B + 9)
+    for c in range(2):
+        eng.SelectFilter(c, eng.CreateFilter(h))
+    x = interleave([make_noise(510 + c, B) for c in range(2)])
+    ref_bq = bbx.BiQuadBank(2)
+    ref_bq.CalcCoeffs(bbx.BIQUAD_LPF12, 1000.0, 48000.0)
+    for it in range(3):
+        y = eng.Convolve(x, bbx.FMT_FLOAT, 2, bbx.FMT_FLOAT, 2, B).view(np.float32)
+        assert torch.cuda.current_device() == 0, "the engine call must give the caller's device back"
+        assert d.WriteSamples(x[:16], bbx.FMT_FLOAT, 0, 2, 16) == 16
+        d.IncrementWritePosition(16)
+        back = np.zeros(16 * 2, dtype=np.float32)
+        assert d.ReadSamples(back, bbx.FMT_FLOAT, 16, 0, 2, 16) == 16
+        assert np.array_equal(back.reshape(16, 2), x[:16])
+        z = np.zeros_like(x)
+        bq.Process(x, z, 2, 2, 2, B)
+        assert np.isfinite(y).all() and np.isfinite(z).all()
+    eng.close()
+    d.close()
+    bq.close()
+    ref_bq.close()

@@ -335,6 +335,9 @@ def allpass_script(lib, nch=5, delays=(7, 1, 23, 4), coeffs=(0.5, -0.7, 0.3, 0.9
     return outs
 
 
+ALLPASS_NARROW = dict(nch=6, delays=(3, 5, 2), coeffs=(0.5, -0.6, 0.8), nsrc=4, ndst=7, seed=779, offs=((0, 0), (1, 1)))
+
+
 def gen_allpass(ref):
     d = {}
     for i, a in enumerate(allpass_script(ref)):
@@ -342,6 +345,9 @@ def gen_allpass(ref):
     # single channel (the reference's unclamped branch): offsets must stay inside the frames
     for i, a in enumerate(allpass_script(ref, nch=1, delays=(5,), coeffs=(0.6,), nsrc=3, ndst=2, seed=778, offs=((1, 1), (2, 0)))):
         d["mono_%03d" % i] = a
+    # source narrower than the destination: the first section fits 4 channels, the following ones (dst geometry) all 6
+    for i, a in enumerate(allpass_script(ref, **ALLPASS_NARROW)):
+        d["narrow_%03d" % i] = a
     np.savez_compressed(os.path.join(OUT, "allpass.npz"), **d)
 
 
