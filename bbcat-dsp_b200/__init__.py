@@ -49,6 +49,9 @@ SYMBOLS = {
     "bbx_transfer_samples": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32]),
     "bbx_transfer_samples_dev": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, vp]),
     "bbx_transfer_samples_linear": (C.c_int, [vp, C.c_int, vp, C.c_int, u32]),
+    "bbx_dither_bits": (C.c_int, [C.c_int, C.c_int]),
+    "bbx_transfer_samples_dither": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, C.c_int, u64]),
+    "bbx_transfer_samples_dither_dev": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, C.c_int, u64, vp]),
     "bbx_mix_samples_f32": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_float]),
     "bbx_mix_samples_f64": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_double]),
     "bbx_mix_samples_interp": (C.c_int, [vp, u32, u32, vp, u32, u32, u32, u32, vp, C.c_float]),
@@ -206,11 +209,21 @@ def BlockTransferSanityChecks(src_channel, src_channels, dst_channel, dst_channe
 
 
 # ---- a3-a7 --------------------------------------------------------------------------------
+DITHER_NONE, DITHER_TPDF = 0, 1
+
+
+def DitherBits(srctype, dsttype):
+    """bit count the reference hands to Ditherer::Dither for this converter, -1 when it has no dither call site."""
+    return lib().bbx_dither_bits(srctype, dsttype)
+
+
 def TransferSamples(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel, dst_channels,
-                    nchannels=0xFFFFFFFF, nframes=1):
-    """Host byte buffers (numpy uint8 or typed arrays); dst is modified in place."""
-    _check(lib().bbx_transfer_samples(_p(src), srctype, int(src_be), src_channel, src_channels, _p(dst), dsttype,
-                                      int(dst_be), dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes))
+                    nchannels=0xFFFFFFFF, nframes=1, dither=DITHER_NONE, seed=0):
+    """Host byte buffers (numpy uint8 or typed arrays); dst is modified in place.  dither=DITHER_TPDF: the device-side
+    TPDF ditherer (a7)."""
+    _check(lib().bbx_transfer_samples_dither(_p(src), srctype, int(src_be), src_channel, src_channels, _p(dst), dsttype,
+                                             int(dst_be), dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes,
+                                             dither, seed))
 
 
 def TransferSamplesDev(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,

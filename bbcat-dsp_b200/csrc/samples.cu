@@ -78,6 +78,8 @@ struct XferGeom {
   uint32_t nchannels, nframes;
   uint64_t src_frame_bytes, dst_frame_bytes;  // frame strides
   bool src_be, dst_be;
+  int dither;          // bbx_dither: 0 none, 1 TPDF (only the converters with a dither call site look at it)
+  uint64_t seed;
 };
 
 template <int SRC, int DST, bool ALIGNED>
@@ -95,6 +97,9 @@ __global__ void __launch_bounds__(256) k_transfer(XferGeom g) {
       bits = (SRC <= FMT_32) ? (uint64_t)((uint32_t)r.i >> (32 - 8 * fmt_bytes(SRC)))
              : (SRC == FMT_F32) ? (uint64_t)__float_as_uint(r.f) : (uint64_t)__double_as_longlong(r.d);
     } else {
+      if constexpr (dither_bits(SRC, DST) >= 0) {
+        if (g.dither == BBX_DITHER_TPDF) dither_tpdf<SRC, dither_bits(SRC, DST)>(r, g.seed, idx);
+      }
       bits = convert_sample<SRC, DST>(r);
     }
     if (ALIGNED) store_sample_aligned_le<DST>(dp, bits);
@@ -129,8 +134,10 @@ static bool is_aligned(const void* p, uint64_t stride, uint32_t len) {
 // Device-pointer rectangle transfer after the sanity checks have been applied.
 static int transfer_dev_checked(const void* src, int srctype, bool src_be, uint32_t src_channel, uint32_t src_channels,
                                 void* dst, int dsttype, bool dst_be, uint32_t dst_channel, uint32_t dst_channels,
-                                uint32_t nchannels, uint32_t nframes, cudaStream_t st) {
+                                uint32_t nchannels, uint32_t nframes, cudaStream_t st, int dither = 0, uint64_t seed = 0) {
   XferGeom g;
+  g.dither = dither;
+  g.seed = seed;
   uint32_t srclen = fmt_bytes(srctype), dstlen = fmt_bytes(dsttype);
   g.src = (const uint8_t*)src + (uint64_t)src_channel * srclen;
   g.dst = (uint8_t*)dst + (uint64_t)dst_channel * dstlen;
@@ -285,20 +292,38 @@ int bbx_block_transfer_sanity_checks(uint32_t* src_channel, uint32_t* src_channe
   return 1;
 }
 
+int bbx_dither_bits(int srctype, int dsttype) { return dither_bits(srctype, dsttype); }
+
 int bbx_transfer_samples_dev(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
                              void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
                              uint32_t nchannels, uint32_t nframes, void* stream) {
+  return bbx_transfer_samples_dither_dev(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                                         dst_channels, nchannels, nframes, BBX_DITHER_NONE, 0, stream);
+}
+
+int bbx_transfer_samples_dither_dev(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
+                                    void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
+                                    uint32_t nchannels, uint32_t nframes, int dither, uint64_t seed, void* stream) {
+  BBX_REQUIRE(dither == BBX_DITHER_NONE || dither == BBX_DITHER_TPDF, "bbx_transfer_samples: unknown dither mode %d", dither);
   if (!bbx_block_transfer_sanity_checks(&src_channel, &src_channels, &dst_channel, &dst_channels, &nchannels, &nframes, 1))
     return BBX_OK;  // silent no-op like the reference
   if (!valid_fmt(srctype) || !valid_fmt(dsttype)) return BBX_OK;
   BBX_REQUIRE(src && dst, "bbx_transfer_samples_dev: null buffer");
   return transfer_dev_checked(src, srctype, src_be != 0, src_channel, src_channels, dst, dsttype, dst_be != 0, dst_channel,
-                              dst_channels, nchannels, nframes, (cudaStream_t)stream);
+                              dst_channels, nchannels, nframes, (cudaStream_t)stream, dither, seed);
 }
 
 int bbx_transfer_samples(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
                          void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
                          uint32_t nchannels, uint32_t nframes) {
+  return bbx_transfer_samples_dither(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                                     dst_channels, nchannels, nframes, BBX_DITHER_NONE, 0);
+}
+
+int bbx_transfer_samples_dither(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
+                                void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
+                                uint32_t nchannels, uint32_t nframes, int dither, uint64_t seed) {
+  BBX_REQUIRE(dither == BBX_DITHER_NONE || dither == BBX_DITHER_TPDF, "bbx_transfer_samples: unknown dither mode %d", dither);
   if (!bbx_block_transfer_sanity_checks(&src_channel, &src_channels, &dst_channel, &dst_channels, &nchannels, &nframes, 1))
     return BBX_OK;
   if (!valid_fmt(srctype) || !valid_fmt(dsttype)) return BBX_OK;
@@ -313,7 +338,7 @@ int bbx_transfer_samples(const void* src, int srctype, int src_be, uint32_t src_
   cudaStream_t st = cudaStreamPerThread;
   if ((rc = copy_rect_h2d(ds.ptr, (const uint8_t*)src, src_channel, src_channels, nchannels, nframes, srclen, st))) return rc;
   if ((rc = transfer_dev_checked(ds.ptr, srctype, src_be != 0, 0, nchannels, dd.ptr, dsttype, dst_be != 0, 0, nchannels,
-                                 nchannels, nframes, st)))
+                                 nchannels, nframes, st, dither, seed)))
     return rc;
   if ((rc = copy_rect_d2h((uint8_t*)dst, dd.ptr, dst_channel, dst_channels, nchannels, nframes, dstlen, st))) return rc;
   BBX_CUDA_TRY(cudaStreamSynchronize(st));

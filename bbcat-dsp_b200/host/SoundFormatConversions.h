@@ -1,10 +1,19 @@
 // Drop-in C++ surface for bbcat-dsp's sample-format entry points, backed by libbbx (CUDA, sm_100a).
 // Same names, argument meaning and error behaviour as src/SoundFormatConversions.h:20-198 of the
-// reference; the work happens in bbx_transfer_samples (include/bbx.h).  Ditherer must be NULL
-// (the reference tree only ships the no-op base class).
+// reference; the work happens in bbx_transfer_samples (include/bbx.h).
+//
+// Ditherer (src/SoundFormatConversions.h:39-54): the class is here with the reference's three virtuals.  A NULL ditherer
+// and converters without a dither call site take the plain GPU path.  TPDFDitherer (Dither_TPDF, which the reference's enum
+// names and its tree never implements) runs on the device (bbx_transfer_samples_dither).  Any other subclass is honoured
+// exactly as the reference would: the rectangle is loaded into the converter's intermediate type (sint32 / float / double)
+// by the GPU path, the caller's Dither() runs on the host for every sample -- same arguments (the frame LOOP counter as
+// `channel`, the converter's bit count) and the same call order as the reference's loops, reversed frame direction
+// included -- and the GPU path quantises the result.
 #pragma once
 
 #include <stdint.h>
+
+#include <vector>
 
 #include "../../include/bbx.h"
 
@@ -25,7 +34,31 @@ typedef enum {
   SampleFormat_Count = BBX_FMT_COUNT,
 } SampleFormat_t;
 
-class Ditherer;  // only NULL is accepted
+class Ditherer {
+public:
+  Ditherer() {}
+  virtual ~Ditherer() {}
+
+  virtual void Dither(uint_t channel, sint32_t& data, uint_t bits) { (void)channel; (void)data; (void)bits; }
+  virtual void Dither(uint_t channel, float& data, uint_t bits) { (void)channel; (void)data; (void)bits; }
+  virtual void Dither(uint_t channel, double& data, uint_t bits) { (void)channel; (void)data; (void)bits; }
+};
+
+typedef enum {
+  Dither_None = BBX_DITHER_NONE,
+  Dither_TPDF = BBX_DITHER_TPDF,
+} Dither_t;
+
+// Dither_TPDF on the device: no host hook, the noise is generated inside the conversion kernel (law: include/bbx.h, a7).
+// Every transfer draws from a fresh stream (the seed advances per call), so repeated blocks do not repeat their noise.
+class TPDFDitherer : public Ditherer {
+public:
+  explicit TPDFDitherer(uint64_t _seed = 0x5eed5eedull) : seed(_seed) {}
+  uint64_t NextSeed() { return seed += 0x9E3779B97F4A7C15ull; }
+
+private:
+  uint64_t seed;
+};
 
 inline SampleFormat_t SampleFormatOf(sint16_t) { return SampleFormat_16bit; }
 inline SampleFormat_t SampleFormatOf(sint32_t) { return SampleFormat_32bit; }
@@ -45,18 +78,59 @@ inline bool BlockTransferSanityChecks(uint_t& src_channel, uint_t& src_channels,
                                           allowsinglechannel ? 1 : 0) != 0;
 }
 
+namespace detail {
+
+// host-hook path for an arbitrary Ditherer subclass on a converter that has a dither call site
+template <typename T>
+inline void TransferSamplesHooked(const void* vsrc, SampleFormat_t srctype, bool src_be, uint_t src_channel, uint_t src_channels,
+                                  void* vdst, SampleFormat_t dsttype, bool dst_be, uint_t dst_channel, uint_t dst_channels,
+                                  uint_t nchannels, uint_t nframes, Ditherer* ditherer, uint_t bits, SampleFormat_t midtype) {
+  // the reference's loops run over the rectangle AFTER the sanity checks (a contiguous rectangle collapses to one frame)
+  if (!BlockTransferSanityChecks(src_channel, src_channels, dst_channel, dst_channels, nchannels, nframes)) return;
+  std::vector<T> mid((size_t)nchannels * nframes);
+  if (bbx_transfer_samples(vsrc, (int)srctype, src_be, src_channel, src_channels, &mid[0], (int)midtype, false, 0, nchannels,
+                           nchannels, nframes) != BBX_OK)
+    return;
+  // frames run backwards when the destination frame is the longer one (src/SoundFormatConversions.cpp:178-185); the hook
+  // still sees the loop counter counting up.  Channels run forwards in every converter that dithers.
+  const bool reversed = (size_t)dst_channels * GetBytesPerSample(dsttype) > (size_t)src_channels * GetBytesPerSample(srctype);
+  for (uint_t i = 0; i < nframes; i++) {
+    T* frame = &mid[(size_t)(reversed ? nframes - 1 - i : i) * nchannels];
+    for (uint_t j = 0; j < nchannels; j++) ditherer->Dither(i, frame[j], bits);
+  }
+  (void)bbx_transfer_samples(&mid[0], (int)midtype, false, 0, nchannels, vdst, (int)dsttype, dst_be, dst_channel, dst_channels,
+                             nchannels, nframes);
+}
+
+}  // namespace detail
+
 inline void TransferSamples(const void* vsrc, SampleFormat_t srctype, bool src_be, uint_t src_channel, uint_t src_channels,
                             void* vdst, SampleFormat_t dsttype, bool dst_be, uint_t dst_channel, uint_t dst_channels,
                             uint_t nchannels = ~0u, uint_t nframes = 1, Ditherer* ditherer = 0) {
-  if (ditherer) return;  // unsupported: the GPU path has no dither hook
-  (void)bbx_transfer_samples(vsrc, (int)srctype, src_be, src_channel, src_channels, vdst, (int)dsttype, dst_be, dst_channel,
-                             dst_channels, nchannels, nframes);
+  const int bits = ditherer ? bbx_dither_bits((int)srctype, (int)dsttype) : -1;
+  if (bits < 0) {  // no ditherer, or a converter that never calls it
+    (void)bbx_transfer_samples(vsrc, (int)srctype, src_be, src_channel, src_channels, vdst, (int)dsttype, dst_be, dst_channel,
+                               dst_channels, nchannels, nframes);
+  } else if (TPDFDitherer* tpdf = dynamic_cast<TPDFDitherer*>(ditherer)) {
+    (void)bbx_transfer_samples_dither(vsrc, (int)srctype, src_be, src_channel, src_channels, vdst, (int)dsttype, dst_be,
+                                      dst_channel, dst_channels, nchannels, nframes, BBX_DITHER_TPDF, tpdf->NextSeed());
+  } else if (srctype == SampleFormat_Float) {
+    detail::TransferSamplesHooked<float>(vsrc, srctype, src_be, src_channel, src_channels, vdst, dsttype, dst_be, dst_channel,
+                                         dst_channels, nchannels, nframes, ditherer, (uint_t)bits, SampleFormat_Float);
+  } else if (srctype == SampleFormat_Double) {
+    detail::TransferSamplesHooked<double>(vsrc, srctype, src_be, src_channel, src_channels, vdst, dsttype, dst_be, dst_channel,
+                                          dst_channels, nchannels, nframes, ditherer, (uint_t)bits, SampleFormat_Double);
+  } else {
+    detail::TransferSamplesHooked<sint32_t>(vsrc, srctype, src_be, src_channel, src_channels, vdst, dsttype, dst_be, dst_channel,
+                                            dst_channels, nchannels, nframes, ditherer, (uint_t)bits, SampleFormat_32bit);
+  }
 }
 
 inline void TransferSamplesLinear(const void* vsrc, SampleFormat_t srctype, void* vdst, SampleFormat_t dsttype,
                                   uint_t nsamples = 1, Ditherer* ditherer = 0) {
-  if (ditherer) return;
-  (void)bbx_transfer_samples_linear(vsrc, (int)srctype, vdst, (int)dsttype, nsamples);
+  // src/SoundFormatConversions.cpp:204-219: one frame of nsamples channels, machine byte order
+  if ((int)srctype <= 0 || srctype >= SampleFormat_Count || (int)dsttype <= 0 || dsttype >= SampleFormat_Count || !nsamples) return;
+  TransferSamples(vsrc, srctype, false, 0, nsamples, vdst, dsttype, false, 0, nsamples, nsamples, 1, ditherer);
 }
 
 template <typename T1, typename T2>

@@ -76,7 +76,7 @@ int bbx_block_transfer_sanity_checks(uint32_t* src_channel, uint32_t* src_channe
 /* ------------------------------------------------------------------------------------------
  * a3-a7  TransferSamples / TransferSamplesLinear
  *        src/SoundFormatConversions.cpp:151-198, :204-219 and the 2x2x6x6 converter table
- *        src/SoundFormatRawConversions.cpp:4516-4869 (all 100 non-NULL entries), ditherer == NULL.
+ *        src/SoundFormatRawConversions.cpp:4516-4869 (all 100 non-NULL entries), ditherer == NULL (a7 below).
  *        Invalid geometry or an Unknown format is a silent no-op returning BBX_OK, like the
  *        reference (.cpp:160-166).  dst == src is allowed for the host form and gives the
  *        out-of-place result; any other overlap is undefined (SoundFormatConversions.h:128-130).
@@ -88,6 +88,25 @@ int bbx_transfer_samples_dev(const void* src, int srctype, int src_be, uint32_t 
                              void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
                              uint32_t nchannels, uint32_t nframes, void* stream);
 int bbx_transfer_samples_linear(const void* src, int srctype, void* dst, int dsttype, uint32_t nsamples);
+
+/* a7  Ditherer (src/SoundFormatConversions.h:39-54).  The reference calls ditherer->Dither(frame, sval, bits) between the
+ * load and the quantisation of the narrowing converters only (src/SoundFormatRawConversions.cpp, e.g. :301, :749):
+ * 24/32-bit -> 16-bit and float/double -> 16-bit with bits = 16, 32-bit/float/double -> 24-bit with bits = 8,
+ * double -> 32-bit with bits = 0.  bbx_dither_bits returns that bit count, or -1 for a converter without a call site.
+ * The tree ships only the no-op base class; arbitrary subclasses are honoured on the host by the C++ shim
+ * (host/SoundFormatConversions.h: load -> hook -> quantise through the two entry points above).  Dither_TPDF -- named
+ * by the reference's Dither_t enum, implemented nowhere in the tree -- is offered as a device option: triangular noise
+ * of +-1 LSB of the destination word plus half an LSB before the truncating quantiser, from a counter-based generator
+ * keyed by (seed, index of the sample in the transfer rectangle); DESIGN.md states the law, oracle/formats.c restates
+ * it (parity unpinned against BBC output: there is none).  dither == BBX_DITHER_NONE is bbx_transfer_samples. */
+typedef enum { BBX_DITHER_NONE = 0, BBX_DITHER_TPDF = 1 } bbx_dither; /* Dither_t, same numeric values */
+int bbx_dither_bits(int srctype, int dsttype);
+int bbx_transfer_samples_dither(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
+                                void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
+                                uint32_t nchannels, uint32_t nframes, int dither, uint64_t seed);
+int bbx_transfer_samples_dither_dev(const void* src, int srctype, int src_be, uint32_t src_channel, uint32_t src_channels,
+                                    void* dst, int dsttype, int dst_be, uint32_t dst_channel, uint32_t dst_channels,
+                                    uint32_t nchannels, uint32_t nframes, int dither, uint64_t seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a8/a9  MixSamples<T> (src/SoundMixing.h:55-81) and MixSamples(..., Interpolator&, inc)

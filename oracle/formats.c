@@ -118,9 +118,53 @@ static void convert_store(const sample_reg* r, int srcfmt, uint8_t* p, int dstfm
   }
 }
 
+/* a7: the converters that call ditherer->Dither(i, sval, bits) and the bit count they pass (SoundFormatRawConversions.cpp:
+ * 24/32 -> 16 and float/double -> 16: 16 (:301, :499, :699, :902); 32/float/double -> 24: 8 (:541, :749, :952);
+ * double -> 32: 0 (:998)); -1 = no call site */
+int orc_dither_bits(int src, int dst) {
+  if (dst == ORC_FMT_16BIT && (src == ORC_FMT_24BIT || src == ORC_FMT_32BIT || src == ORC_FMT_FLOAT || src == ORC_FMT_DOUBLE)) return 16;
+  if (dst == ORC_FMT_24BIT && (src == ORC_FMT_32BIT || src == ORC_FMT_FLOAT || src == ORC_FMT_DOUBLE)) return 8;
+  if (dst == ORC_FMT_32BIT && src == ORC_FMT_DOUBLE) return 0;
+  return -1;
+}
+
+/* Dither_TPDF as libbbx defines it (include/bbx.h, a7): there is no reference implementation, this is the second
+ * statement of OUR law, so GPU-vs-oracle equality checks the kernel, not BBC parity. */
+static uint64_t dither_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static void dither_tpdf(sample_reg* r, int srcfmt, int bits, uint64_t seed, uint64_t index) {
+  const uint64_t z = dither_mix64(seed ^ (index * 0x9E3779B97F4A7C15ull));
+  const uint32_t u1 = (uint32_t)z, u2 = (uint32_t)(z >> 32);
+  if (srcfmt <= ORC_FMT_32BIT) {
+    int64_t v = (int64_t)r->i + (int64_t)(u1 >> (32 - bits)) - (int64_t)(u2 >> (32 - bits)) + ((int64_t)1 << (bits - 1));
+    if (v > 2147483647ll) v = 2147483647ll;
+    if (v < -2147483648ll) v = -2147483648ll;
+    r->i = (int32_t)v;
+  } else {
+    const double t = ((double)u1 - (double)u2) * 2.3283064365386962890625e-10 + (bits > 0 ? 0.5 : 0.0);
+    const double n = t * ((double)(1u << bits) * 4.656612873077392578125e-10);
+    if (srcfmt == ORC_FMT_FLOAT) r->f = (float)((double)r->f + n);
+    else r->d = r->d + n;
+  }
+}
+
 void orc_transfer_samples(const void* vsrc, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
                           void* vdst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
                           unsigned nchannels, unsigned nframes) {
+  orc_transfer_samples_dither(vsrc, srctype, src_be, src_channel, src_channels, vdst, dsttype, dst_be, dst_channel, dst_channels,
+                              nchannels, nframes, 0, 0, 0, 0);
+}
+
+/* dither: 0 none, 1 TPDF(seed).  hook != NULL restates the reference's Ditherer call: hook(user, i, kind, &sval, bits) with
+ * i = the frame LOOP counter (it counts up even when the frames run backwards), kind 0 sint32 / 1 float / 2 double */
+void orc_transfer_samples_dither(const void* vsrc, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                                 void* vdst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                                 unsigned nchannels, unsigned nframes, int dither, uint64_t seed, orc_dither_hook hook,
+                                 void* user) {
   if (!orc_block_transfer_sanity_checks(&src_channel, &src_channels, &dst_channel, &dst_channels, &nchannels, &nframes, 1))
     return;
   if (srctype <= ORC_FMT_UNKNOWN || srctype >= ORC_FMT_COUNT || dsttype <= ORC_FMT_UNKNOWN || dsttype >= ORC_FMT_COUNT)
@@ -136,12 +180,15 @@ void orc_transfer_samples(const void* vsrc, int srctype, int src_be, unsigned sr
 
   src += (size_t)src_channel * srclen;
   dst += (size_t)dst_channel * dstlen;
+  int reversed = 0;
   if (dstflen > srcflen) { /* bigger destination rectangle: run from the last frame backwards */
     src += (long)(nframes - 1) * srcflen;
     dst += (long)(nframes - 1) * dstlen * dst_channels;
     srcflen = -srcflen;
     dstflen = -dstflen;
+    reversed = 1;
   }
+  const int dbits = orc_dither_bits(srctype, dsttype);
 
   if (srctype == dsttype && src_be == dst_be) { /* __CopyMemory_n */
     for (i = 0; i < nframes; i++, src += srcflen, dst += dstflen)
@@ -157,6 +204,17 @@ void orc_transfer_samples(const void* vsrc, int srctype, int src_be, unsigned sr
       unsigned c = backwards ? (nchannels - 1 - j) : j;
       sample_reg r;
       load_sample(src + (size_t)c * srclen, srctype, src_be, &r);
+      if (dbits >= 0) {
+        if (hook) {
+          if (srctype <= ORC_FMT_32BIT) hook(user, i, 0, &r.i, (unsigned)dbits);
+          else if (srctype == ORC_FMT_FLOAT) hook(user, i, 1, &r.f, (unsigned)dbits);
+          else hook(user, i, 2, &r.d, (unsigned)dbits);
+        } else if (dither == 1) {
+          /* our law indexes the sample by its position in the rectangle, whatever the loop direction */
+          const unsigned frame = reversed ? nframes - 1 - i : i;
+          dither_tpdf(&r, srctype, dbits, seed, (uint64_t)frame * nchannels + c);
+        }
+      }
       convert_store(&r, srctype, dst + (size_t)c * dstlen, dsttype, dst_be);
     }
   }
@@ -181,4 +239,34 @@ void orc_transfer_samples_linear(const void* vsrc, int srctype, void* vdst, int 
     load_sample(src + (size_t)c * srclen, srctype, 0, &r);
     convert_store(&r, srctype, dst + (size_t)c * dstlen, dsttype, 0);
   }
+}
+
+/* tests/cpp/test_ditherer.h restated in C: the stateful test Ditherer the reference wrapper and the shim test run */
+static uint32_t test_pattern(uint32_t* calls, unsigned channel) { return ((*calls)++ * 40503u + channel * 7919u) * 2654435761u >> 8; }
+void orc_test_dither_hook(void* user, unsigned channel, int kind, void* data, unsigned bits) {
+  uint32_t* calls = (uint32_t*)user;
+  if (kind == 0) {
+    const uint32_t mask = bits ? ((1u << bits) - 1u) : 0u;
+    int64_t v = (int64_t)(*(int32_t*)data) + (int64_t)(test_pattern(calls, channel) & mask) - (int64_t)(mask >> 1);
+    if (v > 2147483647ll) v = 2147483647ll;
+    if (v < -2147483648ll) v = -2147483648ll;
+    *(int32_t*)data = (int32_t)v;
+  } else {
+    const double n = ((double)(test_pattern(calls, channel) & 0xffffu) / 32768.0 - 1.0) * (double)(1u << bits) / 2147483648.0;
+    if (kind == 1) *(float*)data += (float)n;
+    else *(double*)data += n;
+  }
+}
+
+/* same signature as ref_transfer_samples_ditherer (oracle/ref_wrap.cpp): mode 0 = a no-op Ditherer, 1 = the test Ditherer */
+static void noop_hook(void* user, unsigned channel, int kind, void* data, unsigned bits) {
+  (void)user; (void)channel; (void)kind; (void)data; (void)bits;
+}
+unsigned orc_transfer_samples_ditherer(const void* src, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                                       void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                                       unsigned nchannels, unsigned nframes, int mode) {
+  uint32_t calls = 0;
+  orc_transfer_samples_dither(src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel, dst_channels,
+                              nchannels, nframes, 0, 0, mode ? orc_test_dither_hook : noop_hook, &calls);
+  return calls;
 }

@@ -46,6 +46,19 @@ void orc_transfer_samples(const void* src, int srctype, int src_be, unsigned src
                           void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
                           unsigned nchannels, unsigned nframes);
 void orc_transfer_samples_linear(const void* src, int srctype, void* dst, int dsttype, unsigned nsamples);
+/* a7 Ditherer (SoundFormatConversions.h:39-54): call sites and bit counts of the converter table; the hook form restates
+ * where the reference calls ditherer->Dither, the TPDF form restates libbbx's own law (see formats.c) */
+typedef void (*orc_dither_hook)(void* user, unsigned frame_counter, int kind, void* data, unsigned bits);
+int orc_dither_bits(int srctype, int dsttype);
+void orc_transfer_samples_dither(const void* src, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                                 void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                                 unsigned nchannels, unsigned nframes, int dither, uint64_t seed, orc_dither_hook hook,
+                                 void* user);
+/* the hook of tests/cpp/test_ditherer.h restated in C (user = uint32_t call counter) */
+void orc_test_dither_hook(void* user, unsigned frame_counter, int kind, void* data, unsigned bits);
+unsigned orc_transfer_samples_ditherer(const void* src, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                                       void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                                       unsigned nchannels, unsigned nframes, int mode);
 
 /* ---- mixing.c : SoundMixing.h/.cpp, Interpolator.h ---- */
 void orc_mix_samples_f32(const float* src, unsigned src_channel, unsigned src_channels, float* dst,

@@ -19,6 +19,8 @@
 
 #include <vector>
 
+#include "../tests/cpp/test_ditherer.h"
+
 using namespace bbcat;
 
 extern "C" {
@@ -40,6 +42,18 @@ void ref_transfer_samples(const void* src, int srctype, int src_be, unsigned src
                           unsigned nchannels, unsigned nframes) {
   TransferSamples(src, (SampleFormat_t)srctype, src_be != 0, src_channel, src_channels, dst, (SampleFormat_t)dsttype,
                   dst_be != 0, dst_channel, dst_channels, nchannels, nframes, NULL);
+}
+
+/* the reference's TransferSamples with a Ditherer: mode 0 = its own no-op base class, 1 = the stateful test subclass
+ * (tests/cpp/test_ditherer.h); returns the number of hook calls the test subclass saw */
+unsigned ref_transfer_samples_ditherer(const void* src, int srctype, int src_be, unsigned src_channel, unsigned src_channels,
+                                       void* dst, int dsttype, int dst_be, unsigned dst_channel, unsigned dst_channels,
+                                       unsigned nchannels, unsigned nframes, int mode) {
+  Ditherer base;
+  TestDitherer test;
+  TransferSamples(src, (SampleFormat_t)srctype, src_be != 0, src_channel, src_channels, dst, (SampleFormat_t)dsttype,
+                  dst_be != 0, dst_channel, dst_channels, nchannels, nframes, mode ? (Ditherer*)&test : &base);
+  return test.calls;
 }
 
 void ref_transfer_samples_linear(const void* src, int srctype, void* dst, int dsttype, unsigned nsamples) {

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -35,6 +36,37 @@ int main() {
   uint8_t b[6];
   TransferSamples(f, SampleFormat_Float, false, 0, 2, b, SampleFormat_24bit, false, 0, 2, 2, 1);
   CHECK(b[0] == 0xff && b[1] == 0xff && b[2] == 0x7f && b[3] == 0xff && b[4] == 0xff && b[5] == 0xff);
+  // a7: a Ditherer that does nothing (the reference's base class) converts exactly like NULL; a subclass is called once per
+  // converted sample with the converter's bit count; TPDFDitherer runs on the device and stays within 1.5 LSB
+  {
+    struct Count : Ditherer {
+      uint_t calls, bits;
+      Count() : calls(0), bits(0) {}
+      void Dither(uint_t, float& data, uint_t b) { calls++; bits = b; data += 0.0f; }
+    };
+    float fx[6] = {0.25f, -0.5f, 0.999f, -1.0f, 1e-4f, 0.75f};
+    uint8_t plain[18], viabase[18], viacount[18], viatpdf[18];
+    Ditherer base;
+    Count count;
+    TPDFDitherer tpdf;
+    TransferSamples(fx, SampleFormat_Float, false, 0, 2, plain, SampleFormat_24bit, false, 0, 2, 2, 3);
+    TransferSamples(fx, SampleFormat_Float, false, 0, 2, viabase, SampleFormat_24bit, false, 0, 2, 2, 3, &base);
+    TransferSamples(fx, SampleFormat_Float, false, 0, 2, viacount, SampleFormat_24bit, false, 0, 2, 2, 3, &count);
+    TransferSamples(fx, SampleFormat_Float, false, 0, 2, viatpdf, SampleFormat_24bit, false, 0, 2, 2, 3, &tpdf);
+    CHECK(memcmp(plain, viabase, 18) == 0 && memcmp(plain, viacount, 18) == 0);
+    CHECK(count.calls == 6 && count.bits == 8);
+    for (int i = 0; i < 6; i++) {
+      const int a = (int)((uint32_t)plain[3 * i] | ((uint32_t)plain[3 * i + 1] << 8) | ((uint32_t)(int8_t)plain[3 * i + 2] << 16));
+      const int b = (int)((uint32_t)viatpdf[3 * i] | ((uint32_t)viatpdf[3 * i + 1] << 8) | ((uint32_t)(int8_t)viatpdf[3 * i + 2] << 16));
+      CHECK(abs(a - b) <= 2);
+    }
+    // widening conversions never call the ditherer
+    float wide[2];
+    sint16_t narrow[2] = {1000, -1000};
+    count.calls = 0;
+    TransferSamples(narrow, 0, 2, wide, 0, 2, 2, 1, &count);
+    CHECK(count.calls == 0 && wide[0] == 1000.0f / 32768.0f);
+  }
   // MixSamples with an Interpolator: gains 0, .25, .5 and the object ends at .75
   float ones[3] = {1, 1, 1}, acc[3] = {0, 0, 0};
   Interpolator interp(1.0f, 0.0f);

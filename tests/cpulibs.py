@@ -54,6 +54,12 @@ class CpuLib:
         self._transfer = fn("transfer_samples", None,
                             [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32])
         self._linear = fn("transfer_samples_linear", None, [vp, C.c_int, vp, C.c_int, u32])
+        self._ditherer = fn("transfer_samples_ditherer", u32,
+                            [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, C.c_int])
+        if prefix == "orc_":  # libbbx's own TPDF law and call-site table: restated in the oracle only
+            self._tpdf = fn("transfer_samples_dither", None,
+                            [vp, C.c_int, C.c_int, u32, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, C.c_int, C.c_uint64, vp, vp])
+            self._dbits = fn("dither_bits", C.c_int, [C.c_int, C.c_int])
         self._mix32 = fn("mix_samples_f32", None, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_float])
         self._mix64 = fn("mix_samples_f64", None, [vp, u32, u32, vp, u32, u32, u32, u32, C.c_double])
         self._mixi = fn("mix_samples_interp", None, [vp, u32, u32, vp, u32, u32, u32, u32, vp, C.c_float])
@@ -123,6 +129,21 @@ class CpuLib:
 
     def transfer_linear(self, src, srctype, dst, dsttype, nsamples):
         self._linear(_ptr(src), srctype, _ptr(dst), dsttype, nsamples)
+
+    def transfer_ditherer(self, src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                          dst_channels, nchannels, nframes, mode):
+        """TransferSamples with a Ditherer object: mode 0 = the no-op base class, 1 = the stateful test subclass of
+        tests/cpp/test_ditherer.h.  Returns the number of Dither() calls the test subclass received."""
+        return self._ditherer(_ptr(src), srctype, int(src_be), src_channel, src_channels, _ptr(dst), dsttype, int(dst_be),
+                              dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes, mode)
+
+    def transfer_tpdf(self, src, srctype, src_be, src_channel, src_channels, dst, dsttype, dst_be, dst_channel,
+                      dst_channels, nchannels, nframes, seed):
+        self._tpdf(_ptr(src), srctype, int(src_be), src_channel, src_channels, _ptr(dst), dsttype, int(dst_be),
+                   dst_channel, dst_channels, nchannels & 0xFFFFFFFF, nframes, 1, seed, None, None)
+
+    def dither_bits(self, srctype, dsttype):
+        return self._dbits(srctype, dsttype)
 
     # ---- mixing ----
     def mix(self, src, src_channel, src_channels, dst, dst_channel, dst_channels, nchannels, nframes, mul=1.0):

@@ -412,6 +412,18 @@ CASCADE_CASES = {
 }
 
 
+def gen_dither(ref):
+    """the reference's TransferSamples driven with the stateful test Ditherer (tests/cpp/test_ditherer.h), every converter
+    with a dither call site, both byte orders, three geometries (tests/test_dither.py)"""
+    import test_dither as td
+    d = {}
+    for s, dd, src_be, dst_be, gi, geom in td.all_cases():
+        out, calls = td.run_case(ref.transfer_ditherer, s, dd, src_be, dst_be, geom, 1)
+        assert calls == geom[4] * geom[5]
+        d["hook_%d_%d_%d_%d_%d" % (s, dd, src_be, dst_be, gi)] = out
+    np.savez_compressed(os.path.join(OUT, "dither.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = cl.reference()
@@ -425,6 +437,7 @@ def main():
     gen_biquad(ref)
     gen_allpass(ref)
     gen_cascade(ref)
+    gen_dither(ref)
     gen_conv()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
