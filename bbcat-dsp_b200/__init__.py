@@ -106,8 +106,10 @@ SYMBOLS = {
     "bbx_engine_timer_start": (C.c_int, [vp]),
     "bbx_engine_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "bbx_engine_launch_count": (u64, [vp]),
+    "bbx_engine_mac_kernel": (C.c_char_p, [vp]),
     "bbx_engine_profile_mac": (C.c_int, [vp, C.c_int]),
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+    "bbx_engine_exchange_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64)]),
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
     "bbx_engine_peer_export": (C.c_int, [vp, vp]),
@@ -626,6 +628,9 @@ class Convolver:
     def launch_count(self):
         return lib().bbx_engine_launch_count(self.h)
 
+    def mac_kernel_name(self):
+        return lib().bbx_engine_mac_kernel(self.h).decode()
+
     def profile_mac(self, enable=True):
         _check(lib().bbx_engine_profile_mac(self.h, int(enable)))
 
@@ -633,6 +638,12 @@ class Convolver:
         ms, n, units, nbytes = C.c_float(0), u64(0), u64(0), u64(0)
         _check(lib().bbx_engine_mac_time(self.h, C.byref(ms), C.byref(n), C.byref(units), C.byref(nbytes)))
         return {"ms": ms.value, "launches": n.value, "channel_blocks": units.value, "algorithmic_bytes": nbytes.value}
+
+    def exchange_time(self):
+        """input-sharded MIMO, while profile_mac is on: device time of the exchange step, exchanges, bytes sent to peers"""
+        ms, n, nbytes = C.c_float(0), u64(0), u64(0)
+        _check(lib().bbx_engine_exchange_time(self.h, C.byref(ms), C.byref(n), C.byref(nbytes)))
+        return {"ms": ms.value, "exchanges": n.value, "bytes_sent": nbytes.value}
 
     def set_tuning(self, ctas_per_sm=0, l2_keep_16ths=0, time_tile=0):
         """0 = leave as is; time_tile=1 forces the streaming MAC, l2_keep_16ths > 16 switches the hints off."""

@@ -170,9 +170,14 @@ struct bbx_engine {
   bool profile_mac = false;
   std::vector<cudaEvent_t> mac_events;  // pairs
   size_t mac_events_used = 0;
+  std::vector<cudaEvent_t> xchg_events;  // pairs around the input-sharded MIMO exchange (gather + peer stores / reduce-scatter)
+  size_t xchg_events_used = 0;
+  double xchg_ms_total = 0.0;
+  uint64_t xchg_count = 0, xchg_bytes = 0;
   double mac_ms_total = 0.0;
   uint64_t mac_launches = 0, mac_units = 0, mac_bytes = 0;
   int last_infmt = FMT_F32, last_outfmt = FMT_F32;
+  const char* last_mac_kernel = "none";  // name of the MAC kernel of the most recent call (bbx_engine_mac_kernel)
   // input-sharded MIMO (bbx_config::mimo_shard_*): partial spectra -> reduce-scatter -> local outputs only
   uint32_t sh_world = 1, sh_rank = 0, sh_o0 = 0, sh_nloc = 0;  // local outputs [sh_o0, sh_o0 + sh_nloc)
   uint32_t n_out_pcm = 0;                                      // channels written by bbx_process (= sh_nloc when sharded)
@@ -428,6 +433,7 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     e->launches++;
   }
   if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+  e->last_mac_kernel = use_tb ? (tb == 32 ? "k_fdl_mac_tb<32,256,8>" : "k_fdl_mac_tb<16,256,8>") : "k_fdl_mac";
   if (use_tb) {
     if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
     else launch_mac_tb<16>(e, pl, t0, nt, st);
@@ -824,6 +830,7 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   BBX_CUDA_TRY(cudaGetLastError());
   if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
   e->launches++;
+  e->last_mac_kernel = "k_mimo_tc";
   e->tc_launches++;
   e->mac_launches++;
   e->mac_units += (uint64_t)e->n_streams * T;
@@ -1084,6 +1091,7 @@ int bbx_engine_destroy(bbx_engine* e) {
     staging_free(pl->stg);
   }
   for (cudaEvent_t ev : e->mac_events) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->xchg_events) cudaEventDestroy(ev);
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_stop) cudaEventDestroy(e->ev_stop);
   if (e->ev_upload) cudaEventDestroy(e->ev_upload);
@@ -1408,6 +1416,20 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   // ---- 3b. input-sharded MIMO: sum the partial spectra over the ranks, keep the local outputs ----
   if (e->sh_world > 1 || e->comm) {
     const PlanView pv = use_tc ? tc_plan_view(e) : e->plan_steady.view();
+    cudaEvent_t x0 = nullptr, x1 = nullptr;
+    if (e->profile_mac) {
+      if (e->xchg_events_used + 2 > e->xchg_events.size()) {
+        size_t old = e->xchg_events.size();
+        e->xchg_events.resize(old + 64);
+        for (size_t i = old; i < e->xchg_events.size(); i++) BBX_CUDA_TRY(cudaEventCreate(&e->xchg_events[i]));
+      }
+      x0 = e->xchg_events[e->xchg_events_used++];
+      x1 = e->xchg_events[e->xchg_events_used++];
+      BBX_CUDA_TRY(cudaEventRecord(x0, st));
+      e->xchg_count++;
+      // bytes this rank sends to its peers: the partial spectra of every output it does not own
+      e->xchg_bytes += (uint64_t)(e->n_out - e->sh_nloc) * T * B * sizeof(float2);
+    }
     if (e->px_on) {
       e->px_epoch++;
       const uint32_t parity = e->px_epoch & 1u;
@@ -1425,6 +1447,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
       if ((rc = comm_reduce_scatter_f32(e->comm, (const float*)e->sh_send, (float*)e->sh_recv, (size_t)e->sh_nloc * T * B * 2, st)))
         return rc;
     }
+    if (x1) BBX_CUDA_TRY(cudaEventRecord(x1, st));
   }
   // ---- 4. inverse transforms, crossfade, delay ring ----
   if ((rc = launch_irfft(e, T, n_first, use_tc, st))) return rc;
@@ -1611,6 +1634,7 @@ int bbx_engine_timer_stop(bbx_engine* e, float* elapsed_ms) {
   return BBX_OK;
 }
 uint64_t bbx_engine_launch_count(const bbx_engine* e) { return e ? e->launches : 0; }
+const char* bbx_engine_mac_kernel(const bbx_engine* e) { return e ? e->last_mac_kernel : "none"; }
 
 int bbx_engine_profile_mac(bbx_engine* e, int enable) {
   BBX_REQUIRE(e != nullptr, "null engine");
@@ -1619,6 +1643,24 @@ int bbx_engine_profile_mac(bbx_engine* e, int enable) {
   e->mac_events_used = 0;
   e->mac_ms_total = 0.0;
   e->mac_launches = e->mac_units = e->mac_bytes = 0;
+  e->xchg_events_used = 0;
+  e->xchg_ms_total = 0.0;
+  e->xchg_count = e->xchg_bytes = 0;
+  return BBX_OK;
+}
+
+int bbx_engine_exchange_time(bbx_engine* e, float* total_ms, uint64_t* exchanges, uint64_t* bytes_sent) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i + 1 < e->xchg_events_used; i += 2) {
+    float ms = 0.f;
+    BBX_CUDA_TRY(cudaEventElapsedTime(&ms, e->xchg_events[i], e->xchg_events[i + 1]));
+    e->xchg_ms_total += ms;
+  }
+  e->xchg_events_used = 0;
+  if (total_ms) *total_ms = (float)e->xchg_ms_total;
+  if (exchanges) *exchanges = e->xchg_count;
+  if (bytes_sent) *bytes_sent = e->xchg_bytes;
   return BBX_OK;
 }
 

@@ -381,10 +381,16 @@ uint32_t bbx_allpass_get_state(const bbx_allpass* a, uint32_t filter, float* rin
 int bbx_engine_timer_start(bbx_engine* e);
 int bbx_engine_timer_stop(bbx_engine* e, float* elapsed_ms); /* synchronises the stream */
 uint64_t bbx_engine_launch_count(const bbx_engine* e);
+/* name of the multiply-accumulate kernel the most recent call ran (static string) */
+const char* bbx_engine_mac_kernel(const bbx_engine* e);
 /* when enabled every MAC launch is bracketed by events; _mac_time sums them (synchronises) */
 int bbx_engine_profile_mac(bbx_engine* e, int enable);
 int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint64_t* channel_blocks,
                         uint64_t* algorithmic_bytes);
+/* input-sharded MIMO engine, while _profile_mac is enabled: accumulated device time of the exchange step of every call
+ * (k_gather_spectra_peer + k_peer_wait, or k_gather_spectra + ncclReduceScatter), the number of exchanges and the bytes
+ * this rank sent to its peers (synchronises) */
+int bbx_engine_exchange_time(bbx_engine* e, float* total_ms, uint64_t* exchanges, uint64_t* bytes_sent);
 /* change the tuning knobs of bbx_config at run time (0 = leave as is); takes effect at the next call */
 int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile);
 /* mixdowns of many paths into few outputs (>= 4 paths per output, <= 32 outputs, <= 256 routes) run k_pcm_out_mix, which

@@ -97,6 +97,73 @@ def test_input_sharded_mimo_host_logic_gloo_world2():
 
 
 # ------------------------------------------------------------------------------------------------
+# output-sharded layout (the default MIMO split): rank g holds EVERY input and the rows
+# [g n_out / world, (g+1) n_out / world) of the matrix; no collective, the ranks' PCM outputs are just concatenated
+# ------------------------------------------------------------------------------------------------
+def _output_shard_engine(make_driver, rank, world, nin=NIN, nout=NOUT, **kw):
+    _paths()
+    import bbcat_dsp_b200 as bbx
+    import cpulibs as cl
+    from convkit import make_ir
+    P = -(-L // B)
+    o0, no = bbx.shard_range(nout, rank, world)
+    d = make_driver(B, P, nin, n_outputs=no, mode=cl.MODE_MIMO, max_blocks=T, **kw)
+    for oo in range(no):
+        for i in range(nin):
+            d.select(oo * nin + i, d.filter(make_ir(7000 + 64 * (o0 + oo) + i, L)))
+    return d
+
+
+def _cpu_worker_outputs(rank, world, port, ret):
+    _paths()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from convkit import OracleDriver, interleave, make_noise, run_float
+    o = _output_shard_engine(OracleDriver, rank, world)
+    x = interleave([make_noise(7100 + i, NBLK * B) for i in range(NIN)])  # every rank sees all inputs
+    mine = run_float(o, x, T * B)  # [frames][NOUT / world]
+    bufs = [torch.zeros((NBLK * B, NOUT // world), dtype=torch.float32) for _ in range(world)]
+    dist.all_gather(bufs, torch.from_numpy(np.ascontiguousarray(mine)))
+    if rank == 0:
+        ret["y"] = np.concatenate([b.numpy() for b in bufs], axis=1)
+    dist.destroy_process_group()
+
+
+def test_output_sharded_mimo_host_logic_gloo_world2():
+    """two ranks, each with all inputs and half of the outputs; no reduction.  Every output is summed exactly as in the
+    unsharded convolver (same inputs, same order), so the oracle's shards equal the full oracle bit for bit."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cpu_worker_outputs, args=(2, _free_port(), ret), nprocs=2, join=True)
+    _, y_full = _full_oracle()
+    y = ret["y"]
+    assert y.shape == y_full.shape
+    assert np.array_equal(y.view(np.uint32), y_full.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_off", [0, 1])
+def test_output_sharded_mimo_product_vs_oracle(bbx, tensor_off):
+    """the product's output shards (two engines, each all inputs x half of the outputs; tensor-core and SIMT MAC) against the
+    full oracle.  Tolerance class: the MAC plan of a shard cuts the row space differently from the full engine."""
+    from convkit import GpuDriver, interleave, make_noise, run_float
+    from parity import assert_float_parity
+    x = interleave([make_noise(7100 + i, NBLK * B) for i in range(NIN)])
+    parts = []
+    for rank in range(2):
+        g = _output_shard_engine(lambda *a, **kw: GpuDriver(bbx, *a, **kw), rank, 2, mimo_tensor=tensor_off)
+        parts.append(run_float(g, x, [T * B, 3 * B, (T - 3) * B]))
+        n_tc, status = g.eng.tensor_status()
+        assert status == 0 and (n_tc > 0) == (not tensor_off)
+        g.close()
+    y = np.concatenate(parts, axis=1)
+    _, y_full = _full_oracle()
+    for oo in range(NOUT):
+        assert_float_parity(y[:, oo], y_full[:, oo], "output-sharded out %d" % oo)
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU: the product path
 # ------------------------------------------------------------------------------------------------
 def _gpu_run(bbx, rank, world, comm, tensor_off, nin=NIN, nout=NOUT, peer=False):
