@@ -87,13 +87,17 @@ inline void TransferSamplesHooked(const void* vsrc, SampleFormat_t srctype, bool
                                   uint_t nchannels, uint_t nframes, Ditherer* ditherer, uint_t bits, SampleFormat_t midtype) {
   // the reference's loops run over the rectangle AFTER the sanity checks (a contiguous rectangle collapses to one frame)
   if (!BlockTransferSanityChecks(src_channel, src_channels, dst_channel, dst_channels, nchannels, nframes)) return;
+  // frames run backwards when the destination frame is the longer one (src/SoundFormatConversions.cpp:178-185); the hook
+  // still sees the loop counter counting up.  Channels run forwards in every converter that dithers.
+  const bool reversed = (size_t)dst_channels * GetBytesPerSample(dsttype) > (size_t)src_channels * GetBytesPerSample(srctype);
+  if (nframes == 1) {  // one frame (possibly a collapsed contiguous rectangle): the frame strides no longer matter, but
+    src_channels = src_channel + nchannels;  // the entry points below re-run the checks and must see a consistent geometry
+    dst_channels = dst_channel + nchannels;
+  }
   std::vector<T> mid((size_t)nchannels * nframes);
   if (bbx_transfer_samples(vsrc, (int)srctype, src_be, src_channel, src_channels, &mid[0], (int)midtype, false, 0, nchannels,
                            nchannels, nframes) != BBX_OK)
     return;
-  // frames run backwards when the destination frame is the longer one (src/SoundFormatConversions.cpp:178-185); the hook
-  // still sees the loop counter counting up.  Channels run forwards in every converter that dithers.
-  const bool reversed = (size_t)dst_channels * GetBytesPerSample(dsttype) > (size_t)src_channels * GetBytesPerSample(srctype);
   for (uint_t i = 0; i < nframes; i++) {
     T* frame = &mid[(size_t)(reversed ? nframes - 1 - i : i) * nchannels];
     for (uint_t j = 0; j < nchannels; j++) ditherer->Dither(i, frame[j], bits);
