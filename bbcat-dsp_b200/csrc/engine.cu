@@ -32,6 +32,7 @@
 #include "kernels_fft.cuh"
 #include "kernels_mac.cuh"
 #include "kernels_pcm.cuh"
+#include "mac_tbs.h"
 #include "mimo_tc.cuh"
 
 namespace bbx {
@@ -165,7 +166,10 @@ struct bbx_engine {
   bool upload_pending = false;
   uint32_t mac_occ = 1;          // resident streaming-MAC CTAs per SM; the plan has 148 * mac_occ row ranges
   float mac_l2_keep = 3.f / 16;  // fraction of H / FDL lines given L2 evict-last priority by the streaming MAC
-  uint32_t mac_time_tile = 16;   // TT of the time-batched MAC (0 = streaming kernel only)
+  uint32_t mac_time_tile = 16;   // time-batched MAC: 16 = k_fdl_mac_tbs (shared operand stream), 116 / 32 = round 1's
+                                 // k_fdl_mac_tb<16> / <32> (kept for A/B runs), 0 = streaming kernel only
+  int* mac_status_h = nullptr;   // mapped pinned word k_fdl_mac_tbs sets when a barrier wait timed out
+  int* mac_status = nullptr;
   uint64_t launches = 0;
   bool profile_mac = false;
   std::vector<cudaEvent_t> mac_events;  // pairs
@@ -399,7 +403,7 @@ void launch_mac_tb(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt, c
 
 // the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters and enough block-steps
 bool mac_uses_time_batching(const bbx_engine* e, const MacPlan& pl, uint32_t nt) {
-  const uint32_t tb = e->mac_time_tile;  // 0: streaming only
+  const uint32_t tb = e->mac_time_tile == 116 ? 16 : e->mac_time_tile;  // 0: streaming only
   return tb && nt >= tb / 2 && pl.n_terms && pl.total_rows / pl.n_terms >= 2 * tb;
 }
 
@@ -417,34 +421,58 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     ev1 = e->mac_events[e->mac_events_used++];
   }
   const uint32_t halfB = e->B / 2;
-  // the time-batched kernel pays a window fill of TT-1 rows per term: only worth it for long filters
   const uint32_t tb = e->mac_time_tile;  // 0: streaming only
   const bool use_tb = mac_uses_time_batching(e, pl, nt);
-  if (use_tb) {
-    // Nyquist sums of column 0 (the streaming kernel accumulates them inline): a few hundred latency-bound warps,
-    // forked onto the side stream so they run underneath the MAC instead of after it
-    BBX_CUDA_TRY(cudaEventRecord(e->ev_fork, st));
-    BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
-    k_nyq_mac<<<dim3(pl.n_ctas, ceil_div(nt, 32)), 32, 0, e->s_aux>>>(pl.segs(), pl.cta_seg_begin(), e->fdl,
-                                                                     e->nyq_part + (uint64_t)t0 * e->max_slots, e->B, e->R,
-                                                                     e->head, t0, nt, e->max_slots);
+  // k_fdl_mac_tbs covers calls of more than 16 blocks (two or four time tiles per CTA); shorter batched calls and the
+  // A/B settings run round 1's per-thread-copy kernel
+  const bool use_tbs = use_tb && tb == 16 && nt > 16;
+  if (use_tbs) {
+    MacTbsArgs a;
+    a.segs = pl.segs();
+    a.cta_seg_begin = pl.cta_seg_begin();
+    a.n_plan_ctas = pl.n_ctas;
+    a.fdl = e->fdl;
+    a.ypart = e->ypart + (uint64_t)t0 * e->max_slots * e->B;
+    a.nyq_part = e->nyq_part + (uint64_t)t0 * e->max_slots;
+    a.B = e->B;
+    a.R = e->R;
+    a.head = e->head;
+    a.t0 = t0;
+    a.nt = nt;
+    a.slot_stride = e->max_slots;
+    a.status = e->mac_status;
+    BBX_CUDA_TRY(launch_nyq_mac2(a, st));
+    if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+    BBX_CUDA_TRY(launch_mac_tbs(a, st, &e->last_mac_kernel));
+    if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
+    e->launches += 2;
+  } else {
+    if (use_tb) {
+      // Nyquist sums of column 0 (the streaming kernel accumulates them inline): a few hundred latency-bound warps,
+      // forked onto the side stream so they run underneath the MAC instead of after it
+      BBX_CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+      BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
+      k_nyq_mac<<<dim3(pl.n_ctas, ceil_div(nt, 32)), 32, 0, e->s_aux>>>(pl.segs(), pl.cta_seg_begin(), e->fdl,
+                                                                       e->nyq_part + (uint64_t)t0 * e->max_slots, e->B, e->R,
+                                                                       e->head, t0, nt, e->max_slots);
+      BBX_CUDA_TRY(cudaGetLastError());
+      BBX_CUDA_TRY(cudaEventRecord(e->ev_join, e->s_aux));
+      e->launches++;
+    }
+    if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
+    e->last_mac_kernel = use_tb ? (tb == 32 ? "k_fdl_mac_tb<32,256,8>" : "k_fdl_mac_tb<16,256,8>") : "k_fdl_mac";
+    if (use_tb) {
+      if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
+      else launch_mac_tb<16>(e, pl, t0, nt, st);
+    } else if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
+    else if (halfB == 128) launch_mac_t<128>(e, pl, t0, nt, st);
+    else if (halfB == 64) launch_mac_t<64>(e, pl, t0, nt, st);
+    else launch_mac_t<32>(e, pl, t0, nt, st);
     BBX_CUDA_TRY(cudaGetLastError());
-    BBX_CUDA_TRY(cudaEventRecord(e->ev_join, e->s_aux));
+    if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
     e->launches++;
+    if (use_tb) BBX_CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
   }
-  if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
-  e->last_mac_kernel = use_tb ? (tb == 32 ? "k_fdl_mac_tb<32,256,8>" : "k_fdl_mac_tb<16,256,8>") : "k_fdl_mac";
-  if (use_tb) {
-    if (tb == 32) launch_mac_tb<32>(e, pl, t0, nt, st);
-    else launch_mac_tb<16>(e, pl, t0, nt, st);
-  } else if (halfB >= 256) launch_mac_t<256>(e, pl, t0, nt, st);
-  else if (halfB == 128) launch_mac_t<128>(e, pl, t0, nt, st);
-  else if (halfB == 64) launch_mac_t<64>(e, pl, t0, nt, st);
-  else launch_mac_t<32>(e, pl, t0, nt, st);
-  BBX_CUDA_TRY(cudaGetLastError());
-  if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
-  e->launches++;
-  if (use_tb) BBX_CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
   e->mac_launches++;
   e->mac_units += (uint64_t)e->n_streams * nt;
   // 16 P K + 16 K + (bytes_in + bytes_out) B per channel-block, K = B + 1
@@ -844,7 +872,7 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
 void apply_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile) {
   if (ctas_per_sm) e->mac_occ = std::min(ctas_per_sm, 4u);
   if (l2_keep_16ths) e->mac_l2_keep = (l2_keep_16ths > 16u) ? 0.f : l2_keep_16ths / 16.0f;  // > 16: hints off
-  if (time_tile) e->mac_time_tile = (time_tile == 16 || time_tile == 32) ? time_tile : 0;     // 1: streaming only
+  if (time_tile) e->mac_time_tile = (time_tile == 16 || time_tile == 32 || time_tile == 116) ? time_tile : 0;  // 1: streaming only
   e->steady_dirty = true;
 }
 
@@ -936,6 +964,9 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   BBX_CUDA_TRY(cudaEventCreate(&e->ev_start));
   BBX_CUDA_TRY(cudaEventCreate(&e->ev_stop));
   BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
+  BBX_CUDA_TRY(cudaHostAlloc((void**)&e->mac_status_h, sizeof(int), cudaHostAllocMapped));
+  *e->mac_status_h = 0;
+  BBX_CUDA_TRY(cudaHostGetDevicePointer((void**)&e->mac_status, e->mac_status_h, 0));
 
   const uint32_t B = e->B, N = 2 * B;
   // twiddles exp(-2 pi i j / N), computed in double
@@ -1081,6 +1112,7 @@ int bbx_engine_destroy(bbx_engine* e) {
   cudaFree(e->tc_fparts_d);
   cudaFree(e->tc_view);
   if (e->tc_status_h) cudaFreeHost(e->tc_status_h);
+  if (e->mac_status_h) cudaFreeHost(e->mac_status_h);
   cudaFree(e->tc_trace);
   if (e->tc_ftab_h) cudaFreeHost(e->tc_ftab_h);
   if (e->tc_fparts_h) cudaFreeHost(e->tc_fparts_h);
@@ -1587,6 +1619,11 @@ int bbx_engine_sync(bbx_engine* e) {
   if (e->px_status_h && *(volatile int*)e->px_status_h) {
     set_error("peer mixdown: rank %d never published its partial spectra (timed out); results are invalid",
               *(volatile int*)e->px_status_h - 1);
+    return BBX_ERR_CUDA;
+  }
+  if (e->mac_status_h && *(volatile int*)e->mac_status_h) {
+    set_error("k_fdl_mac_tbs: a barrier wait timed out inside the time-batched MAC (status %d); results are invalid",
+              *(volatile int*)e->mac_status_h);
     return BBX_ERR_CUDA;
   }
   if (e->tc_status_h && *(volatile int*)e->tc_status_h) {

@@ -84,12 +84,13 @@ def test_batching_invariance_bit_exact(bbx):
     assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
 
 
-@pytest.mark.parametrize("kw", [dict(mac_time_tile=1), dict(mac_time_tile=32), dict(mac_time_tile=1, mac_l2_keep_16ths=5),
+@pytest.mark.parametrize("kw", [dict(mac_time_tile=1), dict(mac_time_tile=32), dict(mac_time_tile=116), dict(mac_time_tile=1, mac_l2_keep_16ths=5),
                                 dict(mac_time_tile=1, mac_ctas_per_sm=2)])
 def test_mac_variants_bit_identical(bbx, kw):
-    """Every MAC kernel variant (streaming, time-batched TT = 16 (default) / 32, L2-residency hints, other unroll
-    depth) uses the same plan and the same per-output FMA order: outputs must be bit-identical to the default,
-    including across a crossfaded filter switch, ragged call sizes and a MIMO matrix."""
+    """Every MAC kernel variant (streaming; time-batched: the shared-stream kernel k_fdl_mac_tbs (default) and round 1's
+    per-thread-copy kernels, tile 116 = TT 16, 32 = TT 32; L2-residency hints; other unroll depth) uses the same plan and
+    the same per-output FMA order: outputs must be bit-identical to the default, including across a crossfaded filter
+    switch, ragged call sizes and a MIMO matrix."""
     B, L, nch, nblk = 512, 20000, 5, 76
     irs = [make_ir(400 + c, L) for c in range(nch + 1)]
     xi = interleave([make_noise(410 + c, nblk * B) for c in range(nch)])
@@ -117,6 +118,52 @@ def test_mac_variants_bit_identical(bbx, kw):
         outs.append(run_float(g, xm, 36 * B))
         g.close()
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("B,P,nch,calls,occ", [
+    (64, 40, 3, [64, 17, 33, 100, 9, 64], 0),      # B = 64: four tiles on 64 columns; more than one tile group (100 blocks)
+    (128, 37, 5, [20, 32, 17, 64, 31], 0),          # B = 128: two tiles (17..32 blocks) and four
+    (512, 45, 20, [64, 48, 33, 64], 2),             # 45 partitions (13 mod 16), 296 row ranges: many short segments per CTA
+    (256, 70, 9, [64, 64, 24, 64, 64], 0),          # FDL ring wraps inside the calls (R = 70 + 64 - 1)
+    (512, 33, 150, [64, 40], 0),                    # many channels: several whole filters per row range
+])
+def test_shared_stream_mac_shapes_bit_identical(bbx, B, P, nch, calls, occ):
+    """k_fdl_mac_tbs (TMA-fed shared operand stream, two / four time tiles per CTA, persistent over row ranges) against the
+    streaming kernel on the same plan: bit-identical for every tile count, partial tile groups, ragged segment lengths,
+    ring wrap, and row ranges that hold several segments."""
+    L = P * B - B // 3
+    irs = [make_ir(900 + c, L - 7 * (c % 5) * B // 8) for c in range(nch)]  # a few shorter filters: uneven terms
+    total = sum(calls)
+    xi = interleave([make_noise(950 + c, total * B) for c in range(nch)])
+    outs = []
+    for tile in (0, 1):
+        g = GpuDriver(bbx, B, P, nch, max_blocks=max(calls), mac_time_tile=tile, mac_ctas_per_sm=occ)
+        for c in range(nch):
+            g.select(c, g.filter(irs[c]))
+        outs.append(run_float(g, xi, [n * B for n in calls]))
+        name = g.eng.mac_kernel_name()
+        g.close()
+        assert name.startswith("k_fdl_mac_tbs") if tile == 0 else name == "k_fdl_mac", name
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+def test_shared_stream_mac_vs_oracle(bbx, orc):
+    """the default batched path against the CPU oracle and float64 direct convolution (not only against its sibling kernel)"""
+    B, L, nch, nblk = 256, 256 * 36 + 100, 4, 96
+    g, o = both(bbx, B, 37, nch, max_blocks=64)
+    irs = [make_ir(970 + c, L) for c in range(nch)]
+    xs = [make_noise(980 + c, nblk * B) for c in range(nch)]
+    for c in range(nch):
+        g.select(c, g.filter(irs[c]))
+        o.select(c, o.filter(irs[c]))
+    xi = interleave(xs)
+    yg = run_float(g, xi, [64 * B, 32 * B])
+    yo = run_float(o, xi, [64 * B, 32 * B])
+    assert g.eng.mac_kernel_name().startswith("k_fdl_mac_tbs")
+    g.close()
+    for c in range(nch):
+        assert_float_parity(yg[:, c], yo[:, c], "vs oracle ch %d" % c)
+    assert_float_parity(yg[:, 1], orc.direct(xs[1], irs[1]), "vs float64 direct")
 
 
 @pytest.mark.parametrize("direct", [True, False])
