@@ -23,6 +23,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// test_wait never suspends the thread (try_wait may park it for a hardware time limit when the phase is still open):
+// the one to use for "is the slot free yet?" polls whose answer is usually no
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait: gives up after ~4e6 polls so that a protocol bug ends the kernel with wrong results (caught by the parity
 // tests) instead of hanging the device
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
@@ -53,6 +66,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only) and the arrive that fires on an mbarrier once all of this
+// thread's earlier cp.async copies have landed (noinc: the barrier's expected count already includes it)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned addresses and size)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

@@ -10,13 +10,16 @@
 //   * round 1 fetched those two values per thread with cp.async (LDGSTS): two 8-byte copies + address arithmetic per
 //     32 FFMA2, 21 non-FMA instructions per step, and the LDGSTS rate of the SM (8 cycles per warp instruction) was as
 //     much a bound as the FMA pipe.  Here a CTA is 64 columns x 4 time tiles (256 consumer threads): the four tiles
-//     share every filter row and every FDL row, which ONE producer warp streams into shared-memory rings with
-//     cp.async.bulk (one 512-byte bulk copy per row tile, completion on mbarriers).  Consumers issue two LDS.64 with
-//     immediate offsets per step and nothing else; L2 -> SM traffic per FMA drops 3.4x.
+//     share every filter row and every FDL row.  Rows travel into shared-memory rings in chunks of 4 KB, ONE 16-byte
+//     cp.async per thread per chunk (256 threads = one chunk), completion counted on mbarriers
+//     (cp.async.mbarrier.arrive): 0.25 LDGSTS per thread and step instead of 2.  Consumers issue two LDS.64 with
+//     immediate offsets per step; L2 -> SM traffic per FMA drops 3.4x.  (A first version fed the rings with one
+//     512-byte cp.async.bulk per row from a producer warp: 715 k bulk copies per launch, one per ~160 cycles and SM --
+//     the TMA unit's rate for small copies was the bound and the kernel ran at 0.42 ms; ncu in profiles/.)
 //   * the register window of a new (channel, partition range) segment is filled from the same shared-memory stream
-//     (the producer simply starts the segment's FDL rows TT * NTILE - 1 rows early), and the producer runs ahead across
-//     segment boundaries, so the window fill and the pipeline fill of round 1 (~20 % of a CTA's time) overlap the
-//     previous segment's arithmetic.
+//     (the segment's FDL rows simply start TT * NTILE - 1 rows early), and the copies run ahead across segment
+//     boundaries, so the window fill and the pipeline fill of round 1 (~20 % of a CTA's time) overlap the previous
+//     segment's arithmetic.
 //   * persistent CTAs: one CTA pair per SM walks several consecutive row ranges of the plan, so there is one ramp-up
 //     per launch instead of one per wave.
 #include <algorithm>
@@ -32,21 +35,17 @@ struct TbsCfg {
   static constexpr int TT = 16;                      // block-steps per thread
   static constexpr int COLS = 256 / NTILE;           // bins per CTA
   static constexpr int ROWB = COLS * 8;              // bytes of one row tile
-  static constexpr int CHB = 4096;                   // bytes per chunk = one mbarrier phase
+  static constexpr int CHB = 4096;                   // bytes per chunk: 256 threads x one 16-byte cp.async
   static constexpr int CH = CHB / ROWB;              // rows per chunk: 8 (NTILE = 4), 4 (NTILE = 2)
   static constexpr int GC = TT / CH;                 // chunks per group of 16 steps
   static constexpr int FILL = TT * NTILE;            // FDL rows a segment needs before its first step
   static constexpr int FILLC = FILL / CH;
   static constexpr int XCH = 16;                     // chunks of the FDL ring: the live window + one group + look-ahead
   static constexpr int HCH = 8;                      // chunks of the filter ring: one group + look-ahead
-  static constexpr int LA = (NTILE == 4) ? 4 : 3;    // chunks the producer tries to stay ahead of the current group
-  static constexpr int NCONS = 8;                    // consumer warps (the last one doubles as the producer)
-  static constexpr int THREADS = 32 * NCONS;
-  static constexpr int BAR_BYTES = 8 * 2 * (XCH + HCH) + 8;  // + the "a wait timed out" word
-  static constexpr int SMEM = (XCH + HCH) * CHB + BAR_BYTES;
+  static constexpr int THREADS = 256;
+  static constexpr int SMEM = (XCH + HCH) * CHB;
   static_assert(NTILE == 2 || NTILE == 4, "tiles per CTA");
-  static_assert(FILLC - (TT / CH) + 1 + GC + LA <= XCH, "FDL ring: live window + current group + look-ahead");
-  static_assert(GC + LA <= HCH, "filter ring: current group + look-ahead");
+  static_assert(FILLC + GC <= XCH && GC <= HCH, "a group's chunks must fit the rings next to the live window");
 };
 
 // Chunk streams.  Every segment (a run of partitions p0 .. p0 + np - 1 of one filter against one input's FDL) is two
@@ -54,16 +53,19 @@ struct TbsCfg {
 //   filter stream  q = 0 .. np - 1          row p0 + q of H
 //   FDL stream     j = 0 .. FILL - 2 + np   row (base + FILL - 1 - j) mod R, base = slot of the tile group's first step - p0
 // Tile i (block-steps 16 i .. 16 i + 15 of the group) meets, at step q, FDL stream row j = FILL - 1 - 16 i + q; its
-// register window holds the 15 rows before that.  Chunks are issued in the order the consumers need them: the FILLC
-// chunks of the fill, then filter chunk k / FDL chunk FILLC + k alternately.  Chunk c of a stream lives in ring slot
-// c mod ring size, phase parity (c / ring size) & 1; "full" barriers count the producer's expect_tx + the copied bytes,
-// "empty" barriers one arrival per consumer warp.
+// register window holds the 15 rows before that.  Chunks are issued in the order they are needed: the FILLC chunks of
+// the fill, then filter chunk k / FDL chunk FILLC + k alternately; chunk c of a stream lives in ring slot c mod ring size.
 //
-// The producer is not a warp of its own: a ninth warp would put five warps on one scheduler and cap the kernel at 96
-// registers (the register file is per scheduler), which spills.  The last consumer warp issues the copies at the top
-// of every group of 16 steps instead: what this group needs (blocking, normally long done) and up to LA chunks beyond
-// (only while ring slots are free), so the copies run one to two groups ahead of the arithmetic, across segment
-// boundaries.
+// Synchronisation is one block barrier per group of 16 steps and nothing else.  At the top of a group every thread
+// waits for its own copies (cp.async.wait_all), the barrier makes everybody's pieces visible and proves that everybody
+// has finished the previous group, and then every thread issues its 16 bytes of the following chunks for as far as
+// the rings have room (the chunks all tiles have finished with are known by construction, all warps being at the same
+// step).  The chunks a group reads were therefore issued a whole group earlier -- 16 steps x 32 packed FMAs per warp to
+// cover the L2 / HBM latency -- and the inner loop is LDS + FFMA2 only.  (Two mbarrier-based versions came first: a
+// TMA producer warp with one 512-byte cp.async.bulk per row, 0.42 ms, and per-thread cp.async with
+// cp.async.mbarrier.arrive, 0.31 ms: try_wait / arrive on SM 10.0 cost ~12 instructions each -- the cluster-window
+// address is rebuilt from SR_CgaCtaId --, 16 to 20 barrier operations per group came to 700 instructions next to the 512
+// FFMA2; ncu captures in profiles/.)
 template <int NTILE>
 __global__ void __launch_bounds__(TbsCfg<NTILE>::THREADS, 2)
 k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, uint32_t n_plan_ctas,
@@ -71,11 +73,10 @@ k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
               uint32_t head0, uint32_t t0, uint32_t nt, uint32_t ncoltiles, uint32_t slot_stride, int* __restrict__ status) {
   using C = TbsCfg<NTILE>;
   constexpr int TT = C::TT, COLS = C::COLS, ROWB = C::ROWB, CH = C::CH, CHB = C::CHB, FILL = C::FILL, FILLC = C::FILLC;
-  constexpr int XCH = C::XCH, HCH = C::HCH, NCONS = C::NCONS, GC = C::GC, LA = C::LA;
+  constexpr int XCH = C::XCH, HCH = C::HCH, GC = C::GC;
   extern __shared__ __align__(128) uint8_t tbs_smem[];
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(tbs_smem);
-  const uint32_t xring = smem0, hring = smem0 + XCH * CHB;
-  const uint32_t xfull = hring + HCH * CHB, xempty = xfull + 8 * XCH, hfull = xempty + 8 * XCH, hempty = hfull + 8 * HCH;
+  const uint32_t xring = (uint32_t)__cvta_generic_to_shared(tbs_smem), hring = xring + XCH * CHB;
+  (void)status;
 
   const uint32_t coltile = blockIdx.x % ncoltiles, tgroup = blockIdx.x / ncoltiles;
   const uint32_t tbase0 = tgroup * (TT * NTILE);     // first block-step of this tile group, relative to t0
@@ -84,95 +85,77 @@ k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
   const uint32_t pc0 = blockIdx.y * plan_per_cta, pc1 = min(pc0 + plan_per_cta, n_plan_ctas);
   if (pc0 >= pc1) return;
   const uint32_t sb = cta_seg_begin[pc0], se = cta_seg_begin[pc1];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool is_prod = warp == NCONS - 1;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < XCH; s++) {
-      ac::mbar_init(xfull + 8 * s, 1);
-      ac::mbar_init(xempty + 8 * s, NCONS);
-    }
-    for (int s = 0; s < HCH; s++) {
-      ac::mbar_init(hfull + 8 * s, 1);
-      ac::mbar_init(hempty + 8 * s, NCONS);
-    }
-    ac::mbar_init_fence();
-  }
-  // a wait that times out (protocol bug) poisons the result but never hangs the device: the first time-out sets a word
-  // in shared memory, after which every wait gives up after a handful of polls
-  const uint32_t dead = smem0 + C::SMEM - 8;
-  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(tbs_smem + C::SMEM - 8) = 0u;
-  __syncthreads();
-  auto wait = [&](uint32_t bar, uint32_t parity) {
-    if (!ac::mbar_try_wait(bar, parity)) ac::mbar_wait_or_die(bar, parity, dead);
-  };
-
-  // ---- producer cursor (meaningful in the producer warp only; uniform across its lanes) ----
-  uint32_t p_si = sb;          // segment being issued
-  uint32_t p_xk = 0, p_hk = 0;  // chunks of that segment issued so far
+  // ---- copy cursor (identical in every thread): the chunk sequence is walked with running pointers ----
+  constexpr uint32_t kPiecesPerRow = ROWB / 16;
+  const uint32_t prow = threadIdx.x / kPiecesPerRow;  // my row of every chunk
+  const uint32_t my16 = threadIdx.x * 16;             // offset of my 16 bytes inside a chunk's slot
+  const uint32_t chunk_bytes_g = CH * B * (uint32_t)sizeof(float2);  // global bytes between my pieces of consecutive chunks
+  const uint64_t ring_bytes_g = (uint64_t)R * B * sizeof(float2);
+  uint32_t p_si = sb;           // segment being issued
   uint32_t p_xn = 0, p_hn = 0;  // chunks issued since the kernel started = global index of the next chunk
-  // issue the next chunk of the sequence; blocking = wait for its ring slot, else give up when the slot is still in use
-  auto issue_next = [&](bool blocking) -> bool {
+  int p_xrem = 0, p_hrem = 0;   // rows of the segment's FDL / filter stream not yet issued (first row of the next chunk on)
+  int p_fill = 0;               // > 0: fill chunks still to go; 0: a filter chunk is next; -1: an FDL chunk is next
+  int p_xr = 0;                 // FDL ring row of my piece of the next FDL chunk
+  const char* p_xptr = nullptr;  // ... and its address
+  const char* p_hptr = nullptr;  // address of my piece of the next filter chunk
+  auto open_segment = [&]() {
     const MacSeg sg = segs[p_si];
-    const uint32_t np = sg.np, nx = FILL - 1 + np;
-    const uint32_t nxc = (nx + CH - 1) / CH, nhc = (np + CH - 1) / CH;
-    const bool want_x = p_xk < (uint32_t)FILLC || !(p_hk < nhc && p_hk + FILLC <= p_xk);
-    if (want_x && p_xk < nxc) {
-      const uint32_t slot = p_xn & (XCH - 1), par = ((p_xn / XCH) & 1u) ^ 1u;
-      if (blocking) {
-        wait(xempty + 8 * slot, par);
-      } else if (!ac::mbar_try_wait(xempty + 8 * slot, par)) {
-        return false;
-      }
-      const uint32_t rows = min((uint32_t)CH, nx - p_xk * CH);
-      if (lane == 0) ac::mbar_expect_tx(xfull + 8 * slot, rows * ROWB);
-      __syncwarp();
-      if (lane < rows) {
-        uint32_t base = s0 + R - (sg.p0 % R);
-        if (base >= R) base -= R;
-        int r = (int)(base + FILL - 1) - (int)(p_xk * CH + lane);
-        r %= (int)R;
-        if (r < 0) r += (int)R;
-        const float2* src = fdl + ((uint64_t)sg.fdl_ch * R + (uint32_t)r) * B + col0;
-        ac::bulk_g2s(xring + slot * CHB + lane * ROWB, src, ROWB, xfull + 8 * slot);
-      }
-      p_xk++;
-      p_xn++;
-    } else {
-      const uint32_t slot = p_hn & (HCH - 1), par = ((p_hn / HCH) & 1u) ^ 1u;
-      if (blocking) {
-        wait(hempty + 8 * slot, par);
-      } else if (!ac::mbar_try_wait(hempty + 8 * slot, par)) {
-        return false;
-      }
-      const uint32_t rows = min((uint32_t)CH, np - p_hk * CH);
-      if (lane == 0) ac::mbar_expect_tx(hfull + 8 * slot, rows * ROWB);
-      __syncwarp();
-      if (lane < rows) {
-        const float2* src = reinterpret_cast<const float2*>(sg.H) + (uint64_t)(sg.p0 + p_hk * CH + lane) * B + col0;
-        ac::bulk_g2s(hring + slot * CHB + lane * ROWB, src, ROWB, hfull + 8 * slot);
-      }
-      p_hk++;
-      p_hn++;
-    }
-    if (p_xk >= nxc && p_hk >= nhc) {  // segment complete
-      p_si++;
-      p_xk = p_hk = 0;
-    }
-    return true;
+    p_xrem = (int)(FILL - 1 + sg.np);
+    p_hrem = (int)sg.np;
+    p_fill = FILLC;
+    uint32_t base = s0 + R - (sg.p0 % R);
+    if (base >= R) base -= R;
+    int r = (int)(base + FILL - 1) - (int)prow;  // >= 0; short rings (R < FILL: few blocks per call on 64 columns) wrap twice
+    while (r >= (int)R) r -= (int)R;
+    p_xr = r;
+    const uint32_t poff = (threadIdx.x % kPiecesPerRow) * 16;
+    p_xptr = reinterpret_cast<const char*>(fdl + ((uint64_t)sg.fdl_ch * R + (uint32_t)r) * B + col0) + poff;
+    p_hptr = reinterpret_cast<const char*>(reinterpret_cast<const float2*>(sg.H) + (uint64_t)(sg.p0 + prow) * B + col0) + poff;
   };
-  // everything up to (need_x, need_h) chunks is issued when this returns; then up to LA chunks more, while slots are free
-  auto produce = [&](uint32_t need_x, uint32_t need_h) {
-    while (p_si < se && (p_xn < need_x || p_hn < need_h)) issue_next(true);
-    while (p_si < se && (p_xn < need_x + LA || p_hn < need_h + LA))
-      if (!issue_next(false)) break;
+  if (p_si < se) open_segment();
+  // One synchronisation point: the chunks below (need_x, need_h) are about to be read; the chunks below (done_x, done_h)
+  // have been read by every tile.  Issues this thread's pieces of the following chunks as far as the rings have room.
+  auto sync_point = [&](uint32_t need_x, uint32_t need_h, uint32_t done_x, uint32_t done_h) {
+    ac::cp_async_wait_all();
+    __syncthreads();
+    const bool late = p_xn < need_x || p_hn < need_h;  // only at the start of the kernel: nothing was issued ahead yet
+    while (p_si < se) {
+      if ((p_fill != 0 && p_xrem > 0) || p_hrem <= 0) {
+        if (p_xn >= done_x + XCH) break;
+        if (p_xrem > (int)prow) ac::cp_async16(xring + (p_xn & (XCH - 1)) * CHB + my16, p_xptr);
+        p_xn++;
+        p_xrem -= CH;
+        p_xr -= CH;
+        p_xptr -= chunk_bytes_g;
+        if (p_xr < 0) {  // the ring wraps
+          p_xr += (int)R;
+          p_xptr += ring_bytes_g;
+        }
+        p_fill = p_fill > 0 ? p_fill - 1 : 0;  // after the fill: a filter chunk is next
+      } else {
+        if (p_hn >= done_h + HCH) break;
+        if (p_hrem > (int)prow) ac::cp_async16(hring + (p_hn & (HCH - 1)) * CHB + my16, p_hptr);
+        p_hn++;
+        p_hrem -= CH;
+        p_hptr += chunk_bytes_g;
+        p_fill = -1;  // an FDL chunk is next
+      }
+      if (p_xrem <= 0 && p_hrem <= 0) {  // segment complete
+        p_si++;
+        if (p_si < se) open_segment();
+      }
+    }
+    if (late) {
+      ac::cp_async_wait_all();
+      __syncthreads();
+    }
   };
 
-  // ==================================== consumers: thread = (bin, tile of 16 block-steps) ==============================
+  // ==================================== thread = (bin, tile of 16 block-steps) ========================================
   const uint32_t col = threadIdx.x % COLS, tile = threadIdx.x / COLS;
   const uint32_t xbase = xring + col * 8, hbase = hring + col * 8;
-  // FDL chunk (relative to the segment's first) that holds this tile's row of step 0 -- its last row; tile 0 reads
-  // tile * GC chunks ahead of that
+  // FDL chunk (relative to the segment's first) that holds this tile's row of step 0 -- its last row
   const uint32_t xfirst = (FILL - TT * tile) / CH - 1;
   float2 acc[TT], W[TT];
 #pragma unroll
@@ -181,85 +164,44 @@ k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
   for (uint32_t si = sb; si < se; si++) {
     const MacSeg sg = segs[si];
     const uint32_t np = sg.np;
+    const uint32_t nxc = (FILL - 1 + np + CH - 1) / CH, nhc = (np + CH - 1) / CH;
     if (sg.flags & 1u) {
 #pragma unroll
       for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
     }
-    // ---- the fill: FDL chunks 0 .. FILLC-1 of the segment hold every tile's register window and its row of step 0 ----
-    if (is_prod) produce(xc + FILLC, hc);
-#pragma unroll
-    for (int k = 0; k < FILLC; k++) {
-      const uint32_t c = xc + k;
-      wait(xfull + 8 * (c & (XCH - 1)), (c / XCH) & 1u);
-    }
-    // W[e] = row base_i + e = stream row FILL - 1 - 16 i - e (e = 1 .. 15); W[0] is overwritten by step 0
-    {
-      const uint32_t j0 = FILL - TT * (tile + 1);  // stream row of e = 15
-#pragma unroll
-      for (int e = 1; e < TT; e++) {
-        const uint32_t j = j0 + (TT - 1 - e);
-        const uint32_t c = xc + j / CH;
-        W[e] = ac::lds2(xbase + (c & (XCH - 1)) * CHB + (j % CH) * ROWB);
-      }
-      W[0] = make_float2(0.f, 0.f);
-    }
-    // the chunks before the one that holds my row of step 0 are done (never read by this tile, or read by the fill)
-    __syncwarp();
-    if (lane == 0)
-      for (uint32_t c = xc; c < xc + xfirst; c++) ac::mbar_arrive(xempty + 8 * (c & (XCH - 1)));
-    uint32_t xcur = xbase + ((xc + xfirst) & (XCH - 1)) * CHB;
-    uint32_t hcur = hbase;
-
+    uint32_t xcur = 0, hcur = 0;
     // q + u = step of the segment; u = (q + u) mod 16 because groups start at multiples of 16, so chunk boundaries fall
     // on fixed u.  Filter chunk of the step: hc + (q + u) / CH.  My FDL chunk: xc + xfirst + (q + u + CH - 1) / CH.
-    // A chunk is handed back when the warp moves on to the next one (its last row went through the FMAs a step earlier).
     auto step = [&](const int u, const uint32_t q) {
-      if (u % CH == 0) {
-        const uint32_t hk = hc + q / CH + u / CH;
-        if (q + u != 0) {
-          __syncwarp();
-          if (lane == 0) ac::mbar_arrive(hempty + 8 * ((hk - 1) & (HCH - 1)));
-        }
-        hcur = hbase + (hk & (HCH - 1)) * CHB;
-        wait(hfull + 8 * (hk & (HCH - 1)), (hk / HCH) & 1u);
-      }
-      if (u % CH == 1) {
-        const uint32_t xk = xc + xfirst + q / CH + u / CH + 1;
-        __syncwarp();
-        if (lane == 0) ac::mbar_arrive(xempty + 8 * ((xk - 1) & (XCH - 1)));
-        xcur = xbase + (xk & (XCH - 1)) * CHB;
-        const uint32_t w = xk + tile * GC;  // tile 0's chunk: the newest one any tile touches
-        wait(xfull + 8 * (w & (XCH - 1)), (w / XCH) & 1u);
-      }
+      if (u % CH == 0) hcur = hbase + ((hc + q / CH + u / CH) & (HCH - 1)) * CHB;
+      if (u % CH == 1 || (u == 0 && q == 0)) xcur = xbase + ((xc + xfirst + (q + u + CH - 1) / CH) & (XCH - 1)) * CHB;
       const float2 h = ac::lds2(hcur + (u % CH) * ROWB);
       W[(TT - u) % TT] = ac::lds2(xcur + ((u + CH - 1) % CH) * ROWB);
 #pragma unroll
       for (int i = 0; i < TT; i++) cmac_x2(acc[i], h, W[(i - u + TT) % TT]);
     };
-
-    uint32_t q = 0;
-    for (; q + TT <= np; q += TT) {
-      // chunks the group q .. q + 15 reads: filter chunks up to q / CH + GC, FDL chunks up to FILLC + q / CH + GC
-      if (is_prod) {
-        const uint32_t nxc = (FILL - 1 + np + CH - 1) / CH, nhc = (np + CH - 1) / CH;
-        produce(xc + min(nxc, FILLC + q / CH + GC), hc + min(nhc, q / CH + GC));
+    for (uint32_t q = 0; q < np; q += TT) {
+      // the group q .. q + 15 reads filter chunks below q / CH + GC and FDL chunks below FILLC + q / CH + GC; every tile
+      // is through with the filter chunks below q / CH and (after the first group) the FDL chunks below GC - 1 + q / CH
+      sync_point(xc + min(nxc, FILLC + q / CH + GC), hc + min(nhc, q / CH + GC), xc + (q ? GC - 1 + q / CH : 0u), hc + q / CH);
+      if (q == 0) {
+        // W[e] = row base_i + e = stream row FILL - 1 - 16 i - e (e = 1 .. 15); W[0] is overwritten by step 0
+        const uint32_t j0 = FILL - TT * (tile + 1);  // stream row of e = 15
+#pragma unroll
+        for (int e = 1; e < TT; e++) {
+          const uint32_t j = j0 + (TT - 1 - e);
+          W[e] = ac::lds2(xbase + ((xc + j / CH) & (XCH - 1)) * CHB + (j % CH) * ROWB);
+        }
+        W[0] = make_float2(0.f, 0.f);
       }
+      if (q + TT <= np) {
 #pragma unroll
-      for (int u = 0; u < TT; u++) step(u, q);
-    }
-    const uint32_t nxc = (FILL - 1 + np + CH - 1) / CH, nhc = (np + CH - 1) / CH;
-    if (q < np) {
-      if (is_prod) produce(xc + nxc, hc + nhc);
+        for (int u = 0; u < TT; u++) step(u, q);
+      } else {
 #pragma unroll
-      for (int u = 0; u < TT; u++)
-        if (q + u < np) step(u, q);
-    }
-    // chunks of this segment the warp has not handed back yet: the ones it was still reading, short last chunks, rows
-    // only the other tiles read
-    __syncwarp();
-    if (lane == 0) {
-      for (uint32_t c = xc + xfirst + (np - 1 + CH - 1) / CH; c < xc + nxc; c++) ac::mbar_arrive(xempty + 8 * (c & (XCH - 1)));
-      for (uint32_t c = hc + (np - 1) / CH; c < hc + nhc; c++) ac::mbar_arrive(hempty + 8 * (c & (HCH - 1)));
+        for (int u = 0; u < TT; u++)
+          if (q + u < np) step(u, q);
+      }
     }
     xc += nxc;
     hc += nhc;
@@ -270,7 +212,7 @@ k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
         if (tb + i < nt) ypart[((uint64_t)(tb + i) * slot_stride + sg.slot) * B + col0 + col] = acc[i];
     }
   }
-  if (lane == 0 && status && *reinterpret_cast<volatile uint32_t*>(tbs_smem + C::SMEM - 8)) *status = 2;
+  ac::cp_async_wait_all();
 }
 
 // Nyquist sums next to the time-batched MAC: N[t][run] = sum over the run's rows of Nqh[p] * Nqx[s_t - p] (the

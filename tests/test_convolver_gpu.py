@@ -125,7 +125,7 @@ def test_mac_variants_bit_identical(bbx, kw):
     (128, 37, 5, [20, 32, 17, 64, 31], 0),          # B = 128: two tiles (17..32 blocks) and four
     (512, 45, 20, [64, 48, 33, 64], 2),             # 45 partitions (13 mod 16), 296 row ranges: many short segments per CTA
     (256, 70, 9, [64, 64, 24, 64, 64], 0),          # FDL ring wraps inside the calls (R = 70 + 64 - 1)
-    (512, 33, 150, [64, 40], 0),                    # many channels: several whole filters per row range
+    (512, 36, 150, [64, 40], 0),                    # many channels: several whole filters per row range
 ])
 def test_shared_stream_mac_shapes_bit_identical(bbx, B, P, nch, calls, occ):
     """k_fdl_mac_tbs (TMA-fed shared operand stream, two / four time tiles per CTA, persistent over row ranges) against the
