@@ -22,6 +22,8 @@
 //     segment's arithmetic.
 //   * persistent CTAs: one CTA pair per SM walks several consecutive row ranges of the plan, so there is one ramp-up
 //     per launch instead of one per wave.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "async_copy.cuh"
@@ -30,22 +32,26 @@
 
 namespace bbx {
 
-template <int NTILE>
+template <int NTILE, int NTHREADS, int GPS>
 struct TbsCfg {
   static constexpr int TT = 16;                      // block-steps per thread
-  static constexpr int COLS = 256 / NTILE;           // bins per CTA
+  static constexpr int COLS = NTHREADS / NTILE;      // bins per CTA
   static constexpr int ROWB = COLS * 8;              // bytes of one row tile
-  static constexpr int CHB = 4096;                   // bytes per chunk: 256 threads x one 16-byte cp.async
+  static constexpr int CHB = NTHREADS * 16;          // bytes per chunk: every thread copies one 16-byte piece
   static constexpr int CH = CHB / ROWB;              // rows per chunk: 8 (NTILE = 4), 4 (NTILE = 2)
   static constexpr int GC = TT / CH;                 // chunks per group of 16 steps
   static constexpr int FILL = TT * NTILE;            // FDL rows a segment needs before its first step
   static constexpr int FILLC = FILL / CH;
   static constexpr int XCH = 16;                     // chunks of the FDL ring: the live window + one group + look-ahead
   static constexpr int HCH = 8;                      // chunks of the filter ring: one group + look-ahead
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = NTHREADS;
+  static constexpr int CTAS_PER_SM = 512 / NTHREADS;  // 16 warps per SM: the register file allows no more at ~120 registers
   static constexpr int SMEM = (XCH + HCH) * CHB;
   static_assert(NTILE == 2 || NTILE == 4, "tiles per CTA");
-  static_assert(FILLC + GC <= XCH && GC <= HCH, "a group's chunks must fit the rings next to the live window");
+  static constexpr int IC = GC * GPS;                // chunks per interval between two synchronisation points
+  // during an interval the FDL ring holds the live window (FILLC - GC + 1 chunks) and the interval's IC chunks, and the next
+  // interval's IC chunks are being copied in; the filter ring this interval's and the next one's chunks
+  static_assert(FILLC - GC + 1 + 2 * IC <= XCH && 2 * IC <= HCH, "ring sizes");
 };
 
 // Chunk streams.  Every segment (a run of partitions p0 .. p0 + np - 1 of one filter against one input's FDL) is two
@@ -66,14 +72,14 @@ struct TbsCfg {
 // cp.async.mbarrier.arrive, 0.31 ms: try_wait / arrive on SM 10.0 cost ~12 instructions each -- the cluster-window
 // address is rebuilt from SR_CgaCtaId --, 16 to 20 barrier operations per group came to 700 instructions next to the 512
 // FFMA2; ncu captures in profiles/.)
-template <int NTILE>
-__global__ void __launch_bounds__(TbsCfg<NTILE>::THREADS, 2)
+template <int NTILE, int NTHREADS, int GPS>
+__global__ void __launch_bounds__(NTHREADS, 512 / NTHREADS)
 k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg_begin, uint32_t n_plan_ctas,
               uint32_t plan_per_cta, const float2* __restrict__ fdl, float2* __restrict__ ypart, uint32_t B, uint32_t R,
               uint32_t head0, uint32_t t0, uint32_t nt, uint32_t ncoltiles, uint32_t slot_stride, int* __restrict__ status) {
-  using C = TbsCfg<NTILE>;
+  using C = TbsCfg<NTILE, NTHREADS, GPS>;
   constexpr int TT = C::TT, COLS = C::COLS, ROWB = C::ROWB, CH = C::CH, CHB = C::CHB, FILL = C::FILL, FILLC = C::FILLC;
-  constexpr int XCH = C::XCH, HCH = C::HCH, GC = C::GC;
+  constexpr int XCH = C::XCH, HCH = C::HCH, GC = C::GC, IC = C::IC;
   extern __shared__ __align__(128) uint8_t tbs_smem[];
   const uint32_t xring = (uint32_t)__cvta_generic_to_shared(tbs_smem), hring = xring + XCH * CHB;
   (void)status;
@@ -86,64 +92,71 @@ k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
   if (pc0 >= pc1) return;
   const uint32_t sb = cta_seg_begin[pc0], se = cta_seg_begin[pc1];
 
-  // ---- copy cursor (identical in every thread): the chunk sequence is walked with running pointers ----
+  // ---- copy cursors (identical in every thread): each stream is walked on its own with running pointers ----
   constexpr uint32_t kPiecesPerRow = ROWB / 16;
   const uint32_t prow = threadIdx.x / kPiecesPerRow;  // my row of every chunk
   const uint32_t my16 = threadIdx.x * 16;             // offset of my 16 bytes inside a chunk's slot
+  const uint32_t poff = (threadIdx.x % kPiecesPerRow) * 16;
   const uint32_t chunk_bytes_g = CH * B * (uint32_t)sizeof(float2);  // global bytes between my pieces of consecutive chunks
   const uint64_t ring_bytes_g = (uint64_t)R * B * sizeof(float2);
-  uint32_t p_si = sb;           // segment being issued
-  uint32_t p_xn = 0, p_hn = 0;  // chunks issued since the kernel started = global index of the next chunk
-  int p_xrem = 0, p_hrem = 0;   // rows of the segment's FDL / filter stream not yet issued (first row of the next chunk on)
-  int p_fill = 0;               // > 0: fill chunks still to go; 0: a filter chunk is next; -1: an FDL chunk is next
-  int p_xr = 0;                 // FDL ring row of my piece of the next FDL chunk
-  const char* p_xptr = nullptr;  // ... and its address
-  const char* p_hptr = nullptr;  // address of my piece of the next filter chunk
-  auto open_segment = [&]() {
-    const MacSeg sg = segs[p_si];
+  uint32_t px_si = sb, ph_si = sb;  // segment each stream is in
+  uint32_t p_xn = 0, p_hn = 0;      // chunks issued since the kernel started = global index of the next chunk
+  int p_xrem = 0, p_hrem = 0;       // rows of the segment's stream not yet issued (from the first row of the next chunk)
+  int p_xr = 0;                     // FDL ring row of my piece of the next FDL chunk
+  const char* p_xptr = nullptr;     // ... and its address
+  const char* p_hptr = nullptr;     // address of my piece of the next filter chunk
+  auto open_x = [&]() {
+    const MacSeg sg = segs[px_si];
     p_xrem = (int)(FILL - 1 + sg.np);
-    p_hrem = (int)sg.np;
-    p_fill = FILLC;
     uint32_t base = s0 + R - (sg.p0 % R);
     if (base >= R) base -= R;
     int r = (int)(base + FILL - 1) - (int)prow;  // >= 0; short rings (R < FILL: few blocks per call on 64 columns) wrap twice
     while (r >= (int)R) r -= (int)R;
     p_xr = r;
-    const uint32_t poff = (threadIdx.x % kPiecesPerRow) * 16;
     p_xptr = reinterpret_cast<const char*>(fdl + ((uint64_t)sg.fdl_ch * R + (uint32_t)r) * B + col0) + poff;
+  };
+  auto open_h = [&]() {
+    const MacSeg sg = segs[ph_si];
+    p_hrem = (int)sg.np;
     p_hptr = reinterpret_cast<const char*>(reinterpret_cast<const float2*>(sg.H) + (uint64_t)(sg.p0 + prow) * B + col0) + poff;
   };
-  if (p_si < se) open_segment();
+  if (sb < se) {
+    open_x();
+    open_h();
+  }
   // One synchronisation point: the chunks below (need_x, need_h) are about to be read; the chunks below (done_x, done_h)
-  // have been read by every tile.  Issues this thread's pieces of the following chunks as far as the rings have room.
+  // have been read by every tile.  Issues this thread's pieces of the following chunks: up to kLook intervals beyond what
+  // this interval reads, as far as the rings have room -- across segment boundaries (the next segment's fill comes next
+  // in the FDL stream).
+  constexpr uint32_t kLook = 3;
   auto sync_point = [&](uint32_t need_x, uint32_t need_h, uint32_t done_x, uint32_t done_h) {
     ac::cp_async_wait_all();
     __syncthreads();
-    const bool late = p_xn < need_x || p_hn < need_h;  // only at the start of the kernel: nothing was issued ahead yet
-    while (p_si < se) {
-      if ((p_fill != 0 && p_xrem > 0) || p_hrem <= 0) {
-        if (p_xn >= done_x + XCH) break;
-        if (p_xrem > (int)prow) ac::cp_async16(xring + (p_xn & (XCH - 1)) * CHB + my16, p_xptr);
-        p_xn++;
-        p_xrem -= CH;
-        p_xr -= CH;
-        p_xptr -= chunk_bytes_g;
-        if (p_xr < 0) {  // the ring wraps
-          p_xr += (int)R;
-          p_xptr += ring_bytes_g;
-        }
-        p_fill = p_fill > 0 ? p_fill - 1 : 0;  // after the fill: a filter chunk is next
-      } else {
-        if (p_hn >= done_h + HCH) break;
-        if (p_hrem > (int)prow) ac::cp_async16(hring + (p_hn & (HCH - 1)) * CHB + my16, p_hptr);
-        p_hn++;
-        p_hrem -= CH;
-        p_hptr += chunk_bytes_g;
-        p_fill = -1;  // an FDL chunk is next
+    const bool late = p_xn < need_x || p_hn < need_h;  // the start of the kernel; a fill the FDL ring had no room for earlier
+    const uint32_t tx = min(need_x + kLook * IC, done_x + XCH), th = min(need_h + kLook * IC, done_h + HCH);
+    while (p_xn < tx && px_si < se) {
+      if (p_xrem > (int)prow) ac::cp_async16(xring + (p_xn & (XCH - 1)) * CHB + my16, p_xptr);
+      p_xn++;
+      p_xrem -= CH;
+      p_xr -= CH;
+      p_xptr -= chunk_bytes_g;
+      if (p_xr < 0) {  // the ring wraps
+        p_xr += (int)R;
+        p_xptr += ring_bytes_g;
       }
-      if (p_xrem <= 0 && p_hrem <= 0) {  // segment complete
-        p_si++;
-        if (p_si < se) open_segment();
+      if (p_xrem <= 0) {
+        px_si++;
+        if (px_si < se) open_x();
+      }
+    }
+    while (p_hn < th && ph_si < se) {
+      if (p_hrem > (int)prow) ac::cp_async16(hring + (p_hn & (HCH - 1)) * CHB + my16, p_hptr);
+      p_hn++;
+      p_hrem -= CH;
+      p_hptr += chunk_bytes_g;
+      if (p_hrem <= 0) {
+        ph_si++;
+        if (ph_si < se) open_h();
       }
     }
     if (late) {
@@ -170,37 +183,50 @@ k_fdl_mac_tbs(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
       for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
     }
     uint32_t xcur = 0, hcur = 0;
+    float2 hn = make_float2(0.f, 0.f), xn = hn;  // operands of the next step, loaded under the current step's FMAs
     // q + u = step of the segment; u = (q + u) mod 16 because groups start at multiples of 16, so chunk boundaries fall
     // on fixed u.  Filter chunk of the step: hc + (q + u) / CH.  My FDL chunk: xc + xfirst + (q + u + CH - 1) / CH.
-    auto step = [&](const int u, const uint32_t q) {
+    auto fetch = [&](const int u, const uint32_t q) {
       if (u % CH == 0) hcur = hbase + ((hc + q / CH + u / CH) & (HCH - 1)) * CHB;
-      if (u % CH == 1 || (u == 0 && q == 0)) xcur = xbase + ((xc + xfirst + (q + u + CH - 1) / CH) & (XCH - 1)) * CHB;
-      const float2 h = ac::lds2(hcur + (u % CH) * ROWB);
-      W[(TT - u) % TT] = ac::lds2(xcur + ((u + CH - 1) % CH) * ROWB);
+      if (u % CH == 1 || u == 0) xcur = xbase + ((xc + xfirst + (q + u + CH - 1) / CH) & (XCH - 1)) * CHB;
+      hn = ac::lds2(hcur + (u % CH) * ROWB);
+      xn = ac::lds2(xcur + ((u + CH - 1) % CH) * ROWB);
+    };
+    auto step = [&](const int u, const uint32_t q, const bool more) {
+      const float2 h = hn;
+      W[(TT - u) % TT] = xn;
+      if (more && u + 1 < TT) fetch(u + 1, q);  // the loads of step u + 1 fly under the 32 FFMA2 of step u
 #pragma unroll
       for (int i = 0; i < TT; i++) cmac_x2(acc[i], h, W[(i - u + TT) % TT]);
     };
-    for (uint32_t q = 0; q < np; q += TT) {
-      // the group q .. q + 15 reads filter chunks below q / CH + GC and FDL chunks below FILLC + q / CH + GC; every tile
-      // is through with the filter chunks below q / CH and (after the first group) the FDL chunks below GC - 1 + q / CH
-      sync_point(xc + min(nxc, FILLC + q / CH + GC), hc + min(nhc, q / CH + GC), xc + (q ? GC - 1 + q / CH : 0u), hc + q / CH);
-      if (q == 0) {
-        // W[e] = row base_i + e = stream row FILL - 1 - 16 i - e (e = 1 .. 15); W[0] is overwritten by step 0
-        const uint32_t j0 = FILL - TT * (tile + 1);  // stream row of e = 15
+    for (uint32_t q0 = 0; q0 < np; q0 += TT * GPS) {
+      // the interval q0 .. q0 + 16 GPS - 1 reads filter chunks below q0 / CH + IC and FDL chunks below FILLC + q0 / CH + IC;
+      // every tile is through with the filter chunks below q0 / CH and (after the first group) the FDL chunks below
+      // GC - 1 + q0 / CH
+      sync_point(xc + min(nxc, FILLC + q0 / CH + IC), hc + min(nhc, q0 / CH + IC), xc + (q0 ? GC - 1 + q0 / CH : 0u), hc + q0 / CH);
 #pragma unroll
-        for (int e = 1; e < TT; e++) {
-          const uint32_t j = j0 + (TT - 1 - e);
-          W[e] = ac::lds2(xbase + ((xc + j / CH) & (XCH - 1)) * CHB + (j % CH) * ROWB);
+      for (int g = 0; g < GPS; g++) {
+        const uint32_t q = q0 + g * TT;
+        if (q >= np) break;
+        fetch(0, q);
+        if (q == 0) {
+          // W[e] = row base_i + e = stream row FILL - 1 - 16 i - e (e = 1 .. 15); W[0] is overwritten by step 0
+          const uint32_t j0 = FILL - TT * (tile + 1);  // stream row of e = 15
+#pragma unroll
+          for (int e = 1; e < TT; e++) {
+            const uint32_t j = j0 + (TT - 1 - e);
+            W[e] = ac::lds2(xbase + ((xc + j / CH) & (XCH - 1)) * CHB + (j % CH) * ROWB);
+          }
+          W[0] = make_float2(0.f, 0.f);
         }
-        W[0] = make_float2(0.f, 0.f);
-      }
-      if (q + TT <= np) {
+        if (q + TT <= np) {
 #pragma unroll
-        for (int u = 0; u < TT; u++) step(u, q);
-      } else {
+          for (int u = 0; u < TT; u++) step(u, q, true);
+        } else {
 #pragma unroll
-        for (int u = 0; u < TT; u++)
-          if (q + u < np) step(u, q);
+          for (int u = 0; u < TT; u++)
+            if (q + u < np) step(u, q, q + u + 1 < np);
+        }
       }
     }
     xc += nxc;
@@ -257,25 +283,25 @@ k_nyq_mac2(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_seg
   }
 }
 
-template <int NTILE>
+template <int NTILE, int NTHREADS, int GPS>
 static cudaError_t launch_tbs_t(const MacTbsArgs& a, cudaStream_t st) {
-  using C = TbsCfg<NTILE>;
+  using C = TbsCfg<NTILE, NTHREADS, GPS>;
   static uint32_t attr_set = 0;  // per device: function attributes belong to the device's context
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set & (1u << (dev & 31)))) {
-    cudaError_t e = cudaFuncSetAttribute(k_fdl_mac_tbs<NTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_fdl_mac_tbs<NTILE, NTHREADS, GPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
     attr_set |= 1u << (dev & 31);
   }
   const uint32_t ncol = a.B / C::COLS, ngroups = ceil_div(a.nt, (uint32_t)(C::TT * NTILE));
-  // persistent: about two CTAs per SM in total, each walking consecutive row ranges of the plan
-  uint32_t gy = std::max(1u, (2u * kNumSMs) / (ncol * ngroups));
+  // persistent: one resident wave of CTAs, each walking consecutive row ranges of the plan
+  uint32_t gy = std::max(1u, ((uint32_t)C::CTAS_PER_SM * kNumSMs) / (ncol * ngroups));
   gy = std::min(gy, a.n_plan_ctas);
   const uint32_t per = ceil_div(a.n_plan_ctas, gy);
   gy = ceil_div(a.n_plan_ctas, per);
-  k_fdl_mac_tbs<NTILE><<<dim3(ncol * ngroups, gy), C::THREADS, C::SMEM, st>>>(a.segs, a.cta_seg_begin, a.n_plan_ctas, per, a.fdl, a.ypart,
-                                                                             a.B, a.R, a.head, a.t0, a.nt, ncol, a.slot_stride, a.status);
+  k_fdl_mac_tbs<NTILE, NTHREADS, GPS><<<dim3(ncol * ngroups, gy), C::THREADS, C::SMEM, st>>>(
+      a.segs, a.cta_seg_begin, a.n_plan_ctas, per, a.fdl, a.ypart, a.B, a.R, a.head, a.t0, a.nt, ncol, a.slot_stride, a.status);
   return cudaGetLastError();
 }
 
@@ -286,14 +312,38 @@ cudaError_t launch_nyq_mac2(const MacTbsArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_mac_tbs(const MacTbsArgs& a, cudaStream_t st, const char** kernel_name) {
-  // tiles per CTA: four (64 block-steps per CTA) unless the call is short; the column tile must fit the block size
-  const bool four = a.nt > 32 || a.B < 128;
-  if (four) {
-    *kernel_name = "k_fdl_mac_tbs<4>";
-    return launch_tbs_t<4>(a, st);
+  // tiles per CTA: four (64 block-steps per CTA) unless the call is short; CTA size: BBX_TBS_THREADS for A/B runs
+  static int threads = 0, force_tiles = 0, gps = 0;
+  if (!threads) {
+    const char* t = getenv("BBX_TBS_THREADS");
+    threads = (t && atoi(t) == 256) ? 256 : 128;
+    const char* n = getenv("BBX_TBS_NTILE");
+    force_tiles = n ? atoi(n) : 0;
+    const char* g = getenv("BBX_TBS_GPS");
+    gps = (g && atoi(g) == 1) ? 1 : 2;
   }
-  *kernel_name = "k_fdl_mac_tbs<2>";
-  return launch_tbs_t<2>(a, st);
+  bool four = a.nt > 32;
+  if (force_tiles == 2) four = false;
+  if (force_tiles == 4) four = true;
+  if (threads == 256 && a.B < 128) four = true;  // the column tile (256 / tiles) must fit the block size
+#define BBX_TBS_CASE(NT_, TH_, G_)                       \
+  do {                                                    \
+    *kernel_name = "k_fdl_mac_tbs<" #NT_ "," #TH_ "," #G_ ">"; \
+    return launch_tbs_t<NT_, TH_, G_>(a, st);              \
+  } while (0)
+  if (threads == 256) {
+    if (four) {
+      if (gps == 1) BBX_TBS_CASE(4, 256, 1);
+      BBX_TBS_CASE(4, 256, 2);
+    }
+    BBX_TBS_CASE(2, 256, 1);
+  }
+  if (four) {
+    if (gps == 1) BBX_TBS_CASE(4, 128, 1);
+    BBX_TBS_CASE(4, 128, 2);
+  }
+  BBX_TBS_CASE(2, 128, 1);
+#undef BBX_TBS_CASE
 }
 
 }  // namespace bbx
