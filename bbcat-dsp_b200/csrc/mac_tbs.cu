@@ -29,6 +29,7 @@
 #include "async_copy.cuh"
 #include "mac_common.cuh"
 #include "mac_tbs.h"
+#include "mac_tbw.cuh"
 
 namespace bbx {
 
@@ -311,6 +312,29 @@ cudaError_t launch_nyq_mac2(const MacTbsArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+static cudaError_t launch_tbw(const MacTbsArgs& a, cudaStream_t st) {
+  using C = TbwCfg;
+  static uint32_t attr_set = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set & (1u << (dev & 31)))) {
+    cudaError_t e = cudaFuncSetAttribute(k_fdl_mac_tbw, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set |= 1u << (dev & 31);
+  }
+  const uint32_t ncol = a.B / C::COLS, ngroups = ceil_div(a.nt, (uint32_t)(C::TT * C::NTILE));
+  // persistent: 16 warps per SM in total, each walking consecutive row ranges of the plan
+  uint32_t ranges = std::max(1u, (2u * C::WARPS * kNumSMs) / (ncol * ngroups));
+  ranges = std::min(ranges, a.n_plan_ctas);
+  const uint32_t per = ceil_div(a.n_plan_ctas, ranges);
+  ranges = ceil_div(a.n_plan_ctas, per);
+  const uint32_t nwarps = ranges * ncol * ngroups;
+  k_fdl_mac_tbw<<<ceil_div(nwarps, (uint32_t)C::WARPS), 32 * C::WARPS, C::SMEM, st>>>(a.segs, a.cta_seg_begin, a.n_plan_ctas, per, ranges,
+                                                                                   a.fdl, a.ypart, a.B, a.R, a.head, a.t0, a.nt, ncol,
+                                                                                   ngroups, a.slot_stride);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mac_tbs(const MacTbsArgs& a, cudaStream_t st, const char** kernel_name) {
   // tiles per CTA: four (64 block-steps per CTA) unless the call is short; CTA size: BBX_TBS_THREADS for A/B runs
   static int threads = 0, force_tiles = 0, gps = 0;
@@ -321,6 +345,15 @@ cudaError_t launch_mac_tbs(const MacTbsArgs& a, cudaStream_t st, const char** ke
     force_tiles = n ? atoi(n) : 0;
     const char* g = getenv("BBX_TBS_GPS");
     gps = (g && atoi(g) == 1) ? 1 : 2;
+  }
+  static int use_tbw = -1;
+  if (use_tbw < 0) {
+    const char* w = getenv("BBX_TBW");
+    use_tbw = (w && atoi(w) == 0) ? 0 : 1;
+  }
+  if (use_tbw && a.nt > 32) {  // warp-private streams: four tiles of 16 block-steps per warp
+    *kernel_name = "k_fdl_mac_tbw";
+    return launch_tbw(a, st);
   }
   bool four = a.nt > 32;
   if (force_tiles == 2) four = false;

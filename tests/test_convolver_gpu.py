@@ -128,9 +128,9 @@ def test_mac_variants_bit_identical(bbx, kw):
     (512, 36, 150, [64, 40], 0),                    # many channels: several whole filters per row range
 ])
 def test_shared_stream_mac_shapes_bit_identical(bbx, B, P, nch, calls, occ):
-    """k_fdl_mac_tbs (TMA-fed shared operand stream, two / four time tiles per CTA, persistent over row ranges) against the
-    streaming kernel on the same plan: bit-identical for every tile count, partial tile groups, ragged segment lengths,
-    ring wrap, and row ranges that hold several segments."""
+    """The shared-stream time-batched kernels -- k_fdl_mac_tbw (warp-private rings, four tiles, calls of more than 32 blocks)
+    and k_fdl_mac_tbs<2> (block-shared rings, 17..32 blocks) -- against the streaming kernel on the same plan: bit-identical
+    for every tile count, partial tile groups, ragged segment lengths, ring wrap, and row ranges that hold several segments."""
     L = P * B - B // 3
     irs = [make_ir(900 + c, L - 7 * (c % 5) * B // 8) for c in range(nch)]  # a few shorter filters: uneven terms
     total = sum(calls)
@@ -143,7 +143,7 @@ def test_shared_stream_mac_shapes_bit_identical(bbx, B, P, nch, calls, occ):
         outs.append(run_float(g, xi, [n * B for n in calls]))
         name = g.eng.mac_kernel_name()
         g.close()
-        assert name.startswith("k_fdl_mac_tbs") if tile == 0 else name == "k_fdl_mac", name
+        assert name.startswith(("k_fdl_mac_tbw", "k_fdl_mac_tbs")) if tile == 0 else name == "k_fdl_mac", name
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
@@ -159,7 +159,7 @@ def test_shared_stream_mac_vs_oracle(bbx, orc):
     xi = interleave(xs)
     yg = run_float(g, xi, [64 * B, 32 * B])
     yo = run_float(o, xi, [64 * B, 32 * B])
-    assert g.eng.mac_kernel_name().startswith("k_fdl_mac_tbs")
+    assert g.eng.mac_kernel_name().startswith("k_fdl_mac_tbs<2")  # the last call has 32 blocks: two tiles per CTA
     g.close()
     for c in range(nch):
         assert_float_parity(yg[:, c], yo[:, c], "vs oracle ch %d" % c)
