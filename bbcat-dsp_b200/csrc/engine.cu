@@ -441,10 +441,15 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     a.nt = nt;
     a.slot_stride = e->max_slots;
     a.status = e->mac_status;
-    BBX_CUDA_TRY(launch_nyq_mac2(a, st));
+    // the Nyquist sums of column 0 (a few microseconds) run next to the MAC on the side stream
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+    BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
+    BBX_CUDA_TRY(launch_nyq_mac2(a, e->s_aux));
+    BBX_CUDA_TRY(cudaEventRecord(e->ev_join, e->s_aux));
     if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
     BBX_CUDA_TRY(launch_mac_tbs(a, st, &e->last_mac_kernel));
     if (ev1) BBX_CUDA_TRY(cudaEventRecord(ev1, st));
+    BBX_CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
     e->launches += 2;
   } else {
     if (use_tb) {
