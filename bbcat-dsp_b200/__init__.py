@@ -117,6 +117,8 @@ SYMBOLS = {
     "bbx_engine_set_direct_io": (C.c_int, [vp, C.c_size_t]),
     "bbx_engine_set_mixdown_kernel": (C.c_int, [vp, C.c_int]),
     "bbx_engine_direct_calls": (u64, [vp]),
+    "bbx_engine_set_fused": (C.c_int, [vp, C.c_int, u32]),
+    "bbx_engine_fused_calls": (u64, [vp]),
     "bbx_biquad_calc_coeffs": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "bbx_biquad_create": (C.c_int, [u32, C.POINTER(vp)]),
     "bbx_biquad_destroy": (C.c_int, [vp]),
@@ -671,6 +673,14 @@ class Convolver:
 
     def direct_calls(self):
         return int(lib().bbx_engine_direct_calls(self.h))
+
+    def set_fused(self, enable, max_partitions=0):
+        """single-launch latency path (k_block_fused) for one-block calls of PER_CHANNEL / ROUTED engines; False keeps the
+        multi-kernel path (identical bytes)"""
+        _check(lib().bbx_engine_set_fused(self.h, int(bool(enable)), int(max_partitions)))
+
+    def fused_calls(self):
+        return int(lib().bbx_engine_fused_calls(self.h))
 
     def SetComm(self, comm):
         """Attach the communicator of the input-sharded MIMO engine (None detaches)."""

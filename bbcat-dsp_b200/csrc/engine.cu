@@ -32,6 +32,7 @@
 #include "kernels_fft.cuh"
 #include "kernels_mac.cuh"
 #include "kernels_pcm.cuh"
+#include "kernels_fused.cuh"
 #include "mac_tbs.h"
 #include "mimo_tc.cuh"
 
@@ -95,12 +96,14 @@ struct MacPlan {
   uint8_t* d_blob = nullptr;
   size_t blob_bytes = 0;
   // offsets inside the blob
-  size_t off_segs = 0, off_cta = 0, off_first = 0, off_count = 0, off_xjob = 0;
+  size_t off_segs = 0, off_cta = 0, off_first = 0, off_count = 0, off_xjob = 0, off_jseg = 0;
   uint32_t n_ctas = 0, n_slots = 0, n_jobs = 0, total_rows = 0, n_terms = 0;
+  uint32_t max_job_rows = 0;  // longest job in partitions (the fused single-launch path walks a job inside one CTA)
   uint32_t occ = 1;  // streaming-MAC variant this plan was cut for (CTAs per SM <-> unroll depth)
   bool valid = false;
   const MacSeg* segs() const { return (const MacSeg*)(d_blob + off_segs); }
   const uint32_t* cta_seg_begin() const { return (const uint32_t*)(d_blob + off_cta); }
+  const uint32_t* job_seg_first() const { return (const uint32_t*)(d_blob + off_jseg); }
   PlanView view() const {
     PlanView v;
     v.job_slot_first = (const uint32_t*)(d_blob + off_first);
@@ -150,7 +153,10 @@ struct bbx_engine {
   uint8_t* h_route = nullptr;  // the slot being filled by upload_routes
   uint8_t* d_route = nullptr;
   size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0,
-         roff_icur = 0, roff_iold = 0, roff_entry = 0;
+         roff_icur = 0, roff_iold = 0, roff_entry = 0, roff_input = 0;
+  bool fused_on = true;         // streaming calls of PER_CHANNEL / ROUTED engines with short filters: one launch (k_block_fused)
+  uint32_t fused_max_rows = 32;  // ... "short" = at most this many partitions per path
+  uint64_t fused_calls = 0;
   bool route_dirty = true;
   // plans
   MacPlan plan_first, plan_steady;
@@ -554,12 +560,21 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
   uint32_t* jfirst = (uint32_t*)(pl.h_blob + pl.off_first);
   uint32_t* jcount = (uint32_t*)(pl.h_blob + pl.off_count);
   uint32_t* xj = (uint32_t*)(pl.h_blob + pl.off_xjob);
+  uint32_t* jseg = (uint32_t*)(pl.h_blob + pl.off_jseg);
   BBX_REQUIRE(jobs.size() <= e->max_jobs, "internal: too many jobs");
+  pl.max_job_rows = 0;
+  for (auto& j : jobs) {
+    uint32_t rows = 0;
+    for (auto& tm : j)
+      if (tm.f) rows += tm.f->P;
+    pl.max_job_rows = std::max(pl.max_job_rows, rows);
+  }
   pl.n_jobs = (uint32_t)jobs.size();
   pl.total_rows = total;
   for (uint32_t s = 0; s < e->n_streams; s++) xj[s] = s < xjob.size() ? xjob[s] : kNoJob;
   if (total == 0) {
     for (uint32_t j = 0; j < jobs.size(); j++) jfirst[j] = jcount[j] = 0;
+    for (uint32_t j = 0; j <= jobs.size(); j++) jseg[j] = 0;
     pl.n_ctas = 0;
     pl.n_slots = 0;
   } else {
@@ -576,6 +591,7 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
     int run_job = -1;  // job of the open run inside the current CTA
     for (uint32_t j = 0; j < jobs.size(); j++) {
       jfirst[j] = nslot;
+      jseg[j] = nseg;  // a job's segments are consecutive: the fused single-launch path walks them in this order
       uint32_t before = nslot;
       for (auto& tm : jobs[j]) {
         if (!tm.f) continue;
@@ -614,6 +630,7 @@ int build_plan(bbx_engine* e, MacPlan& pl, const std::vector<std::vector<JobTerm
       }
       jcount[j] = nslot - before;
     }
+    jseg[jobs.size()] = nseg;
     for (uint32_t c = cur_cta + 1; c <= G; c++) cta[c] = nseg;
     pl.n_ctas = G;
     pl.n_slots = nslot;
@@ -634,6 +651,7 @@ int alloc_plan(bbx_engine* e, MacPlan& pl) {
   pl.off_first = take(sizeof(uint32_t) * e->max_jobs);
   pl.off_count = take(sizeof(uint32_t) * e->max_jobs);
   pl.off_xjob = take(sizeof(uint32_t) * std::max(1u, e->n_streams));
+  pl.off_jseg = take(sizeof(uint32_t) * (e->max_jobs + 1));
   pl.blob_bytes = off;
   {
     int src = staging_alloc(pl.stg, off);
@@ -709,6 +727,11 @@ int upload_routes(bbx_engine* e, bool first_block_transition) {
       iold[k] = (uint32_t)dold[k] % e->Rd;
       flags[k] = (sw && p.xfade && p.pend_delay != p.delay) ? 1u : 0u;
     }
+  }
+  // stream -> input (what the fused single-launch kernel reads; MIMO streams have many inputs and never take that path)
+  {
+    uint32_t* sin = (uint32_t*)(e->h_route + e->roff_input);
+    for (uint32_t k = 0; k < e->n_streams; k++) sin[k] = (e->mode == BBX_MODE_MIMO) ? 0u : e->paths[k].input;
   }
   // per-route entries in mixdown order (what k_pcm_out reads)
   {
@@ -870,6 +893,37 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   const uint64_t K = e->B + 1;
   e->mac_bytes += (uint64_t)T * (16ull * e->plan_steady.total_rows * K + 16ull * K * e->n_streams +
                                  (uint64_t)e->B * (fmt_bytes(e->last_infmt) * e->n_in + fmt_bytes(e->last_outfmt) * e->n_out));
+  return BBX_OK;
+}
+
+template <int M, bool FUSE_OUT>
+void launch_fused_t(const FusedArgs& a, cudaStream_t st) {
+  constexpr int FPB = FftCfg<M>::FPB;
+  constexpr size_t smem = sizeof(float2) * (size_t)FPB * (M + FftCfg<M>::MP);
+  if (smem > 48 * 1024) {
+    static uint32_t attr_set = 0;  // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set & (1u << (dev & 31)))) {
+      cudaFuncSetAttribute(k_block_fused<M, FUSE_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set |= 1u << (dev & 31);
+    }
+  }
+  k_block_fused<M, FUSE_OUT><<<ceil_div(a.n_streams, (uint32_t)FPB), dim3(FftCfg<M>::NT, FPB), smem, st>>>(a);
+}
+template <bool FUSE_OUT>
+int launch_fused(uint32_t B, const FusedArgs& a, cudaStream_t st) {
+  switch (B) {
+    case 64: launch_fused_t<64, FUSE_OUT>(a, st); break;
+    case 128: launch_fused_t<128, FUSE_OUT>(a, st); break;
+    case 256: launch_fused_t<256, FUSE_OUT>(a, st); break;
+    case 512: launch_fused_t<512, FUSE_OUT>(a, st); break;
+    case 1024: launch_fused_t<1024, FUSE_OUT>(a, st); break;
+    case 2048: launch_fused_t<2048, FUSE_OUT>(a, st); break;
+    case 4096: launch_fused_t<4096, FUSE_OUT>(a, st); break;
+    default: set_error("unsupported block size %u", B); return BBX_ERR_UNSUPPORTED;
+  }
+  BBX_CUDA_TRY(cudaGetLastError());
   return BBX_OK;
 }
 
@@ -1053,6 +1107,7 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
     e->roff_icur = take(sizeof(uint32_t) * ns);
     e->roff_iold = take(sizeof(uint32_t) * ns);
     e->roff_entry = take(sizeof(RouteEntry) * ns);
+    e->roff_input = take(sizeof(uint32_t) * ns);
     e->route_bytes = off;
     {
       int src = staging_alloc(e->route_stg, off);
@@ -1412,6 +1467,46 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     if ((rc = tc_pack_filters(e))) return rc;
   }
 
+  // ---- streaming call of a PER_CHANNEL / ROUTED engine with short filters: one launch does steps 1 - 4 (and 5) ----
+  const MacPlan& fpl = n_first ? e->plan_first : e->plan_steady;
+  const bool fuse = e->fused_on && T == 1 && e->mode != BBX_MODE_MIMO && e->sh_world <= 1 && !e->comm && fpl.max_job_rows <= e->fused_max_rows;
+  const bool fuse_out = fuse && e->mode == BBX_MODE_PER_CHANNEL;
+  if (fuse) {
+    FusedArgs a;
+    const uint32_t ibps = fmt_bytes(infmt), obps = fmt_bytes(outfmt);
+    a.pcm_in = (const uint8_t*)in;
+    a.pcm_out = (uint8_t*)out;
+    a.infmt = infmt;
+    a.in_be = in_be;
+    a.in_fast = (!in_be && ibps != 3 && ((uintptr_t)in % ibps) == 0) ? 1 : 0;
+    a.outfmt = outfmt;
+    a.out_be = out_be;
+    a.out_fast = (!out_be && obps != 3 && ((uintptr_t)out % obps) == 0) ? 1 : 0;
+    a.in_channels = in_channels;
+    a.out_channels = out_channels;
+    a.n_streams = e->n_streams;
+    a.stream_input = (e->mode == BBX_MODE_ROUTED) ? (const uint32_t*)(e->d_route + e->roff_input) : nullptr;
+    a.xin_cur = e->xin[e->parity];
+    a.xin_prev = e->xin[e->parity ^ 1];
+    a.xstride = e->xstride;
+    a.prev_off = e->tprev * B;
+    a.fdl = e->fdl;
+    a.R = e->R;
+    a.head = e->head;
+    a.tw = e->tw;
+    a.segs = fpl.segs();
+    a.job_seg_first = fpl.job_seg_first();
+    a.xjob = n_first ? fpl.view().xjob : nullptr;
+    a.ybuf = e->ybuf;
+    a.Rd = e->Rd;
+    a.wpos = e->wpos;
+    a.fractional = e->cfg.fractional_delay;
+    a.entry = route_view(e).entry;
+    if ((rc = fuse_out ? launch_fused<true>(B, a, st) : launch_fused<false>(B, a, st))) return rc;
+    e->launches++;
+    e->fused_calls++;
+    e->last_mac_kernel = "k_block_fused";
+  } else {
   // ---- 1. PCM -> planar fp32 ----
   {
     PcmInArgs a;
@@ -1489,6 +1584,8 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   // ---- 4. inverse transforms, crossfade, delay ring ----
   if ((rc = launch_irfft(e, T, n_first, use_tc, st))) return rc;
   e->launches++;
+  }  // !fuse
+  if (!fuse_out) {
   // ---- 5. delay read, mixdown, output format ----
   {
     PcmOutArgs a;
@@ -1520,6 +1617,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     BBX_CUDA_TRY(cudaGetLastError());
     e->launches++;
   }
+  }  // !fuse_out
   // ---- advance the state ----
   e->head = (e->head + T) % e->R;
   e->wpos = (e->wpos + T * B) % e->Rd;
@@ -1742,6 +1840,14 @@ int bbx_engine_set_direct_io(bbx_engine* e, size_t max_bytes) {
   return BBX_OK;
 }
 uint64_t bbx_engine_direct_calls(const bbx_engine* e) { return e ? e->direct_calls : 0; }
+
+int bbx_engine_set_fused(bbx_engine* e, int enable, uint32_t max_partitions) {
+  BBX_REQUIRE(e != nullptr, "bbx_engine_set_fused: null engine");
+  e->fused_on = enable != 0;
+  if (max_partitions) e->fused_max_rows = max_partitions;
+  return BBX_OK;
+}
+uint64_t bbx_engine_fused_calls(const bbx_engine* e) { return e ? e->fused_calls : 0; }
 
 int bbx_engine_set_comm(bbx_engine* e, bbx_comm* c) {
   BBX_REQUIRE(e != nullptr, "null engine");

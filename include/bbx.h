@@ -406,6 +406,13 @@ int bbx_engine_set_mixdown_kernel(bbx_engine* e, int per_output);
  * at least one side took this path. */
 int bbx_engine_set_direct_io(bbx_engine* e, size_t max_bytes);
 uint64_t bbx_engine_direct_calls(const bbx_engine* e);
+/* single-launch latency path: a streaming call (one block) of a PER_CHANNEL or ROUTED engine whose paths have at most
+ * max_partitions partitions (default 32) runs k_block_fused -- PCM in, forward transform, MAC, inverse transform,
+ * crossfade, delay ring and, for PER_CHANNEL engines, the output stage in ONE launch (ROUTED engines add their mixdown
+ * launch) -- instead of five dependent launches.  The bytes are identical to the multi-kernel path; enable = 0 keeps
+ * every call on the multi-kernel path (A/B, tests), max_partitions = 0 leaves the limit as is.  _fused_calls counts. */
+int bbx_engine_set_fused(bbx_engine* e, int enable, uint32_t max_partitions);
+uint64_t bbx_engine_fused_calls(const bbx_engine* e);
 /* tensor-core MIMO path: number of k_mimo_tc launches so far and the device status word (0 = ok; non-zero =
  * a barrier wait timed out inside the kernel, results invalid).  Synchronises the stream. */
 int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status);
