@@ -134,6 +134,8 @@ struct bbx_engine {
   uint8_t* d_in[2] = {nullptr, nullptr};
   uint8_t* d_out[2] = {nullptr, nullptr};
   size_t d_io_bytes = 0;
+  uint8_t *d_lat_in = nullptr, *d_lat_out = nullptr;  // staging of small (latency-mode) host calls, used on the engine stream
+  size_t d_lat_bytes = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaStream_t s_aux = nullptr;  // side stream: k_nyq_mac runs next to the time-batched MAC
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -154,6 +156,7 @@ struct bbx_engine {
   uint8_t* d_route = nullptr;
   size_t route_bytes = 0, roff_first = 0, roff_stream = 0, roff_gain = 0, roff_dcur = 0, roff_dold = 0, roff_flags = 0,
          roff_icur = 0, roff_iold = 0, roff_entry = 0, roff_input = 0;
+  bool in_is_host = false, out_is_host = false;  // this call's PCM buffers are pinned host memory read / written in place
   bool fused_on = true;         // streaming calls of PER_CHANNEL / ROUTED engines with short filters: one launch (k_block_fused)
   uint32_t fused_max_rows = 32;  // ... "short" = at most this many partitions per path
   uint64_t fused_calls = 0;
@@ -1157,6 +1160,8 @@ int bbx_engine_destroy(bbx_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   cudaFree(e->flush_buf);
+  cudaFree(e->d_lat_in);
+  cudaFree(e->d_lat_out);
   for (void* pp : e->px_peer)
     if (pp) cudaIpcCloseMemHandle(pp);
   cudaFree(e->px_mem);
@@ -1360,6 +1365,34 @@ int bbx_set_filters(bbx_engine* e, uint32_t n, const uint32_t* paths, const bbx_
     }                                                                                       \
   } while (0)
 
+static int launch_pcm_in(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, uint32_t T, cudaStream_t st) {
+  const uint32_t B = e->B;
+  {
+    PcmInArgs a;    a.pcm = (const uint8_t*)in;
+    a.fmt = infmt;
+    a.be = in_be;
+    a.in_channels = in_channels;
+    a.n_inputs = e->n_in;
+    a.B = B;
+    a.T = T;
+    a.xin_cur = e->xin[e->parity];
+    a.xin_prev = e->xin[e->parity ^ 1];
+    a.xstride = e->xstride;
+    a.prev_off = e->tprev * B;
+    {
+      const uint32_t bps = fmt_bytes(infmt);
+      a.fast = (!in_be && bps != 3 && ((uintptr_t)in % bps) == 0) ? 1 : 0;  // frame stride = in_channels * bps is aligned too
+    }
+    // wide tiles pay when the channel axis fills the lanes; few-channel engines keep the finer grid
+    if (B % 128 == 0 && e->n_in >= 16)
+      BBX_PCM_LAUNCH(k_pcm_in128, infmt, in_be, a.fast, dim3((T + 1) * B / 128, ceil_div(e->n_in, 32)), st, a);
+    else BBX_PCM_LAUNCH(k_pcm_in, infmt, in_be, a.fast, dim3((T + 1) * B / 32, ceil_div(e->n_in, 32)), st, a);
+    BBX_CUDA_TRY(cudaGetLastError());
+    e->launches++;
+  }
+  return BBX_OK;
+}
+
 // argument and geometry checks shared by every form of bbx_process: they run before anything is staged, copied or latched
 static int validate_call(const bbx_engine* e, const void* in, int infmt, uint32_t in_channels, const void* out, int outfmt,
                          uint32_t out_channels, uint32_t nframes) {
@@ -1470,10 +1503,17 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   // ---- streaming call of a PER_CHANNEL / ROUTED engine with short filters: one launch does steps 1 - 4 (and 5) ----
   const MacPlan& fpl = n_first ? e->plan_first : e->plan_steady;
   const bool fuse = e->fused_on && T == 1 && e->mode != BBX_MODE_MIMO && e->sh_world <= 1 && !e->comm && fpl.max_job_rows <= e->fused_max_rows;
-  const bool fuse_out = fuse && e->mode == BBX_MODE_PER_CHANNEL;
+  const uint32_t ibps = fmt_bytes(infmt), obps = fmt_bytes(outfmt);
+  // PCM in host memory behind PCIe: a stream's strided picks out of wide frames would be one small bus request each, so
+  // wide host layouts go through the transposing PCM kernels (lanes over channels) on that side
+  const bool planar_in = fuse && e->in_is_host && (size_t)in_channels * ibps > 32;
+  const bool fuse_out = fuse && e->mode == BBX_MODE_PER_CHANNEL && !(e->out_is_host && (size_t)out_channels * obps > 32);
   if (fuse) {
     FusedArgs a;
-    const uint32_t ibps = fmt_bytes(infmt), obps = fmt_bytes(outfmt);
+    if (planar_in) {
+      if ((rc = launch_pcm_in(e, in, infmt, in_be, in_channels, T, st))) return rc;
+    }
+    a.planar_in = planar_in ? 1 : 0;
     a.pcm_in = (const uint8_t*)in;
     a.pcm_out = (uint8_t*)out;
     a.infmt = infmt;
@@ -1508,30 +1548,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     e->last_mac_kernel = "k_block_fused";
   } else {
   // ---- 1. PCM -> planar fp32 ----
-  {
-    PcmInArgs a;
-    a.pcm = (const uint8_t*)in;
-    a.fmt = infmt;
-    a.be = in_be;
-    a.in_channels = in_channels;
-    a.n_inputs = e->n_in;
-    a.B = B;
-    a.T = T;
-    a.xin_cur = e->xin[e->parity];
-    a.xin_prev = e->xin[e->parity ^ 1];
-    a.xstride = e->xstride;
-    a.prev_off = e->tprev * B;
-    {
-      const uint32_t bps = fmt_bytes(infmt);
-      a.fast = (!in_be && bps != 3 && ((uintptr_t)in % bps) == 0) ? 1 : 0;  // frame stride = in_channels * bps is aligned too
-    }
-    // wide tiles pay when the channel axis fills the lanes; few-channel engines keep the finer grid
-    if (B % 128 == 0 && e->n_in >= 16)
-      BBX_PCM_LAUNCH(k_pcm_in128, infmt, in_be, a.fast, dim3((T + 1) * B / 128, ceil_div(e->n_in, 32)), st, a);
-    else BBX_PCM_LAUNCH(k_pcm_in, infmt, in_be, a.fast, dim3((T + 1) * B / 32, ceil_div(e->n_in, 32)), st, a);
-    BBX_CUDA_TRY(cudaGetLastError());
-    e->launches++;
-  }
+  if ((rc = launch_pcm_in(e, in, infmt, in_be, in_channels, T, st))) return rc;
   // ---- 2. forward transforms into the FDL ----
   if ((rc = launch_rfft(B, e->xin[e->parity], e->xstride, B, e->fdl, (uint64_t)e->R * B, e->R, e->head, e->tw, 1.0f, e->n_in, T, st)))
     return rc;
@@ -1658,12 +1675,44 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   void *din = nullptr, *dout = nullptr;
   const bool typed_in = !in_be && ibps != 3 && ((uintptr_t)in % ibps) == 0;
   const bool typed_out = !out_be && obps != 3 && ((uintptr_t)out % obps) == 0;
-  const bool direct_in = in_bytes <= e->direct_io_max_bytes && typed_in && (size_t)e->n_in * ibps >= 128 && mapped_device_ptr(in, &din);
-  const bool direct_out =
-      out_bytes <= e->direct_io_max_bytes && typed_out && (size_t)e->n_out_pcm * obps >= 128 && mapped_device_ptr(out, &dout);
+  // a side suits the bus when a warp's accesses fill whole PCIe requests: at least 128 bytes of used channels per frame, or
+  // frames of at most 32 bytes altogether (stereo float: consecutive frames share the sectors, nothing is fetched in vain)
+  const bool dense_in = (size_t)e->n_in * ibps >= 128 || (size_t)in_channels * ibps <= 32;
+  const bool dense_out = (size_t)e->n_out_pcm * obps >= 128 || (size_t)out_channels * obps <= 32;
+  const bool direct_in = in_bytes <= e->direct_io_max_bytes && typed_in && dense_in && mapped_device_ptr(in, &din);
+  const bool direct_out = out_bytes <= e->direct_io_max_bytes && typed_out && dense_out && mapped_device_ptr(out, &dout);
   if (direct_in && direct_out) {
     e->direct_calls++;
-    return bbx_process_dev(e, din, infmt, in_be, in_channels, dout, outfmt, out_be, out_channels, nframes);
+    e->in_is_host = e->out_is_host = true;
+    const int drc = bbx_process_dev(e, din, infmt, in_be, in_channels, dout, outfmt, out_be, out_channels, nframes);
+    e->in_is_host = e->out_is_host = false;
+    return drc;
+  }
+  if (need <= e->direct_io_max_bytes) {
+    // Latency mode for the sides that are staged after all (24-bit or sparse layouts, pageable memory): the copies go on
+    // the engine stream itself into staging buffers of their own -- no copy streams, no cross-stream events; a call this
+    // small has nothing to overlap, and the event hops cost more than its kernels.
+    if (e->d_lat_bytes < need) {
+      BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+      cudaFree(e->d_lat_in);
+      cudaFree(e->d_lat_out);
+      e->d_lat_in = e->d_lat_out = nullptr;
+      e->d_lat_bytes = std::max<size_t>(need, 64 << 10);
+      BBX_CUDA_TRY(cudaMalloc((void**)&e->d_lat_in, e->d_lat_bytes));
+      BBX_CUDA_TRY(cudaMalloc((void**)&e->d_lat_out, e->d_lat_bytes));
+    }
+    if (direct_in || direct_out) e->direct_calls++;
+    e->in_is_host = direct_in;
+    e->out_is_host = direct_out;
+    if (!direct_in) BBX_CUDA_TRY(cudaMemcpyAsync(e->d_lat_in, in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    if (!direct_out && out_channels > e->n_out_pcm)  // channels beyond n_outputs keep the caller's bytes
+      BBX_CUDA_TRY(cudaMemcpyAsync(e->d_lat_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
+    int lrc = bbx_process_dev(e, direct_in ? din : e->d_lat_in, infmt, in_be, in_channels, direct_out ? dout : e->d_lat_out, outfmt,
+                              out_be, out_channels, nframes);
+    e->in_is_host = e->out_is_host = false;
+    if (lrc) return lrc;
+    if (!direct_out) BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_lat_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    return BBX_OK;
   }
   if (!e->d_in[0] || e->d_io_bytes < need) {
     BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));

@@ -29,6 +29,7 @@ struct FusedArgs {
   const uint8_t* pcm_in;
   uint8_t* pcm_out;
   int infmt, in_be, in_fast, outfmt, out_be, out_fast;
+  int planar_in;  // 1: k_pcm_in ran first, this block is already in the history row (wide interleaved PCM in host memory)
   uint32_t in_channels, out_channels;
   // streams and their inputs
   uint32_t n_streams;
@@ -71,19 +72,32 @@ __device__ __forceinline__ void fused_job_mac(const FusedArgs& a, uint32_t job, 
     const float2* xch = a.fdl + (uint64_t)sg.fdl_ch * a.R * M + tid;
     int slot = (int)a.head - (int)(sg.p0 % a.R);
     if (slot < 0) slot += (int)a.R;
-    for (uint32_t p = 0; p < sg.np; p++) {
-      const float2* xrow = xch + (uint64_t)slot * M;
-      float2 hv[RAD], xv[RAD];
+    // rows in batches of four: the loads of a batch are all in flight before its FMAs (the FMAs stay in row order)
+    constexpr int UB = (RAD == 8) ? 2 : 4;
+    for (uint32_t p = 0; p < sg.np; p += UB) {
+      float2 hv[UB][RAD], xv[UB][RAD];
 #pragma unroll
-      for (int h = 0; h < RAD; h++) {
-        hv[h] = __ldg(hrow + h * NT);
-        xv[h] = xrow[h * NT];  // plain load: the newest row was written by this very thread a moment ago
+      for (int u = 0; u < UB; u++) {
+        const bool on = p + u < sg.np;
+        int sl = slot - u;
+        if (sl < 0) sl += (int)a.R;
+        const float2* xrow = xch + (uint64_t)sl * M;
+#pragma unroll
+        for (int h = 0; h < RAD; h++) {
+          hv[u][h] = on ? __ldg(hrow + (uint64_t)u * M + h * NT) : make_float2(0.f, 0.f);
+          xv[u][h] = on ? xrow[h * NT] : make_float2(0.f, 0.f);  // plain load: this thread wrote the newest row a moment ago
+        }
       }
 #pragma unroll
-      for (int h = 0; h < RAD; h++) cmac(acc[h].x, acc[h].y, hv[h].x, hv[h].y, xv[h].x, xv[h].y);
-      nacc = fmaf(hv[0].y, xv[0].y, nacc);  // meaningful in the thread that owns bin 0 only
-      hrow += M;
-      slot = slot ? slot - 1 : (int)a.R - 1;
+      for (int u = 0; u < UB; u++)
+        if (p + u < sg.np) {
+#pragma unroll
+          for (int h = 0; h < RAD; h++) cmac(acc[h].x, acc[h].y, hv[u][h].x, hv[u][h].y, xv[u][h].x, xv[u][h].y);
+          nacc = fmaf(hv[u][0].y, xv[u][0].y, nacc);  // meaningful in the thread that owns bin 0 only
+        }
+      hrow += (uint64_t)UB * M;
+      slot -= UB;
+      if (slot < 0) slot += (int)a.R;
     }
     if (sg.flags & 2u) {
 #pragma unroll
@@ -124,6 +138,8 @@ __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB) k_block_fused(
       const uint32_t n = tid + r * NT;  // z index, 0 .. M-1; the first M/2 come from the previous block
       if (n < (uint32_t)M / 2) {
         v[r] = prev[n];
+      } else if (a.planar_in) {
+        v[r] = cur[n - M / 2];
       } else {
         const uint32_t f = 2 * n - M;  // frame inside this block
         const uint8_t* p = a.pcm_in + ((uint64_t)f * a.in_channels + input) * ibps;
@@ -233,7 +249,8 @@ __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB) k_block_fused(
   const RouteEntry en = a.entry[stream];
   const uint32_t obps = fmt_bytes(a.outfmt);
   const float inc = 1.0f / (float)M;
-#pragma unroll 1
+  // four samples at a time: their ring reads (and the 14-tap double-precision chains of the fractional mode) overlap
+#pragma unroll 4
   for (int r = 0; r < RAD; r++) {
     const uint32_t n = tid + r * NT;
     float bus = 0.f;

@@ -331,6 +331,25 @@ def block_latency(eng, bbx, fmt_in, in_ch, fmt_out, out_ch, blk, n=10000, warm=2
     return r
 
 
+def launch_sync_floor(torch, n=2000):
+    """host round trip of the smallest possible GPU call on this box -- one trivial kernel on a stream + a stream
+    synchronise -- the floor under every per-block latency below (virtualised hosts sit well above bare metal)"""
+    x = torch.zeros(1, device="cuda")
+    s = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    lat = np.empty(n)
+    for i in range(n + 200):
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s):
+            x.add_(1)
+        s.synchronize()
+        if i >= 200:
+            lat[i - 200] = time.perf_counter() - t0
+    lat *= 1e6
+    return {"p50_us": float(np.percentile(lat, 50)), "min_us": float(lat.min()),
+            "what": "torch: one 1-element kernel on a side stream + stream.synchronize(), host clock"}
+
+
 def timed_steps(eng, step, steps, warm=5):
     for i in range(warm):
         step(i)
@@ -1006,6 +1025,7 @@ def main():
     # ---- BASELINE.json's other configs on one GPU (rank 0, N = 1) ----
     configs = None
     roofline_mimo = None
+    floor = launch_sync_floor(torch) if (rank == 0 and world == 1 and not args.no_latency) else None
     if rank == 0 and world == 1:
         configs = {"C3": {"config": WORKLOAD, "channels": NCH, "value": value, "unit": "channel-s/s", "ms_per_step": ms / args.steps,
                           "blocks_per_step": nblk, "parity": parity, "snr_db": parity["snr_db"] if parity else None, "latency": latency}}
@@ -1056,7 +1076,7 @@ def main():
             "roofline": roofline, "roofline_streaming": roofline_streaming, "roofline_mimo": roofline_mimo, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "channel-s/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
                     "ms_per_step": ms_e2e / args.steps, "roofline": e2e_roofline},
-            "gpu_launches": int(launches), "clocks": clocks, "latency": latency, "configs": configs,
+            "gpu_launches": int(launches), "clocks": clocks, "latency": latency, "launch_sync_floor": floor, "configs": configs,
             "strong_scaling": strong, "mimo_sharded": mimo_sharded,
         }
         print(json.dumps(line))
