@@ -785,7 +785,10 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C2 / C4 legs")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling C3 leg")
     ap.add_argument("--leg-steps", type=int, default=200, help="timed steps of the secondary legs")
+    ap.add_argument("--channels", type=int, default=0, help="channels per GPU of the headline workload (tuning runs; default 128)")
     args = ap.parse_args()
+    if args.channels:
+        globals()["NCH"] = args.channels
     if args.impl == "reference":
         return run_reference(args)
 
