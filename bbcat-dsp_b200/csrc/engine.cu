@@ -1582,7 +1582,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     if (e->px_on) {
       e->px_epoch++;
       const uint32_t parity = e->px_epoch & 1u;
-      k_gather_spectra_peer<<<dim3(e->n_out, T), 256, 0, st>>>(e->ypart, use_tc ? nullptr : e->nyq_part, e->max_slots, pv,
+      k_gather_spectra_peer<<<dim3(e->n_out, ceil_div(T, kPeerTPB)), 256, 0, st>>>(e->ypart, use_tc ? nullptr : e->nyq_part, e->max_slots, pv,
                                                                e->px_table, e->sh_world, e->sh_rank, e->sh_nloc, B, T, e->px_half,
                                                                parity, e->px_epoch, e->px_done);
       BBX_CUDA_TRY(cudaGetLastError());
