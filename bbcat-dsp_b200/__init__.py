@@ -110,6 +110,8 @@ SYMBOLS = {
     "bbx_engine_profile_mac": (C.c_int, [vp, C.c_int]),
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "bbx_engine_exchange_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64)]),
+    "bbx_engine_io_trace": (C.c_int, [vp, u32]),
+    "bbx_engine_io_trace_read": (C.c_int, [vp, C.POINTER(C.c_float), u32, C.POINTER(u32)]),
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
     "bbx_engine_flush_l2": (C.c_int, [vp, C.c_size_t]),
     "bbx_engine_peer_export": (C.c_int, [vp, vp]),
@@ -640,6 +642,17 @@ class Convolver:
         ms, n, units, nbytes = C.c_float(0), u64(0), u64(0), u64(0)
         _check(lib().bbx_engine_mac_time(self.h, C.byref(ms), C.byref(n), C.byref(units), C.byref(nbytes)))
         return {"ms": ms.value, "launches": n.value, "channel_blocks": units.value, "algorithmic_bytes": nbytes.value}
+
+    def io_trace(self, calls):
+        """Trace the next `calls` ConvolveHostPtrAsync calls (bbx_engine_io_trace)."""
+        _check(lib().bbx_engine_io_trace(self.h, calls))
+
+    def io_trace_read(self, cap=4096):
+        """[n][6] ms: h2d start/end, kernels start/end, d2h start/end of every traced call."""
+        buf = (C.c_float * (6 * cap))()
+        n = u32(0)
+        _check(lib().bbx_engine_io_trace_read(self.h, buf, cap, C.byref(n)))
+        return [[buf[6 * i + j] for j in range(6)] for i in range(n.value)]
 
     def exchange_time(self):
         """input-sharded MIMO, while profile_mac is on: device time of the exchange step, exchanges, bytes sent to peers"""

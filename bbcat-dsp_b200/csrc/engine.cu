@@ -129,19 +129,26 @@ struct bbx_engine {
   float2* ypart = nullptr;
   float* nyq_part = nullptr;  // [Tmax][max_slots] Nyquist partial sums (see cmac)
   float* ybuf = nullptr;
-  // host-pointer path: double-buffered PCM staging, copies on their own streams so that the H2D of call
-  // n+1 and the D2H of call n-1 overlap the kernels of call n
-  uint8_t* d_in[2] = {nullptr, nullptr};
-  uint8_t* d_out[2] = {nullptr, nullptr};
+  // host-pointer path: PCM staging in kIoSlots buffers per direction, copies on their own streams so that the H2D of
+  // call n+1 and the D2H of call n-1 overlap the kernels of call n.  Three slots, not two: with two, every call sits on
+  // the cycle "kernels of n-2 done -> H2D of n -> kernels of n" (and the same through the D2H side), so each
+  // cross-stream hand-off (5..30 us on this part, tools/e2e_timeline.py) adds to the step; with three the copies run
+  // back to back and the step is the copy time.
+  static constexpr int kIoSlots = 3;
+  uint8_t* d_in[kIoSlots] = {};
+  uint8_t* d_out[kIoSlots] = {};
   size_t d_io_bytes = 0;
   uint8_t *d_lat_in = nullptr, *d_lat_out = nullptr;  // staging of small (latency-mode) host calls, used on the engine stream
   size_t d_lat_bytes = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaStream_t s_aux = nullptr;  // side stream: k_nyq_mac runs next to the time-batched MAC
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[kIoSlots] = {}, ev_comp[kIoSlots] = {}, ev_d2h[kIoSlots] = {};
   cudaEvent_t ev_join_in = nullptr, ev_join_out = nullptr;
   uint64_t host_calls = 0;
+  // optional trace of the host-buffer pipeline (bbx_engine_io_trace): six timing events per call
+  std::vector<cudaEvent_t> io_ev;
+  size_t io_calls = 0, io_cap = 0;
   // short host calls: the PCM kernels read / write the caller's pinned (device-mapped) buffers directly over PCIe
   // instead of going through the copy engines and the staging buffers; 0 disables
   size_t direct_io_max_bytes = 1u << 20;
@@ -1016,7 +1023,7 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
   BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
   BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < bbx_engine::kIoSlots; i++) {
     BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
     BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
     BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming));
@@ -1145,7 +1152,8 @@ int bbx_engine_destroy(bbx_engine* e) {
   cudaFree(e->ypart);
   cudaFree(e->nyq_part);
   cudaFree(e->ybuf);
-  for (int i = 0; i < 2; i++) {
+  for (cudaEvent_t ev : e->io_ev) cudaEventDestroy(ev);
+  for (int i = 0; i < bbx_engine::kIoSlots; i++) {
     cudaFree(e->d_in[i]);
     cudaFree(e->d_out[i]);
     if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
@@ -1719,7 +1727,7 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
     BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
     BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
     e->d_io_bytes = std::max(need, e->d_io_bytes);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < bbx_engine::kIoSlots; i++) {
       cudaFree(e->d_in[i]);
       cudaFree(e->d_out[i]);
       e->d_in[i] = e->d_out[i] = nullptr;
@@ -1727,14 +1735,17 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
       BBX_CUDA_TRY(cudaMalloc((void**)&e->d_out[i], e->d_io_bytes));
     }
   }
-  const int k = (int)(e->host_calls & 1);
+  const int k = (int)(e->host_calls % bbx_engine::kIoSlots);
   e->host_calls++;
   if (direct_in || direct_out) e->direct_calls++;
-  // H2D on the input-copy stream, once the kernels of call n-2 have finished reading this staging buffer
+  // H2D on the input-copy stream, once the kernels of call n - kIoSlots have finished reading this staging buffer
   bool fed = false;
+  cudaEvent_t* tr = (e->io_calls < e->io_cap) ? &e->io_ev[6 * e->io_calls++] : nullptr;
   if (!direct_in) {
     BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_comp[k], 0));
+    if (tr) BBX_CUDA_TRY(cudaEventRecord(tr[0], e->s_in));
     BBX_CUDA_TRY(cudaMemcpyAsync(e->d_in[k], in, in_bytes, cudaMemcpyHostToDevice, e->s_in));
+    if (tr) BBX_CUDA_TRY(cudaEventRecord(tr[1], e->s_in));
     fed = true;
   }
   if (!direct_out && out_channels > e->n_out_pcm) {
@@ -1749,14 +1760,18 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   }
   // kernels on the engine stream
   if (!direct_out) BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_d2h[k], 0));
+  if (tr) BBX_CUDA_TRY(cudaEventRecord(tr[2], e->stream));
   int rc = bbx_process_dev(e, direct_in ? din : e->d_in[k], infmt, in_be, in_channels, direct_out ? dout : e->d_out[k], outfmt, out_be,
                            out_channels, nframes);
   if (rc) return rc;
+  if (tr) BBX_CUDA_TRY(cudaEventRecord(tr[3], e->stream));
   BBX_CUDA_TRY(cudaEventRecord(e->ev_comp[k], e->stream));
   if (!direct_out) {
     // D2H on the output-copy stream
     BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_comp[k], 0));
+    if (tr) BBX_CUDA_TRY(cudaEventRecord(tr[4], e->s_out));
     BBX_CUDA_TRY(cudaMemcpyAsync(out, e->d_out[k], out_bytes, cudaMemcpyDeviceToHost, e->s_out));
+    if (tr) BBX_CUDA_TRY(cudaEventRecord(tr[5], e->s_out));
     BBX_CUDA_TRY(cudaEventRecord(e->ev_d2h[k], e->s_out));
   }
   return BBX_OK;
@@ -1835,6 +1850,42 @@ int bbx_engine_profile_mac(bbx_engine* e, int enable) {
   e->xchg_events_used = 0;
   e->xchg_ms_total = 0.0;
   e->xchg_count = e->xchg_bytes = 0;
+  return BBX_OK;
+}
+
+int bbx_engine_io_trace(bbx_engine* e, uint32_t calls) {
+  BBX_REQUIRE(e != nullptr, "null engine");
+  DeviceGuard dg(e->device);
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  while (e->io_ev.size() < (size_t)6 * calls) {
+    cudaEvent_t ev;
+    BBX_CUDA_TRY(cudaEventCreate(&ev));
+    e->io_ev.push_back(ev);
+  }
+  e->io_cap = calls;
+  e->io_calls = 0;
+  return BBX_OK;
+}
+
+int bbx_engine_io_trace_read(bbx_engine* e, float* ms, uint32_t cap, uint32_t* n) {
+  BBX_REQUIRE(e != nullptr && ms != nullptr && n != nullptr, "bbx_engine_io_trace_read: null argument");
+  DeviceGuard dg(e->device);
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  const uint32_t m = (uint32_t)std::min<size_t>(cap, e->io_calls);
+  for (uint32_t i = 0; i < m; i++)
+    for (int j = 0; j < 6; j++) {
+      ms[6 * i + j] = 0.f;
+      if (cudaEventElapsedTime(&ms[6 * i + j], e->io_ev[0], e->io_ev[6 * i + j]) != cudaSuccess) {
+        cudaGetLastError();  // an event of a side the call did not use (direct I/O) was never recorded
+        ms[6 * i + j] = -1.f;
+      }
+    }
+  *n = m;
+  e->io_cap = e->io_calls = 0;
   return BBX_OK;
 }
 

@@ -259,7 +259,7 @@ int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in
 int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
                     int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
 /* Host pointers, asynchronous: returns once the H2D copy, the kernels and the D2H copy are enqueued (copies on
- * their own streams, staging double-buffered), so consecutive calls overlap transfer and compute.  `in` and
+ * their own streams, three staging buffers per direction), so consecutive calls overlap transfer and compute.  `in` and
  * `out` must stay valid and untouched until bbx_engine_sync(); use pinned buffers (bbx_host_alloc). */
 int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
                       int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
@@ -391,6 +391,11 @@ int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint
  * (k_gather_spectra_peer + k_peer_wait, or k_gather_spectra + ncclReduceScatter), the number of exchanges and the bytes
  * this rank sent to its peers (synchronises) */
 int bbx_engine_exchange_time(bbx_engine* e, float* total_ms, uint64_t* exchanges, uint64_t* bytes_sent);
+/* Trace of the host-buffer pipeline: the next `calls` bbx_process_async calls record a timing event at the start and end
+ * of their H2D copy, their kernels and their D2H copy; _read returns, per traced call, those six times in ms relative to
+ * the first call's H2D start ([n][6]: h2d0, h2d1, kernels0, kernels1, d2h0, d2h1; -1 = that side was not used). */
+int bbx_engine_io_trace(bbx_engine* e, uint32_t calls);
+int bbx_engine_io_trace_read(bbx_engine* e, float* ms, uint32_t cap, uint32_t* n);
 /* change the tuning knobs of bbx_config at run time (0 = leave as is); takes effect at the next call */
 int bbx_engine_set_tuning(bbx_engine* e, uint32_t ctas_per_sm, uint32_t l2_keep_16ths, uint32_t time_tile);
 /* mixdowns of many paths into few outputs (>= 4 paths per output, <= 32 outputs, <= 256 routes) run k_pcm_out_mix, which
