@@ -130,6 +130,19 @@ SYMBOLS = {
     "bbx_biquad_process_dev": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, vp]),
     "bbx_biquad_get_state": (C.c_int, [vp, vp, vp, vp]),
     "bbx_biquad_reset": (C.c_int, [vp]),
+    "bbx_fbank_create": (C.c_int, [u32, u32, C.POINTER(vp)]),
+    "bbx_fbank_destroy": (C.c_int, [vp]),
+    "bbx_fbank_set_filters": (C.c_int, [vp, u32]),
+    "bbx_fbank_add_filter": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "bbx_fbank_set_channels": (C.c_int, [vp, u32]),
+    "bbx_fbank_get_size": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32)]),
+    "bbx_fbank_set_coeffs": (C.c_int, [vp, u32, C.POINTER(C.c_double), C.c_double]),
+    "bbx_fbank_calc": (C.c_int, [vp, u32, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "bbx_fbank_process": (C.c_int, [vp, vp, vp, u32, u32, u32, u32]),
+    "bbx_fbank_process_dev": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, vp]),
+    "bbx_fbank_get_state": (C.c_int, [vp, u32, vp, vp, vp]),
+    "bbx_fbank_reset": (C.c_int, [vp]),
+    "bbx_fbank_launches": (C.c_int, [vp, C.POINTER(u64)]),
     "bbx_allpass_create": (C.c_int, [u32, u32, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(vp)]),
     "bbx_allpass_destroy": (C.c_int, [vp]),
     "bbx_allpass_process": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, u32]),
@@ -428,6 +441,71 @@ class BiQuadBank:
 
     def Reset(self):
         _check(lib().bbx_biquad_reset(self.h))
+
+
+class BiQuadFilterBank:
+    """BiQuadFilterBank (src/BiQuad.h:247-353): `filters` biquads in series on each of `channels` channels, one coefficient
+    object per filter; Process runs all filters in one pass over the block (k_fbank)."""
+
+    def __init__(self, channels=0, filters=0):
+        h = vp()
+        _check(lib().bbx_fbank_create(channels, filters, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_fbank_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _size(self):
+        a, b = u32(0), u32(0)
+        _check(lib().bbx_fbank_get_size(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def GetChannels(self):
+        return self._size()[0]
+
+    def GetFilters(self):
+        return self._size()[1]
+
+    def SetFilters(self, n):
+        _check(lib().bbx_fbank_set_filters(self.h, n))
+
+    def AddFilter(self, c5):
+        _check(lib().bbx_fbank_add_filter(self.h, (C.c_double * 5)(*[float(v) for v in c5])))
+
+    def SetChannels(self, n):
+        _check(lib().bbx_fbank_set_channels(self.h, n))
+
+    def SetCoeffs(self, filter, c5, interp_samples=0.0):
+        _check(lib().bbx_fbank_set_coeffs(self.h, filter, (C.c_double * 5)(*[float(v) for v in c5]), interp_samples))
+
+    def CalcCoeffs(self, filter, ftype, freq, fs, gain=0.0, bandwidth=1.0, interp_time=0.0):
+        _check(lib().bbx_fbank_calc(self.h, filter, ftype, freq, fs, gain, bandwidth, interp_time))
+
+    def Process(self, src, dst, nchannels, nsrcchannels, ndstchannels, nframes):
+        _check(lib().bbx_fbank_process(self.h, _p(src), _p(dst), nchannels, nsrcchannels, ndstchannels, nframes))
+
+    def ProcessDev(self, src_ptr, dst_ptr, nchannels, nsrcchannels, ndstchannels, nframes, stream=None):
+        _check(lib().bbx_fbank_process_dev(self.h, src_ptr, dst_ptr, nchannels, nsrcchannels, ndstchannels, nframes, stream))
+
+    def GetState(self, filter):
+        nch = self.GetChannels()
+        w = np.zeros(2 * max(1, nch), dtype=np.float64)
+        cur = np.zeros(5, dtype=np.float64)
+        md = np.zeros(2, dtype=np.float64)
+        _check(lib().bbx_fbank_get_state(self.h, filter, _p(w), _p(cur), _p(md)))
+        return w[:2 * nch], cur, md
+
+    def Reset(self):
+        _check(lib().bbx_fbank_reset(self.h))
+
+    def Launches(self):
+        n = u64(0)
+        _check(lib().bbx_fbank_launches(self.h, C.byref(n)))
+        return n.value
 
 
 class AllPassChain:

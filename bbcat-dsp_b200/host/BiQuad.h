@@ -49,6 +49,74 @@ private:
   bbx_biquad* b;
 };
 
+// BiQuadFilterBank surface (src/BiQuad.h:247-353): filters in series on every channel, one coefficient object per filter.
+// Process runs all filters in ONE pass over the block on the GPU (k_fbank) and is bit-exact against the reference's
+// filter-by-filter loop (src/BiQuad.cpp:639-662).  GetFilterCoeffs(i) returns a small handle with the reference's
+// SetCoeffs / CalcCoeffs signatures instead of a BiQuadCoeffs pointer.
+class BiQuadFilterBank {
+public:
+  typedef BiQuadBank::Filter_t Filter_t;
+  typedef BiQuadBank::COEFFS COEFFS;
+
+  class Coeffs {  // what GetFilterCoeffs(i) hands out: the coefficient object of filter i
+  public:
+    void SetCoeffs(double num0, double num1 = 0.0, double num2 = 0.0, double den1 = 0.0, double den2 = 0.0, double interp_samples = 0.0) {
+      const double c[5] = {num0, num1, num2, den1, den2};
+      Check(bbx_fbank_set_coeffs(f, i, c, interp_samples));
+    }
+    void CalcCoeffs(Filter_t type, double freq, double fs, double gain = 0.0, double bandwidth = 1.0, double interp_time = 0.0) {
+      Check(bbx_fbank_calc(f, i, (int)type, freq, fs, gain, bandwidth, interp_time));
+    }
+    COEFFS GetCurrent() const {
+      double c[5];
+      Check(bbx_fbank_get_state(f, i, 0, c, 0));
+      COEFFS r = {c[0], c[1], c[2], c[3], c[4]};
+      return r;
+    }
+    bool Valid() const { return f != 0; }
+
+  private:
+    friend class BiQuadFilterBank;
+    Coeffs(bbx_fbank* _f, uint_t _i) : f(_f), i(_i) {}
+    bbx_fbank* f;
+    uint_t i;
+  };
+
+  BiQuadFilterBank() : f(0) { Check(bbx_fbank_create(0, 0, &f)); }
+  ~BiQuadFilterBank() { bbx_fbank_destroy(f); }
+
+  void SetFilters(uint_t n) { Check(bbx_fbank_set_filters(f, n)); }
+  void AddFilter(const COEFFS& c) {
+    const double c5[5] = {c.num0, c.num1, c.num2, c.den1, c.den2};
+    Check(bbx_fbank_add_filter(f, c5));
+  }
+  uint_t GetFilters() const {
+    uint32_t n = 0;
+    Check(bbx_fbank_get_size(f, 0, &n));
+    return n;
+  }
+  void Reset() { Check(bbx_fbank_reset(f)); }
+  void SetChannels(uint_t n) { Check(bbx_fbank_set_channels(f, n)); }
+  uint_t GetChannels() const {
+    uint32_t n = 0;
+    Check(bbx_fbank_get_size(f, &n, 0));
+    return n;
+  }
+  // the reference returns NULL beyond the last filter; here the handle's Valid() is false
+  Coeffs GetFilterCoeffs(uint_t i) { return Coeffs(i < GetFilters() ? f : 0, i); }
+  void Process(const Sample_t* src, Sample_t* dst, uint_t nchannels, uint_t nsrcchannels, uint_t ndstchannels, uint_t nframes) {
+    Check(bbx_fbank_process(f, src, dst, nchannels, nsrcchannels, ndstchannels, nframes));
+  }
+
+private:
+  static void Check(int rc) {
+    if (rc != BBX_OK) throw std::runtime_error(std::string("libbbx: ") + bbx_last_error());
+  }
+  BiQuadFilterBank(const BiQuadFilterBank&);
+  BiQuadFilterBank& operator=(const BiQuadFilterBank&);
+  bbx_fbank* f;
+};
+
 // BiQuadCascade surface (src/BiQuad.h:373-792) for a bank of independent per-channel cascades on the GPU: numfilters (1..12)
 // float biquads per channel, plain or "vectorised" (pipelined) Tick, coefficient vector (g, b1[0], b2[0], a1[0], a2[0], ...).
 // The reference object filters one mono stream (ProcessCascade(input, dest, blocksize)); the bank runs `channels` of

@@ -338,6 +338,35 @@ int bbx_biquad_process_dev(bbx_biquad* b, const float* src, float* dst, uint32_t
 int bbx_biquad_get_state(const bbx_biquad* b, double* w, double* cur5, double* mul_dec);
 int bbx_biquad_reset(bbx_biquad* b); /* BiQuad::Reset on every filter */
 
+/* BiQuadFilterBank  src/BiQuad.h:247-353, src/BiQuad.cpp:498-662: nfilters biquads in series on each of nchannels
+ * channels, one coefficient object (with its own ramp) per filter.  Process (src/BiQuad.cpp:639-662) is the reference's
+ * filter-by-filter loop -- BiQuad::Process from src to dst for the first filter, in place on dst for the others -- fused
+ * into ONE pass: a thread takes a frame of its channel through all filters before the next frame (one read of src, one
+ * write of dst; banks of more than 16 filters run in passes of 16).  Same IEEE operations in the same order per
+ * (filter, channel): bit-exact against the reference build.  SetFilters / SetChannels semantics: filters are dropped
+ * from / appended at the end, surviving (filter, channel) pairs keep their audio state, new ones start at zero with
+ * flat coefficients; AddFilter appends a filter with the given coefficients (no ramp). */
+typedef struct bbx_fbank bbx_fbank;
+int bbx_fbank_create(uint32_t nchannels, uint32_t nfilters, bbx_fbank** out);
+int bbx_fbank_destroy(bbx_fbank* f);
+int bbx_fbank_set_filters(bbx_fbank* f, uint32_t n);           /* BiQuadFilterBank::SetFilters */
+int bbx_fbank_add_filter(bbx_fbank* f, const double* c5);      /* BiQuadFilterBank::AddFilter */
+int bbx_fbank_set_channels(bbx_fbank* f, uint32_t n);          /* BiQuadFilterBank::SetChannels */
+int bbx_fbank_get_size(const bbx_fbank* f, uint32_t* nchannels, uint32_t* nfilters); /* GetChannels / GetFilters */
+/* GetFilterCoeffs(filter)->SetCoeffs / ->CalcCoeffs (interp_samples in SAMPLES, interp_time in SECONDS) */
+int bbx_fbank_set_coeffs(bbx_fbank* f, uint32_t filter, const double* c5, double interp_samples);
+int bbx_fbank_calc(bbx_fbank* f, uint32_t filter, int type, double freq, double fs, double gain, double bandwidth,
+                   double interp_time);
+/* BiQuadFilterBank::Process(src, dst, nchannels, nsrcchannels, ndstchannels, nframes); host pointers / device pointers */
+int bbx_fbank_process(bbx_fbank* f, const float* src, float* dst, uint32_t nchannels, uint32_t nsrcchannels,
+                      uint32_t ndstchannels, uint32_t nframes);
+int bbx_fbank_process_dev(bbx_fbank* f, const float* src, float* dst, uint32_t nchannels, uint32_t nsrcchannels,
+                          uint32_t ndstchannels, uint32_t nframes, void* stream);
+/* state of one filter: w[nchannels][2], current coefficients, {mul, dec} of its ramp (any pointer may be NULL) */
+int bbx_fbank_get_state(const bbx_fbank* f, uint32_t filter, double* w, double* cur5, double* mul_dec);
+int bbx_fbank_reset(bbx_fbank* f);                             /* BiQuadFilterBank::Reset */
+int bbx_fbank_launches(const bbx_fbank* f, uint64_t* launches); /* kernels launched so far (one per 16 filters per call) */
+
 /* BiQuadCascade  src/BiQuad.h:373-792: a bank of nchannels independent cascades of numfilters (1..12) biquads in float,
  * both forms of Tick -- the plain cascade and the "vectorised" pipeline of the SSE3 build (numfilters a multiple of four,
  * else switched off like the reference; it delays the signal by numfilters - 1 samples).  unroll is accepted for signature

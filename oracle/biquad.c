@@ -152,3 +152,79 @@ void orc_biquad_get_state(const orc_biquad* b, double* w, double* cur5, double* 
 }
 
 void orc_biquad_reset(orc_biquad* b) { memset(b->w, 0, 2 * (size_t)b->nch * sizeof(double)); }
+
+/* ---- BiQuadFilterBank (src/BiQuad.h:247-353, src/BiQuad.cpp:498-662) ----
+ * nfilters coefficient objects, each with one filter state per channel.  Process is the reference's loop as written
+ * (src/BiQuad.cpp:639-662): filter 0 from src to dst, every later filter in place on dst, each a full pass of
+ * BiQuad::Process with that filter's own ramp.  SetFilters / SetChannels (src/BiQuad.cpp:528-600) drop or append at the end;
+ * surviving (filter, channel) pairs keep their state, new ones start flat and silent. */
+struct orc_fbank {
+  unsigned nch, nfilters;
+  orc_biquad** f;
+};
+
+orc_fbank* orc_fbank_create(unsigned nch, unsigned nfilters) {
+  orc_fbank* b = (orc_fbank*)calloc(1, sizeof(*b));
+  b->nch = nch;
+  orc_fbank_set_filters(b, nfilters);
+  return b;
+}
+
+void orc_fbank_destroy(orc_fbank* b) {
+  if (!b) return;
+  orc_fbank_set_filters(b, 0);
+  free(b->f);
+  free(b);
+}
+
+void orc_fbank_set_filters(orc_fbank* b, unsigned n) {
+  for (unsigned i = n; i < b->nfilters; i++) orc_biquad_destroy(b->f[i]);
+  b->f = (orc_biquad**)realloc(b->f, sizeof(*b->f) * (n ? n : 1));
+  for (unsigned i = b->nfilters; i < n; i++) b->f[i] = orc_biquad_create(b->nch);
+  b->nfilters = n;
+}
+
+void orc_fbank_add_filter(orc_fbank* b, const double* c5) {
+  orc_fbank_set_filters(b, b->nfilters + 1);
+  orc_biquad_set_coeffs(b->f[b->nfilters - 1], c5, 0.0);
+}
+
+void orc_fbank_set_channels(orc_fbank* b, unsigned n) {
+  for (unsigned i = 0; i < b->nfilters; i++) {
+    orc_biquad* q = b->f[i];
+    double* w = (double*)calloc(2 * (size_t)(n ? n : 1), sizeof(double));
+    memcpy(w, q->w, 2 * (size_t)(n < q->nch ? n : q->nch) * sizeof(double));
+    free(q->w);
+    q->w = w;
+    q->nch = n;
+  }
+  b->nch = n;
+}
+
+void orc_fbank_set_coeffs(orc_fbank* b, unsigned filter, const double* c5, double interp_samples) {
+  if (filter < b->nfilters) orc_biquad_set_coeffs(b->f[filter], c5, interp_samples);
+}
+
+void orc_fbank_calc(orc_fbank* b, unsigned filter, int type, double freq, double fs, double gain, double bandwidth,
+                    double interp_time) {
+  if (filter < b->nfilters) orc_biquad_calc(b->f[filter], type, freq, fs, gain, bandwidth, interp_time);
+}
+
+void orc_fbank_process(orc_fbank* b, const float* src, float* dst, unsigned nchannels, unsigned nsrc, unsigned ndst,
+                       unsigned nframes) {
+  if (nchannels > nsrc) nchannels = nsrc;
+  if (nchannels > ndst) nchannels = ndst;
+  for (unsigned i = 0; i < b->nfilters; i++) {
+    orc_biquad_process(b->f[i], src, dst, nchannels, nsrc, ndst, nframes);
+    src = dst; /* every later filter works in place on the destination (src/BiQuad.cpp:656-660) */
+    nsrc = ndst;
+  }
+}
+
+void orc_fbank_get_state(const orc_fbank* b, unsigned filter, double* w, double* cur5, double* mul_dec) {
+  if (filter < b->nfilters) orc_biquad_get_state(b->f[filter], w, cur5, mul_dec);
+}
+
+void orc_fbank_reset(orc_fbank* b) {
+  for (unsigned i = 0; i < b->nfilters; i++) orc_biquad_reset(b->f[i]);
+}

@@ -125,6 +125,20 @@ void orc_biquad_process(orc_biquad* b, const float* src, float* dst, unsigned nc
                         unsigned nframes);
 void orc_biquad_get_state(const orc_biquad* b, double* w, double* cur5, double* mul_dec);
 void orc_biquad_reset(orc_biquad* b);
+/* BiQuadFilterBank (src/BiQuad.cpp:498-662): the reference's filter-by-filter loop */
+typedef struct orc_fbank orc_fbank;
+orc_fbank* orc_fbank_create(unsigned nch, unsigned nfilters);
+void orc_fbank_destroy(orc_fbank* b);
+void orc_fbank_set_filters(orc_fbank* b, unsigned n);
+void orc_fbank_add_filter(orc_fbank* b, const double* c5);
+void orc_fbank_set_channels(orc_fbank* b, unsigned n);
+void orc_fbank_set_coeffs(orc_fbank* b, unsigned filter, const double* c5, double interp_samples);
+void orc_fbank_calc(orc_fbank* b, unsigned filter, int type, double freq, double fs, double gain, double bandwidth,
+                    double interp_time);
+void orc_fbank_process(orc_fbank* b, const float* src, float* dst, unsigned nchannels, unsigned nsrc, unsigned ndst,
+                       unsigned nframes);
+void orc_fbank_get_state(const orc_fbank* b, unsigned filter, double* w, double* cur5, double* mul_dec);
+void orc_fbank_reset(orc_fbank* b);
 
 /* ---- allpass.c : AllPassFilterChain<float> ("next" row) ---- */
 typedef struct orc_allpass orc_allpass;

@@ -220,6 +220,59 @@ void ref_biquad_reset(void* h) {
   for (size_t j = 0; j < b->filters.size(); j++) b->filters[j].Reset();
 }
 
+/* ---- BiQuadFilterBank (src/BiQuad.h:247-353, src/BiQuad.cpp:498-662): the reference's own class ---- */
+namespace {
+struct PeekFbank : public BiQuadFilterBank {
+  const BiQuad& Ch(size_t f, size_t j) const { return filters[f]->channels[j]; }
+  size_t NCh(size_t f) const { return filters[f]->channels.size(); }
+};
+}  // namespace
+void* ref_fbank_create(unsigned nch, unsigned nfilters) {
+  PeekFbank* b = new PeekFbank();
+  b->SetChannels(nch);
+  b->SetFilters(nfilters);
+  return b;
+}
+void ref_fbank_destroy(void* h) { delete (PeekFbank*)h; }
+void ref_fbank_set_filters(void* h, unsigned n) { ((PeekFbank*)h)->SetFilters(n); }
+void ref_fbank_add_filter(void* h, const double* c5) {
+  BiQuadCoeffs c;
+  c.SetCoeffs(c5[0], c5[1], c5[2], c5[3], c5[4], 0.0);
+  ((PeekFbank*)h)->AddFilter(c);
+}
+void ref_fbank_set_channels(void* h, unsigned n) { ((PeekFbank*)h)->SetChannels(n); }
+void ref_fbank_set_coeffs(void* h, unsigned filter, const double* c5, double interp_samples) {
+  BiQuadCoeffs* c = ((PeekFbank*)h)->GetFilterCoeffs(filter);
+  if (c) c->SetCoeffs(c5[0], c5[1], c5[2], c5[3], c5[4], interp_samples);
+}
+void ref_fbank_calc(void* h, unsigned filter, int type, double freq, double fs, double gain, double bandwidth, double interp_time) {
+  BiQuadCoeffs* c = ((PeekFbank*)h)->GetFilterCoeffs(filter);
+  if (c) c->CalcCoeffs((BiQuadCoeffs::Filter_t)type, freq, fs, gain, bandwidth, interp_time);
+}
+void ref_fbank_process(void* h, const float* src, float* dst, unsigned nchannels, unsigned nsrc, unsigned ndst, unsigned nframes) {
+  PeekFbank* b = (PeekFbank*)h;
+  if (!b->GetChannels()) return;  /* the reference would index an empty vector (src/BiQuad.cpp:653) */
+  b->Process(src, dst, nchannels, nsrc, ndst, nframes);
+}
+void ref_fbank_get_state(void* h, unsigned filter, double* w, double* cur5, double* mul_dec) {
+  PeekFbank* b = (PeekFbank*)h;
+  if (filter >= b->GetFilters()) return;
+  for (size_t j = 0; j < b->NCh(filter); j++) {
+    const double* ww = static_cast<const PeekBiQuad&>(b->Ch(filter, j)).W();
+    w[2 * j] = ww[0];
+    w[2 * j + 1] = ww[1];
+  }
+  const BiQuadCoeffs* c = b->GetFilterCoeffs(filter);
+  cur5[0] = c->current.num0;
+  cur5[1] = c->current.num1;
+  cur5[2] = c->current.num2;
+  cur5[3] = c->current.den1;
+  cur5[4] = c->current.den2;
+  mul_dec[0] = static_cast<const PeekCoeffs*>(c)->Mul();
+  mul_dec[1] = static_cast<const PeekCoeffs*>(c)->Dec();
+}
+void ref_fbank_reset(void* h) { ((PeekFbank*)h)->Reset(); }
+
 
 /* ---- AllPassFilterChain<float> (src/AllPassFilter.h:12-262, ring semantics src/RingBuffer.h:17-121) ---- */
 namespace {

@@ -119,6 +119,26 @@ int main() {
     bank.CalcCoeffs(BiQuadBank::FLAT, 1000.0, 48000.0);
     CHECK(bank.GetCurrent().num0 == 1.0 && bank.GetCurrent().den1 == 0.0);
   }
+  // BiQuadFilterBank: two of those filters in series equal two passes of one (exact), and AddFilter / GetFilterCoeffs work
+  {
+    BiQuadFilterBank fb;
+    fb.SetChannels(2);
+    fb.SetFilters(1);
+    fb.GetFilterCoeffs(0).SetCoeffs(1.0, 0.5, 0.0, 0.25, 0.0);
+    BiQuadFilterBank::COEFFS c2 = {1.0, 0.5, 0.0, 0.25, 0.0};
+    fb.AddFilter(c2);
+    CHECK(fb.GetFilters() == 2 && fb.GetChannels() == 2 && !fb.GetFilterCoeffs(2).Valid());
+    BiQuadBank one(2), two(2);
+    one.SetCoeffs(1.0, 0.5, 0.0, 0.25, 0.0);
+    two.SetCoeffs(1.0, 0.5, 0.0, 0.25, 0.0);
+    float bx[16], by[16], bz[16];
+    for (int i = 0; i < 16; i++) bx[i] = (float)((i * 7) % 5) - 2.0f, by[i] = 9.0f;
+    fb.Process(bx, by, 2, 2, 2, 8);
+    one.Process(bx, bz, 2, 2, 2, 8);
+    two.Process(bz, bz, 2, 2, 2, 8);
+    CHECK(memcmp(by, bz, sizeof(by)) == 0);
+    CHECK(fb.GetFilterCoeffs(1).GetCurrent().num1 == 0.5);
+  }
   // SoundRingBuffer: one frame always stays free; writes are limited by the read position
   {
     SoundRingBuffer ring;

@@ -97,6 +97,16 @@ class CpuLib:
         self._bq_process = fn("biquad_process", None, [vp, vp, vp, u32, u32, u32, u32])
         self._bq_state = fn("biquad_get_state", None, [vp, vp, vp, vp])
         self._bq_reset = fn("biquad_reset", None, [vp])
+        self._fb_create = fn("fbank_create", vp, [u32, u32])
+        self._fb_destroy = fn("fbank_destroy", None, [vp])
+        self._fb_set_filters = fn("fbank_set_filters", None, [vp, u32])
+        self._fb_add = fn("fbank_add_filter", None, [vp, vp])
+        self._fb_set_channels = fn("fbank_set_channels", None, [vp, u32])
+        self._fb_set = fn("fbank_set_coeffs", None, [vp, u32, vp, dbl])
+        self._fb_calc = fn("fbank_calc", None, [vp, u32, C.c_int, dbl, dbl, dbl, dbl, dbl])
+        self._fb_process = fn("fbank_process", None, [vp, vp, vp, u32, u32, u32, u32])
+        self._fb_state = fn("fbank_get_state", None, [vp, u32, vp, vp, vp])
+        self._fb_reset = fn("fbank_reset", None, [vp])
         self._ap_create = fn("allpass_create", vp, [u32, u32, vp, vp])
         self._ap_destroy = fn("allpass_destroy", None, [vp])
         self._ap_process = fn("allpass_process", None, [vp, vp, vp, u32, u32, u32, u32, u32])
@@ -191,6 +201,9 @@ class CpuLib:
     def biquad(self, channels):
         return CpuBiquad(self, channels)
 
+    def fbank(self, channels, filters):
+        return CpuFbank(self, channels, filters)
+
     def allpass(self, channels, delays, coeffs):
         return CpuAllpass(self, channels, delays, coeffs)
 
@@ -276,6 +289,49 @@ class CpuBiquad:
 
     def reset(self):
         self.l._bq_reset(self.h)
+
+
+class CpuFbank:
+    """BiQuadFilterBank: the reference's own class (oracle/_ref) or the C restatement of its filter-by-filter loop."""
+
+    def __init__(self, lib, channels, filters):
+        self.l, self.channels, self.filters = lib, channels, filters
+        self.h = lib._fb_create(channels, filters)
+
+    def close(self):
+        if self.h:
+            self.l._fb_destroy(self.h)
+            self.h = None
+
+    def set_filters(self, n):
+        self.l._fb_set_filters(self.h, n)
+        self.filters = n
+
+    def add_filter(self, c5):
+        self.l._fb_add(self.h, _ptr(np.ascontiguousarray(c5, dtype=np.float64)))
+        self.filters += 1
+
+    def set_channels(self, n):
+        self.l._fb_set_channels(self.h, n)
+        self.channels = n
+
+    def set_coeffs(self, filter, c5, interp_samples=0.0):
+        self.l._fb_set(self.h, filter, _ptr(np.ascontiguousarray(c5, dtype=np.float64)), interp_samples)
+
+    def calc(self, filter, ftype, freq, fs, gain=0.0, bandwidth=1.0, interp_time=0.0):
+        self.l._fb_calc(self.h, filter, ftype, freq, fs, gain, bandwidth, interp_time)
+
+    def process(self, src, dst, nchannels, nsrc, ndst, nframes):
+        self.l._fb_process(self.h, _ptr(src), _ptr(dst), nchannels, nsrc, ndst, nframes)
+
+    def state(self, filter):
+        w = np.zeros(2 * max(1, self.channels), dtype=np.float64)
+        cur, md = np.zeros(5, dtype=np.float64), np.zeros(2, dtype=np.float64)
+        self.l._fb_state(self.h, filter, _ptr(w), _ptr(cur), _ptr(md))
+        return w[:2 * self.channels], cur, md
+
+    def reset(self):
+        self.l._fb_reset(self.h)
 
 
 class CpuMultilayer:

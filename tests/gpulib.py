@@ -52,6 +52,9 @@ class GpuLib:
     def biquad(self, channels):
         return GpuBiquad(self.b, channels)
 
+    def fbank(self, channels, filters):
+        return GpuFbank(self.b, channels, filters)
+
     def allpass(self, channels, delays, coeffs):
         return GpuAllpass(self.b, channels, delays, coeffs)
 
@@ -115,6 +118,38 @@ class GpuBiquad:
 
     def state(self):
         return self.q.GetState()
+
+    def reset(self):
+        self.q.Reset()
+
+
+class GpuFbank:
+    def __init__(self, b, channels, filters):
+        self.q = b.BiQuadFilterBank(channels, filters)
+
+    def close(self):
+        self.q.close()
+
+    def set_filters(self, n):
+        self.q.SetFilters(n)
+
+    def add_filter(self, c5):
+        self.q.AddFilter(c5)
+
+    def set_channels(self, n):
+        self.q.SetChannels(n)
+
+    def set_coeffs(self, filter, c5, interp_samples=0.0):
+        self.q.SetCoeffs(filter, c5, interp_samples)
+
+    def calc(self, filter, ftype, freq, fs, gain=0.0, bandwidth=1.0, interp_time=0.0):
+        self.q.CalcCoeffs(filter, ftype, freq, fs, gain, bandwidth, interp_time)
+
+    def process(self, src, dst, nchannels, nsrc, ndst, nframes):
+        self.q.Process(src, dst, nchannels, nsrc, ndst, nframes)
+
+    def state(self, filter):
+        return self.q.GetState(filter)
 
     def reset(self):
         self.q.Reset()

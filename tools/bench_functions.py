@@ -58,6 +58,24 @@ def main():
     res["mix_32_mono_paths_to_stereo"] = timed(mix32, 32 * nfr, reps=5)
     res["fractional_sample_f32"] = timed(lambda: chk(lib.bbx_fractional_samples_f32_dev(vp(ring.data_ptr()), 0, 1, 4096, vp(pos.data_ptr()), npos,
                                                                                          vp(outp.data_ptr()), st)), npos)
+    # BiQuadFilterBank: 8 filters on 1024 channels x 16 Ki frames -- the fused pass against the same filters run one bank
+    # after the other (the reference's loop, one kernel per filter)
+    fch, ffr, nf = 1024, 1 << 14, 8
+    xs = (torch.rand(fch * ffr, device="cuda") * 2 - 1).contiguous()
+    ys = torch.zeros(fch * ffr, device="cuda")
+    fb = bbx.BiQuadFilterBank(fch, nf)
+    singles = [bbx.BiQuadBank(fch) for _ in range(nf)]
+    for f in range(nf):
+        c = bbx.BiQuadCalcCoeffs(7, 300.0 * (f + 1), 48000.0, 3.0, 1.0)
+        fb.SetCoeffs(f, c)
+        singles[f].SetCoeffs(c)
+    res["fbank_8_filters_fused_1024ch"] = timed(lambda: fb.ProcessDev(vp(xs.data_ptr()), vp(ys.data_ptr()), fch, fch, fch, ffr, st), fch * ffr, reps=5)
+
+    def chain():
+        chk(lib.bbx_biquad_process_dev(singles[0].h, vp(xs.data_ptr()), vp(ys.data_ptr()), fch, fch, fch, ffr, st))
+        for q in singles[1:]:
+            chk(lib.bbx_biquad_process_dev(q.h, vp(ys.data_ptr()), vp(ys.data_ptr()), fch, fch, fch, ffr, st))
+    res["fbank_8_filters_one_pass_each_1024ch"] = timed(chain, fch * ffr, reps=5)
     print(json.dumps({"gpu_functions": res}))
 
 

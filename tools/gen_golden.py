@@ -306,6 +306,67 @@ def gen_biquad(ref):
     np.savez_compressed(os.path.join(OUT, "biquad.npz"), **d)
 
 
+# ---- BiQuadFilterBank (src/BiQuad.h:247-353, src/BiQuad.cpp:498-662) ----
+def fbank_script(lib, nch=5, nfilters=3, nsrc=7, ndst=6, seed=9191):
+    """One scenario on any implementation: filters designed and set explicitly, ramps on some filters only, a ramp that ends
+    inside a call, partial channel counts, in-place processing, AddFilter / SetFilters / SetChannels between calls, Reset.
+    Returns every output block and, after every call, the state of every filter."""
+    rng = np.random.default_rng(seed)
+    fb = lib.fbank(nch, nfilters)
+    outs = []
+    size = [nch, nfilters]
+
+    def run(nframes, nchannels=None, s=nsrc, d=ndst, inplace=False):
+        nchannels = size[0] if nchannels is None else nchannels
+        x = rng.uniform(-1, 1, nframes * s).astype(np.float32)
+        if inplace:
+            y = x.copy()
+            fb.process(y, y, nchannels, s, s, nframes)
+        else:
+            y = np.full(nframes * d, 7.0, dtype=np.float32)
+            fb.process(x, y, nchannels, s, d, nframes)
+        outs.append(y)
+        for f in range(size[1]):
+            w, cur, md = fb.state(f)
+            outs.extend([w.copy(), cur.copy(), md.copy()])
+
+    run(21)                                                       # default filters: flat
+    for f in range(nfilters):
+        fb.calc(f, (7, 8, 9, 3, 4, 5, 6)[f % 7], 300.0 * (f + 1), 48000.0, 3.0 - f, 1.0, 0.0)
+    run(100)
+    fb.calc(1 % nfilters, 3, 2500.0, 48000.0, 0.0, 1.0, 0.003)  # one filter ramps for 144 samples, the others stay
+    run(50)
+    run(61, nchannels=3)                                          # two channels keep their state, the ramp goes on
+    fb.set_coeffs(0, lib.biquad_coeffs(8, 200.0, 48000.0, -5.0, 1.0), 29.5)   # a second ramp while the first still runs
+    run(70)                                                       # both end inside this call
+    run(40, inplace=True)
+    fb.add_filter(lib.biquad_coeffs(7, 4000.0, 48000.0, 4.0, 0.7))
+    size[1] += 1
+    run(33)
+    fb.set_channels(nch + 2)                                      # new channels start silent, old ones keep their state
+    size[0] = nch + 2
+    run(25, s=nch + 3, d=nch + 2)
+    fb.set_filters(2)                                             # filters leave from the end
+    size[1] = 2
+    run(19, s=nch + 3, d=nch + 2)
+    fb.set_channels(2)
+    size[0] = 2
+    run(16, nchannels=99)                                         # clamped to the channels that exist
+    fb.reset()
+    run(9)
+    fb.close()
+    return outs
+
+
+def gen_fbank(ref):
+    d = {}
+    for i, a in enumerate(fbank_script(ref)):
+        d["script_%03d" % i] = a
+    for i, a in enumerate(fbank_script(ref, nch=70, nfilters=19, nsrc=72, ndst=71, seed=77)):   # more than one pass of 16
+        d["long_%03d" % i] = a
+    np.savez_compressed(os.path.join(OUT, "fbank.npz"), **d)
+
+
 # ---- AllPassFilterChain<float> (src/AllPassFilter.h), SURVEY 8f.4 ----
 def allpass_script(lib, nch=5, delays=(7, 1, 23, 4), coeffs=(0.5, -0.7, 0.3, 0.9), nsrc=8, ndst=6, seed=777, offs=((1, 1), (2, 3))):
     """Chain processed in several calls (ring wrap inside a call, positions carried over), a channel offset, a geometry
@@ -435,6 +496,7 @@ def main():
     gen_delay(ref)
     gen_ring(ref)
     gen_biquad(ref)
+    gen_fbank(ref)
     gen_allpass(ref)
     gen_cascade(ref)
     gen_dither(ref)
