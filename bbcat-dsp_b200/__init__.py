@@ -110,6 +110,9 @@ SYMBOLS = {
     "bbx_engine_profile_mac": (C.c_int, [vp, C.c_int]),
     "bbx_engine_mac_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "bbx_engine_exchange_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(u64)]),
+    "bbx_engine_state_size": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "bbx_engine_get_state": (C.c_int, [vp, vp, C.c_size_t]),
+    "bbx_engine_set_state": (C.c_int, [vp, vp, C.c_size_t]),
     "bbx_engine_io_trace": (C.c_int, [vp, u32]),
     "bbx_engine_io_trace_read": (C.c_int, [vp, C.POINTER(C.c_float), u32, C.POINTER(u32)]),
     "bbx_engine_set_tuning": (C.c_int, [vp, u32, u32, u32]),
@@ -720,6 +723,19 @@ class Convolver:
         ms, n, units, nbytes = C.c_float(0), u64(0), u64(0), u64(0)
         _check(lib().bbx_engine_mac_time(self.h, C.byref(ms), C.byref(n), C.byref(units), C.byref(nbytes)))
         return {"ms": ms.value, "launches": n.value, "channel_blocks": units.value, "algorithmic_bytes": nbytes.value}
+
+    def GetState(self):
+        """The engine's audio state as a uint8 array (bbx_engine_get_state): checkpoint."""
+        n = C.c_size_t(0)
+        _check(lib().bbx_engine_state_size(self.h, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        _check(lib().bbx_engine_get_state(self.h, _p(buf), buf.size))
+        return buf
+
+    def SetState(self, state):
+        """Resume from a GetState() blob; this engine must hold the same filters in the same order."""
+        buf = np.ascontiguousarray(state, dtype=np.uint8)
+        _check(lib().bbx_engine_set_state(self.h, _p(buf), buf.size))
 
     def io_trace(self, calls):
         """Trace the next `calls` ConvolveHostPtrAsync calls (bbx_engine_io_trace)."""

@@ -27,6 +27,8 @@
 #include <unordered_set>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op (one pointer test per call) unless a profiler is attached
+
 #include "common.cuh"
 #include "kernels_common.cuh"
 #include "kernels_fft.cuh"
@@ -54,6 +56,14 @@ using namespace bbx;
 // ==========================================================================================
 // host side
 // ==========================================================================================
+// NVTX range around a stage of a call (host side: the range covers the stage's launches, the tool correlates the kernels)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 struct bbx_filter {
   bbx_engine* engine;
   float2* H;  // device [P][B]
@@ -1419,6 +1429,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
                     int out_be, uint32_t out_channels, uint32_t nframes) {
   int rc = validate_call(e, in, infmt, in_channels, out, outfmt, out_channels, nframes);
   if (rc) return rc;
+  NvtxRange nv_call("bbx_process_dev");
   const uint32_t B = e->B, T = nframes / B;
   DeviceGuard dg(e->device);
   cudaStream_t st = e->stream;
@@ -1517,6 +1528,7 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
   const bool planar_in = fuse && e->in_is_host && (size_t)in_channels * ibps > 32;
   const bool fuse_out = fuse && e->mode == BBX_MODE_PER_CHANNEL && !(e->out_is_host && (size_t)out_channels * obps > 32);
   if (fuse) {
+    NvtxRange nv("bbx.block_fused");
     FusedArgs a;
     if (planar_in) {
       if ((rc = launch_pcm_in(e, in, infmt, in_be, in_channels, T, st))) return rc;
@@ -1556,22 +1568,32 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     e->last_mac_kernel = "k_block_fused";
   } else {
   // ---- 1. PCM -> planar fp32 ----
-  if ((rc = launch_pcm_in(e, in, infmt, in_be, in_channels, T, st))) return rc;
+  {
+    NvtxRange nv("bbx.pcm_in");
+    if ((rc = launch_pcm_in(e, in, infmt, in_be, in_channels, T, st))) return rc;
+  }
   // ---- 2. forward transforms into the FDL ----
-  if ((rc = launch_rfft(B, e->xin[e->parity], e->xstride, B, e->fdl, (uint64_t)e->R * B, e->R, e->head, e->tw, 1.0f, e->n_in, T, st)))
-    return rc;
-  e->launches++;
+  {
+    NvtxRange nv("bbx.rfft");
+    if ((rc = launch_rfft(B, e->xin[e->parity], e->xstride, B, e->fdl, (uint64_t)e->R * B, e->R, e->head, e->tw, 1.0f, e->n_in, T, st)))
+      return rc;
+    e->launches++;
+  }
   // ---- 3. FDL multiply-accumulate ----
-  if (use_tc) {
-    if ((rc = launch_mimo_tc(e, T))) return rc;
-  } else if (n_first) {
-    if ((rc = launch_mac(e, e->plan_first, 0, 1))) return rc;
-    if ((rc = launch_mac(e, e->plan_steady, 1, T - 1))) return rc;
-  } else {
-    if ((rc = launch_mac(e, e->plan_steady, 0, T))) return rc;
+  {
+    NvtxRange nv(use_tc ? "bbx.mac_tensor" : "bbx.mac");
+    if (use_tc) {
+      if ((rc = launch_mimo_tc(e, T))) return rc;
+    } else if (n_first) {
+      if ((rc = launch_mac(e, e->plan_first, 0, 1))) return rc;
+      if ((rc = launch_mac(e, e->plan_steady, 1, T - 1))) return rc;
+    } else {
+      if ((rc = launch_mac(e, e->plan_steady, 0, T))) return rc;
+    }
   }
   // ---- 3b. input-sharded MIMO: sum the partial spectra over the ranks, keep the local outputs ----
   if (e->sh_world > 1 || e->comm) {
+    NvtxRange nv("bbx.exchange");
     const PlanView pv = use_tc ? tc_plan_view(e) : e->plan_steady.view();
     cudaEvent_t x0 = nullptr, x1 = nullptr;
     if (e->profile_mac) {
@@ -1607,12 +1629,16 @@ int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_
     if (x1) BBX_CUDA_TRY(cudaEventRecord(x1, st));
   }
   // ---- 4. inverse transforms, crossfade, delay ring ----
-  if ((rc = launch_irfft(e, T, n_first, use_tc, st))) return rc;
-  e->launches++;
+  {
+    NvtxRange nv("bbx.irfft");
+    if ((rc = launch_irfft(e, T, n_first, use_tc, st))) return rc;
+    e->launches++;
+  }
   }  // !fuse
   if (!fuse_out) {
   // ---- 5. delay read, mixdown, output format ----
   {
+    NvtxRange nv("bbx.pcm_out");
     PcmOutArgs a;
     const uint32_t obps = fmt_bytes(outfmt);
     a.pcm = (uint8_t*)out;
@@ -1669,6 +1695,7 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
     const int vrc = validate_call(e, in, infmt, in_channels, out, outfmt, out_channels, nframes);
     if (vrc) return vrc;  // nothing staged, no copy queued
   }
+  NvtxRange nv_call("bbx_process_async");
   DeviceGuard dg(e->device);
   const uint32_t ibps = fmt_bytes(infmt), obps = fmt_bytes(outfmt);
   size_t in_bytes = (size_t)nframes * in_channels * ibps;
@@ -1850,6 +1877,134 @@ int bbx_engine_profile_mac(bbx_engine* e, int enable) {
   e->xchg_events_used = 0;
   e->xchg_ms_total = 0.0;
   e->xchg_count = e->xchg_bytes = 0;
+  return BBX_OK;
+}
+
+// ---- checkpoint / resume of an engine's audio state --------------------------------------------------------------------
+// Everything a later call depends on: the FDL ring, the previous call's last input block, the delay rings, the ring
+// positions, and per path the selected / latched filter, delays and gain.  Filters are referred to by their position in
+// the engine's filter list (creation order among the live ones): the restoring engine must hold the same filters in the
+// same order.  Plans, routes and the tensor-core operand pack are derived data and are rebuilt by the next call.
+namespace {
+struct StateHeader {
+  uint32_t magic, version;
+  uint32_t B, Pmax, n_in, n_out, n_paths, n_streams, Tmax, R, Rd, xstride, mode, n_filters;
+  uint32_t head, wpos, parity, tprev;
+  uint64_t xin_bytes, fdl_bytes, ybuf_bytes, path_bytes;
+};
+struct StatePath {
+  int32_t cur, pend;  // index into the filter list, -1 = none
+  uint32_t has_pending, xfade;
+  float gain;
+  uint32_t pad;
+  double delay, pend_delay;
+};
+constexpr uint32_t kStateMagic = 0x58424253u /* "SBBX" */, kStateVersion = 1;
+
+StateHeader state_header(const bbx_engine* e) {
+  StateHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = kStateMagic, h.version = kStateVersion;
+  h.B = e->B, h.Pmax = e->Pmax, h.n_in = e->n_in, h.n_out = e->n_out, h.n_paths = e->n_paths, h.n_streams = e->n_streams;
+  h.Tmax = e->Tmax, h.R = e->R, h.Rd = e->Rd, h.xstride = e->xstride, h.mode = (uint32_t)e->mode;
+  h.n_filters = (uint32_t)e->filters.size();
+  h.head = e->head, h.wpos = e->wpos, h.parity = e->parity, h.tprev = e->tprev;
+  h.xin_bytes = sizeof(float) * (uint64_t)e->n_in * e->xstride;
+  h.fdl_bytes = sizeof(float2) * (uint64_t)e->n_in * e->R * e->B;
+  h.ybuf_bytes = sizeof(float) * (uint64_t)e->n_streams * e->Rd;
+  h.path_bytes = sizeof(StatePath) * (uint64_t)e->paths.size();
+  return h;
+}
+size_t state_bytes(const StateHeader& h) { return sizeof(StateHeader) + h.path_bytes + 2 * h.xin_bytes + h.fdl_bytes + h.ybuf_bytes; }
+int filter_index(const bbx_engine* e, const bbx_filter* f) {
+  if (!f) return -1;
+  for (size_t i = 0; i < e->filters.size(); i++)
+    if (e->filters[i] == f) return (int)i;
+  return -1;
+}
+int drain(bbx_engine* e) {
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  return BBX_OK;
+}
+}  // namespace
+
+int bbx_engine_state_size(const bbx_engine* e, size_t* bytes) {
+  BBX_REQUIRE(e && bytes, "bbx_engine_state_size: null argument");
+  *bytes = state_bytes(state_header(e));
+  return BBX_OK;
+}
+
+int bbx_engine_get_state(bbx_engine* e, void* buf, size_t capacity) {
+  BBX_REQUIRE(e && buf, "bbx_engine_get_state: null argument");
+  BBX_REQUIRE(e->sh_world <= 1 && !e->comm && !e->px_on, "bbx_engine_get_state: not available for an input-sharded engine");
+  const StateHeader h = state_header(e);
+  BBX_REQUIRE(capacity >= state_bytes(h), "bbx_engine_get_state: buffer of %zu bytes, state needs %zu", capacity, state_bytes(h));
+  DeviceGuard dg(e->device);
+  int rc = drain(e);
+  if (rc) return rc;
+  uint8_t* p = (uint8_t*)buf;
+  memcpy(p, &h, sizeof(h));
+  p += sizeof(h);
+  for (const PathState& ps : e->paths) {
+    StatePath sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.cur = filter_index(e, ps.cur), sp.pend = filter_index(e, ps.pend);
+    sp.has_pending = ps.has_pending, sp.xfade = ps.xfade;
+    sp.gain = ps.gain, sp.delay = ps.delay, sp.pend_delay = ps.pend_delay;
+    memcpy(p, &sp, sizeof(sp));
+    p += sizeof(sp);
+  }
+  for (int i = 0; i < 2; i++, p += h.xin_bytes) BBX_CUDA_TRY(cudaMemcpy(p, e->xin[i], h.xin_bytes, cudaMemcpyDeviceToHost));
+  BBX_CUDA_TRY(cudaMemcpy(p, e->fdl, h.fdl_bytes, cudaMemcpyDeviceToHost));
+  p += h.fdl_bytes;
+  BBX_CUDA_TRY(cudaMemcpy(p, e->ybuf, h.ybuf_bytes, cudaMemcpyDeviceToHost));
+  return BBX_OK;
+}
+
+int bbx_engine_set_state(bbx_engine* e, const void* buf, size_t bytes) {
+  BBX_REQUIRE(e && buf, "bbx_engine_set_state: null argument");
+  BBX_REQUIRE(e->sh_world <= 1 && !e->comm && !e->px_on, "bbx_engine_set_state: not available for an input-sharded engine");
+  BBX_REQUIRE(bytes >= sizeof(StateHeader), "bbx_engine_set_state: %zu bytes is not a state", bytes);
+  StateHeader h;
+  memcpy(&h, buf, sizeof(h));
+  BBX_REQUIRE(h.magic == kStateMagic && h.version == kStateVersion, "bbx_engine_set_state: not an engine state (magic %08x, version %u)",
+              h.magic, h.version);
+  const StateHeader own = state_header(e);
+  BBX_REQUIRE(h.B == own.B && h.Pmax == own.Pmax && h.n_in == own.n_in && h.n_out == own.n_out && h.n_paths == own.n_paths &&
+                  h.n_streams == own.n_streams && h.Tmax == own.Tmax && h.R == own.R && h.Rd == own.Rd && h.xstride == own.xstride &&
+                  h.mode == own.mode && h.path_bytes == own.path_bytes,
+              "bbx_engine_set_state: the state was saved by an engine of a different geometry");
+  BBX_REQUIRE(h.n_filters == own.n_filters, "bbx_engine_set_state: the state refers to %u filters, this engine holds %u", h.n_filters,
+              own.n_filters);
+  BBX_REQUIRE(bytes >= state_bytes(h), "bbx_engine_set_state: %zu bytes, the state needs %zu", bytes, state_bytes(h));
+  const uint8_t* p = (const uint8_t*)buf + sizeof(h);
+  // validate the path table before anything is changed
+  for (size_t k = 0; k < e->paths.size(); k++) {
+    StatePath sp;
+    memcpy(&sp, p + k * sizeof(sp), sizeof(sp));
+    BBX_REQUIRE(sp.cur >= -1 && sp.cur < (int)own.n_filters && sp.pend >= -1 && sp.pend < (int)own.n_filters,
+                "bbx_engine_set_state: path %zu refers to a filter that does not exist", k);
+  }
+  DeviceGuard dg(e->device);
+  int rc = drain(e);
+  if (rc) return rc;
+  for (size_t k = 0; k < e->paths.size(); k++, p += sizeof(StatePath)) {
+    StatePath sp;
+    memcpy(&sp, p, sizeof(sp));
+    PathState& ps = e->paths[k];
+    ps.cur = sp.cur >= 0 ? e->filters[sp.cur] : nullptr;
+    ps.pend = sp.pend >= 0 ? e->filters[sp.pend] : nullptr;
+    ps.has_pending = sp.has_pending != 0, ps.xfade = sp.xfade != 0;
+    ps.gain = sp.gain, ps.delay = sp.delay, ps.pend_delay = sp.pend_delay;
+  }
+  for (int i = 0; i < 2; i++, p += h.xin_bytes) BBX_CUDA_TRY(cudaMemcpy(e->xin[i], p, h.xin_bytes, cudaMemcpyHostToDevice));
+  BBX_CUDA_TRY(cudaMemcpy(e->fdl, p, h.fdl_bytes, cudaMemcpyHostToDevice));
+  p += h.fdl_bytes;
+  BBX_CUDA_TRY(cudaMemcpy(e->ybuf, p, h.ybuf_bytes, cudaMemcpyHostToDevice));
+  e->head = h.head, e->wpos = h.wpos, e->parity = h.parity, e->tprev = h.tprev;
+  e->steady_dirty = e->route_dirty = e->tc_dirty = true;
   return BBX_OK;
 }
 

@@ -420,6 +420,14 @@ int bbx_engine_mac_time(bbx_engine* e, float* total_ms, uint64_t* launches, uint
  * (k_gather_spectra_peer + k_peer_wait, or k_gather_spectra + ncclReduceScatter), the number of exchanges and the bytes
  * this rank sent to its peers (synchronises) */
 int bbx_engine_exchange_time(bbx_engine* e, float* total_ms, uint64_t* exchanges, uint64_t* bytes_sent);
+/* Checkpoint / resume (SURVEY.md aux): the audio state of an engine -- FDL ring, previous input block, delay rings, ring
+ * positions, and per path the selected / latched filter, delays and gain -- as one host blob.  Filters are referred to by
+ * their position among the engine's live filters, so the restoring engine (the same one later, or a fresh one of the same
+ * bbx_config) must hold the same filters created in the same order.  Calls made after set_state produce the bytes the
+ * saving engine produced after get_state.  Both calls drain the engine first.  Not available on input-sharded engines. */
+int bbx_engine_state_size(const bbx_engine* e, size_t* bytes);
+int bbx_engine_get_state(bbx_engine* e, void* buf, size_t capacity);
+int bbx_engine_set_state(bbx_engine* e, const void* buf, size_t bytes);
 /* Trace of the host-buffer pipeline: the next `calls` bbx_process_async calls record a timing event at the start and end
  * of their H2D copy, their kernels and their D2H copy; _read returns, per traced call, those six times in ms relative to
  * the first call's H2D start ([n][6]: h2d0, h2d1, kernels0, kernels1, d2h0, d2h1; -1 = that side was not used). */

@@ -746,3 +746,68 @@ def test_objects_keep_their_device(bbx, gpu):
     d.close()
     bq.close()
     ref_bq.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["per_channel", "routed", "mimo"])
+def test_state_checkpoint_resume(bbx, mode):
+    """bbx_engine_get_state / set_state: a fresh engine with the same filters, resumed from a checkpoint taken in the middle
+    of a crossfaded, delayed switch sequence, produces the bytes the original engine goes on to produce; so does the original
+    engine rewound to the checkpoint."""
+    B, L, nin = 128, 700, 3
+    rng = np.random.default_rng(77)
+    irs = [rng.standard_normal(L).astype(np.float32) * 0.05 for _ in range(6)]
+
+    def make():
+        if mode == "per_channel":
+            e = bbx.Convolver(B, 8, nin, max_blocks=4, max_delay=300, fractional_delay=True)
+            npaths, nout = nin, nin
+        elif mode == "routed":
+            npaths, nout = 5, 2
+            e = bbx.Convolver(B, 8, nin, n_outputs=nout, n_paths=npaths, mode=bbx.MODE_ROUTED, max_blocks=4, max_delay=300)
+            for k in range(npaths):
+                e.SetRoute(k, k % nin, k % nout, 0.5 + 0.1 * k)
+        else:
+            nout = 2
+            npaths = nin * nout
+            e = bbx.Convolver(B, 8, nin, n_outputs=nout, mode=bbx.MODE_MIMO, max_blocks=4)
+        fl = [e.CreateFilter(h) for h in irs]
+        for k in range(npaths):
+            e.SelectFilter(k, fl[k % len(fl)], delay=(0.0 if mode == "mimo" else 3.25 * k if mode == "per_channel" else 2.0 * k))
+        return e, fl, npaths, nout
+
+    def block(i, nblk):
+        return np.random.default_rng(1000 + i).uniform(-1, 1, (nblk * B, nin)).astype(np.float32)
+
+    def run(e, fl, npaths, nout, i, nblk):
+        return e.Convolve(block(i, nblk), bbx.FMT_FLOAT, nin, bbx.FMT_FLOAT, nout, nblk * B).copy()
+
+    sizes = [2, 1, 3, 1, 4, 2]
+    a = make()
+    for i in range(2):
+        run(*a, i, sizes[i])
+    # latch a crossfaded switch, THEN checkpoint: the pending selection is part of the state
+    for k in range(a[2]):
+        a[0].SelectFilter(k, a[1][(k + 2) % len(irs)], delay=(0.0 if mode == "mimo" else 7.5 + k if mode == "per_channel" else 5.0 + k),
+                          crossfade=True)
+    state = a[0].GetState()
+    want = [run(*a, i, sizes[i]) for i in range(2, 6)]
+    b = make()
+    b[0].SetState(state)
+    got = [run(*b, i, sizes[i]) for i in range(2, 6)]
+    assert any(np.any(w) for w in want)
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
+    a[0].SetState(state)  # rewind the original
+    again = [run(*a, i, sizes[i]) for i in range(2, 6)]
+    for w, g in zip(want, again):
+        assert np.array_equal(w, g)
+    # a state of another geometry is refused and changes nothing
+    c = bbx.Convolver(B, 8, nin + 1, max_blocks=4)
+    with pytest.raises(bbx.BbxError):
+        c.SetState(state)
+    with pytest.raises(bbx.BbxError):
+        b[0].SetState(state[:100])
+    c.close()
+    a[0].close()
+    b[0].close()
