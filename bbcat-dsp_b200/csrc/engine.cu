@@ -840,7 +840,7 @@ int tc_pack_filters(bbx_engine* e) {
   BBX_CUDA_TRY(cudaMemcpyAsync(e->tc_ftab_d, e->tc_ftab_h, sizeof(float2*) * npaths, cudaMemcpyHostToDevice, e->stream));
   BBX_CUDA_TRY(cudaMemcpyAsync(e->tc_fparts_d, e->tc_fparts_h, sizeof(uint32_t) * npaths, cudaMemcpyHostToDevice, e->stream));
   if ((rc = mark_upload(e))) return rc;
-  k_mimo_pack_h<<<dim3(e->B / 32, e->tc_G, e->tc_nog), 256, 0, e->stream>>>(e->tc_ftab_d, e->tc_fparts_d, e->tc_hpack, e->B, e->n_in,
+  k_mimo_pack_h<<<dim3(e->B / 32, e->tc_G / 2, e->tc_nog), 256, 0, e->stream>>>(e->tc_ftab_d, e->tc_fparts_d, e->tc_hpack, e->B, e->n_in,
                                                                         e->n_out, e->tc_P2log, e->tc_G);
   BBX_CUDA_TRY(cudaGetLastError());
   e->launches++;

@@ -3,16 +3,22 @@
 // Y_o[k] = sum_i sum_p H_{o,i}[p][k] * FDL_i[(head - p)][k].  With T block-steps in one
 // call this is, for every bin k, a dense complex GEMM
 //       Y[o][t] = sum_j  H[o][j] * X[j][t],     j = (i, p),  X[(i,p)][t] = FDL_i[slot(t - p)]
-// (M = n_out, K = n_in * P, N = T).  The complex product is embedded in a real one so that ONE accumulator
-// tile fills the 128 TMEM lanes:
-//       rows 0..63   (re of output o):  [ Hr, -Hi ] . [ Xr, Xi ]
-//       rows 64..127 (im of output o):  [ Hi,  Hr ] . [ Xr, Xi ]
-// i.e. A = 128 x 2K (built on the fly from the raw complex spectra), B = 2K x N (the FDL values as stored).
+// (M = n_out, K = n_in * P, N = T).  The complex product is embedded in a real one with PLANAR operands, so that one
+// MMA is 128 rows x 2N columns and its K index is the complex index j itself:
+//       A = [ Hr ]  (rows 0..63:  re of H for output o)        B = [ Xr | Xi ]  (columns 0..N-1: re of X at block-step t,
+//           [ Hi ]  (rows 64..127: im of H for output o)                         columns N..2N-1: im)
+//       D = A B = [ HrXr  HrXi ]        Y.re = HrXr - HiXi   (quadrants 00 and 11)
+//                 [ HiXr  HiXi ]        Y.im = HrXi + HiXr   (quadrants 01 and 10), combined by the epilogue.
+// Against the interleaved embedding of round 1 ([Hr, -Hi; Hi, Hr] x [Xr; Xi], 128 x N x 2K) the flops are the same, but
+// every MMA is twice as long (N = 128: 64 cycles instead of 32 -- round 1's issue loop could not feed 32-cycle MMAs) and the
+// A operand is half as large (every H value is split into TF32 parts once, not twice), which halves the producers' work.
 // fp32 accuracy (SNR >= 110 dB) needs more than one TF32 pass: both operands are split v = hi + lo with
 // hi = tf32_rna(v), and three MMAs (lo*hi, hi*lo, hi*hi) accumulate into fp32 TMEM tiles (see kTcAccTiles).
 //
 // Operand layouts in HBM (bin-major, written by the pack kernels below):
-//   Hpack[og][k][g][64] float4   g indexes pairs of complex K elements j = 2g, 2g+1;  j = i*P2 + p',
+//   Hpack[og][k][chunk][re | im][g][64] float4
+//                                 planar: the real (then the imaginary) parts of the four complex K elements
+//                                 j = 16 chunk + 4g .. + 3 of one output per float4;  j = i*P2 + p',
 //                                 p' = P2-1-p (partition order reversed so a column of B is a contiguous
 //                                 run of the time axis), P2 = power of two >= P, K padded to 16 with zeros
 //   Xq[k][column tile][chunk][hi | lo][input row of the chunk][seg] float2
@@ -21,13 +27,14 @@
 //                                 a row is block (tile start + p'0 + wl - (P2-1)) of this call (negative = history,
 //                                 beyond the call = 0); seg = N + P2 (P2 < 16: 16/P2 rows per chunk) or N + 16 (one row)
 // One CTA owns kTcBins adjacent bins (their 8-byte output writes fill one 32-byte sector in L2) and walks K in chunks
-// of 16 complex in three decoupled pipelines (mbarriers only, no block-wide barrier in the main loop):
+// of 16 complex (two MMA k-steps) in three decoupled pipelines (mbarriers only, no block-wide barrier in the main loop):
 //   loader warp   TMA bulk copies (cp.async.bulk) of the chunk's raw H and FDL runs into a raw smem ring
-//   4 x 4 producer warps (group g: chunks g mod 4)  raw H -> hi/lo split + sign/swap expansion -> A tile into TENSOR MEMORY (tcgen05.st); raw FDL
-//                 (already split by k_mimo_pack_x) -> B tile in shared memory (canonical no-swizzle K-major layout)
-//   4 epilogue warps  accumulators (TMEM) -> sum of the four tiles -> (re, im) pairs -> HBM
-//   2 MMA warps   one lane each issues tcgen05.mma (A from TMEM, B from smem): warp 20 the 4 hi*hi MMAs of the chunk,
-//                 warp 21 the 8 small-term MMAs (independent accumulator tiles); their tcgen05.commit's release the stage
+//   4 x 4 producer warps (group g: chunks g mod 4)  raw H -> re (rows < 64) or im (rows >= 64) part -> hi/lo split -> A tile
+//                 into TENSOR MEMORY (tcgen05.st); raw FDL runs (already split by k_mimo_pack_x) -> the Toeplitz B tile in
+//                 shared memory (canonical no-swizzle K-major layout: a 16-byte row = four consecutive j of one column)
+//   4 epilogue warps  accumulators (TMEM) -> sum of the three tiles -> quadrants through two smem tiles -> (re, im) -> HBM
+//   2 MMA warps   one lane each issues tcgen05.mma (A from TMEM, B from smem): warp 20 the 2 hi*hi MMAs of the chunk,
+//                 warp 21 the 4 small-term MMAs (independent accumulator tiles); their tcgen05.commit's release the stage
 #pragma once
 
 #include <cuda_runtime.h>
@@ -47,13 +54,16 @@ static constexpr int kTcLoadWarps = 1;
 static constexpr int kTcThreads = 736;
 static constexpr int kTcBins = 4;      // adjacent bins per CTA
 static constexpr int kTcStages = 4;    // converted operand stages: A in TMEM, B in shared memory
+static constexpr int kTcPrefetch = 16;    // chunks of packed H prefetched into L2 ahead of their copy
 static constexpr int kTcRawStagesMax = 8; // raw operand stages (TMA bulk copies from HBM): as many as fit, even
-static constexpr int kTcChunk = 16;    // complex K elements per stage = 32 tf32 = 4 MMA k-steps
-static constexpr int kTcRows = 128;    // accumulator rows: 64 outputs x (re, im)
-static constexpr int kTcNmax = 64;     // columns (block-steps) per accumulator tile
-static constexpr uint32_t kTcBHalf = kTcNmax * kTcChunk * 2 * 4;          // 8 KB:  B_hi (then B_lo)
+static constexpr int kTcChunk = 16;    // complex K elements per stage = 16 tf32 = 2 MMA k-steps
+static constexpr int kTcRows = 128;    // accumulator rows: 64 outputs x (Hr, Hi)
+static constexpr int kTcNmax = 64;     // block-steps per CTA
+static constexpr int kTcN2max = 2 * kTcNmax;  // MMA columns: (Xr | Xi) of every block-step
+static constexpr uint32_t kTcBHalf = kTcN2max * kTcChunk * 4;             // 8 KB:  B_hi (then B_lo)
 static constexpr uint32_t kTcStageBytes = 2 * kTcBHalf;                   // 16 KB of shared memory per stage
-static constexpr uint32_t kTcTileBytes = kTcNmax * 2 * 64 * 4;            // 32 KB: epilogue tile [t][re/im][o]
+static constexpr uint32_t kTcTileBytes = kTcNmax * 64 * 16;               // 64 KB: epilogue tile [t][o][bin pair] float2
+static_assert(kTcBins % 2 == 0, "the epilogue stores pairs of bins");
 // raw stage: 8 KB of packed H (64 outputs x 16 complex) + the FDL runs of the chunk: (16 / P2) input rows of
 // N + P2 complex (P2 < 16) or one row of N + 16, hi and lo parts.  Its size depends on (P2, N): the host passes
 // the stage size and the number of stages that fit (MimoTcArgs::raw_stage_bytes / raw_stages).
@@ -61,17 +71,17 @@ static constexpr uint32_t kTcOffTile = kTcStages * kTcStageBytes;
 static constexpr uint32_t kTcOffBar = kTcOffTile + kTcTileBytes;
 static constexpr uint32_t kTcOffRaw = kTcOffBar + 256;
 static constexpr uint32_t kTcSmemMax = 227 * 1024;
-// TMEM (512 columns x 128 lanes): columns 0..255 = four 64-column accumulator tiles, columns 256..511 = the A
-// operand ring (per stage 32 columns of A_hi and 32 of A_lo: row = lane, K along columns).  A never touches
+// TMEM (512 columns x 128 lanes): columns 0..383 = three 128-column accumulator tiles, columns 384..511 = the A
+// operand ring (per stage 16 columns of A_hi and 16 of A_lo: row = lane, K along columns).  A never touches
 // shared memory: the producers write it with tcgen05.st, the MMA reads it from TMEM ([a-tmem] operand form), which
-// takes 2/3 of the operand traffic off the shared-memory pipe (the bottleneck of the SS form, profiles/).
+// takes the larger operand off the shared-memory pipe (the bottleneck of the SS form, profiles/).
 // The tensor core truncates the fp32 accumulator on every MMA, a bias that grows with the number of sequential
-// accumulations (one tile for everything: 109 dB SNR at K = 512 complex).  The hi*hi products therefore rotate
-// over three tiles (k-step mod 3) and the small lo*hi / hi*lo terms have their own tile, so the dominant sums see
-// K/12 accumulations instead of 3K/4; the epilogue adds the four tiles in fp32 round-to-nearest.
-static constexpr uint32_t kTcAccTiles = 4;
-static constexpr uint32_t kTcAccCols = kTcAccTiles * kTcNmax;             // 256
-static constexpr uint32_t kTcAStageCols = 4 * kTcChunk;                   // 64: A_hi | A_lo
+// accumulations (one tile for everything: 109 dB SNR at K = 512 complex).  The hi*hi products therefore alternate
+// between two tiles (the two k-steps of a chunk) and the small lo*hi / hi*lo terms have their own tile, so the dominant
+// sums see K/16 accumulations (32 at K = 512); the epilogue adds the three tiles in fp32 round-to-nearest.
+static constexpr int kTcAccTiles = 3;
+static constexpr uint32_t kTcAccCols = kTcAccTiles * kTcN2max;            // 384
+static constexpr uint32_t kTcAStageCols = 2 * kTcChunk;                   // 32: A_hi | A_lo
 static constexpr uint32_t kTcTmemCols = 512;
 static constexpr uint32_t kTcMaxK = 1024;                                 // complex K verified against the tolerance
 
@@ -218,6 +228,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// L2 prefetch of a run the loader will copy a few chunks later (16-byte aligned address and size)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void st_shared4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -262,28 +276,25 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_
         : "memory");
 }
 
-// the 12 MMAs of one chunk (4 k-steps of 8); FIRST = first chunk of a bin (accumulators start from zero)
-// the MMAs of one chunk (4 k-steps of 8) issued by one of the two issuer warps; FIRST = first chunk of a bin
-// (accumulators start from zero):
-//   PROD 0  hi*hi, one MMA per k-step, rotating over tiles 0..2 (k-step mod 3, rot0 = first k-step of the chunk mod 3)
-//   PROD 1  lo*hi and hi*lo, two MMAs per k-step into tile 3 (same issuing thread: program order)
-template <uint32_t N, int PROD, bool FIRST>
-__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tA, uint32_t blo, uint32_t rot0) {
+// the MMAs of one chunk (2 k-steps of 8) issued by one of the two issuer warps; N2 = MMA columns; FIRST = first chunk
+// of a bin (accumulators start from zero):
+//   PROD 0  hi*hi, one MMA per k-step, k-step s into tile s
+//   PROD 1  lo*hi and hi*lo, two MMAs per k-step into tile 2 (same issuing thread: program order)
+template <uint32_t N2, int PROD, bool FIRST>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tA, uint32_t blo) {
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 @17, M >> 4 @24
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N2 >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 #pragma unroll
-  for (int k8 = 0; k8 < kTcChunk / 4; k8++) {
-    const uint32_t a_hi = tA + k8 * 8, a_lo = a_hi + 2 * kTcChunk;
-    const uint32_t b_hi = blo + k8 * ((2 * N * 16) >> 4), b_lo = b_hi + (kTcBHalf >> 4);
+  for (int k8 = 0; k8 < kTcChunk / 8; k8++) {
+    const uint32_t a_hi = tA + k8 * 8, a_lo = a_hi + kTcChunk;
+    const uint32_t b_hi = blo + k8 * ((2 * N2 * 16) >> 4), b_lo = b_hi + (kTcBHalf >> 4);
     if (PROD == 0) {
-      uint32_t r = rot0 + k8;
-      r = r >= 3 ? r - 3 : r;
-      if (FIRST && k8 < 3) mma_ts<false>(tmem + r * kTcNmax, a_hi, b_hi, idesc);
-      else mma_ts<true>(tmem + r * kTcNmax, a_hi, b_hi, idesc);
+      if (FIRST) mma_ts<false>(tmem + k8 * kTcN2max, a_hi, b_hi, idesc);
+      else mma_ts<true>(tmem + k8 * kTcN2max, a_hi, b_hi, idesc);
     } else {
-      if (FIRST && k8 == 0) mma_ts<false>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
-      else mma_ts<true>(tmem + 3 * kTcNmax, a_lo, b_hi, idesc);
-      mma_ts<true>(tmem + 3 * kTcNmax, a_hi, b_lo, idesc);
+      if (FIRST && k8 == 0) mma_ts<false>(tmem + 2 * kTcN2max, a_lo, b_hi, idesc);
+      else mma_ts<true>(tmem + 2 * kTcN2max, a_lo, b_hi, idesc);
+      mma_ts<true>(tmem + 2 * kTcN2max, a_hi, b_lo, idesc);
     }
   }
 }
@@ -294,7 +305,8 @@ template <int NLOG>
 __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   using namespace tc;
-  constexpr uint32_t N = 1u << NLOG;  // columns of the accumulator tile = block-steps per CTA
+  constexpr uint32_t N = 1u << NLOG;  // block-steps per CTA
+  constexpr uint32_t N2 = 2 * N;      // columns of the accumulator tiles: (Xr | Xi)
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t kb = blockIdx.x * kTcBins, og = blockIdx.y, t0 = blockIdx.z * N;
   const uint32_t smem0 = smem_u32(tc_smem);
@@ -358,6 +370,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       const char* xbase = reinterpret_cast<const char*>(a.xb + (uint64_t)kb * a.xbin) + (uint64_t)blockIdx.z * nchunk * bbytes;
       const uint64_t xbin_bytes = a.xbin * 8;
       uint32_t d = lw % RD, ph = 0, j = 0, c = lw;
+      if (elect_one()) bulk_prefetch_l2(asrc, 8192u * (total < (uint32_t)kTcPrefetch ? total : (uint32_t)kTcPrefetch));
+      __syncwarp();
       for (uint32_t it = lw; it < total; it += kTcLoadWarps) {
         while (c >= nchunk) {
           c -= nchunk;
@@ -368,6 +382,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         }
         if (elect_one()) {
           const uint32_t dst = raw0 + d * RSB, bar = bar_rawf + 8 * d;
+          // the packed H of the CTA's bins is one contiguous run: pull the chunk kTcPrefetch ahead into L2 now, so that its
+          // copy later meets L2 latency, not HBM latency (the raw ring holds only ~80 KB of copies in flight per SM)
+          if (it + kTcPrefetch < total) bulk_prefetch_l2(asrc + (uint64_t)kTcPrefetch * 8192, 8192);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
           bulk_g2s(dst, asrc, 8192, bar);
           bulk_g2s(dst + 8192, xbase + j * xbin_bytes + (uint64_t)c * bbytes, bbytes, bar);
@@ -389,12 +406,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     }
   } else if (warp >= kTcWarpMma && warp < kTcWarpMma + kTcMmaWarps) {
     // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
-    // accumulator tiles 0..2: hi*hi products by k-step mod 3 (warp 20); tile 3: the small lo*hi / hi*lo terms (warp 21)
-    const uint32_t blo0 = kDescLo<N> + (smem0 >> 4);  // low descriptor word of stage 0's B_hi tile
+    // accumulator tiles 0, 1: hi*hi products of the chunk's two k-steps (warp 20); tile 2: the small lo*hi / hi*lo terms (warp 21)
+    const uint32_t blo0 = kDescLo<N2> + (smem0 >> 4);  // low descriptor word of stage 0's B_hi tile
     uint32_t s = 0, ph = 0;
     for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
       if (j >= 1 && ok && !mbar_wait_t(bar_acce, (j - 1) & 1, tr, tw1)) ok = false;  // the previous bin has been read out
-      uint32_t rot0 = 0;
       for (uint32_t c = 0; c < nchunk; c++) {
         if (ok && !mbar_wait_t(bar_full + 8 * s, ph, tr, tw0)) ok = false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -402,17 +418,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
           const uint32_t tA = tmem + kTcAccCols + s * kTcAStageCols;
           const uint32_t blo = blo0 + s * (kTcStageBytes >> 4);
           if (warp == kTcWarpMma) {
-            if (c == 0) issue_chunk<N, 0, true>(tmem, tA, blo, rot0);
-            else issue_chunk<N, 0, false>(tmem, tA, blo, rot0);
+            if (c == 0) issue_chunk<N2, 0, true>(tmem, tA, blo);
+            else issue_chunk<N2, 0, false>(tmem, tA, blo);
           } else {
-            if (c == 0) issue_chunk<N, 1, true>(tmem, tA, blo, rot0);
-            else issue_chunk<N, 1, false>(tmem, tA, blo, rot0);
+            if (c == 0) issue_chunk<N2, 1, true>(tmem, tA, blo);
+            else issue_chunk<N2, 1, false>(tmem, tA, blo);
           }
           commit(bar_empty + 8 * s);
           if (c + 1 == nchunk) commit(bar_accf);
         }
         __syncwarp();
-        rot0 = rot0 == 2 ? 0 : rot0 + 1;  // 4 k-steps per chunk: (rot0 + 4) mod 3
         if (++s == kTcStages) {
           s = 0;
           ph ^= 1;
@@ -427,44 +442,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     }
   } else if (warp >= kTcWarpEpi && warp < kTcWarpEpi + 4) {
     // ================= epilogue (4 warps, one per TMEM lane quarter) =================
-    // read out the accumulators of bin j: sum the four tiles, release them, pair (re, im) through the smem tile,
-    // store 8 bytes per (t, output).  The four bins of a CTA fill one 32-byte sector within microseconds: L2 merges.
+    // Read out the accumulators of bin j and combine the quadrants.  Lane l < 16 of warp q holds the Hr row of output
+    // o = 16 q + l, lane l + 16 the Hi row of the same output; per block-step t the first has (HrXr, HrXi) in columns t and
+    // N + t, the second (HiXr, HiXi).  One shuffle of the Xi column gives re = HrXr - HiXi to the first lane and
+    // im = HrXi + HiXr to the second.  Packed bin 0 = (DC, Nyquist) is two real products: re = HrXr, im = HiXi.
+    // Results of two bins are collected in shared memory ([t][o][bin pair] float2) and stored 16 bytes per (t, output):
+    // the four bins of a CTA fill one 32-byte sector of ypart[t][o][.] with two stores instead of four.
     const uint32_t q = warp & 3, et = tid - kTcWarpEpi * 32;
-    const uint32_t m = 32 * q + lane, cc = m >> 6, o = m & 63;
+    const uint32_t part = lane >> 4, o = 16 * q + (lane & 15);
     for (uint32_t j = 0; j < (uint32_t)kTcBins; j++) {
       if (ok && !mbar_wait_t(bar_accf, j & 1, tr, tw0)) ok = false;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool bin0 = (kb + j) == 0;
+      float* const outp = tile + (j & 1) * 2 + part;  // float index of (t = 0, o = 0) for this lane's component
 #pragma unroll 1
-      for (uint32_t cg = 0; cg < (N >> 4); cg++) {
-        // ((t0 + t1) + t2) + t3, one tile in flight (few registers: 704 threads share the register file)
-        float v[16];
-#pragma unroll 1
-        for (uint32_t z = 0; z < kTcAccTiles; z++) {
-          uint32_t r[16];
-          const uint32_t taddr = tmem + ((32 * q) << 16) + z * kTcNmax + cg * 16;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (uint32_t cg = 0; cg < (N >> 3); cg++) {
+        // columns cg*8 .. +7 (x Xr) and N + cg*8 .. +7 (x Xi) of this row in the three tiles: six loads in flight, one wait
+        uint32_t r[2][kTcAccTiles][8];
 #pragma unroll
-          for (int u = 0; u < 16; u++) v[u] = z == 0 ? __uint_as_float(r[u]) : v[u] + __uint_as_float(r[u]);
+        for (int xi = 0; xi < 2; xi++)
+#pragma unroll
+          for (uint32_t z = 0; z < kTcAccTiles; z++) {
+            const uint32_t taddr = tmem + ((32 * q) << 16) + z * kTcN2max + cg * 8 + (xi ? N : 0u);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[xi][z][0]), "=r"(r[xi][z][1]), "=r"(r[xi][z][2]), "=r"(r[xi][z][3]), "=r"(r[xi][z][4]),
+                           "=r"(r[xi][z][5]), "=r"(r[xi][z][6]), "=r"(r[xi][z][7])
+                         : "r"(taddr));
+          }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          // (t0 + t1) + t2 in fp32 round-to-nearest
+          const float vr = (__uint_as_float(r[0][0][u]) + __uint_as_float(r[0][1][u])) + __uint_as_float(r[0][2][u]);
+          const float vi = (__uint_as_float(r[1][0][u]) + __uint_as_float(r[1][1][u])) + __uint_as_float(r[1][2][u]);
+          const float pvi = __shfl_xor_sync(0xffffffffu, vi, 16);
+          // lane < 16 (Hr row): re = HrXr - HiXi;  lane >= 16 (Hi row): im = HrXi + HiXr
+          float res = part ? pvi + vr : vr - pvi;
+          if (bin0) res = part ? vi : vr;
+          outp[((cg * 8 + u) * 64 + o) * 4] = res;
         }
-#pragma unroll
-        for (int u = 0; u < 16; u++) tile[((cg * 16 + u) * 2 + cc) * 64 + o] = v[u];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acce);  // this thread's reads of the accumulators are complete: the next bin may start
-      asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
-      for (uint32_t idx = et; idx < N * 64; idx += kTcEpiThreads) {
-        const uint32_t oo = idx & 63, t = idx >> 6;
-        const uint32_t og_o = og * 64 + oo, tt = t0 + t;
-        if (tt < a.T && og_o < a.n_out)
-          a.ypart[((uint64_t)tt * a.slot_stride + og_o) * a.B + kb + j] = make_float2(tile[(t * 2) * 64 + oo], tile[(t * 2 + 1) * 64 + oo]);
+      if (j & 1) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
+        for (uint32_t idx = et; idx < N * 64; idx += kTcEpiThreads) {
+          const uint32_t oo = idx & 63, t = idx >> 6;
+          const uint32_t og_o = og * 64 + oo, tt = t0 + t;
+          if (tt < a.T && og_o < a.n_out)
+            *reinterpret_cast<float4*>(&a.ypart[((uint64_t)tt * a.slot_stride + og_o) * a.B + kb + j - 1]) =
+                *reinterpret_cast<const float4*>(tile + (size_t)idx * 4);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");  // tile free for the next pair of bins
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");  // tile free for the next bin
     }
     if (!ok && lane == 0) report_timeout(a.status, 4);
     if (tr && et == 0) {
@@ -476,93 +506,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     // Group g converts chunks it = g (mod 4) into operand stage g: four chunks are in flight at different points of
     // the chain (raw wait -> split -> TMEM / smem stores -> store wait + proxy fence -> hand-off).
     // A lives in tensor memory (row = lane, K along columns): warp w owns TMEM lanes 32 (w & 3) .. + 31 = rows m of
-    // the expanded matrix (m < 64: re of output m, m >= 64: im of output m - 64), all 32 K columns of the chunk in
-    // two halves of 16.
+    // the planar matrix (m < 64: re of H for output m, m >= 64: im of H for output m - 64), the 16 K columns of the
+    // chunk in two halves of 8.
     const uint32_t grp = warp >> 2, gtid = tid & (kTcProducers - 1);
     const uint32_t q = warp & 3;
-    const uint32_t m = 32 * q + lane, ao = m & 63;
-    const bool im_row = (q >> 1) != 0;  // warp-uniform
-    const uint32_t srcA = ao * 16;                                         // raw [g][o] float4
-    const uint32_t dstA = ((32 * q) << 16) + kTcAccCols + grp * kTcAStageCols;  // this group's stage (+ 32 for lo)
-    // B (pre-split by k_mimo_pack_x): items e = gtid + 128 r -> (pair member, column t, K group); 16 N complex per chunk
-    constexpr int NBR = 16 * N / kTcProducers;  // 8, 4, 2
+    // row m = 32 q + lane of the planar matrix: lanes 0..15 = re of H for outputs 16 q .. + 15, lanes 16..31 = im of the same
+    // outputs, so that the epilogue finds the two rows of an output in one warp (lane ^ 16)
+    const uint32_t ao = 16 * q + (lane & 15);
+    const uint32_t srcA = (lane >> 4) * 4096 + ao * 16;                    // raw [re | im][g][o] float4
+    const uint32_t dstA = ((32 * q) << 16) + kTcAccCols + grp * kTcAStageCols;  // this group's stage (+ 16 for lo)
+    // B (pre-split by k_mimo_pack_x): item e = gtid + 128 r -> (K group kg of four complex j, column t): four complex of
+    // the raw runs -> the 16-byte row (kg, t) of their real parts and the row (kg, N + t) of their imaginary parts
+    constexpr int NBR = (4 * N + kTcProducers - 1) / kTcProducers;  // 2, 1, 1
     uint32_t offB[NBR], srcB[NBR];
 #pragma unroll
     for (int r = 0; r < NBR; r++) {
       const uint32_t e = gtid + kTcProducers * r;
-      const uint32_t kg = (e >> (1 + NLOG)) & 7, t = (e >> 1) & (N - 1), jl = (kg << 1) | (e & 1);
-      offB[r] = kg * (N * 16) + t * 16 + (e & 1) * 8;
+      const uint32_t kg = (e >> NLOG) & 3, t = e & (N - 1), jl = kg << 2;
+      offB[r] = kg * (N2 * 16) + t * 16;
       // element (local K index jl, column t) of the raw segment: row jl / P2, position t + p'
       srcB[r] = 8192 + 8 * ((P2log < 4) ? (jl >> P2log) * seg + (jl & P2m) + t : jl + t);
     }
+    // byte distance of the complex elements jl + 1, + 2, + 3 from jl (jl a multiple of four)
+    const uint32_t dj1 = P2log == 0 ? 8 * seg : 8, dj2 = P2log == 0 ? 16 * seg : (P2log == 1 ? 8 * seg : 16),
+                   dj3 = P2log == 0 ? 24 * seg : (P2log == 1 ? 8 * seg + 8 : 24);
     static_assert(kTcStages == kTcGroups, "one operand stage per producer group");
+#ifdef BBX_TC_FINE_TRACE
+    unsigned long long fa = 0, fb = 0, fc = 0, fd = 0;  // A part, B part, tcgen05.wait::st, fences + arrive
+#endif
     const uint32_t total = kTcBins * nchunk;
     const uint32_t s = grp, sB = smem0 + s * kTcStageBytes;
     uint32_t ph = 0, d = grp % RD, phd = 0;
-    uint32_t cnext = grp;  // chunk index inside the bin, to find the bin of `it`
-    uint32_t j = 0;
     for (uint32_t it = grp; it < total; it += kTcGroups) {
-      while (cnext >= nchunk) {
-        cnext -= nchunk;
-        j++;
-      }
-      cnext += kTcGroups;
-      const bool bin0 = (kb + j) == 0;  // packed bin 0 = (DC, Nyquist): two real products, no cross terms
       const uint32_t raw = raw0 + d * RSB;
       // ---- raw operands of this chunk have landed (TMA) ----
       if (ok && !mbar_wait_t(bar_rawf + 8 * d, phd, tr, tw0)) ok = false;
+#ifdef BBX_TC_FINE_TRACE
+      const long long f0 = clock64();
+      const unsigned long long w1_before = tw1;
+#endif
+      // Everything that does not touch the operand stage comes first, so that the time between "stage free" and "stage
+      // full" -- the part of a chunk that the four stages cannot hide -- is only the stores.
+      // ---- A: the real (rows < 64) or imaginary (rows >= 64) parts of sixteen complex of output ao -> 16 K columns of row m
+      float hi[16], lo[16];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const float4 qa = ld_shared4(raw + srcA + g * 1024);
+        split(qa.x, hi[4 * g], lo[4 * g]);
+        split(qa.y, hi[4 * g + 1], lo[4 * g + 1]);
+        split(qa.z, hi[4 * g + 2], lo[4 * g + 2]);
+        split(qa.w, hi[4 * g + 3], lo[4 * g + 3]);
+      }
+      // ---- B, hi part of the first item: four complex of column t (the register budget of a 736-thread CTA ends here) ----
+      float2 bh[4];
+      bh[0] = ld_shared2(raw + srcB[0]), bh[1] = ld_shared2(raw + srcB[0] + dj1), bh[2] = ld_shared2(raw + srcB[0] + dj2),
+      bh[3] = ld_shared2(raw + srcB[0] + dj3);
+      if (it >= (uint32_t)kTcStages) {
+        // ---- the MMAs that read this stage kTcStages chunks ago have completed ----
+        if (ok && !mbar_wait_t(bar_empty + 8 * s, ph ^ 1, tr, tw1)) ok = false;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
 #pragma unroll
       for (int half = 0; half < 2; half++) {
-        // ---- A: eight complex (a_i, b_i) of output ao -> 16 K columns of row m: re row (a, -b), im row (b, a) ----
-        // (converting both halves before the stage wait needs 64 live registers: it spills at the 80-register cap
-        // of a 768-thread CTA and measured slower)
-        float4 qa[4];
+        float h8[8], l8[8];
 #pragma unroll
-        for (int g = 0; g < 4; g++) qa[g] = ld_shared4(raw + srcA + (4 * half + g) * 1024);
-        float hi[16], lo[16];
-        if (!im_row) {
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            split(qa[g].x, hi[4 * g], lo[4 * g]);
-            split(-qa[g].y, hi[4 * g + 1], lo[4 * g + 1]);
-            split(qa[g].z, hi[4 * g + 2], lo[4 * g + 2]);
-            split(-qa[g].w, hi[4 * g + 3], lo[4 * g + 3]);
-          }
-          if (bin0) {
-#pragma unroll
-            for (int u = 1; u < 16; u += 2) hi[u] = lo[u] = 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            split(qa[g].y, hi[4 * g], lo[4 * g]);
-            split(qa[g].x, hi[4 * g + 1], lo[4 * g + 1]);
-            split(qa[g].w, hi[4 * g + 2], lo[4 * g + 2]);
-            split(qa[g].z, hi[4 * g + 3], lo[4 * g + 3]);
-          }
-          if (bin0) {
-#pragma unroll
-            for (int u = 0; u < 16; u += 2) {
-              hi[u + 1] = hi[u];
-              lo[u + 1] = lo[u];
-              hi[u] = lo[u] = 0.f;
-            }
-          }
-        }
-        if (half == 0 && it >= (uint32_t)kTcStages) {
-          // ---- the MMAs that read this stage kTcStages chunks ago have completed ----
-          if (ok && !mbar_wait_t(bar_empty + 8 * s, ph ^ 1, tr, tw1)) ok = false;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        st_tmem16(tmem + dstA + 16 * half, hi);
-        st_tmem16(tmem + dstA + 16 * half + 2 * kTcChunk, lo);
+        for (int u = 0; u < 8; u++) h8[u] = hi[8 * half + u], l8[u] = lo[8 * half + u];
+        st_tmem8(tmem + dstA + 8 * half, h8);
+        st_tmem8(tmem + dstA + 8 * half + kTcChunk, l8);
       }
-      // ---- B: one complex of column t -> 8 bytes of the K-major tile, hi and lo (plain copies) ----
+#ifdef BBX_TC_FINE_TRACE
+      const long long f1 = clock64();
+#endif
+      // ---- B: two 16-byte rows of the K-major tile per item (re | im), hi then lo ----
+      const bool b_all = 4 * N >= kTcProducers * NBR;  // N = 16: half of the threads have an item
 #pragma unroll
       for (int r = 0; r < NBR; r++) {
-        const float2 qh = ld_shared2(raw + srcB[r]), ql = ld_shared2(raw + srcB[r] + bhalf);
-        st_shared2(sB + offB[r], qh.x, qh.y);
-        st_shared2(sB + kTcBHalf + offB[r], ql.x, ql.y);
+        if (b_all || gtid + kTcProducers * r < 4 * N) {
+          const uint32_t src = raw + srcB[r], dst = sB + offB[r];
+          if (r > 0) bh[0] = ld_shared2(src), bh[1] = ld_shared2(src + dj1), bh[2] = ld_shared2(src + dj2), bh[3] = ld_shared2(src + dj3);
+          st_shared4(dst, bh[0].x, bh[1].x, bh[2].x, bh[3].x);
+          st_shared4(dst + N * 16, bh[0].y, bh[1].y, bh[2].y, bh[3].y);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NBR; r++) {
+        if (b_all || gtid + kTcProducers * r < 4 * N) {
+          const uint32_t src = raw + srcB[r] + bhalf, dst = sB + kTcBHalf + offB[r];
+          const float2 c0 = ld_shared2(src), c1 = ld_shared2(src + dj1), c2 = ld_shared2(src + dj2), c3 = ld_shared2(src + dj3);
+          st_shared4(dst, c0.x, c1.x, c2.x, c3.x);
+          st_shared4(dst + N * 16, c0.y, c1.y, c2.y, c3.y);
+        }
       }
       mbar_arrive(bar_rawe + 8 * d);  // raw slot free for the loader
       d += kTcGroups;
@@ -570,19 +603,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         d -= RD;
         phd ^= 1;
       }
+#ifdef BBX_TC_FINE_TRACE
+      const long long f2 = clock64();
+#endif
       // TMEM stores complete, smem writes visible to the tensor core (async proxy); hand the stage to the issuer
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#ifdef BBX_TC_FINE_TRACE
+      const long long f3 = clock64();
+#endif
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_full + 8 * s);
       ph ^= 1;
+#ifdef BBX_TC_FINE_TRACE
+      const long long f4 = clock64();
+      fa += (unsigned long long)(f1 - f0) - (tw1 - w1_before);
+      fb += (unsigned long long)(f2 - f1);
+      fc += (unsigned long long)(f3 - f2);
+      fd += (unsigned long long)(f4 - f3);
+#endif
     }
     if (!ok && gtid == 0) report_timeout(a.status, 1);
+#ifdef BBX_TC_FINE_TRACE
+    if (tr && gtid == 0 && grp == 0) {
+      trow[7] = (unsigned long long)(clock64() - tstart);
+      trow[8] = tw0;
+      trow[9] = tw1;
+      trow[10] = fa;
+      trow[11] = fb;
+      trow[12] = fc;
+      trow[13] = fd;
+    }
+#else
     if (tr && gtid == 0) {
       trow[7 + 3 * grp] = (unsigned long long)(clock64() - tstart);  // producer group: total, raw wait, stage wait
       trow[8 + 3 * grp] = tw0;
       trow[9 + 3 * grp] = tw1;
     }
+#endif
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -637,32 +695,39 @@ __global__ void __launch_bounds__(256) k_mimo_pack_x(const float2* __restrict__ 
   }
 }
 
-// Hpack[og][k][g][o] = (H_{o,i0}[p0][k], H_{o,i1}[p1][k]) for the complex K indices j = 2g, 2g+1 (j = i*P2 + p',
-// p = P2-1-p'); zero where the filter is null / shorter / beyond n_in.  Runs when the filter matrix changes.
+// Hpack[og][k][chunk][part][g][o] = the real (part 0) / imaginary (part 1) parts of H_{o,i}[p][k] for the four complex K
+// indices j = 16 chunk + 4 g .. + 3 (j = i*P2 + p', p = P2-1-p'); zero where the filter is null / shorter / beyond n_in.
+// One CTA: 32 bins x one group of four j x 64 outputs (two passes of 32 outputs).  Runs when the filter matrix changes.
 __global__ void __launch_bounds__(256) k_mimo_pack_h(const float2* const* __restrict__ ftab, const uint32_t* __restrict__ fparts,
                                                      float4* __restrict__ hpack, uint32_t B, uint32_t n_in, uint32_t n_out,
                                                      uint32_t P2log, uint32_t G) {
-  __shared__ float2 tile[32][129];  // [k][o*2 + jj]
-  const uint32_t k0 = blockIdx.x * 32, g = blockIdx.y, og = blockIdx.z;
+  __shared__ float2 tile[32][129];  // [k][o_local * 4 + jj]
+  const uint32_t k0 = blockIdx.x * 32, g4 = blockIdx.y, og = blockIdx.z;  // g4 = group of four complex K indices
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t P2 = 1u << P2log;
-  for (uint32_t pr = warp; pr < 128; pr += 8) {  // (o, jj) pairs, lanes over k
-    const uint32_t o = pr >> 1, jj = pr & 1;
-    const uint32_t j = 2 * g + jj, i = j >> P2log, p = P2 - 1 - (j & (P2 - 1));
-    const uint32_t og_o = og * 64 + o;
-    float2 v = make_float2(0.f, 0.f);
-    if (og_o < n_out && i < n_in) {
-      const float2* H = ftab[(uint64_t)og_o * n_in + i];
-      if (H && p < fparts[(uint64_t)og_o * n_in + i]) v = H[(uint64_t)p * B + k0 + lane];
+  const uint32_t chunk = g4 >> 2, gl = g4 & 3;
+  for (uint32_t oh = 0; oh < 2; oh++) {
+    for (uint32_t pr = warp; pr < 128; pr += 8) {  // (o_local, jj) pairs, lanes over k
+      const uint32_t o = 32 * oh + (pr >> 2), jj = pr & 3;
+      const uint32_t j = 4 * g4 + jj, i = j >> P2log, p = P2 - 1 - (j & (P2 - 1));
+      const uint32_t og_o = og * 64 + o;
+      float2 v = make_float2(0.f, 0.f);
+      if (og_o < n_out && i < n_in) {
+        const float2* H = ftab[(uint64_t)og_o * n_in + i];
+        if (H && p < fparts[(uint64_t)og_o * n_in + i]) v = H[(uint64_t)p * B + k0 + lane];
+      }
+      tile[lane][pr] = v;
     }
-    tile[lane][pr] = v;
+    __syncthreads();
+    for (uint32_t kl = warp; kl < 32; kl += 8) {
+      const float2 c0 = tile[kl][4 * lane], c1 = tile[kl][4 * lane + 1], c2 = tile[kl][4 * lane + 2], c3 = tile[kl][4 * lane + 3];
+      // float4 index of (og, k, chunk, part, gl, o): G float4 groups of 64 per (og, k) = chunks x 2 parts x 4 groups
+      const uint64_t at = ((((uint64_t)og * B + k0 + kl) * (G / 8) + chunk) * 8 + gl) * 64 + 32 * oh + lane;
+      hpack[at] = make_float4(c0.x, c1.x, c2.x, c3.x);
+      hpack[at + 4 * 64] = make_float4(c0.y, c1.y, c2.y, c3.y);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (uint32_t kl = warp; kl < 32; kl += 8)
-    for (uint32_t o = lane; o < 64; o += 32) {
-      const float2 u = tile[kl][2 * o], w = tile[kl][2 * o + 1];
-      hpack[(((uint64_t)og * B + k0 + kl) * G + g) * 64 + o] = make_float4(u.x, u.y, w.x, w.y);
-    }
 }
 
 }  // namespace bbx
