@@ -890,9 +890,9 @@ int launch_mimo_tc(bbx_engine* e, uint32_t T) {
   a.xbin = xbin;
   a.trace = nullptr;
   if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
-  // raw ring: 8 KB of H + hi and lo FDL runs per chunk (see mimo_tc.cuh); as many stages as fit, an even number
+  // raw ring: the hi and lo FDL runs of a chunk (see mimo_tc.cuh); as many stages as fit, an even number
   {
-    a.raw_stage_bytes = (8192 + 2 * ninp * seg * 8 + 127) & ~127u;
+    a.raw_stage_bytes = (2 * ninp * seg * 8 + 127) & ~127u;
     uint32_t nst = (kTcSmemMax - kTcOffRaw) / a.raw_stage_bytes;
     nst = std::min(nst, (uint32_t)kTcRawStagesMax) & ~1u;
     a.raw_stages = nst;

@@ -64,7 +64,7 @@ static constexpr uint32_t kTcBHalf = kTcN2max * kTcChunk * 4;             // 8 K
 static constexpr uint32_t kTcStageBytes = 2 * kTcBHalf;                   // 16 KB of shared memory per stage
 static constexpr uint32_t kTcTileBytes = kTcNmax * 64 * 16;               // 64 KB: epilogue tile [t][o][bin pair] float2
 static_assert(kTcBins % 2 == 0, "the epilogue stores pairs of bins");
-// raw stage: 8 KB of packed H (64 outputs x 16 complex) + the FDL runs of the chunk: (16 / P2) input rows of
+// raw stage: the FDL runs of the chunk: (16 / P2) input rows of
 // N + P2 complex (P2 < 16) or one row of N + 16, hi and lo parts.  Its size depends on (P2, N): the host passes
 // the stage size and the number of stages that fit (MimoTcArgs::raw_stage_bytes / raw_stages).
 static constexpr uint32_t kTcOffTile = kTcStages * kTcStageBytes;
@@ -361,47 +361,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
   if (warp >= kTcWarpLoad) {
     // ================= loader: one lane issues the bulk copies (TMA) of the raw operands =================
     {
-      // two bulk copies per chunk, both sources advance linearly: the packed H of the CTA's bins is one contiguous run
-      // of 8 KB chunks, the pre-staged FDL runs (k_mimo_pack_x) one run of 2 * bhalf bytes per chunk.  Loader warp l
-      // handles chunks it = l (mod 2).
-      const uint32_t lw = warp - kTcWarpLoad;
-      const uint32_t bbytes = 2 * bhalf, bytes = 8192 + bbytes, total = kTcBins * nchunk;
-      const char* asrc = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64) + (uint64_t)lw * 8192;
-      const char* xbase = reinterpret_cast<const char*>(a.xb + (uint64_t)kb * a.xbin) + (uint64_t)blockIdx.z * nchunk * bbytes;
-      const uint64_t xbin_bytes = a.xbin * 8;
-      uint32_t d = lw % RD, ph = 0, j = 0, c = lw;
-      if (elect_one()) bulk_prefetch_l2(asrc, 8192u * (total < (uint32_t)kTcPrefetch ? total : (uint32_t)kTcPrefetch));
-      __syncwarp();
-      for (uint32_t it = lw; it < total; it += kTcLoadWarps) {
-        while (c >= nchunk) {
-          c -= nchunk;
-          j++;
-        }
+      // One bulk copy per chunk: the pre-staged FDL runs (k_mimo_pack_x), 2 * bhalf contiguous bytes.  The packed H does not
+      // pass through shared memory at all (the producers read it from L2 into registers and prefetch it themselves).
+      // This loop is a serial chain on one warp and paces the whole ring: running pointers only, no multiplies.
+      const uint32_t bbytes = 2 * bhalf, total = kTcBins * nchunk;
+      const char* xsrc = reinterpret_cast<const char*>(a.xb + (uint64_t)kb * a.xbin) + (uint64_t)blockIdx.z * nchunk * bbytes;
+      const uint64_t bin_skip = a.xbin * 8 - (uint64_t)nchunk * bbytes;  // from the last chunk of a bin to the first of the next
+      uint32_t d = 0, ph = 0, c = 0;
+      uint32_t dst = raw0, bar = bar_rawf, bare = bar_rawe;
+      const bool leader = elect_one();
+      for (uint32_t it = 0; it < total; it++) {
         if (it >= RD) {
-          if (ok && !mbar_wait_t(bar_rawe + 8 * d, ph ^ 1, tr, tw0)) ok = false;
+          if (ok && !mbar_wait_t(bare, ph ^ 1, tr, tw0)) ok = false;
         }
-        if (elect_one()) {
-          const uint32_t dst = raw0 + d * RSB, bar = bar_rawf + 8 * d;
-          // the packed H of the CTA's bins is one contiguous run: pull the chunk kTcPrefetch ahead into L2 now, so that its
-          // copy later meets L2 latency, not HBM latency (the raw ring holds only ~80 KB of copies in flight per SM)
-          if (it + kTcPrefetch < total) bulk_prefetch_l2(asrc + (uint64_t)kTcPrefetch * 8192, 8192);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-          bulk_g2s(dst, asrc, 8192, bar);
-          bulk_g2s(dst + 8192, xbase + j * xbin_bytes + (uint64_t)c * bbytes, bbytes, bar);
+        if (leader) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bbytes) : "memory");
+          bulk_g2s(dst, xsrc, bbytes, bar);
         }
-        __syncwarp();
-        asrc += kTcLoadWarps * 8192;
-        c += kTcLoadWarps;
-        d += kTcLoadWarps;
-        while (d >= RD) {
-          d -= RD;
-          ph ^= 1;
+        xsrc += bbytes;
+        if (++c == nchunk) {
+          c = 0;
+          xsrc += bin_skip;
+        }
+        dst += RSB, bar += 8, bare += 8;
+        if (++d == RD) {
+          d = 0, ph ^= 1;
+          dst = raw0, bar = bar_rawf, bare = bar_rawe;
         }
       }
       if (!ok && lane == 0) report_timeout(a.status, 3);
-      if (tr && lane == 0 && lw == 0) {
+      if (tr && lane == 0) {
         trow[0] = (unsigned long long)(clock64() - tstart);  // loader: total, waiting for a free raw slot
         trow[1] = tw0;
+
       }
     }
   } else if (warp >= kTcWarpMma && warp < kTcWarpMma + kTcMmaWarps) {
@@ -513,7 +505,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     // row m = 32 q + lane of the planar matrix: lanes 0..15 = re of H for outputs 16 q .. + 15, lanes 16..31 = im of the same
     // outputs, so that the epilogue finds the two rows of an output in one warp (lane ^ 16)
     const uint32_t ao = 16 * q + (lane & 15);
-    const uint32_t srcA = (lane >> 4) * 4096 + ao * 16;                    // raw [re | im][g][o] float4
+    // packed H of this CTA's bins: chunk `it` (over all its bins) at hsrc + it * 8192; this row reads [re | im][g][ao]
+    const char* hsrc = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64) + (lane >> 4) * 4096 + ao * 16;
     const uint32_t dstA = ((32 * q) << 16) + kTcAccCols + grp * kTcAStageCols;  // this group's stage (+ 16 for lo)
     // B (pre-split by k_mimo_pack_x): item e = gtid + 128 r -> (K group kg of four complex j, column t): four complex of
     // the raw runs -> the 16-byte row (kg, t) of their real parts and the row (kg, N + t) of their imaginary parts
@@ -525,7 +518,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       const uint32_t kg = (e >> NLOG) & 3, t = e & (N - 1), jl = kg << 2;
       offB[r] = kg * (N2 * 16) + t * 16;
       // element (local K index jl, column t) of the raw segment: row jl / P2, position t + p'
-      srcB[r] = 8192 + 8 * ((P2log < 4) ? (jl >> P2log) * seg + (jl & P2m) + t : jl + t);
+      srcB[r] = 8 * ((P2log < 4) ? (jl >> P2log) * seg + (jl & P2m) + t : jl + t);
     }
     // byte distance of the complex elements jl + 1, + 2, + 3 from jl (jl a multiple of four)
     const uint32_t dj1 = P2log == 0 ? 8 * seg : 8, dj2 = P2log == 0 ? 16 * seg : (P2log == 1 ? 8 * seg : 16),
@@ -537,6 +530,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
     const uint32_t total = kTcBins * nchunk;
     const uint32_t s = grp, sB = smem0 + s * kTcStageBytes;
     uint32_t ph = 0, d = grp % RD, phd = 0;
+    // H of the group's first chunk; afterwards the loads of chunk it + 4 are issued as soon as the registers of chunk it
+    // are free (after its TMEM stores) and land while the B tile is written
+    float4 qa[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) qa[g] = ld_stream4(reinterpret_cast<const float4*>(hsrc + (uint64_t)grp * 8192 + g * 1024));
+    // L2 prefetch of the 16 lines this warp reads per chunk ([re | im][g][256 bytes of outputs 16 q ..]): lane l < 16 takes
+    // line l of the chunk kTcPrefetch ahead, one instruction per warp and chunk
+    const char* const hpf = reinterpret_cast<const char*>(a.hpack + ((uint64_t)(og * a.B + kb) * a.G) * 64) + ((lane >> 3) & 1) * 4096 +
+                            ((lane >> 1) & 3) * 1024 + q * 256 + (lane & 1) * 128;
+    if (lane < 16) {
+#pragma unroll
+      for (uint32_t k = kTcGroups; k < (uint32_t)kTcPrefetch; k += kTcGroups)
+        if (grp + k < kTcBins * nchunk) asm volatile("prefetch.global.L2 [%0];" ::"l"(hpf + (uint64_t)(grp + k) * 8192));
+    }
     for (uint32_t it = grp; it < total; it += kTcGroups) {
       const uint32_t raw = raw0 + d * RSB;
       // ---- raw operands of this chunk have landed (TMA) ----
@@ -551,12 +558,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
       float hi[16], lo[16];
 #pragma unroll
       for (int g = 0; g < 4; g++) {
-        const float4 qa = ld_shared4(raw + srcA + g * 1024);
-        split(qa.x, hi[4 * g], lo[4 * g]);
-        split(qa.y, hi[4 * g + 1], lo[4 * g + 1]);
-        split(qa.z, hi[4 * g + 2], lo[4 * g + 2]);
-        split(qa.w, hi[4 * g + 3], lo[4 * g + 3]);
+        split(qa[g].x, hi[4 * g], lo[4 * g]);
+        split(qa[g].y, hi[4 * g + 1], lo[4 * g + 1]);
+        split(qa[g].z, hi[4 * g + 2], lo[4 * g + 2]);
+        split(qa[g].w, hi[4 * g + 3], lo[4 * g + 3]);
       }
+
       // ---- B, hi part of the first item: four complex of column t (the register budget of a 736-thread CTA ends here) ----
       float2 bh[4];
       bh[0] = ld_shared2(raw + srcB[0]), bh[1] = ld_shared2(raw + srcB[0] + dj1), bh[2] = ld_shared2(raw + srcB[0] + dj2),
@@ -573,6 +580,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mimo_tc(MimoTcArgs a) {
         for (int u = 0; u < 8; u++) h8[u] = hi[8 * half + u], l8[u] = lo[8 * half + u];
         st_tmem8(tmem + dstA + 8 * half, h8);
         st_tmem8(tmem + dstA + 8 * half + kTcChunk, l8);
+      }
+      if (lane < 16 && it + kTcPrefetch < total)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(hpf + (uint64_t)(it + kTcPrefetch) * 8192));
+      // the registers of this chunk's A values are free: H of the group's next chunk (lands while the B tile is written)
+      if (it + kTcGroups < total) {
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+          qa[g] = ld_stream4(reinterpret_cast<const float4*>(hsrc + (uint64_t)(it + kTcGroups) * 8192 + g * 1024));
       }
 #ifdef BBX_TC_FINE_TRACE
       const long long f1 = clock64();

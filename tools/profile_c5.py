@@ -19,7 +19,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "trace":
     names = ["loader total", "loader wait raw slot", "mma total", "mma wait operands", "mma wait read-out", "epi total",
              "epi wait acc"] + ["prod%d %s" % (g, w) for g in range(3) for w in ("total", "wait raw", "wait stage")]
     if len(sys.argv) > 3 and sys.argv[3] == "fine":   # libbbx built with -DBBX_TC_FINE_TRACE: group 0 only, split by phase
-        names = names[:10] + ["prod0 A part", "prod0 B part", "prod0 wait::st", "prod0 fences+arrive"]
+        names = names[:10] + ["prod0 A part", "prod0 B part", "prod0 wait::st", "prod0 fences+arrive", "loader prefetch issue", "loader copy issue"]
     for k, nme in enumerate(names):
         print("%-22s mean %9.0f  min %9.0f  max %9.0f cycles" % (nme, tr[:, k].mean(), tr[:, k].min(), tr[:, k].max()))
 eng.close()
