@@ -536,7 +536,7 @@ def leg_c5(bbx, torch, dev, steps, peaks):
     flops = 3 * 2 * 128 * (2 * nin * Pm) * Tm * B
     peak = peaks["bf16_tflops"] / 2
     ach = flops / (lms * 1e-3) / 1e12 if lms > 0 else 0.0
-    roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 180.8e6,
+    roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 190.9e6,
             "traffic_source": "ncu --set full capture under profiles/ (dram__bytes_read + write of one launch), not this run",
             "kernel": "k_mimo_tc", "launch_ms": lms, "tf32_flops_per_launch": flops,
             "peak_source": peaks["bf16_src"] + " / 2 (TF32 = half the bf16 rate)",
