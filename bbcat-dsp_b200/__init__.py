@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbx.so")
+# BBX_LIB: another build of the same library (A/B runs of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("BBX_LIB") or os.path.join(_HERE, "libbbx.so")
 
 FMT_UNKNOWN, FMT_16BIT, FMT_24BIT, FMT_32BIT, FMT_FLOAT, FMT_DOUBLE = 0, 1, 2, 3, 4, 5
 FMT_BYTES = {1: 2, 2: 3, 3: 4, 4: 4, 5: 8}
@@ -146,6 +147,17 @@ SYMBOLS = {
     "bbx_fbank_get_state": (C.c_int, [vp, u32, vp, vp, vp]),
     "bbx_fbank_reset": (C.c_int, [vp]),
     "bbx_fbank_launches": (C.c_int, [vp, C.POINTER(u64)]),
+    "bbx_sofa_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "bbx_sofa_open_memory": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "bbx_sofa_close": (C.c_int, [vp]),
+    "bbx_sofa_get_sizes": (C.c_int, [vp] + [C.POINTER(u32)] * 4),
+    "bbx_sofa_get_samplerate": (C.c_int, [vp, u32, C.POINTER(C.c_double)]),
+    "bbx_sofa_get_ir": (C.c_int, [vp, u32, u32, u32, vp, u32]),
+    "bbx_sofa_get_delay": (C.c_int, [vp, u32, u32, u32, C.POINTER(C.c_double)]),
+    "bbx_sofa_get_position": (C.c_int, [vp, C.c_int, u32, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "bbx_sofa_nearest_measurement": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int, C.POINTER(u32)]),
+    "bbx_sofa_get_attribute": (C.c_int, [vp, C.c_char_p, C.c_char_p, u32]),
+    "bbx_sofa_create_filters": (C.c_int, [vp, vp, u32, u32, C.POINTER(vp), u32]),
     "bbx_allpass_create": (C.c_int, [u32, u32, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(vp)]),
     "bbx_allpass_destroy": (C.c_int, [vp]),
     "bbx_allpass_process": (C.c_int, [vp, vp, vp, u32, u32, u32, u32, u32]),
@@ -509,6 +521,76 @@ class BiQuadFilterBank:
         n = u64(0)
         _check(lib().bbx_fbank_launches(self.h, C.byref(n)))
         return n.value
+
+
+class SOFA:
+    """SOFA (AES69) impulse-response set (README:77-78 lists src/SOFA.{h,cpp}; absent from the tree, so the method names
+    follow the SOFA conventions, not a BBC header).  Reads the netCDF classic container; see include/bbx.h."""
+
+    SOURCE, LISTENER, RECEIVER, EMITTER = 0, 1, 2, 3
+
+    def __init__(self, path=None, data=None):
+        self.h = None
+        h = vp()
+        if data is not None:
+            self._data = bytes(data)
+            _check(lib().bbx_sofa_open_memory(self._data, len(self._data), C.byref(h)))
+        else:
+            _check(lib().bbx_sofa_open(os.fsencode(path), C.byref(h)))
+        self.h = h
+        m, r, e, n = u32(), u32(), u32(), u32()
+        _check(lib().bbx_sofa_get_sizes(h, C.byref(m), C.byref(r), C.byref(e), C.byref(n)))
+        self.num_measurements, self.num_receivers, self.num_emitters, self.ir_length = m.value, r.value, e.value, n.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bbx_sofa_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def get_samplerate(self, measurement=0):
+        v = C.c_double()
+        _check(lib().bbx_sofa_get_samplerate(self.h, measurement, C.byref(v)))
+        return v.value
+
+    def get_ir(self, measurement, receiver, emitter=0, n=None):
+        out = np.zeros(self.ir_length if n is None else n, dtype=np.float32)
+        _check(lib().bbx_sofa_get_ir(self.h, measurement, receiver, emitter, _p(out), out.size))
+        return out
+
+    def get_delay(self, measurement, receiver, emitter=0):
+        v = C.c_double()
+        _check(lib().bbx_sofa_get_delay(self.h, measurement, receiver, emitter, C.byref(v)))
+        return v.value
+
+    def get_position(self, which, index):
+        xyz, sph = (C.c_double * 3)(), C.c_int()
+        _check(lib().bbx_sofa_get_position(self.h, which, index, xyz, C.byref(sph)))
+        return np.array(list(xyz)), bool(sph.value)
+
+    def nearest_measurement(self, pos, spherical=True):
+        m = u32()
+        _check(lib().bbx_sofa_nearest_measurement(self.h, (C.c_double * 3)(*[float(v) for v in pos]), int(spherical), C.byref(m)))
+        return m.value
+
+    def get_attribute(self, name):
+        buf = C.create_string_buffer(4096)
+        _check(lib().bbx_sofa_get_attribute(self.h, name.encode(), buf, len(buf)))
+        return buf.value.decode("utf-8", "replace")
+
+    def create_filters(self, convolver, receiver, emitter=0):
+        """One filter object per measurement on `convolver` (a Convolver): the bank SelectFilter chooses from."""
+        arr = (vp * self.num_measurements)()
+        _check(lib().bbx_sofa_create_filters(self.h, convolver.h, receiver, emitter, arr, self.num_measurements))
+        out = []
+        for m in range(self.num_measurements):
+            f = Filter.__new__(Filter)
+            f.h, f.engine = vp(arr[m]), convolver
+            f.partitions = lib().bbx_filter_partitions(f.h)
+            convolver._filters.append(f)
+            out.append(f)
+        return out
 
 
 class AllPassChain:

@@ -469,6 +469,39 @@ int bbx_probe_fp32_tflops(int device, float seconds, float* burst, float* sustai
 /* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
 
+/* ---- SOFA (AES69) impulse-response sets: the on-disk side of IR selection ------------------------------------------
+ * Replaces: src/SOFA.{h,cpp} ("SOFA file support via the netcdf-bbc libraries", README:77-78; libnetcdf dependency in
+ * debian/control:5) -- listed by the reference, ABSENT from the mounted tree, so the interface below is ours and parity is
+ * unpinned against BBC; the container parser is pinned against an independent netCDF implementation (scipy.io.netcdf_file,
+ * tests/test_sofa.py).  Reads the netCDF classic container (CDF-1 / CDF-2) with the SOFA names: Data.IR [M][R][N] (DataType
+ * FIR) or [M][R][E][N] (FIRE), Data.Delay [I|M][R]([E]) in samples, Data.SamplingRate [I|M], Source/ListenerPosition
+ * [I|M][C], Receiver/EmitterPosition [R|E][C][I|M].  A netCDF-4 (HDF5) container is refused with BBX_ERR_UNSUPPORTED and a
+ * message (no HDF5 implementation in this build).  Host-side objects: no device needed except for _create_filters. */
+typedef struct bbx_sofa bbx_sofa;
+enum { BBX_SOFA_SOURCE = 0, BBX_SOFA_LISTENER = 1, BBX_SOFA_RECEIVER = 2, BBX_SOFA_EMITTER = 3 };
+int bbx_sofa_open(const char* path, bbx_sofa** out);
+int bbx_sofa_open_memory(const void* data, size_t bytes, bbx_sofa** out);
+int bbx_sofa_close(bbx_sofa* s);
+/* M measurements, R receivers (ears), E emitters (1 for FIR), N samples per impulse response; any pointer may be NULL */
+int bbx_sofa_get_sizes(const bbx_sofa* s, uint32_t* M, uint32_t* R, uint32_t* E, uint32_t* N);
+int bbx_sofa_get_samplerate(const bbx_sofa* s, uint32_t measurement, double* hz);
+/* impulse response (measurement, receiver, emitter) as fp32 (Data.IR is stored in double), n values: truncated or
+ * zero-padded to n */
+int bbx_sofa_get_ir(const bbx_sofa* s, uint32_t measurement, uint32_t receiver, uint32_t emitter, float* dst, uint32_t n);
+/* Data.Delay of (measurement, receiver, emitter) in samples: the `delay_samples` of bbx_set_filter */
+int bbx_sofa_get_delay(const bbx_sofa* s, uint32_t measurement, uint32_t receiver, uint32_t emitter, double* samples);
+/* position variable `which` (BBX_SOFA_*): row `index` (a measurement for source / listener, an object otherwise), the three
+ * coordinates as stored, *spherical = 1 when the variable's Type attribute says so (degrees, degrees, metres) */
+int bbx_sofa_get_position(const bbx_sofa* s, int which, uint32_t index, double xyz[3], int* spherical);
+/* the measurement whose SourcePosition is nearest to pos (Euclidean distance after conversion to cartesian; a spherical
+ * query with radius <= 0 selects by direction only); ties go to the lowest index */
+int bbx_sofa_nearest_measurement(const bbx_sofa* s, const double pos[3], int spherical, uint32_t* measurement);
+/* global attribute as text (numeric attributes printed with %.17g) */
+int bbx_sofa_get_attribute(const bbx_sofa* s, const char* name, char* buf, uint32_t buflen);
+/* one filter object per measurement for (receiver, emitter): the IR bank a renderer selects from with bbx_set_filter;
+ * count must equal M; on failure nothing is left allocated */
+int bbx_sofa_create_filters(const bbx_sofa* s, bbx_engine* e, uint32_t receiver, uint32_t emitter, bbx_filter** out, uint32_t count);
+
 #ifdef __cplusplus
 }
 #endif

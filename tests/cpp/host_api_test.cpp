@@ -12,6 +12,7 @@
 #include "BiQuad.h"
 #include "Convolver.h"
 #include "FractionalSample.h"
+#include "SOFA.h"
 #include "SoundDelayBuffer.h"
 #include "SoundMixing.h"
 
@@ -169,6 +170,16 @@ int main() {
     float ax[6] = {1, 0, 0, 0, 0, 0}, ay[6] = {0};
     chain.Process(ax, ay, 0, 1, 0, 1, 6);
     CHECK(ay[0] == 0.5f && ay[1] == 0.0f && ay[2] == 0.75f && ay[3] == 0.0f && ay[4] == -0.375f);
+  }
+  // SOFA: a file that does not exist throws with the library's message (reading real sets: tests/test_sofa.py)
+  {
+    bool threw = false;
+    try {
+      SOFA sofa("/nonexistent/set.sofa");
+    } catch (const std::runtime_error& e) {
+      threw = strstr(e.what(), "cannot open") != NULL;
+    }
+    CHECK(threw);
   }
   printf("PASS max_err=%g\n", err);
   return 0;
