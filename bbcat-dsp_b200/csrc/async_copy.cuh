@@ -38,7 +38,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: gives up after ~4e6 polls so that a protocol bug ends the kernel with wrong results (caught by the parity
 // tests) instead of hanging the device
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
   for (int spin = 0; spin < (1 << 22); spin++)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
@@ -71,6 +71,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // thread's earlier cp.async copies have landed (noinc: the barrier's expected count already includes it)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// 8- and 4-byte forms (LDGSTS through L1): a thread that copies exactly the elements it reads back needs no barrier
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

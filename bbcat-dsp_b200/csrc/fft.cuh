@@ -13,8 +13,8 @@
 // Several transforms share a CTA (threadIdx.y) so that small sizes still launch 128-256 threads.
 // Twiddles come from a table computed in double precision on the host
 // (tw[j] = exp(-2 pi i j / N), j < N; the M-point twiddle exp(-2 pi i j / M) is tw[2j]).
-// Shared-memory indices are padded by one element per eight (PAD) so that the stride-R stores of the
-// first passes are bank-conflict free.
+// Shared-memory indices go through PADM<M>: one element of padding per eight for the radix-4 sizes, an XOR swizzle
+// for the radix-8 sizes, so that the stride-R stores of the first passes are bank-conflict free.
 //
 // Spectra are stored PACKED: B complex values per row, bin 0 holds (X[0].re, X[B].re) -- DC and
 // Nyquist are both real for real input -- so a row is exactly 8B bytes (4 KB at B = 512).
@@ -43,7 +43,24 @@ struct FftCfg {
   static constexpr int FPB = (NT >= 256) ? 1 : ((256 / NT) > 16 ? 16 : (256 / NT));  // transforms per CTA
   static constexpr int MP = M + M / 8;                                  // padded smem elements per transform
 };
+// Index of element i inside a transform's shared-memory workspace.
+//  * radix-4 sizes: one float2 of padding per 8 elements.
+//  * radix-8 sizes: an XOR swizzle of the low four index bits with bits 3..6 (a bijection inside every aligned group of
+//    128 elements, so the workspace needs no padding; the allocation keeps MP elements per transform so that the
+//    transforms of a CTA stay staggered).  A half-warp moves 16 float2 per wavefront, i.e. the bank pair is the low four
+//    bits: 16 consecutive elements (every pass's reads, the last passes' writes) keep distinct low bits under the XOR
+//    with a constant; the first pass's transposed writes 8 j + r and the second pass's two runs of eight 64 elements apart
+//    get theirs from bits 3..6.  With the padding those sequential reads straddled a pad and took two wavefronts each
+//    (ncu: 42 % of k_rfft8's shared-memory wavefronts were conflict replays; k_rfft8 19.9 -> 17.1 us per C3 step).
 __device__ __forceinline__ int PAD(int i) { return i + (i >> 3); }
+template <int M>
+__device__ __forceinline__ int PADM(int i) {
+  if constexpr (M == 64 || M == 512 || M == 4096) return i ^ ((i >> 3) & 15);
+  else return PAD(i);
+}
+#ifndef BBX_FFT_MINB
+#define BBX_FFT_MINB 2
+#endif
 
 // 4-point DFT, outputs in natural order
 template <bool INV>
@@ -92,7 +109,7 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
       const int k = j & (Ns - 1);
       float2 v[8];
 #pragma unroll
-      for (int r = 0; r < 8; r++) v[r] = s[PAD(j + r * NT)];
+      for (int r = 0; r < 8; r++) v[r] = s[PADM<M>(j + r * NT)];
       if (Ns > 1) {
         const int stride = 2 * (M / (8 * Ns));  // tw index of exp(-2 pi i k / (8 Ns))
 #pragma unroll
@@ -106,14 +123,14 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
       const int j0 = ((j - k) << 3) + k;
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < 8; r++) s[PAD(j0 + r * Ns)] = v[r];
+      for (int r = 0; r < 8; r++) s[PADM<M>(j0 + r * Ns)] = v[r];
       __syncthreads();
     }
   } else {
 #pragma unroll 1
     for (; Ns * 4 <= M; Ns *= 4) {
       const int k = j & (Ns - 1);
-      float2 v0 = s[PAD(j)], v1 = s[PAD(j + NT)], v2 = s[PAD(j + 2 * NT)], v3 = s[PAD(j + 3 * NT)];
+      float2 v0 = s[PADM<M>(j)], v1 = s[PADM<M>(j + NT)], v2 = s[PADM<M>(j + 2 * NT)], v3 = s[PADM<M>(j + 3 * NT)];
       if (Ns > 1) {
         const int stride = 2 * (M / (4 * Ns));
         float2 w1 = __ldg(&tw[k * stride]), w2 = __ldg(&tw[2 * k * stride]), w3 = __ldg(&tw[3 * k * stride]);
@@ -129,10 +146,10 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
       fft4<INV>(v0, v1, v2, v3);
       const int j0 = ((j - k) << 2) + k;
       __syncthreads();
-      s[PAD(j0)] = v0;
-      s[PAD(j0 + Ns)] = v1;
-      s[PAD(j0 + 2 * Ns)] = v2;
-      s[PAD(j0 + 3 * Ns)] = v3;
+      s[PADM<M>(j0)] = v0;
+      s[PADM<M>(j0 + Ns)] = v1;
+      s[PADM<M>(j0 + 2 * Ns)] = v2;
+      s[PADM<M>(j0 + 3 * Ns)] = v3;
       __syncthreads();
     }
     if (Ns < M) {
@@ -142,7 +159,7 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
       for (int h = 0; h < 2; h++) {
         const int jj = j + h * NT;  // jj < M/2
         const int k = jj & (Ns - 1);
-        float2 v0 = s[PAD(jj)], v1 = s[PAD(jj + M / 2)];
+        float2 v0 = s[PADM<M>(jj)], v1 = s[PADM<M>(jj + M / 2)];
         float2 w = __ldg(&tw[2 * k * (M / (2 * Ns))]);
         if (INV) w.y = -w.y;
         v1 = cmul(v1, w);
@@ -155,8 +172,8 @@ __device__ __forceinline__ void cfft_smem(float2* __restrict__ s, const float2* 
         const int jj = j + h * NT;
         const int k = jj & (Ns - 1);
         const int j0 = ((jj - k) << 1) + k;
-        s[PAD(j0)] = r[2 * h];
-        s[PAD(j0 + Ns)] = r[2 * h + 1];
+        s[PADM<M>(j0)] = r[2 * h];
+        s[PADM<M>(j0 + Ns)] = r[2 * h + 1];
       }
       __syncthreads();
     }
@@ -203,7 +220,7 @@ template <int M, bool INV>
 __device__ __forceinline__ void pass8_first(float2 (&v)[8], float2* __restrict__ s, int j) {
   fft8<INV>(v);
 #pragma unroll
-  for (int r = 0; r < 8; r++) s[PAD(8 * j + r)] = v[r];
+  for (int r = 0; r < 8; r++) s[PADM<M>(8 * j + r)] = v[r];
   fft_bar<M>();
 }
 
@@ -214,7 +231,7 @@ __device__ __forceinline__ void pass8(float2* __restrict__ s, const float2 (&w)[
   const int k = j & (NS - 1);
   float2 v[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) v[r] = s[PAD(j + r * NT)];
+  for (int r = 0; r < 8; r++) v[r] = s[PADM<M>(j + r * NT)];
 #pragma unroll
   for (int r = 1; r < 8; r++) {
     float2 ww = w[r - 1];
@@ -225,7 +242,7 @@ __device__ __forceinline__ void pass8(float2* __restrict__ s, const float2 (&w)[
   const int j0 = ((j - k) << 3) + k;
   fft_bar<M>();
 #pragma unroll
-  for (int r = 0; r < 8; r++) s[PAD(j0 + r * NS)] = v[r];
+  for (int r = 0; r < 8; r++) s[PADM<M>(j0 + r * NS)] = v[r];
   fft_bar<M>();
 }
 
@@ -250,7 +267,7 @@ __device__ __forceinline__ void rfft_split_store8(const float2* __restrict__ s, 
       float2 z0 = s[0];
       x = make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
     } else {
-      float2 a = s[PAD(k)], b = s[PAD(M - k)];
+      float2 a = s[PADM<M>(k)], b = s[PADM<M>(M - k)];
       float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
       float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
       float2 o = make_float2(d.y, -d.x);
@@ -299,7 +316,7 @@ __device__ __forceinline__ void rfft_split_store(const float2* __restrict__ s, c
       float2 z0 = s[0];
       x = make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
     } else {
-      float2 a = s[PAD(k)], b = s[PAD(M - k)];
+      float2 a = s[PADM<M>(k)], b = s[PADM<M>(M - k)];
       float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
       float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
       float2 o = make_float2(d.y, -d.x);
@@ -333,7 +350,7 @@ __device__ __forceinline__ void irfft_unsplit(const float2* __restrict__ x, cons
       float2 t = cmul(d, w);
       z = make_float2(e.x - t.y, e.y + t.x);
     }
-    s[PAD(k)] = z;
+    s[PADM<M>(k)] = z;
   }
 }
 

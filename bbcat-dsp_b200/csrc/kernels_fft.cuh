@@ -3,6 +3,7 @@
 #pragma once
 
 #include "kernels_common.cuh"
+#include "async_copy.cuh"
 #include "fft.cuh"
 
 namespace bbx {
@@ -23,7 +24,7 @@ k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, f
   const uint32_t ch = active ? chq : nch - 1;  // idle transforms of the last CTA recompute a valid one, stores masked
   const float2* win = reinterpret_cast<const float2*>(src + ch * ch_stride + (uint64_t)t * win_stride);
 #pragma unroll
-  for (int h = 0; h < RAD; h++) s[PAD(tid + h * NT)] = win[tid + h * NT];
+  for (int h = 0; h < RAD; h++) s[PADM<M>(tid + h * NT)] = win[tid + h * NT];
   __syncthreads();
   cfft_smem<M, false>(s, tw, tid);
   const uint32_t slot = (slot0 + t) % R;
@@ -34,7 +35,7 @@ k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, f
 // item's window prefetched into registers, the first pass straight from those registers, and (for M = 512) one named
 // barrier per transform instead of the block barrier.
 template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB, (FftCfg<M>::NT * FftCfg<M>::FPB <= 256) ? BBX_FFT_MINB : 1)
 k_rfft8(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, float2* __restrict__ dst, uint64_t dst_ch_stride,
         uint32_t R, uint32_t slot0, const float2* __restrict__ tw, float scale, uint32_t nch, uint32_t T) {
   constexpr int NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
@@ -126,7 +127,7 @@ __device__ __forceinline__ void job_to_block(const float2* __restrict__ ypart_t,
   // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(tid + h NT) + {0,1}, h < R/2
 #pragma unroll
   for (int h = 0; h < RAD / 2; h++) {
-    float2 z = s[PAD(M / 2 + tid + h * NT)];
+    float2 z = s[PADM<M>(M / 2 + tid + h * NT)];
     o[2 * h] = z.x;
     o[2 * h + 1] = z.y;
   }
@@ -232,39 +233,138 @@ __device__ __forceinline__ void job_to_block8(const float2* __restrict__ ypart_t
   // overlap-save: y[B+n] = component (n&1) of z[M/2 + n/2]; this thread keeps n = 2(tid + h NT) + {0,1}, h < 4
 #pragma unroll
   for (int h = 0; h < 4; h++) {
-    float2 z = s[PAD(M / 2 + tid + h * NT)];
+    float2 z = s[PADM<M>(M / 2 + tid + h * NT)];
     o[2 * h] = z.x;
     o[2 * h + 1] = z.y;
   }
 }
 
+// The persistent inverse kernel keeps the partial-sum rows of its NEXT item in flight while it transforms the current one:
+// every thread copies exactly the elements it will add (8-byte cp.async into a per-transform staging area, up to
+// kIrfftPre slots of a job; further slots are read directly), so no barrier stands between the copies and their use, and
+// the staging area is free again as soon as the thread has the sums in registers.  Without it the kernel alternated
+// between a load phase with 64 bytes in flight per thread and a transform phase with none (34 us per 64-block C3 step for
+// 90 MB of traffic).
+#ifndef BBX_IRFFT_PRE
+#define BBX_IRFFT_PRE 3
+#endif
+static constexpr int kIrfftPre = BBX_IRFFT_PRE;
 template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB)
+constexpr size_t irfft8_smem_bytes() {
+  return sizeof(float2) * (size_t)FftCfg<M>::FPB * (M + FftCfg<M>::MP + kIrfftPre * M) + sizeof(float) * FftCfg<M>::FPB * 4;
+}
+
+template <int M>
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB, (FftCfg<M>::NT * FftCfg<M>::FPB <= 256) ? BBX_FFT_MINB : 1)
 k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
          const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
          const float* __restrict__ nyq_part, uint64_t t_stride, uint64_t s_stride, uint32_t stream0, uint32_t T) {
-  constexpr int RAD = 8, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
-  extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M] + padded FFT workspace s[MP]
-  float2* x = k_irfft_smem + (size_t)threadIdx.y * (M + MP);
+  constexpr int RAD = 8, NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP, PRE = kIrfftPre;
+  constexpr int PER = M + MP + PRE * M;
+  extern __shared__ float2 k_irfft_smem[];  // per transform: summed spectrum x[M], padded FFT workspace s[MP], staging pre[PRE][M]
+  float2* x = k_irfft_smem + (size_t)threadIdx.y * PER;
   float2* s = x + M;
+  const float2* pre = s + MP;
+  const float* pre_nyq = reinterpret_cast<const float*>(k_irfft_smem + (size_t)FPB * PER) + threadIdx.y * 4;
+  const uint32_t pre_sm = (uint32_t)__cvta_generic_to_shared(pre), nyq_sm = (uint32_t)__cvta_generic_to_shared(pre_nyq);
   const int tid = threadIdx.x;
   Tw8<M> tw8;
   load_tw8<M>(tw8, tw, tid);
   const uint32_t nsg = ceil_div_dev(n_streams, (uint32_t)FPB), nitems = nsg * T;
-  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const uint32_t t = item / nsg, sq = (item - t * nsg) * FPB + threadIdx.y;
-    const bool active = sq < n_streams;
-    const uint32_t stream = stream0 + (active ? sq : n_streams - 1);
-    const bool first = t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
-    const PlanView pv = first ? first_blk : steady;
-    const float2* ypart_t = ypart + (uint64_t)t * t_stride;
-    const float* nyq_t = nyq_part ? nyq_part + (uint64_t)t * slot_stride : nullptr;
+  struct Item {
+    uint32_t t, stream, first, count;
+    bool active, firstblk;
+  };
+  auto describe = [&](uint32_t item) {
+    Item it;
+    it.t = item / nsg;
+    const uint32_t sq = (item - it.t * nsg) * FPB + threadIdx.y;
+    it.active = sq < n_streams;
+    it.stream = stream0 + (it.active ? sq : n_streams - 1);
+    it.firstblk = it.t < n_first;  // blocks covered by the transitional plan (0 or 1 of them)
+    const PlanView& pv = it.firstblk ? first_blk : steady;
+    it.first = pv.job_slot_first[it.stream];
+    it.count = pv.job_slot_count[it.stream];
+    return it;
+  };
+  auto prefetch = [&](const Item& it) {
+    const uint32_t npre = min(it.count, (uint32_t)PRE);
+    const float2* row = ypart + (uint64_t)it.t * t_stride + (uint64_t)it.first * s_stride + tid;
+    for (uint32_t sl = 0; sl < npre; sl++, row += s_stride) {
+#pragma unroll
+      for (int h = 0; h < 8; h++) ac::cp_async8(pre_sm + (sl * M + tid + h * NT) * 8u, row + h * NT);
+    }
+    if (tid == 0 && nyq_part)
+      for (uint32_t sl = 0; sl < npre; sl++) ac::cp_async4(nyq_sm + sl * 4u, nyq_part + (uint64_t)it.t * slot_stride + it.first + sl);
+    ac::cp_async_commit();
+  };
+  uint32_t item = blockIdx.x;
+  Item cur = Item();
+  if (item < nitems) {
+    cur = describe(item);
+    prefetch(cur);
+  }
+  for (; item < nitems; item += gridDim.x) {
+    const bool more = item + gridDim.x < nitems;
+    Item nxt = cur;
+    if (more) nxt = describe(item + gridDim.x);  // plan entries of the next item: loaded under the wait below
+    const float2* ypart_t = ypart + (uint64_t)cur.t * t_stride;
+    const float* nyq_t = nyq_part ? nyq_part + (uint64_t)cur.t * slot_stride : nullptr;
+    // ---- sums of the job's slots in fixed order: staged slots first, the rest (jobs of more than PRE slots) directly ----
+    float2 a[8];
+#pragma unroll
+    for (int h = 0; h < 8; h++) a[h] = make_float2(0.f, 0.f);
+    float n = 0.f;
+    ac::cp_async_wait_all();
+    const uint32_t npre = min(cur.count, (uint32_t)PRE);
+    for (uint32_t sl = 0; sl < npre; sl++) {
+      float2 v[8];
+#pragma unroll
+      for (int h = 0; h < 8; h++) v[h] = pre[sl * M + tid + h * NT];
+#pragma unroll
+      for (int h = 0; h < 8; h++) {
+        a[h].x += v[h].x;
+        a[h].y += v[h].y;
+      }
+      if (tid == 0 && nyq_t) n += pre_nyq[sl];
+    }
+    for (uint32_t sl = npre; sl < cur.count; sl++) {
+      const float2* row = ypart_t + (uint64_t)(cur.first + sl) * s_stride;
+      float2 v[8];
+#pragma unroll
+      for (int h = 0; h < 8; h++) v[h] = row[tid + h * NT];
+#pragma unroll
+      for (int h = 0; h < 8; h++) {
+        a[h].x += v[h].x;
+        a[h].y += v[h].y;
+      }
+      if (tid == 0 && nyq_t) n += nyq_t[cur.first + sl];
+    }
+    // bin 0: the MAC kernels left G = DC - N in the real part; add the Nyquist sum back (same slot order)
+    if (tid == 0 && nyq_t) a[0] = make_float2(a[0].x + n, n);
+    if (more) prefetch(nxt);  // this thread's staging elements are in registers now: the next item's rows go in flight
+    // ---- summed spectrum -> time domain ----
     float o[RAD];
-    job_to_block8<M>(ypart_t, nyq_t, s_stride, pv.job_slot_first[stream], pv.job_slot_count[stream], x, s, tw8, tid, o);
-    const uint32_t xj = first ? pv.xjob[stream] : kNoJob;
+#pragma unroll
+    for (int h = 0; h < 8; h++) x[tid + h * NT] = a[h];
+    fft_bar<M>();  // x complete; also: every thread of the transform is past its reads of s from the previous item
+    {
+      float2 v[8];
+      irfft_unsplit8<M>(x, tw8, v, tid);
+      pass8_first<M, true>(v, s, tid);
+      passes8_rest<M, true>(s, tw8, tid);
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        float2 z = s[PADM<M>(M / 2 + tid + h * NT)];
+        o[2 * h] = z.x;
+        o[2 * h + 1] = z.y;
+      }
+    }
+    const PlanView& pv = cur.firstblk ? first_blk : steady;
+    const uint32_t xj = cur.firstblk ? pv.xjob[cur.stream] : kNoJob;
     // the barriers inside job_to_block8 span one transform (M = 512) or the CTA: the decision to run the second
     // pass is made CTA-uniform so that both cases are safe
-    const int any_x = __syncthreads_or(xj != kNoJob && xj != kSameJob);
+    const int any_x = n_first ? __syncthreads_or(xj != kNoJob && xj != kSameJob) : 0;
     float o2[RAD];
     if (any_x) {
       const bool mine = (xj != kNoJob && xj != kSameJob);
@@ -282,20 +382,20 @@ k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_
       for (int h = 0; h < RAD / 2; h++)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-          const uint32_t n = 2 * (tid + h * NT) + c;
-          const float g = __fmul_rn((float)n, inc);
-          const float a = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
-          const float b = __fmul_rn(g, o2[2 * h + c]);
-          o[2 * h + c] = __fadd_rn(a, b);
+          const uint32_t nn = 2 * (tid + h * NT) + c;
+          const float g = __fmul_rn((float)nn, inc);
+          const float aa = __fmul_rn(__fsub_rn(1.0f, g), o[2 * h + c]);
+          const float bb = __fmul_rn(g, o2[2 * h + c]);
+          o[2 * h + c] = __fadd_rn(aa, bb);
         }
     }
-    if (active) {
-      float* ring = ybuf + (uint64_t)stream * Rd;
-      const uint32_t w = (wpos0 + t * (uint32_t)M) % Rd;
+    if (cur.active) {
+      float* ring = ybuf + (uint64_t)cur.stream * Rd;
+      const uint32_t w = (wpos0 + cur.t * (uint32_t)M) % Rd;
 #pragma unroll
       for (int h = 0; h < RAD / 2; h++) {
-        const uint32_t n = 2 * (tid + h * NT);
-        uint32_t idx = w + n;  // w and n are even, Rd is a multiple of the block size: the pair never straddles the wrap
+        const uint32_t nn = 2 * (tid + h * NT);
+        uint32_t idx = w + nn;  // w and nn are even, Rd is a multiple of the block size: the pair never straddles the wrap
         if (idx >= Rd) idx -= Rd;
         if ((Rd & 1u) == 0 && (w & 1u) == 0) {
           *reinterpret_cast<float2*>(ring + idx) = make_float2(o[2 * h], o[2 * h + 1]);
@@ -307,6 +407,7 @@ k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_
         }
       }
     }
+    cur = nxt;
   }
 }
 

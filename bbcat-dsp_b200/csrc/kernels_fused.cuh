@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB) k_block_fused(
       rfft_split_store8<M>(s, tw8, row, 1.0f, tid, active);
     } else {
 #pragma unroll
-      for (int r = 0; r < RAD; r++) s[PAD(tid + r * NT)] = v[r];
+      for (int r = 0; r < RAD; r++) s[PADM<M>(tid + r * NT)] = v[r];
       __syncthreads();
       cfft_smem<M, false>(s, a.tw, tid);
       rfft_split_store<M>(s, a.tw, row, 1.0f, tid, active);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB) k_block_fused(
       passes8_rest<M, true>(s, tw8, tid);
 #pragma unroll
       for (int h = 0; h < 4; h++) {
-        const float2 z = s[PAD(M / 2 + tid + h * NT)];
+        const float2 z = s[PADM<M>(M / 2 + tid + h * NT)];
         out[2 * h] = z.x;
         out[2 * h + 1] = z.y;
       }
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB) k_block_fused(
       cfft_smem<M, true>(s, a.tw, tid);
 #pragma unroll
       for (int h = 0; h < RAD / 2; h++) {
-        const float2 z = s[PAD(M / 2 + tid + h * NT)];
+        const float2 z = s[PADM<M>(M / 2 + tid + h * NT)];
         out[2 * h] = z.x;
         out[2 * h + 1] = z.y;
       }
