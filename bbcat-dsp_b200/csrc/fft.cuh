@@ -58,9 +58,6 @@ __device__ __forceinline__ int PADM(int i) {
   if constexpr (M == 64 || M == 512 || M == 4096) return i ^ ((i >> 3) & 15);
   else return PAD(i);
 }
-#ifndef BBX_FFT_MINB
-#define BBX_FFT_MINB 2
-#endif
 
 // 4-point DFT, outputs in natural order
 template <bool INV>

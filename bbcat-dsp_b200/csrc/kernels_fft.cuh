@@ -35,7 +35,7 @@ k_rfft(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, f
 // item's window prefetched into registers, the first pass straight from those registers, and (for M = 512) one named
 // barrier per transform instead of the block barrier.
 template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB, (FftCfg<M>::NT * FftCfg<M>::FPB <= 256) ? BBX_FFT_MINB : 1)
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB, (FftCfg<M>::NT * FftCfg<M>::FPB <= 256) ? 2 : 1)
 k_rfft8(const float* __restrict__ src, uint64_t ch_stride, uint32_t win_stride, float2* __restrict__ dst, uint64_t dst_ch_stride,
         uint32_t R, uint32_t slot0, const float2* __restrict__ tw, float scale, uint32_t nch, uint32_t T) {
   constexpr int NT = FftCfg<M>::NT, FPB = FftCfg<M>::FPB, MP = FftCfg<M>::MP;
@@ -245,17 +245,14 @@ __device__ __forceinline__ void job_to_block8(const float2* __restrict__ ypart_t
 // the staging area is free again as soon as the thread has the sums in registers.  Without it the kernel alternated
 // between a load phase with 64 bytes in flight per thread and a transform phase with none (34 us per 64-block C3 step for
 // 90 MB of traffic).
-#ifndef BBX_IRFFT_PRE
-#define BBX_IRFFT_PRE 3
-#endif
-static constexpr int kIrfftPre = BBX_IRFFT_PRE;
+static constexpr int kIrfftPre = 3;
 template <int M>
 constexpr size_t irfft8_smem_bytes() {
   return sizeof(float2) * (size_t)FftCfg<M>::FPB * (M + FftCfg<M>::MP + kIrfftPre * M) + sizeof(float) * FftCfg<M>::FPB * 4;
 }
 
 template <int M>
-__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB, (FftCfg<M>::NT * FftCfg<M>::FPB <= 256) ? BBX_FFT_MINB : 1)
+__global__ void __launch_bounds__(FftCfg<M>::NT * FftCfg<M>::FPB, (FftCfg<M>::NT * FftCfg<M>::FPB <= 256) ? 2 : 1)
 k_irfft8(const float2* __restrict__ ypart, uint32_t slot_stride, PlanView first_blk, PlanView steady, uint32_t n_first,
          const float2* __restrict__ tw, float* __restrict__ ybuf, uint32_t Rd, uint32_t wpos0, uint32_t n_streams,
          const float* __restrict__ nyq_part, uint64_t t_stride, uint64_t s_stride, uint32_t stream0, uint32_t T) {

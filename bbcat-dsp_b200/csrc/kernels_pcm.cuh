@@ -311,48 +311,71 @@ __global__ void __launch_bounds__(256) k_pcm_out128(PcmOutArgs a) {
   const bool cached = nr <= kPcmOutCache;
   if (cached && threadIdx.x < nr) s_rt[threadIdx.x] = a.rv.entry[r0 + threadIdx.x];
   __syncthreads();
-  // phase 1: lanes over frames; thread: outputs warp + {0, 8, 16, 24}, 4 x 32 frames each
+  // phase 1: lanes over frames; thread: outputs warp + {0, 8, 16, 24}, 4 x 32 frames each.  The route entries of the
+  // four outputs are resolved first, then the ring reads of every single-path output are issued together (up to 16
+  // loads in flight per thread: with one output after the other the kernel was a chain of four DRAM round trips per
+  // CTA behind the two of the route tables), then the general outputs take the per-route loop.
+  const uint32_t nb = f0 - t * a.B + lane;  // frame inside the block of the first of the four chunks
+  uint32_t q_rb[4], q_re[4], q_stream[4], q_icur[4];
+  float q_gain[4];
+  bool q_simple[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    const uint32_t cl = warp + 8 * q, o = c0 + cl;
-    float bus[4] = {0.f, 0.f, 0.f, 0.f};
-    if (o < a.n_outputs) {
-      const uint32_t rb = s_first[cl], re = s_first[cl + 1];
-      const uint32_t nb = f0 - t * a.B + lane;  // frame inside the block of the first of the four chunks
-      bool done = false;
-      if (re == rb + 1 && !a.fractional) {
-        const RouteEntry en = cached ? s_rt[rb - r0] : a.rv.entry[rb];
+    const uint32_t cl = warp + 8 * q;
+    q_simple[q] = false;
+    q_rb[q] = q_re[q] = 0;
+    q_stream[q] = q_icur[q] = 0;
+    q_gain[q] = 0.f;
+    if (c0 + cl < a.n_outputs) {
+      q_rb[q] = s_first[cl];
+      q_re[q] = s_first[cl + 1];
+      if (q_re[q] == q_rb[q] + 1 && !a.fractional) {
+        const RouteEntry en = cached ? s_rt[q_rb[q] - r0] : a.rv.entry[q_rb[q]];
         if (!(t == 0 && (en.flags & 1u))) {
-          done = true;
-          if (en.gain != 0.0f) {
-            const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = delayed_read(ring, a.Rd, w, nb + 32 * k, 0.0, en.icur, 0);
-#pragma unroll
-            for (int k = 0; k < 4; k++) bus[k] = __fadd_rn(0.f, __fmul_rn(en.gain, v[k]));
-          }
+          q_simple[q] = true;
+          q_stream[q] = en.stream;
+          q_icur[q] = en.icur;
+          q_gain[q] = en.gain;
         }
       }
-      if (!done) {
+    }
+  }
+  float v[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float* ring = a.ybuf + (uint64_t)q_stream[q] * a.Rd;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      v[q][k] = (q_simple[q] && q_gain[q] != 0.0f) ? delayed_read(ring, a.Rd, w, nb + 32 * k, 0.0, q_icur[q], 0) : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t cl = warp + 8 * q;
+    float bus[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q_simple[q]) {
+      if (q_gain[q] != 0.0f) {  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
+#pragma unroll
+        for (int k = 0; k < 4; k++) bus[k] = __fadd_rn(0.f, __fmul_rn(q_gain[q], v[q][k]));
+      }
+    } else if (c0 + cl < a.n_outputs) {
+      const uint32_t rb = q_rb[q], re = q_re[q];
 #pragma unroll 1
-        for (int k = 0; k < 4; k++) {
-          const uint32_t n = nb + 32 * k;
-          float b = 0.f;
-          for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
-            const RouteEntry en = cached ? s_rt[r - r0] : a.rv.entry[r];
-            if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
-            const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
-            float v = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
-            if (t == 0 && (en.flags & 1u)) {
-              const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
-              const float g = __fmul_rn((float)n, inc);
-              v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, v));
-            }
-            b = __fadd_rn(b, __fmul_rn(en.gain, v));  // dst += mul * src, rounded separately
+      for (int k = 0; k < 4; k++) {
+        const uint32_t n = nb + 32 * k;
+        float b = 0.f;
+        for (uint32_t r = rb; r < re; r++) {  // ascending stream order == MixSamples call order
+          const RouteEntry en = cached ? s_rt[r - r0] : a.rv.entry[r];
+          if (!(en.gain != 0.0f)) continue;  // (mul != T()): a zero gain is a no-op (src/SoundMixing.h:65-69)
+          const float* ring = a.ybuf + (uint64_t)en.stream * a.Rd;
+          float vv = delayed_read(ring, a.Rd, w, n, en.dcur, en.icur, a.fractional);
+          if (t == 0 && (en.flags & 1u)) {
+            const float vo = delayed_read(ring, a.Rd, w, n, en.dold, en.iold, a.fractional);
+            const float g = __fmul_rn((float)n, inc);
+            vv = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, g), vo), __fmul_rn(g, vv));
           }
-          bus[k] = b;
+          b = __fadd_rn(b, __fmul_rn(en.gain, vv));  // dst += mul * src, rounded separately
         }
+        bus[k] = b;
       }
     }
 #pragma unroll
