@@ -56,6 +56,7 @@ k_fdl_mac_tbw(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
   const uint32_t crow = lane >> 2, cpiece = (lane & 3) * 16;
   const uint32_t chunk_bytes_g = CH * B * (uint32_t)sizeof(float2);
   const uint64_t ring_bytes_g = (uint64_t)R * B * sizeof(float2);
+  const uint64_t ystride = (uint64_t)slot_stride * B;  // float2 elements between the partial sums of consecutive block-steps
 
   float2 acc[TT], W[TT];
 #pragma unroll
@@ -69,7 +70,7 @@ k_fdl_mac_tbw(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
       for (int i = 0; i < TT; i++) acc[i] = make_float2(0.f, 0.f);
     }
     // ---- this lane's copy cursors for the segment ----
-    uint32_t base = s0 + R - (sg.p0 % R);
+    uint32_t base = s0 + R - sg.p0;  // p0 < P <= R (R = P + T_max - 1): no reduction of p0 needed
     if (base >= R) base -= R;
     int xr = (int)(base + FILL - 1) - (int)crow;  // FDL ring row of my row of the next FDL chunk
     while (xr >= (int)R) xr -= (int)R;
@@ -154,10 +155,17 @@ k_fdl_mac_tbw(const MacSeg* __restrict__ segs, const uint32_t* __restrict__ cta_
     xrow0 = (xrow0 + ((nx + 15) & ~15u)) & (C::XR - 1);
     hrow0 = (hrow0 + ((np + 15) & ~15u)) & (C::HR - 1);
     if (sg.flags & 2u) {
+      // one address, then a constant stride per block-step; full tiles (every tile of a 64-block call) skip the bound checks
       const uint32_t tb = tbase0 + tile * TT;
+      float2* yp = ypart + ((uint64_t)tb * slot_stride + sg.slot) * B + col0 + col;
+      if (tb + TT <= nt) {
 #pragma unroll
-      for (int i = 0; i < TT; i++)
-        if (tb + i < nt) ypart[((uint64_t)(tb + i) * slot_stride + sg.slot) * B + col0 + col] = acc[i];
+        for (int i = 0; i < TT; i++, yp += ystride) *yp = acc[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < TT; i++, yp += ystride)
+          if (tb + i < nt) *yp = acc[i];
+      }
     }
   }
   ac::cp_async_wait_all();
