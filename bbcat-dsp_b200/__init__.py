@@ -147,6 +147,8 @@ SYMBOLS = {
     "bbx_fbank_get_state": (C.c_int, [vp, u32, vp, vp, vp]),
     "bbx_fbank_reset": (C.c_int, [vp]),
     "bbx_fbank_launches": (C.c_int, [vp, C.POINTER(u64)]),
+    "bbx_probe_launch_sync": (C.c_int, [C.c_int, u32, u32, C.POINTER(C.c_double)]),
+    "bbx_block_latency": (C.c_int, [vp, vp, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, u32, u32, u32, u32, C.POINTER(C.c_double)]),
     "bbx_sofa_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "bbx_sofa_open_memory": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "bbx_sofa_close": (C.c_int, [vp]),
@@ -769,6 +771,14 @@ class Convolver:
         """Raw host pointers (e.g. pinned buffers); synchronous, copies included."""
         _check(lib().bbx_process(self.h, vp(in_ptr), infmt, 0, in_channels, vp(out_ptr), outfmt, 0, out_channels, nframes))
 
+    def BlockLatency(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes, ncalls, warmup=100):
+        """Host time (us) of each of ncalls synchronous bbx_process calls on the same buffers, measured inside libbbx
+        (bbx_block_latency): what a C / C++ caller sees, without the ctypes call around every block."""
+        us = np.empty(ncalls, dtype=np.float64)
+        _check(lib().bbx_block_latency(self.h, vp(in_ptr), infmt, 0, in_channels, vp(out_ptr), outfmt, 0, out_channels, nframes,
+                                       ncalls, warmup, us.ctypes.data_as(C.POINTER(C.c_double))))
+        return us
+
     def ConvolveHostPtrAsync(self, in_ptr, infmt, in_channels, out_ptr, outfmt, out_channels, nframes):
         """Raw PINNED host pointers; returns after enqueueing (H2D, kernels, D2H on separate streams).  The buffers
         must stay untouched until Sync()."""
@@ -900,6 +910,13 @@ def probe_fp32_tflops(device=0, seconds=0.5):
     b, s_ = C.c_float(0), C.c_float(0)
     _check(lib().bbx_probe_fp32_tflops(device, seconds, C.byref(b), C.byref(s_)))
     return b.value, s_.value
+
+
+def probe_launch_sync(device=0, ncalls=2000, warmup=200):
+    """Host time (us) of ncalls round trips "one trivial kernel + cudaStreamSynchronize", timed inside libbbx."""
+    us = np.empty(ncalls, dtype=np.float64)
+    _check(lib().bbx_probe_launch_sync(device, ncalls, warmup, us.ctypes.data_as(C.POINTER(C.c_double))))
+    return us
 
 
 def comm_unique_id():

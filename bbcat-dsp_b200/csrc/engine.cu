@@ -27,6 +27,8 @@
 #include <unordered_set>
 #include <vector>
 
+#include <time.h>
+
 #include <nvtx3/nvToolsExt.h>  // header-only; a no-op (one pointer test per call) unless a profiler is attached
 
 #include "common.cuh"
@@ -163,6 +165,7 @@ struct bbx_engine {
   // instead of going through the copy engines and the staging buffers; 0 disables
   size_t direct_io_max_bytes = 1u << 20;
   uint64_t direct_calls = 0;
+  bool copy_streams_busy = true;  // work has been enqueued on s_in / s_out since the last full synchronise
   float4* flush_buf = nullptr;
   size_t flush_bytes = 0;
   // route tables (device blob + pinned staging)
@@ -1776,6 +1779,7 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
   }
   const int k = (int)(e->host_calls % bbx_engine::kIoSlots);
   e->host_calls++;
+  e->copy_streams_busy = true;
   if (direct_in || direct_out) e->direct_calls++;
   // H2D on the input-copy stream, once the kernels of call n - kIoSlots have finished reading this staging buffer
   bool fed = false;
@@ -1819,9 +1823,15 @@ int bbx_process_async(bbx_engine* e, const void* in, int infmt, int in_be, uint3
 int bbx_engine_sync(bbx_engine* e) {
   BBX_REQUIRE(e != nullptr, "bbx_engine_sync: null engine");
   DeviceGuard dg(e->device);
-  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
+  // the copy streams only carry work of the staged host path and of the timer: a latency call (everything on the engine
+  // stream) does not pay two driver calls for idle streams
+  const bool copies = e->copy_streams_busy;
+  if (copies) BBX_CUDA_TRY(cudaStreamSynchronize(e->s_in));
   BBX_CUDA_TRY(cudaStreamSynchronize(e->stream));
-  BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  if (copies) {
+    BBX_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+    e->copy_streams_busy = false;
+  }
   if (e->px_status_h && *(volatile int*)e->px_status_h) {
     set_error("peer mixdown: rank %d never published its partial spectra (timed out); results are invalid",
               *(volatile int*)e->px_status_h - 1);
@@ -1848,6 +1858,20 @@ int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in
   return bbx_engine_sync(e);
 }
 
+int bbx_block_latency(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt, int out_be,
+                      uint32_t out_channels, uint32_t nframes, uint32_t ncalls, uint32_t warmup, double* us) {
+  BBX_REQUIRE(e && us && ncalls, "bbx_block_latency: null argument");
+  for (uint32_t i = 0; i < warmup + ncalls; i++) {
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    const int rc = bbx_process(e, in, infmt, in_be, in_channels, out, outfmt, out_be, out_channels, nframes);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (rc) return rc;
+    if (i >= warmup) us[i - warmup] = (double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3;
+  }
+  return BBX_OK;
+}
+
 int bbx_blockconvolver_convolve(bbx_engine* e, const float* in, float* out) {
   BBX_REQUIRE(e && in && out, "bbx_blockconvolver_convolve: null argument");
   BBX_REQUIRE(e->n_in == 1 && e->n_out == 1, "bbx_blockconvolver_convolve: engine must be single-channel");
@@ -1859,6 +1883,7 @@ int bbx_engine_timer_start(bbx_engine* e) {
   // nothing of the timed region may start before the start event: drain, record, and fence the other streams
   int rc = bbx_engine_sync(e);
   if (rc) return rc;
+  e->copy_streams_busy = true;
   BBX_CUDA_TRY(cudaEventRecord(e->ev_start, e->s_in));
   BBX_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_start, 0));
   BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_start, 0));
@@ -2206,6 +2231,37 @@ int bbx_engine_tensor_status(bbx_engine* e, uint64_t* launches, int* status) {
     *status = 0;
     if (e->tc_status_h) *status = *(volatile int*)e->tc_status_h;
   }
+  return BBX_OK;
+}
+
+__global__ void k_touch(float* x) { x[threadIdx.x] += 1.0f; }
+
+int bbx_probe_launch_sync(int device, uint32_t ncalls, uint32_t warmup, double* us) {
+  BBX_REQUIRE(us && ncalls, "bbx_probe_launch_sync: null argument");
+  int rc = require_device();
+  if (rc) return rc;
+  DeviceGuard dg(device);
+  float* x = nullptr;
+  cudaStream_t s = nullptr;
+  BBX_CUDA_TRY(cudaMalloc((void**)&x, 32 * sizeof(float)));
+  BBX_CUDA_TRY(cudaMemset(x, 0, 32 * sizeof(float)));
+  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (uint32_t i = 0; i < warmup + ncalls; i++) {
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    k_touch<<<1, 32, 0, s>>>(x);
+    const cudaError_t se = cudaStreamSynchronize(s);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (se != cudaSuccess) {
+      set_error("bbx_probe_launch_sync: %s", cudaGetErrorString(se));
+      cudaStreamDestroy(s);
+      cudaFree(x);
+      return BBX_ERR_CUDA;
+    }
+    if (i >= warmup) us[i - warmup] = (double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3;
+  }
+  cudaStreamDestroy(s);
+  cudaFree(x);
   return BBX_OK;
 }
 

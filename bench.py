@@ -324,9 +324,14 @@ def block_latency(eng, bbx, fmt_in, in_ch, fmt_out, out_ch, blk, n=10000, warm=2
         if i >= warm:
             lat[i - warm] = time.perf_counter() - t0
     lat *= 1e6
-    r = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "max_us": float(lat.max()), "blocks": n,
+    # the same calls timed inside libbbx (bbx_block_latency: CLOCK_MONOTONIC around each bbx_process): the latency at the
+    # C ABI, which is what a C++ host of the reference sees; the loop above adds a Python / ctypes call per block
+    clat = eng.BlockLatency(hin.ptr, fmt_in, in_ch, hout.ptr, fmt_out, out_ch, blk, n, warm)
+    r = {"p50_us": float(np.percentile(clat, 50)), "p99_us": float(np.percentile(clat, 99)), "max_us": float(clat.max()), "blocks": n,
+         "python_p50_us": float(np.percentile(lat, 50)), "python_p99_us": float(np.percentile(lat, 99)),
          "block_period_us": 1e6 * blk / FS, "direct_calls": eng.direct_calls() - d0,
-         "mode": "T=1, bbx_process with pinned host buffers, host clock around the synchronous call"}
+         "mode": "T=1, bbx_process with pinned host buffers, host clock around the synchronous call; p50 / p99 / max = timed at "
+                 "the C ABI (bbx_block_latency), python_* = the same call through ctypes"}
     hin.close()
     hout.close()
     return r
@@ -1048,6 +1053,10 @@ def main():
     configs = None
     roofline_mimo = None
     floor = launch_sync_floor(torch) if (rank == 0 and world == 1 and not args.no_latency) else None
+    if floor is not None:
+        cf = bbx.probe_launch_sync(local)
+        floor["c_p50_us"], floor["c_min_us"] = float(np.percentile(cf, 50)), float(cf.min())
+        floor["c_what"] = "the same round trip from C inside libbbx (bbx_probe_launch_sync): the floor under latency.p50_us"
     if rank == 0 and world == 1:
         configs = {"C3": {"config": WORKLOAD, "channels": NCH, "value": value, "unit": "channel-s/s", "ms_per_step": ms / args.steps,
                           "blocks_per_step": nblk, "parity": parity, "snr_db": parity["snr_db"] if parity else None, "latency": latency}}

@@ -258,6 +258,11 @@ int bbx_process(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in
                 int out_be, uint32_t out_channels, uint32_t nframes);
 int bbx_process_dev(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out,
                     int outfmt, int out_be, uint32_t out_channels, uint32_t nframes);
+/* measurement aid: warmup + ncalls synchronous bbx_process calls on the same buffers, the host time of each of the last
+ * ncalls (CLOCK_MONOTONIC around the call, microseconds) into us[ncalls] -- the per-block latency a C / C++ host sees at this
+ * boundary, without the cost of a scripting language's foreign-function call around it */
+int bbx_block_latency(bbx_engine* e, const void* in, int infmt, int in_be, uint32_t in_channels, void* out, int outfmt, int out_be,
+                      uint32_t out_channels, uint32_t nframes, uint32_t ncalls, uint32_t warmup, double* us);
 /* Host pointers, asynchronous: returns once the H2D copy, the kernels and the D2H copy are enqueued (copies on
  * their own streams, three staging buffers per direction), so consecutive calls overlap transfer and compute.  `in` and
  * `out` must stay valid and untouched until bbx_engine_sync(); use pinned buffers (bbx_host_alloc). */
@@ -466,6 +471,9 @@ int bbx_engine_tensor_trace(bbx_engine* e, uint64_t* out, uint32_t max_ctas);
 /* FP32 roofline probe: the rate (TFLOP/s) a pure packed-FMA kernel with the MAC's operand pattern reaches on this GPU:
  * best of five isolated launches (burst) and averaged over `seconds` of back-to-back launches (sustained, power cap) */
 int bbx_probe_fp32_tflops(int device, float seconds, float* burst, float* sustained);
+/* the floor under every per-block latency on this host: one trivial kernel on a stream + cudaStreamSynchronize, the host
+ * time of each of ncalls round trips (after warmup) in microseconds, timed inside the library like bbx_block_latency */
+int bbx_probe_launch_sync(int device, uint32_t ncalls, uint32_t warmup, double* us);
 /* write `bytes` of a scratch buffer on the engine stream (L2 flush between timed iterations) */
 int bbx_engine_flush_l2(bbx_engine* e, size_t bytes);
 
