@@ -323,6 +323,22 @@ PlanView shard_plan_view(const bbx_engine* e) {
   return v;
 }
 
+// persistent grid of k_irfft8<M> on the current device; its dynamic shared memory (workspace + staging of the next item) is
+// above the 48 KB default, and function attributes belong to a device's context: set once per device, not once per process
+template <int M>
+uint32_t irfft8_grid() {
+  static uint32_t grid[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!grid[dev]) {
+    constexpr size_t smem8 = irfft8_smem_bytes<M>();
+    if (smem8 > 48 * 1024) cudaFuncSetAttribute(k_irfft8<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+    grid[dev] = persistent_grid(k_irfft8<M>, FftCfg<M>::NT * FftCfg<M>::FPB, smem8, 1u << 30);
+  }
+  return grid[dev];
+}
+
 template <int M>
 void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaStream_t st) {
   const float2* ypart = e->ypart;
@@ -338,11 +354,7 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaSt
     const float2* spectra = e->px_on ? (const float2*)e->px_mem + (uint64_t)(e->px_epoch & 1u) * e->px_half : e->sh_recv;
     if constexpr (FftCfg<M>::R == 8) {
       constexpr size_t smem8 = irfft8_smem_bytes<M>();
-      static uint32_t per_sm_grid = 0;
-      if (!per_sm_grid) {
-        if (smem8 > 48 * 1024) cudaFuncSetAttribute(k_irfft8<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-        per_sm_grid = persistent_grid(k_irfft8<M>, FftCfg<M>::NT * FPB, smem8, 1u << 30);
-      }
+      const uint32_t per_sm_grid = irfft8_grid<M>();
       const uint32_t nitems = ceil_div(e->sh_nloc, FPB) * T;
       k_irfft8<M><<<std::min(nitems, per_sm_grid), dim3(FftCfg<M>::NT, FPB), smem8, st>>>(
           spectra, e->max_slots, v, v, 0, e->tw, e->ybuf, e->Rd, e->wpos, e->sh_nloc, nullptr, (uint64_t)M, (uint64_t)T * M,
@@ -358,11 +370,7 @@ void launch_irfft_t(bbx_engine* e, uint32_t T, uint32_t n_first, bool tc, cudaSt
   const PlanView steady = tc ? tc_plan_view(e) : e->plan_steady.view();
   if constexpr (FftCfg<M>::R == 8) {
     constexpr size_t smem8 = irfft8_smem_bytes<M>();
-    static uint32_t per_sm_grid = 0;
-    if (!per_sm_grid) {
-      if (smem8 > 48 * 1024) cudaFuncSetAttribute(k_irfft8<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-      per_sm_grid = persistent_grid(k_irfft8<M>, FftCfg<M>::NT * FPB, smem8, 1u << 30);
-    }
+    const uint32_t per_sm_grid = irfft8_grid<M>();
     const uint32_t nitems = ceil_div(e->n_streams, FPB) * T;
     k_irfft8<M><<<std::min(nitems, per_sm_grid), dim3(FftCfg<M>::NT, FPB), smem8, st>>>(
         ypart, e->max_slots, first, steady, n_first, e->tw, e->ybuf, e->Rd, wpos, e->n_streams, tc ? nullptr : nyq_part,
