@@ -749,6 +749,28 @@ def test_objects_keep_their_device(bbx, gpu):
 
 
 @pytest.mark.gpu
+def test_same_engine_on_two_devices_of_one_process(bbx, gpu):
+    """Kernels that need more than the default dynamic shared memory (k_irfft8 with its staging area, the batched MAC) set
+    their function attributes per device: the same engine created on GPU 0 and then on GPU 1 of one process gives the
+    same bytes (block sizes of both radix-8 kinds, calls long enough for the multi-kernel and the time-batched paths)."""
+    if bbx.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    for B, P, T in ((512, 3, 2), (64, 40, 40), (4096, 2, 2)):
+        nch = 3
+        irs = [make_ir(900 + c, P * B - 5) for c in range(nch)]
+        x = interleave([make_noise(910 + c, T * B) for c in range(nch)])
+        outs = []
+        for dev in (0, 1):
+            eng = bbx.Convolver(B, P, nch, max_blocks=T, device=dev)
+            for c in range(nch):
+                eng.SelectFilter(c, eng.CreateFilter(irs[c]))
+            outs.append(np.concatenate([eng.Convolve(x, bbx.FMT_FLOAT, nch, bbx.FMT_FLOAT, nch, T * B) for _ in range(2)]))
+            eng.close()
+        assert np.array_equal(outs[0], outs[1]), "B = %d: GPU 1 differs from GPU 0" % B
+        assert np.abs(outs[0].view(np.float32)).max() > 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["per_channel", "routed", "mimo"])
 def test_state_checkpoint_resume(bbx, mode):
     """bbx_engine_get_state / set_state: a fresh engine with the same filters, resumed from a checkpoint taken in the middle
