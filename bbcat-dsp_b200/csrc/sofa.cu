@@ -452,16 +452,15 @@ int bbx_sofa_nearest_measurement(const bbx_sofa* s, const double pos[3], int sph
   const bbx_sofa::Pos& p = s->pos[BBX_SOFA_SOURCE];
   BBX_REQUIRE(p.present, "bbx_sofa_nearest_measurement: the file has no SourcePosition");
   double q[3];
-  to_cartesian(pos, spherical != 0, q);
-  // a query without a usable radius selects by direction: both sides are normalised
-  const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-  bool by_direction = false;
-  if (spherical && !(pos[2] > 0.0)) {
-    const double one[3] = {pos[0], pos[1], 1.0};
-    to_cartesian(one, true, q);
-    by_direction = true;
+  // a spherical query without a usable radius selects by direction: the query becomes a unit vector and the measurements
+  // are normalised below
+  const bool by_direction = spherical && !(pos[2] > 0.0);
+  if (by_direction) {
+    const double unit[3] = {pos[0], pos[1], 1.0};
+    to_cartesian(unit, true, q);
+  } else {
+    to_cartesian(pos, spherical != 0, q);
   }
-  (void)qn;
   double best = 0.0;
   uint32_t best_m = 0;
   for (uint32_t i = 0; i < s->M; i++) {
