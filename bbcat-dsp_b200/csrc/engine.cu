@@ -1050,10 +1050,17 @@ int bbx_engine_create(const bbx_config* cfg, bbx_engine** out) {
       p.input = p.output = k;
     }
   }
-  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-  BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
+  {
+    // the engine stream outranks the side stream: when the MAC and its side kernel become ready together, the MAC's persistent
+    // CTAs are placed first and the side kernel fills what is left (launch_mac: the enqueue order alone did not hold in every
+    // process -- a 2-rank run still showed the MAC 12 us longer, the side kernel's duration)
+    int prio_low = 0, prio_high = 0;
+    BBX_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    BBX_CUDA_TRY(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_high));
+    BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    BBX_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    BBX_CUDA_TRY(cudaStreamCreateWithPriority(&e->s_aux, cudaStreamNonBlocking, prio_low));
+  }
   BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   BBX_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < bbx_engine::kIoSlots; i++) {
