@@ -518,6 +518,13 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     if (use_tb) {
       // Nyquist sums of column 0 (the streaming kernel accumulates them inline): a few hundred latency-bound warps on the
       // side stream, enqueued after the MAC so that they run underneath it without taking its CTAs' places (see above)
+      {
+        static uint32_t carve_set = 0;  // per device; same reason as in launch_nyq_mac2 (mac_tbs.cu)
+        if (!(carve_set & (1u << (e->device & 31)))) {
+          cudaFuncSetAttribute(k_nyq_mac, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          carve_set |= 1u << (e->device & 31);
+        }
+      }
       k_nyq_mac<<<dim3(pl.n_ctas, ceil_div(nt, 32)), 32, 0, e->s_aux>>>(pl.segs(), pl.cta_seg_begin(), e->fdl,
                                                                        e->nyq_part + (uint64_t)t0 * e->max_slots, e->B, e->R,
                                                                        e->head, t0, nt, e->max_slots);

@@ -307,6 +307,16 @@ static cudaError_t launch_tbs_t(const MacTbsArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_nyq_mac2(const MacTbsArgs& a, cudaStream_t st) {
+  // The side kernel asks for the shared-memory carve-out the MAC needs (all of it).  An SM changes its carve-out only when
+  // it is empty: where a side CTA had been placed first under a smaller carve-out, the MAC's CTAs (102 KB each) had to wait
+  // for it to leave -- the MAC launch then took the side kernel's 12 us longer.  With the same carve-out they join it.
+  static uint32_t carve_set = 0;  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(carve_set & (1u << (dev & 31)))) {
+    cudaFuncSetAttribute(k_nyq_mac2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve_set |= 1u << (dev & 31);
+  }
   k_nyq_mac2<<<dim3(a.n_plan_ctas, ceil_div(a.nt, 64u)), 64, 0, st>>>(a.segs, a.cta_seg_begin, a.fdl, a.nyq_part, a.B, a.R, a.head, a.t0,
                                                                       a.nt, a.slot_stride);
   return cudaGetLastError();
