@@ -484,11 +484,12 @@ int launch_mac(bbx_engine* e, const MacPlan& pl, uint32_t t0, uint32_t nt) {
     a.nt = nt;
     a.slot_stride = e->max_slots;
     a.status = e->mac_status;
-    // the Nyquist sums of column 0 run next to the MAC on the side stream.  The MAC is enqueued FIRST: its persistent
-    // CTAs (two per SM, all of the shared memory) then take their places before the 148 small CTAs of the side kernel
-    // arrive, which fit into what is left.  Enqueued the other way round, the side kernel's CTAs were often placed first
-    // and every SM's second MAC CTA started only when they had finished: the MAC launch took 0.202 instead of 0.190 ms
-    // in four runs of six (same box, same binary).
+    // the Nyquist sums of column 0 run next to the MAC on the side stream.  The MAC is enqueued FIRST, on the stream of
+    // higher priority, so that its persistent CTAs (two per SM, all of the shared memory) usually take their places before
+    // the 148 small CTAs of the side kernel arrive.  Enqueued the other way round, the MAC launch took 0.202 instead of
+    // 0.190 ms in four runs of six (same box, same binary): the difference is the side kernel's duration.  An SM that a side
+    // CTA reaches first keeps that CTA's shared-memory carve-out until it is empty; the side kernels therefore ask for the
+    // MAC's carve-out (launch_nyq_mac2), so that MAC CTAs can join them instead of waiting.
     BBX_CUDA_TRY(cudaEventRecord(e->ev_fork, st));
     BBX_CUDA_TRY(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
     if (ev0) BBX_CUDA_TRY(cudaEventRecord(ev0, st));
