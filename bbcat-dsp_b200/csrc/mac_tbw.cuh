@@ -34,8 +34,8 @@ struct TbwCfg {
 };
 
 // Register budget: two CTAs of 256 threads per SM.  The register file is allocated in units of 8 per thread, and with 121 - 128
-// registers two CTAs would need all 64 K of it: such builds ran at ONE CTA per SM (0.2068 ms per C3 launch, whatever else
-// they changed).  Below that, fewer is better down to 112 (0.1833 ms at 116, 0.1806 at 112 for the same source; 104 and 96
+// registers two CTAs would need all 64 K of it: two unrelated builds in that range both took 0.2068 ms per C3 launch, which
+// is what one CTA per SM in two waves would give.  Below that, fewer is better down to 112 (0.1833 ms at 116, 0.1806 at 112 for the same source; 104 and 96
 // spill: 0.187 / 0.195 ms), so the budget is stated instead of left to __launch_bounds__.
 #ifndef BBX_TBW_MAXNREG
 #define BBX_TBW_MAXNREG 112
