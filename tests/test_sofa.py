@@ -4,7 +4,6 @@ The container parser of bbx_sofa_* is pinned against an independent netCDF imple
 the files (CDF-1 and CDF-2, fixed and record dimensions) and reads them back next to libbbx.  Parity against BBC's SOFA
 class is unpinned (no source, no libnetcdf here).  The GPU test builds a filter bank from a file and renders through it.
 """
-import io
 
 import numpy as np
 import pytest
